@@ -1,0 +1,246 @@
+"""Generate the committed golden vectors by RUNNING THE UNMODIFIED REFERENCE (/root/reference).
+
+Build container only (the reference is not on the GPU box):
+    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|all]
+
+Outputs (np.savez_compressed, all small):
+    env_config1.npz  BASELINE.json configs[0]: B=24, torch.manual_seed(42), 10 000 steps, episode
+                     protocol of train_torch.py:184-187, actions from Generator(1234)
+    env_fuzz.npz     SURVEY.md Appendix B: random synthetic states (bricks rows 0-4, ball anywhere)
+    env_play.npz     ball-following play from reset() (wins, losses, row -1 wrap-around)
+    mcts_fake.npz    MCTSSearchVec.search with injected RNG + deterministic fake networks
+    mcts_real.npz    same with the real fp32 MuZeroAgent (seed 0, perturbed BN), B=4; doubles as the
+                     network golden (rep-net output, per-simulation dynamics/prediction outputs)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import refshim  # noqa: E402
+from common import FakeNet, dirichlet_noise, pack_state, perturb_bn  # noqa: E402
+
+refshim.install()
+from environment.parallel_breakout import BreakoutEnvironment  # noqa: E402  (the reference)
+
+CFG = refshim.load_cfg()
+
+
+def _rec_step(env, state, action, done):
+    nxt, reward, done_out, valid = env.step(state, action, done)
+    assert done_out is done
+    return nxt, dict(state=pack_state(nxt), reward=reward.numpy().copy(), done=done.numpy().astype(np.uint8),
+                     valid=valid.numpy().astype(np.uint8), dx=env.ball_dx.numpy().astype(np.int8),
+                     dy=env.ball_dy.numpy().astype(np.float32).copy())
+
+
+def _stack(recs):
+    return {k: np.stack([r[k] for r in recs]) for k in recs[0]}
+
+
+def gen_env_config1(steps=10000, B=24):
+    torch.manual_seed(42)
+    env = BreakoutEnvironment(CFG["environment"])
+    assert env.batch == B
+    ga = torch.Generator().manual_seed(1234)
+    recs, actions, reset_at, reset_state, reset_dx = [], [], [], [], []
+    t = 0
+    while t < steps:
+        state, _ = env.reset()
+        reset_at.append(t); reset_state.append(pack_state(state)); reset_dx.append(env.ball_dx.numpy().astype(np.int8))
+        done = torch.zeros(B, dtype=torch.bool)
+        length = 0
+        while not torch.all(done) and length <= 260 and t < steps:      # train_torch.py:184-187
+            a = torch.randint(0, 3, (B,), generator=ga)
+            state, rec = _rec_step(env, state, a, done)
+            recs.append(rec); actions.append(a.numpy().astype(np.int8))
+            length += 1; t += 1
+    out = _stack(recs)
+    out.update(actions=np.stack(actions), reset_at=np.array(reset_at), reset_state=np.stack(reset_state),
+               reset_dx=np.stack(reset_dx))
+    np.savez_compressed(os.path.join(HERE, "env_config1.npz"), **out)
+    print("env_config1: steps", t, "resets", len(reset_at), "dones", int(out["done"][-1].sum()))
+
+
+def synth_state(B, g):
+    """Appendix B synthetic state: paddle x in [0,14], ball anywhere, brick PAIRS with density
+    U(0,0.3) in rows 0-4, dx in {-1,+1}, dy in {-1.0,+1.0}."""
+    s = torch.zeros(B, 3, 16, 20)
+    px = torch.randint(0, 15, (B,), generator=g)
+    for b in range(B):
+        s[b, 0, 15, px[b]:px[b] + 6] = 1
+    by = torch.randint(0, 16, (B,), generator=g)
+    bx = torch.randint(0, 20, (B,), generator=g)
+    s[torch.arange(B), 1, by, bx] = 1
+    dens = torch.rand(B, generator=g) * 0.3
+    pairs = (torch.rand(B, 5, 10, generator=g) < dens[:, None, None]).float()
+    s[:, 2, :5, :] = pairs.repeat_interleave(2, dim=2)
+    dx = torch.randint(0, 2, (B,), generator=g) * 2 - 1
+    dy = (torch.randint(0, 2, (B,), generator=g) * 2 - 1).float()
+    return s, dx, dy
+
+
+def gen_env_fuzz(seeds=60, steps=60, B=24):
+    env = BreakoutEnvironment(CFG["environment"])
+    init_state, init_dx, init_dy, all_actions, outs = [], [], [], [], []
+    for seed in range(seeds):
+        g = torch.Generator().manual_seed(1000 + seed)
+        state, dx, dy = synth_state(B, g)
+        env.ball_dx, env.ball_dy = dx.clone(), dy.clone()
+        init_state.append(pack_state(state)); init_dx.append(dx.numpy().astype(np.int8)); init_dy.append(dy.numpy().copy())
+        done = torch.zeros(B, dtype=torch.bool)
+        recs, acts = [], []
+        for _ in range(steps):
+            a = torch.randint(0, 3, (B,), generator=g)
+            state, rec = _rec_step(env, state, a, done)
+            recs.append(rec); acts.append(a.numpy().astype(np.int8))
+        outs.append(_stack(recs)); all_actions.append(np.stack(acts))
+    out = {k: np.stack([o[k] for o in outs]) for k in outs[0]}
+    out.update(init_state=np.stack(init_state), init_dx=np.stack(init_dx), init_dy=np.stack(init_dy),
+               actions=np.stack(all_actions))
+    np.savez_compressed(os.path.join(HERE, "env_fuzz.npz"), **out)
+    print("env_fuzz: env-steps", seeds * steps * B, "reward sum", float(out["reward"].sum()))
+
+
+def gen_env_play(seeds=4, steps=1000, B=24):
+    """Real play from reset() with a 90 %-ball-following policy (random play never wins)."""
+    env = BreakoutEnvironment(CFG["environment"])
+    outs, all_actions, reset_state, reset_dx = [], [], [], []
+    wins = losses = wraps = 0
+    for seed in range(seeds):
+        torch.manual_seed(2000 + seed)
+        g = torch.Generator().manual_seed(3000 + seed)
+        state, _ = env.reset()
+        reset_state.append(pack_state(state)); reset_dx.append(env.ball_dx.numpy().astype(np.int8))
+        done = torch.zeros(B, dtype=torch.bool)
+        recs, acts = [], []
+        for _ in range(steps):
+            ball = torch.where(state[:, 1] == 1)
+            bx = ball[2]
+            px = torch.argmax(state[:, 0, -1, :], dim=1) + 3
+            follow = torch.where(bx + env.ball_dx < px, 0, torch.where(bx + env.ball_dx > px, 2, 1))
+            rnd = torch.randint(0, 3, (B,), generator=g)
+            a = torch.where(torch.rand(B, generator=g) < 0.9, follow, rnd)
+            prev_done = done.clone()
+            state, rec = _rec_step(env, state, a, done)
+            newly = done & ~prev_done
+            wins += int((newly & (rec["reward"] >= 5)).sum()); losses += int((newly & (rec["reward"] == -1)).sum())
+            wraps += int(((state[:, 1, 15].sum(1) == 1) & (state[:, 2].sum((1, 2)) > 0) & (torch.tensor(rec["dy"]) == -1)).sum())
+            recs.append(rec); acts.append(a.numpy().astype(np.int8))
+        outs.append(_stack(recs)); all_actions.append(np.stack(acts))
+    out = {k: np.stack([o[k] for o in outs]) for k in outs[0]}
+    out.update(reset_state=np.stack(reset_state), reset_dx=np.stack(reset_dx), actions=np.stack(all_actions))
+    np.savez_compressed(os.path.join(HERE, "env_play.npz"), **out)
+    print("env_play: env-steps", seeds * steps * B, "wins", wins, "losses", losses, "row-15 balls moving up", wraps)
+
+
+# ----------------------------------------------------------------------------------------------- MCTS
+
+def _slots_from_trace(trace, B):
+    """Reference node names -> slot numbers in order of first expansion (root 'state_0' = 0; the
+    re-expanded sim-0 leaf keeps its name, hence its slot)."""
+    names = [{"state_0": 0} for _ in range(B)]
+    parent = np.zeros((len(trace), B), np.int32); action = np.zeros_like(parent); leaf = np.zeros_like(parent)
+    for s, t in enumerate(trace):
+        for b, (prev, a, node) in enumerate(t["last_nodes"]):
+            if node not in names[b]:
+                names[b][node] = len(names[b])
+            parent[s, b], action[s, b], leaf[s, b] = names[b][prev], a, names[b][node]
+    return parent, action, leaf
+
+
+def _run_ref_search(mu_zero, transforms, hidden, seed, noise, S, noise_weight=0.175, c1=None, c2=None):
+    from src.mcts import MCTSSearchVec
+
+    cfg = dict(CFG); cfg["num_simulations"] = S
+    cfg["search"] = dict(CFG["search"])
+    if c1 is not None: cfg["search"]["c1"] = c1
+    if c2 is not None: cfg["search"]["c2"] = c2
+    m = MCTSSearchVec(cfg, mu_zero, transforms)
+    m.noise_weight = noise_weight
+    trace = []
+    B = hidden.shape[0]
+    value, visits, proxy = refshim.injected_search(m, hidden, torch.ones(B, 3), seed, noise, trace)
+    parent, action, leaf = _slots_from_trace(trace, B)
+    return dict(value=value.numpy().astype(np.float32), visits=visits.numpy().astype(np.int64),
+                parent=parent, action=action, leaf=leaf,
+                reward=np.stack([t["rewards"].numpy() for t in trace]).astype(np.float32),
+                leaf_value=np.stack([t["values"].numpy() for t in trace]).astype(np.float32),
+                pi=np.stack([t["policies"].numpy() for t in trace]).astype(np.float32),
+                ucb_calls=np.array([proxy.ctr.get(b, 0) for b in range(B)], np.int32))
+
+
+def gen_mcts_fake():
+    from utils import ScalarTransforms
+
+    tr = ScalarTransforms(CFG["model"])
+    out = {}
+    cases = [("varied", 6, 50, 7, 0.175, None, None), ("deep", 6, 50, 8, 0.175, None, None),
+             ("flat", 6, 50, 9, 0.175, None, None), ("varied", 5, 20, 10, 0.1, 2.0, 100.0),
+             ("deep", 3, 80, 11, 0.25, None, None), ("mild", 8, 50, 12, 0.175, None, None),
+             ("mild", 4, 50, 13, 0.1, None, None)]
+    for i, (mode, B, S, seed, w, c1, c2) in enumerate(cases):
+        net = FakeNet(mode)
+        g = torch.Generator().manual_seed(seed)
+        hidden = torch.rand(B, 8, generator=g)
+        noise = dirichlet_noise(B, seed)
+        with torch.no_grad():
+            pol, val = net.evaluate_state(hidden)
+        rec = _run_ref_search(net, tr, hidden, seed, noise, S, w, c1, c2)
+        rec.update(hidden=hidden.numpy(), noise=noise.numpy(), v_root=tr.inverted_softmax_expectation(val).numpy(),
+                   pi_root=torch.softmax(pol, dim=1).numpy(),
+                   meta=np.array([B, S, seed, w, c1 or CFG["search"]["c1"], c2 or CFG["search"]["c2"]], np.float64))
+        for k, v in rec.items():
+            out[f"c{i}_{k}"] = v
+        print(f"mcts_fake case {i} {mode}: visits[0]={rec['visits'][0]} value[0]={rec['value'][0]:.6f} "
+              f"max depth parent slot={rec['parent'].max()} ucb_calls={rec['ucb_calls'].tolist()}")
+    out["modes"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(HERE, "mcts_fake.npz"), **out)
+
+
+def gen_mcts_real(B=4, S=50, seed=7):
+    from src.networks import MuZeroAgent
+    from utils import ScalarTransforms
+
+    torch.manual_seed(0)
+    agent = MuZeroAgent(CFG["model"])
+    perturb_bn(agent, 1)
+    agent.eval_mode()
+    tr = ScalarTransforms(CFG["model"])
+    g = torch.Generator().manual_seed(5)
+    rep_in = torch.rand(B, 64, 16, 20, generator=g)
+    with torch.no_grad():
+        rep_raw = agent.rep_net(rep_in)
+        hidden = agent.create_hidden_state_root(rep_in)
+        pol, val = agent.evaluate_state(hidden)
+        # one explicit dynamics + prediction call for the pure network golden
+        planes = torch.zeros(B, 3, 4, 5); planes[torch.arange(B), torch.tensor([0, 1, 2, 1][:B])] = 1
+        h2, rew = agent.hidden_state_transition(hidden, planes)
+        dyn_raw, _ = agent.dyn_net(torch.cat([hidden, planes], 1))
+        pol2, val2 = agent.evaluate_state(h2)
+    noise = dirichlet_noise(B, seed)
+    rec = _run_ref_search(agent, tr, hidden, seed, noise, S)
+    rec.update(rep_in=rep_in.numpy(), rep_raw=rep_raw.numpy(), hidden=hidden.numpy(), noise=noise.numpy(),
+               root_policy_logits=pol.numpy(), root_value_logits=val.numpy(),
+               v_root=tr.inverted_softmax_expectation(val).numpy(), pi_root=torch.softmax(pol, 1).numpy(),
+               dyn_actions=np.array([0, 1, 2, 1][:B]), dyn_raw=dyn_raw.numpy(), dyn_h=h2.numpy(), dyn_reward_logits=rew.numpy(),
+               pred_policy_logits=pol2.numpy(), pred_value_logits=val2.numpy(),
+               meta=np.array([B, S, seed], np.float64))
+    np.savez_compressed(os.path.join(HERE, "mcts_real.npz"), **rec)
+    print("mcts_real: visits", rec["visits"].tolist(), "value", rec["value"].tolist())
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    os.chdir("/tmp")
+    if what in ("env", "all"): gen_env_config1()
+    if what in ("fuzz", "all"): gen_env_fuzz()
+    if what in ("play", "all"): gen_env_play()
+    if what in ("mcts", "all"): gen_mcts_fake()
+    if what in ("net", "all"): gen_mcts_real()
