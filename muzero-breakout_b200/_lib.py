@@ -1,0 +1,92 @@
+"""Build + ctypes loader of libmzb200.so (the C ABI declared in include/mzb200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+_SO = os.path.join(_PKG, "libmzb200.so")
+_HDR = os.path.join(os.path.dirname(_PKG), "include", "mzb200.h")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lib = None
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
+
+
+def _stale() -> bool:
+    if not os.path.exists(_SO):
+        return True
+    t = os.path.getmtime(_SO)
+    deps = _sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + [_HDR]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> muzero-breakout_b200/libmzb200.so (in-tree)."""
+    if not (force or _stale()):
+        return _SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("libmzb200.so is missing/stale and nvcc was not found; there is no CPU fallback")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO + ".tmp"] + _sources() + ["-lcuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(_SO + ".tmp", _SO)
+    if verbose:
+        print(r.stderr)
+    return _SO
+
+
+def _declare(L: C.CDLL) -> None:
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    L.mzb_version.restype = i32
+    L.mzb_last_error.restype = C.c_char_p
+    L.mzb_launch_count.restype = u64
+    sig = {
+        "bk_env_reset": [i32] + [vp] * 8,
+        "bk_env_reset_device_rng": [i32, vp, vp, u64, u64, vp, vp],
+        "bk_env_step": [i32] + [vp] * 11,
+        "bk_env_ingest": [i32] + [vp] * 7,
+        "bk_env_render": [i32] + [vp] * 4,
+        "bk_env_velocity": [i32] + [vp] * 4,
+        "bk_gray": [i32] + [vp] * 3,
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes, f.restype = args, i32
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises (never falls back) when it cannot be built or loaded."""
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libmzb200 error {rc}: {lib().mzb_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().mzb_launch_count())
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("muzero_breakout_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")

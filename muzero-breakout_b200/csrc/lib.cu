@@ -1,0 +1,29 @@
+// Library-wide state of libmzb200.so: last-error string (per thread) and the launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace mzb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace mzb
+
+extern "C" {
+int mzb_version(void) { return MZB_VERSION; }
+const char *mzb_last_error(void) { return mzb::g_err; }
+uint64_t mzb_launch_count(void) { return mzb::g_launches.load(std::memory_order_relaxed); }
+}

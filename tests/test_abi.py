@@ -1,0 +1,70 @@
+"""CPU-side checks of the boundary: the C-ABI library builds for sm_100a, loads, and exports every
+symbol include/mzb200.h declares; the Python hosts mirror the reference signatures and refuse to run
+without a CUDA device (no CPU fallback).  No compute calls here."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import muzero_breakout_b200 as mzb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENV_CFG = dict(n_parallel=24, paddle_hit_reward=0.0, brick_hit_reward=1.0, game_lost_reward=-1.0, game_won_reward=5.0)
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mzb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:bk|mz|mzb)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    so = mzb.build()
+    L = ctypes.CDLL(so)
+    names = _declared()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mzb200.h but not exported by libmzb200.so"
+    assert mzb.lib().mzb_version() == 1
+
+
+def test_library_is_sm100a_native():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", mzb.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_env_class_mirrors_reference_signature():
+    from muzero_breakout_b200.environment.parallel_breakout import BreakoutEnvironment, MuZeroEnvironment
+    env = BreakoutEnvironment(ENV_CFG)
+    assert isinstance(env, MuZeroEnvironment)
+    assert list(inspect.signature(BreakoutEnvironment.__init__).parameters)[:6] == ["self", "cfg", "width", "height", "paddle_width", "brick_rows"]
+    assert list(inspect.signature(env.step).parameters)[:3] == ["state", "action", "done_mask"]
+    assert env.state_shape == (24, 3, 16, 20) and env.action_space_size == 3
+    env.batch = 2                                   # train_torch.py:448
+    assert env.state_shape == (2, 3, 16, 20)
+    v = env.get_valid_actions(None, torch.tensor([0, 5, 14]))
+    assert v.tolist() == [[0, 1, 1], [1, 1, 1], [1, 1, 0]]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from muzero_breakout_b200.environment.parallel_breakout import BreakoutEnvironment
+    env = BreakoutEnvironment(ENV_CFG)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.reset()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.step(torch.zeros(24, 3, 16, 20), torch.zeros(24, dtype=torch.long), torch.zeros(24, dtype=torch.bool))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "muzero-breakout_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+                assert "liboracle" not in text

@@ -78,4 +78,4 @@ def test_inverse_transform_is_the_reference_formula():
     assert abs(abs(float(inverted_softmax_expectation(logits))) - (1 - 0.999 ** 2)) < 1e-5
     x = torch.tensor([[0.0] * 5 + [20.0, 12.4] + [0.0] * 4])
     e = float(torch.sum(torch.softmax(x, -1) * torch.arange(-5, 6).float()))
-    assert np.isclose(float(inverted_softmax_expectation(x)), np.sign(e) * ((abs(e) + 0.999) ** 2 - 1), rtol=1e-6)
+    assert np.isclose(float(inverted_softmax_expectation(x)), np.sign(e) * ((abs(e) + 0.999) ** 2 - 1), rtol=1e-4)
