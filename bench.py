@@ -130,6 +130,9 @@ def bench_env(args, rank, local, world):
     p = lambda t: t.data_ptr()
 
     def step(i):
+        if i % args.reset_every == 0:                          # episode protocol: new games, SoA only (device RNG)
+            _lib.check(L.bk_env_reset_device_rng(B, p(env._hdr), p(env._bricks), 1234 + rank, i, None, stream))
+            done.zero_()
         _lib.check(L.bk_env_step(B, p(env._hdr), p(env._bricks), p(actions[i]), p(done), p(frames[i & 1]), p(reward), p(valid),
                                  None, env._rewards, p(env._status), stream))
 
@@ -172,7 +175,7 @@ def bench_env(args, rank, local, world):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32 logic -> f32 frames", "data": "synthetic",
         "config": {"workload": "env: BreakoutEnvironment.step, reference-format outputs (fp32 (B,3,16,20) frames + reward + done + valid)",
-                   "envs_per_gpu": B, "actions": "uniform random, resident in HBM", "l2": "per-step frame output 3840*B bytes exceeds the 126 MB L2",
+                   "envs_per_gpu": B, "actions": "uniform random, resident in HBM", "reset_every": args.reset_every, "l2": "per-step frame output 3840*B bytes exceeds the 126 MB L2",
                    "done_fraction_at_end": done_frac},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
                      "traffic": None, "peak_source": peaks["src"], "kernel": "env_step_kernel<frame>", "bytes_per_env_step": ENV_BYTES_PER_STEP,
@@ -218,6 +221,7 @@ def main():
     ap.add_argument("--workload", default="env", choices=["env"])
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

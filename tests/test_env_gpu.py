@@ -105,6 +105,7 @@ def test_large_ragged_batch_vs_oracle():
     done = torch.zeros(B, dtype=torch.bool, device="cuda")
     odone = np.zeros(B, np.uint8)
     g = torch.Generator().manual_seed(11)
+    mixed = 0
     for t in range(400):
         # ball-following 70 % of the time so that games last and bricks get hit
         bx = torch.from_numpy(ostate[:, 1].reshape(B, -1).argmax(1) % 20)
@@ -120,8 +121,9 @@ def test_large_ragged_batch_vs_oracle():
         if t % 50 == 0:
             _eq(gray, oracle.gray(ostate), f"step {t} fused gray")
         state = nxt
+        mixed += int(0 < odone.sum() < B)
     env.check()
-    assert odone.sum() > 0 and (1 - odone).sum() > 0
+    assert mixed > 20                                          # finished and running games side by side
 
 
 def test_full_size_properties_65536():
