@@ -30,6 +30,8 @@ int mzb_version(void);
 const char *mzb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 uint64_t mzb_launch_count(void);
+/* ABI check for foreign-language bindings: sizeof(mz_tree_args) (which=0), sizeof(mz_op) (which=1) */
+size_t mzb_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
  * Breakout environment  (reference: environment/parallel_breakout.py)
@@ -83,6 +85,116 @@ int bk_env_velocity(int B, const uint64_t *hdr, int64_t *ball_dx, float *ball_dy
 
 /* convert_to_grayscale(): train_torch.py:334-358 on an arbitrary dense state */
 int bk_gray(int B, const float *state, float *gray, void *stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent MCTS tree bookkeeping  (reference: src/mcts.py)
+ *
+ * One flat, preallocated block per root in HBM (mz_tree_bytes(num_simulations) bytes each, 16-byte
+ * rows: Q|vsum, P, R, N|child, then selection meta + path); num_simulations + 2 node slots per tree,
+ * slot 0 = root.  Latents of expanded nodes live in a caller-owned store
+ * latent_store[tree][slot][latent_bytes].
+ *
+ * A search is: root prediction -> mz_tree_root -> for sim in 0..S-1 { dynamics+prediction on the
+ * selected leaves -> mz_tree_step(sim) }.  mz_tree_step(sim) = _backup of simulation `sim`
+ * (mcts.py:203-234) fused with _select_nodes of simulation sim+1 (:136-182) and the gather of the
+ * selected parent latents into dyn_in; on the last simulation it writes _compute_results (:236-250)
+ * instead.  Inputs value/reward are ALREADY inverse-transformed scalars
+ * (ScalarTransforms.inverted_softmax_expectation, utils.py:74-81) and pi are softmax probabilities
+ * (mcts.py:100,199), float32.
+ */
+typedef struct mz_tree_args {
+    int32_t B;               /* number of roots */
+    int32_t num_simulations; /* cfg["num_simulations"] (mcts.py:13) */
+    int32_t sim;             /* mz_tree_step: index of the simulation being backed up */
+    int32_t reserved;
+    void *trees;             /* [B] blocks of mz_tree_bytes() */
+    const float *s_tab;      /* [S+1] float32(sqrt(n))                       } from mz_puct_tables, */
+    const float *k_tab;      /* [S+1] float32(c1 + log((n + c2 + 1) / c2))   } uploaded by the caller */
+    double discount;         /* cfg["search"]["discount_factor"] (mcts.py:17) */
+    double noise_weight;     /* MCTSSearchVec.noise_weight (mcts.py:22), root only */
+    uint64_t seed;           /* tie-break stream key */
+    const float *reward;     /* [B]    leaf edge rewards (step) */
+    const float *value;      /* [B]    leaf values (step) / root values (root) */
+    const float *pi;         /* [B][3] leaf priors (step) / root priors before noise (root) */
+    const float *noise;      /* [B][3] Dirichlet(0.25) samples (root; mcts.py:114) */
+    int32_t *leaf_parent;    /* [B] out: slot of the selected leaf's parent */
+    int32_t *leaf_action;    /* [B] out: action on that edge */
+    int32_t *leaf_slot;      /* [B] out: slot the new leaf will occupy */
+    const void *latent_store; /* may be NULL together with dyn_in */
+    void *dyn_in;            /* [B][latent_bytes] out: parent latents, input of the dynamics network */
+    int64_t latent_bytes;    /* multiple of 16 */
+    float *out_value;        /* [B]    root value (last step) */
+    int64_t *out_visits;     /* [B][3] root visit counts (last step) */
+    int32_t *depth_hist;     /* optional [S+1] histogram of selection depths, or NULL */
+    const uint64_t *seed_dev; /* optional device word: if not NULL it replaces `seed` (lets a captured CUDA graph
+                                 be replayed with a new stream key) */
+} mz_tree_args;
+
+size_t mz_tree_bytes(int num_simulations);
+int mz_tree_nodes(int num_simulations);
+/* host-side: the two pUCT terms the reference computes in Python doubles (mcts.py:286-289) */
+int mz_puct_tables(int num_simulations, double c1, double c2, float *s_tab_host, float *k_tab_host);
+int mz_tree_root(const mz_tree_args *args, void *stream);
+int mz_tree_step(const mz_tree_args *args, void *stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * MuZero networks  (reference: src/networks.py, utils.py:74-81)
+ *
+ * Activations are channels-last: [sample][y][x][channel], float32 (exact path, CUDA-core FFMA,
+ * 1e-5 parity mode) or bfloat16 (tcgen05 tensor-core path, fp32 accumulation in TMEM).  A network
+ * evaluation is a short program of mz_op records run in order by mz_run() on one stream; the host
+ * builds the programs once per (weights, batch size) from MuZeroAgent.state_dict()
+ * (muzero-breakout_b200/src/networks.py) with every pointer already resolved.
+ *
+ *   MZ_OP_CONV      dst = act((conv_k(src) [+ act_bias[act_idx]]) * scale + shift [+ res])
+ *                   conv_k: k x k, stride 1, zero padding k/2 (nn.Conv2d of networks.py:12,26,28,47,65);
+ *                   scale/shift = conv bias + eval-mode BatchNorm folded per channel (:16-17,31-35);
+ *                   act_bias = contribution of the three spatially-constant one-hot action planes of
+ *                   the dynamics input (:295), a [3][H*W][cout] table, selected per sample by act_idx
+ *   MZ_OP_POOL2     2x2 average pool, stride 2 (:43,82,92)
+ *   MZ_OP_SCALE     MuZeroAgent._scale_state (:314-328): per sample (x - min) / (max - min + 1e-8) over
+ *                   all H*W*C elements of the fp32 src; written to dst and, if dst2 != NULL, also to
+ *                   dst2 + (i * dst2_stride + dst2_slot[i]) * (H*W*C*elsize)   (the tree's latent store)
+ *   MZ_OP_HEAD      Flatten(C,H,W) -> Linear (:147-149,207-209,221-223) on a channels-last src, then
+ *                   head_mode 0: raw logits; 1: inverted_softmax_expectation (utils.py:74-81) -> out[n];
+ *                   2: softmax probabilities -> out[n][nout] (mcts.py:100,199)
+ *   MZ_OP_NCHW_IN   float32 NCHW src -> channels-last dst (+ optional dst2 as for MZ_OP_SCALE)
+ *   MZ_OP_NHWC_OUT  channels-last src -> float32 NCHW dst
+ */
+enum { MZ_OP_CONV = 0, MZ_OP_POOL2 = 1, MZ_OP_SCALE = 2, MZ_OP_HEAD = 3, MZ_OP_NCHW_IN = 4, MZ_OP_NHWC_OUT = 5 };
+enum { MZ_F32 = 0, MZ_BF16 = 1 };
+enum { MZ_ACT_NONE = 0, MZ_ACT_RELU = 1, MZ_ACT_LEAKY_RELU = 2, MZ_ACT_SILU = 3, MZ_ACT_GELU = 4 }; /* utils.py:99-108 */
+
+typedef struct mz_op {
+    int32_t op;        /* MZ_OP_* */
+    int32_t dtype;     /* MZ_F32 / MZ_BF16: element type of src / dst / res / w */
+    int32_t H, W;      /* spatial size of src */
+    int32_t cin, cout; /* channels of src / dst */
+    int32_t ksize;     /* conv: 1 or 3 */
+    int32_t act;       /* MZ_ACT_* */
+    int32_t use_tc;    /* conv, bf16: 1 = tcgen05 kernel, 0 = CUDA-core kernel */
+    int32_t nout;      /* head: output features (<= 16) */
+    int32_t head_mode; /* head: 0 logits, 1 scalar, 2 probabilities */
+    int32_t reserved;
+    const void *src;
+    void *dst;
+    const void *res;         /* conv: residual (same shape as dst) or NULL */
+    float *dst_f32;          /* conv / pool: optional extra float32 copy of dst (input of MZ_OP_SCALE) */
+    const void *w;           /* conv: [cout][ksize*ksize*cin], tap-major then channel; head: float32 [nout][H*W*cin] in (y,x,c) order */
+    const float *scale;      /* [cout] */
+    const float *shift;      /* [cout]; head: bias [nout] */
+    const float *act_bias;   /* conv: [3][H*W][cout] or NULL */
+    const int32_t *act_idx;  /* conv: [n] */
+    void *dst2;              /* scale / nchw_in: second destination base or NULL */
+    const int32_t *dst2_slot; /* [n] or NULL (= slot 0) */
+    int64_t dst2_stride;     /* slots per sample in dst2 */
+    float *out;              /* head: see head_mode */
+    float *out_logits;       /* head: optional raw logits [n][nout] */
+} mz_op;
+
+int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream);
 
 #ifdef __cplusplus
 }

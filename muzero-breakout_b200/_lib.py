@@ -46,11 +46,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return _SO
 
 
+class TreeArgs(C.Structure):
+    """mirror of struct mz_tree_args (include/mzb200.h)"""
+    _fields_ = [("B", C.c_int32), ("num_simulations", C.c_int32), ("sim", C.c_int32), ("reserved", C.c_int32),
+                ("trees", C.c_void_p), ("s_tab", C.c_void_p), ("k_tab", C.c_void_p),
+                ("discount", C.c_double), ("noise_weight", C.c_double), ("seed", C.c_uint64),
+                ("reward", C.c_void_p), ("value", C.c_void_p), ("pi", C.c_void_p), ("noise", C.c_void_p),
+                ("leaf_parent", C.c_void_p), ("leaf_action", C.c_void_p), ("leaf_slot", C.c_void_p),
+                ("latent_store", C.c_void_p), ("dyn_in", C.c_void_p), ("latent_bytes", C.c_int64),
+                ("out_value", C.c_void_p), ("out_visits", C.c_void_p), ("depth_hist", C.c_void_p),
+                ("seed_dev", C.c_void_p)]
+
+
 def _declare(L: C.CDLL) -> None:
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     L.mzb_version.restype = i32
     L.mzb_last_error.restype = C.c_char_p
     L.mzb_launch_count.restype = u64
+    L.mzb_sizeof.argtypes, L.mzb_sizeof.restype = [i32], C.c_size_t
     sig = {
         "bk_env_reset": [i32] + [vp] * 8,
         "bk_env_reset_device_rng": [i32, vp, vp, u64, u64, vp, vp],
@@ -60,6 +73,14 @@ def _declare(L: C.CDLL) -> None:
         "bk_env_velocity": [i32] + [vp] * 4,
         "bk_gray": [i32] + [vp] * 3,
     }
+    L.mz_tree_bytes.argtypes, L.mz_tree_bytes.restype = [i32], C.c_size_t
+    L.mz_tree_nodes.argtypes, L.mz_tree_nodes.restype = [i32], i32
+    sig.update({
+        "mz_puct_tables": [i32, C.c_double, C.c_double, vp, vp],
+        "mz_tree_root": [C.POINTER(TreeArgs), vp],
+        "mz_tree_step": [C.POINTER(TreeArgs), vp],
+        "mz_run": [vp, i32, i32, vp],
+    })
     for name, args in sig.items():
         f = getattr(L, name)
         f.argtypes, f.restype = args, i32

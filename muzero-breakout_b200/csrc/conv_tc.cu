@@ -1,0 +1,384 @@
+// 3x3 / 1x1 convolution on the B200 5th-generation tensor cores (sm_100a): implicit GEMM with
+// tcgen05.mma (bf16 x bf16 -> fp32 accumulators in TMEM), operands staged in shared memory by TMA.
+//
+//   M = output pixels: one tile = S samples x hb rows x W columns (120 rows of the 128-lane UMMA tile)
+//   N = cout (128 or 256: the whole output-channel range, one UMMA N)
+//   K = taps x cin, walked as (tap, 64-channel chunk); one pipeline stage = A[128 x 64] + B[N x 64] bf16
+//
+// The 3x3 taps need no im2col and no padded copy: the activation tensor is described to TMA as a 4-D
+// tensor (channel, x, y, sample) and the tap (dy,dx) is just the box start coordinate (dx, y0+dy);
+// out-of-range x / y (the conv's zero padding) and samples past the end are zero-filled by the TMA
+// unit.  Both operands are K-major with the 128-byte swizzle, so a stage is one swizzle atom wide and
+// the four K=16 MMAs of a stage advance the descriptor start address by 32 bytes.
+//
+// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4): tcgen05.ld ->
+// (+ per-action bias) * scale + shift (+ residual) -> activation -> bf16 (and optional fp32) stores.
+// Two TMEM accumulator buffers (2 x N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
+//
+// Replaces the cuDNN convolutions + separate BN / ReLU / add kernels the reference launches for
+// src/networks.py ConvBlock :7-17 and ResidualBlock :19-35 (K4-K6 of SURVEY.md section 2d).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // bf16 per smem row = 128 bytes = one SWIZZLE_128B atom
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
+constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;        // 32 KB (N <= 256)
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256;
+
+struct ConvParams {
+    int n, H, W, cin, cout, taps, pad, act;
+    int S, hb, tile_rows, ytiles, ntiles;
+    __nv_bfloat16 *dst;
+    const __nv_bfloat16 *res;
+    float *dst_f32;
+    const float *scale, *shift, *act_bias;
+    const int *act_idx;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    // bounded spin: a protocol bug traps (launch error reported to the host) instead of hanging the GPU
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
+// 8-row groups 1024 bytes apart (SBO), LBO unused (=1), version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N
+__device__ __forceinline__ uint32_t instr_desc(int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ float activate(float v, int act)
+{
+    switch (act) {
+        case MZ_ACT_RELU: return fmaxf(v, 0.0f);
+        case MZ_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
+        case MZ_ACT_SILU: return v / (1.0f + __expf(-v));
+        case MZ_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        default: return v;
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *s_scale = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+    float *s_shift = s_scale + 256;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + 256);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.cout;
+    const int kchunks = p.cin / BLOCK_K;
+    const int ksteps = p.taps * kchunks;
+    const uint32_t smem_base = smem_u32(smem);
+
+    for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t a_bytes = (uint32_t)p.tile_rows * BLOCK_K * 2, b_bytes = (uint32_t)N * BLOCK_K * 2;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
+                const int s0 = sg * p.S, y0 = yt * p.hb;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int dy = p.taps == 1 ? 0 : tap / 3 - 1, dx = p.taps == 1 ? 0 : tap % 3 - 1;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                        mbar_expect_tx(bar_full + 8 * stage, a_bytes + b_bytes);
+                        tma_load_4d(sa, &map_a, bar_full + 8 * stage, kc * BLOCK_K, dx, y0 + dy, s0);
+                        tma_load_2d(sb, &map_b, bar_full + 8 * stage, tap * p.cin + kc * BLOCK_K, 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(bar_full + 8 * stage, phase);                 // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                  (ks | k) ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * stage);                     // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * buf);                           // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter+32)
+        const int r = quarter * 32 + lane;             // row of the tile
+        const int rows_per_sample = p.hb * p.W;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
+            const int sl = r / rows_per_sample, rr = r - sl * rows_per_sample;
+            const int s = sg * p.S + sl, y = yt * p.hb + rr / p.W, x = rr % p.W;
+            const bool valid = r < p.tile_rows && s < p.n;
+            const size_t m = ((size_t)s * p.H + y) * p.W + x;            // global output row
+            const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
+            mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0), acc);
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = __uint_as_float(acc[j]);
+                        if (ab) t += __ldg(ab + c0 + j);
+                        v[j] = t * s_scale[c0 + j] + s_shift[c0 + j];
+                    }
+                    if (p.res) {
+                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + m * N + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 u = __ldg(rp + q);
+                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(h[e]);
+                                v[q * 8 + e * 2] += f.x;
+                                v[q * 8 + e * 2 + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
+                    uint4 *op = reinterpret_cast<uint4 *>(p.dst + m * N + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 u;
+                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                        op[q] = u;
+                    }
+                    if (p.dst_f32) {
+                        float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+}  // namespace
+
+namespace mzb {
+
+int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
+{
+    MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift, "conv_tc: null pointer");
+    MZB_CHECK_ARG((o.ksize == 1 || o.ksize == 3) && o.cin % BLOCK_K == 0 && (o.cout == 128 || o.cout == 256), "conv_tc: unsupported shape");
+    MZB_CHECK_ARG(!o.act_bias || o.act_idx, "conv_tc: act_bias needs act_idx");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+
+    ConvParams p{};
+    p.n = n; p.H = o.H; p.W = o.W; p.cin = o.cin; p.cout = o.cout; p.taps = o.ksize * o.ksize; p.pad = o.ksize / 2; p.act = o.act;
+    // tile = S samples x hb rows x W columns with S*hb*W <= 128, hb | H, as many rows as possible
+    int best = 0;
+    for (int hb = 1; hb <= o.H; ++hb) {
+        if (o.H % hb || hb * o.W > BLOCK_M) continue;
+        int S = BLOCK_M / (hb * o.W);
+        if (S > 256) S = 256;
+        const int rows = S * hb * o.W;
+        if (rows > best || (rows == best && hb > p.hb)) { best = rows; p.hb = hb; p.S = S; }
+    }
+    MZB_CHECK_ARG(best > 0 && o.W <= 256, "conv_tc: image row does not fit a tile");
+    p.tile_rows = best;
+    p.ytiles = o.H / p.hb;
+    p.ntiles = ((n + p.S - 1) / p.S) * p.ytiles;
+    p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
+    p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)o.cin, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)n};
+        cuuint64_t strides[3] = {(cuuint64_t)o.cin * 2, (cuuint64_t)o.W * o.cin * 2, (cuuint64_t)o.H * o.W * o.cin * 2};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)o.W, (cuuint32_t)p.hb, (cuuint32_t)p.S};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(o.src), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return -2; }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)p.taps * o.cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)o.cout};
+        cuuint64_t strides[1] = {K * 2};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)o.cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return -2; }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+    conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mzb

@@ -1,0 +1,311 @@
+// MuZero network evaluation on B200: the op-program runner (mz_run) and the CUDA-core kernels:
+// exact fp32 implicit-GEMM convolution (the 1e-5 parity path; also runs bf16 activations as the
+// on-device cross-check of the tcgen05 kernel in conv_tc.cu), fused heads (Linear + softmax +
+// support expectation + inverse transform), _scale_state, average pool and layout conversion.
+//
+// Replaces (behaviour, not code) src/networks.py ConvBlock :7-17, ResidualBlock :19-35, the three
+// network forwards :94-99,151-167,225-241, MuZeroAgent._scale_state :314-328 and
+// utils.py ScalarTransforms.inverted_softmax_expectation :74-81 of the reference.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mzb {
+int conv_tc_launch(const mz_op &op, int nsamples, cudaStream_t st);   // conv_tc.cu
+}
+
+namespace {
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float activate(float v, int act)
+{
+    switch (act) {
+        case MZ_ACT_RELU: return fmaxf(v, 0.0f);
+        case MZ_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
+        case MZ_ACT_SILU: return v / (1.0f + expf(-v));
+        case MZ_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        default: return v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution on CUDA cores.  M = n*H*W output pixels, N = cout, K = k*k*cin.
+// 64x64 output tile per CTA, K in chunks of 16, 256 threads x (4x4) outputs, fp32 FFMA accumulation.
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(int M, int H, int W, int cin, int cout, int ksize, int act, const T *__restrict__ src, T *__restrict__ dst,
+                 const T *__restrict__ res, float *__restrict__ dst_f32, const T *__restrict__ w, const float *__restrict__ scale,
+                 const float *__restrict__ shift, const float *__restrict__ act_bias, const int *__restrict__ act_idx)
+{
+    __shared__ float As[TK][TM + 4];
+    __shared__ float Bs[TK][TN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int HW = H * W, K = ksize * ksize * cin, pad = ksize / 2;
+    // loader roles: thread -> (row, 4-channel group) of the 64 x 16 A chunk / (col, 4-k group) of B
+    const int lr = tid >> 2, lc = (tid & 3) * 4;
+    const int am = m0 + lr;
+    const int a_s = am / HW, a_p = am - a_s * HW, a_y = a_p / W, a_x = a_p - a_y * W;
+    const int ty = tid >> 4, tx = tid & 15;   // compute roles: 4 rows x 4 cols each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int tap = 0; tap < ksize * ksize; ++tap) {
+        const int dy = tap / ksize - pad, dx = tap % ksize - pad;
+        const int yy = a_y + dy, xx = a_x + dx;
+        const bool inb = am < M && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const T *ap = src + ((size_t)(a_s * HW + yy * W + xx)) * cin + lc;
+        const T *bp = w + (size_t)(n0 + lr) * K + tap * cin + lc;
+        for (int c0 = 0; c0 < cin; c0 += TK) {
+            float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4];
+            if (inb) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a4[q] = to_f(ap[c0 + q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b4[q] = to_f(bp[c0 + q]);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { As[lc + q][lr] = a4[q]; Bs[lc + q][lr] = b4[q]; }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < TK; ++k) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+        }
+    }
+    // epilogue: (+ action bias) * scale + shift (+ residual) -> activation
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const int s = m / HW, p = m - s * HW;
+        const float *ab = act_bias ? act_bias + ((size_t)act_idx[s] * HW + p) * cout : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            float v = acc[i][j];
+            if (ab) v += ab[n];
+            v = v * scale[n] + shift[n];
+            if (res) v += to_f(res[(size_t)m * cout + n]);
+            v = activate(v, act);
+            dst[(size_t)m * cout + n] = from_f<T>(v);
+            if (dst_f32) dst_f32[(size_t)m * cout + n] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pool2_kernel(size_t total, int H, int W, int C, const T *__restrict__ src, T *__restrict__ dst, float *__restrict__ dst_f32)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Ho = H / 2, Wo = W / 2;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho);
+    const size_t s = r / Ho;
+    const T *b = src + ((s * H + 2 * yo) * W + 2 * xo) * C + c;
+    const float v = ((to_f(b[0]) + to_f(b[C])) + (to_f(b[(size_t)W * C]) + to_f(b[(size_t)W * C + C]))) * 0.25f;
+    dst[i] = from_f<T>(v);
+    if (dst_f32) dst_f32[i] = v;
+}
+
+// _scale_state: one CTA per sample
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst, T *__restrict__ dst2,
+                   const int *__restrict__ dst2_slot, long long dst2_stride)
+{
+    __shared__ float s_lo[8], s_hi[8];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float *x = src + (size_t)i * elems;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int e = tid; e < elems; e += 256) { const float v = x[e]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
+    __syncthreads();
+    lo = s_lo[0]; hi = s_hi[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { lo = fminf(lo, s_lo[q]); hi = fmaxf(hi, s_hi[q]); }
+    const float den = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);                 // s_max - s_min + 1e-8  (:327)
+    T *d1 = dst ? dst + (size_t)i * elems : nullptr;
+    T *d2 = dst2 ? dst2 + ((size_t)i * dst2_stride + (dst2_slot ? dst2_slot[i] : 0)) * elems : nullptr;
+    for (int e = tid; e < elems; e += 256) {
+        const T v = from_f<T>(__fdiv_rn(__fsub_rn(x[e], lo), den));
+        if (d1) d1[e] = v;
+        if (d2) d2[e] = v;
+    }
+}
+
+// Flatten + Linear + (softmax -> expectation -> inverse transform | softmax).  One CTA per sample.
+constexpr int HEAD_MAX_OUT = 16;
+template <typename T>
+__global__ void __launch_bounds__(128)
+head_kernel(int feat, int nout, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
+            float *__restrict__ out, float *__restrict__ out_logits)
+{
+    __shared__ float s_part[4][HEAD_MAX_OUT];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const T *x = src + (size_t)i * feat;
+    float acc[HEAD_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < HEAD_MAX_OUT; ++o) acc[o] = 0.0f;
+    for (int e = tid; e < feat; e += 128) {
+        const float v = to_f(x[e]);
+#pragma unroll
+        for (int o = 0; o < HEAD_MAX_OUT; ++o)
+            if (o < nout) acc[o] = fmaf(v, __ldg(w + (size_t)o * feat + e), acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < HEAD_MAX_OUT; ++o) {
+        float v = acc[o];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if ((tid & 31) == 0) s_part[tid >> 5][o] = v;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    float logit[HEAD_MAX_OUT];
+    float mx = -INFINITY;
+    for (int o = 0; o < nout; ++o) {
+        logit[o] = ((s_part[0][o] + s_part[1][o]) + (s_part[2][o] + s_part[3][o])) + bias[o];
+        mx = fmaxf(mx, logit[o]);
+        if (out_logits) out_logits[(size_t)i * nout + o] = logit[o];
+    }
+    if (mode == 0) return;
+    float den = 0.0f, e[HEAD_MAX_OUT];
+    for (int o = 0; o < nout; ++o) { e[o] = expf(logit[o] - mx); den += e[o]; }
+    if (mode == 2) {                                                   // softmax probabilities (mcts.py:100,199)
+        for (int o = 0; o < nout; ++o) out[(size_t)i * nout + o] = e[o] / den;
+        return;
+    }
+    // utils.py:66-81: supports = linspace(-5, 5, 11) (integers), x = sum p*s, y = sign(x)((|x| + 0.999)^2 - 1)
+    const float half = 0.5f * (float)(nout - 1);
+    float ex = 0.0f;
+    for (int o = 0; o < nout; ++o) ex += (e[o] / den) * ((float)o - half);
+    const float sg = ex > 0.0f ? 1.0f : (ex < 0.0f ? -1.0f : 0.0f);
+    const float t = fabsf(ex) + 0.999f;                                  // float32(1 - epsilon), utils.py:14,28
+    out[i] = sg * (t * t - 1.0f);
+}
+
+template <typename T>
+__global__ void nchw_in_kernel(size_t total, int C, int HW, const float *__restrict__ src, T *__restrict__ dst, T *__restrict__ dst2,
+                               const int *__restrict__ dst2_slot, long long dst2_stride)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // index into channels-last dst
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const size_t r = i / C;
+    const int p = (int)(r % HW);
+    const size_t s = r / HW;
+    const T v = from_f<T>(src[(s * C + c) * HW + p]);
+    if (dst) dst[i] = v;
+    if (dst2) dst2[((s * dst2_stride + (dst2_slot ? dst2_slot[s] : 0)) * HW + p) * C + c] = v;
+}
+
+template <typename T>
+__global__ void nhwc_out_kernel(size_t total, int C, int HW, const T *__restrict__ src, float *__restrict__ dst)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // index into NCHW dst
+    if (i >= total) return;
+    const int p = (int)(i % HW);
+    const size_t r = i / HW;
+    const int c = (int)(r % C);
+    const size_t s = r / C;
+    dst[i] = to_f(src[(s * HW + p) * C + c]);
+}
+
+template <typename T>
+int run_op(const mz_op &o, int n, cudaStream_t st)
+{
+    switch (o.op) {
+        case MZ_OP_CONV: {
+            MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift, "conv: null pointer");
+            MZB_CHECK_ARG((o.ksize == 1 || o.ksize == 3) && o.cin % TK == 0 && o.cout % TN == 0, "conv: unsupported shape");
+            MZB_CHECK_ARG(!o.act_bias || o.act_idx, "conv: act_bias needs act_idx");
+            const int M = n * o.H * o.W;
+            dim3 grid((M + TM - 1) / TM, o.cout / TN);
+            conv_simt_kernel<T><<<grid, 256, 0, st>>>(M, o.H, o.W, o.cin, o.cout, o.ksize, o.act, (const T *)o.src, (T *)o.dst,
+                                                     (const T *)o.res, o.dst_f32, (const T *)o.w, o.scale, o.shift, o.act_bias, o.act_idx);
+            break;
+        }
+        case MZ_OP_POOL2: {
+            MZB_CHECK_ARG(o.src && o.dst && o.H % 2 == 0 && o.W % 2 == 0, "pool: bad argument");
+            const size_t total = (size_t)n * (o.H / 2) * (o.W / 2) * o.cin;
+            pool2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, o.H, o.W, o.cin, (const T *)o.src, (T *)o.dst, o.dst_f32);
+            break;
+        }
+        case MZ_OP_SCALE: {
+            MZB_CHECK_ARG(o.src && (o.dst || o.dst2), "scale: null pointer");
+            scale_state_kernel<T><<<n, 256, 0, st>>>(o.H * o.W * o.cin, (const float *)o.src, (T *)o.dst, (T *)o.dst2, o.dst2_slot, o.dst2_stride);
+            break;
+        }
+        case MZ_OP_HEAD: {
+            MZB_CHECK_ARG(o.src && o.w && o.shift && o.nout > 0 && o.nout <= HEAD_MAX_OUT, "head: bad argument");
+            MZB_CHECK_ARG(o.head_mode == 0 ? o.out_logits != nullptr : o.out != nullptr, "head: missing output");
+            head_kernel<T><<<n, 128, 0, st>>>(o.H * o.W * o.cin, o.nout, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits);
+            break;
+        }
+        case MZ_OP_NCHW_IN: {
+            MZB_CHECK_ARG(o.src && (o.dst || o.dst2), "nchw_in: null pointer");
+            const size_t total = (size_t)n * o.H * o.W * o.cin;
+            nchw_in_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, o.cin, o.H * o.W, (const float *)o.src, (T *)o.dst, (T *)o.dst2,
+                                                                               o.dst2_slot, o.dst2_stride);
+            break;
+        }
+        case MZ_OP_NHWC_OUT: {
+            MZB_CHECK_ARG(o.src && o.dst, "nhwc_out: null pointer");
+            const size_t total = (size_t)n * o.H * o.W * o.cin;
+            nhwc_out_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, o.cin, o.H * o.W, (const T *)o.src, (float *)o.dst);
+            break;
+        }
+        default:
+            mzb::set_error("mz_run: unknown op %d", o.op);
+            return -1;
+    }
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream)
+{
+    MZB_CHECK_ARG(ops && n_ops > 0 && nsamples > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_ops; ++i) {
+        const mz_op &o = ops[i];
+        int rc;
+        if (o.dtype == MZ_F32) rc = run_op<float>(o, nsamples, st);
+        else if (o.dtype == MZ_BF16) {
+            if (o.op == MZ_OP_CONV && o.use_tc) rc = mzb::conv_tc_launch(o, nsamples, st);
+            else rc = run_op<__nv_bfloat16>(o, nsamples, st);
+        } else {
+            mzb::set_error("mz_run: op %d has unknown dtype %d", i, o.dtype);
+            return -1;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,322 @@
+"""Host side of the MuZero networks on B200: packs the weights of a reference `MuZeroAgent`
+(reference src/networks.py:245-350; state_dict layout in SURVEY.md Appendix D) into the layouts the
+kernels of libmzb200.so want, and builds the op programs (struct mz_op, include/mzb200.h) that
+evaluate the representation / dynamics / prediction networks.
+
+    PackedNetworks(agent_or_state_dict, model_cfg, precision="bf16"|"f32")
+        .representation(state)                 <-> MuZeroAgent.create_hidden_state_root  :271-280
+        .dynamics(hidden, action_planes)       <-> MuZeroAgent.hidden_state_transition   :282-298
+        .prediction(hidden)                    <-> MuZeroAgent.evaluate_state            :300-312
+        .inverted_softmax_expectation(logits)  <-> ScalarTransforms (utils.py:74-81)
+
+precision "bf16": bf16 weights and activations, tcgen05 tensor-core convolutions (csrc/conv_tc.cu),
+fp32 accumulation and epilogues; "f32": fp32 everything on CUDA cores (the 1e-5 parity path).
+Eval-mode BatchNorm and the conv bias are folded into a per-channel fp32 (scale, shift) applied in the
+convolution epilogue; the three one-hot action planes of the dynamics input become a per-action bias
+table (they are spatially constant, so their convolution is a [3][20][256] lookup).
+There is no CPU path: everything here needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+OP_CONV, OP_POOL2, OP_SCALE, OP_HEAD, OP_NCHW_IN, OP_NHWC_OUT = range(6)
+F32, BF16 = 0, 1
+ACT = {"none": 0, "relu": 1, "leaky_relu": 2, "silu": 3, "gelu": 4}   # utils.py:99-108
+
+
+class MzOp(C.Structure):
+    """mirror of struct mz_op (include/mzb200.h)"""
+    _fields_ = [("op", C.c_int32), ("dtype", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cin", C.c_int32),
+                ("cout", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32), ("use_tc", C.c_int32), ("nout", C.c_int32),
+                ("head_mode", C.c_int32), ("reserved", C.c_int32),
+                ("src", C.c_void_p), ("dst", C.c_void_p), ("res", C.c_void_p), ("dst_f32", C.c_void_p), ("w", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("act_bias", C.c_void_p), ("act_idx", C.c_void_p),
+                ("dst2", C.c_void_p), ("dst2_slot", C.c_void_p), ("dst2_stride", C.c_int64),
+                ("out", C.c_void_p), ("out_logits", C.c_void_p)]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Program:
+    """A list of mz_op records with every pointer resolved; run() enqueues it on the current stream."""
+
+    def __init__(self, n: int):
+        self.n = n
+        self.ops = []
+        self.keep = []            # tensors the ops point into
+        self._arr = None
+
+    def add(self, **kw):
+        op = MzOp()
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                self.keep.append(v)
+                v = v.data_ptr()
+            setattr(op, k, v)
+        self.ops.append(op)
+        self._arr = None
+        return op
+
+    def extend(self, other: "Program"):
+        self.ops += other.ops
+        self.keep += other.keep
+        self._arr = None
+
+    def run(self, stream=None):
+        if self._arr is None:
+            self._arr = (MzOp * len(self.ops))(*self.ops)
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().mz_run(self._arr, len(self.ops), self.n, st))
+
+    @property
+    def n_kernels(self) -> int:
+        return len(self.ops)
+
+
+class _Conv:
+    """One packed convolution: w [cout][k*k*cin] (tap-major, then input channel), fp32 scale/shift."""
+
+    def __init__(self, w, scale, shift, ksize, act, act_bias=None):
+        self.w, self.scale, self.shift, self.ksize, self.act, self.act_bias = w, scale, shift, ksize, act, act_bias
+        self.cout = w.shape[0]
+        self.cin = w.shape[1] // (ksize * ksize)
+
+
+class PackedNetworks:
+    def __init__(self, agent, model_cfg: dict | None = None, precision: str = "bf16", device="cuda", use_tc: bool | None = None):
+        _lib.require_cuda()
+        if precision not in ("bf16", "f32"):
+            raise ValueError("precision must be 'bf16' or 'f32'")
+        sd = agent if isinstance(agent, dict) else agent.state_dict()
+        cfg = model_cfg or getattr(agent, "cfg", None) or {}
+        self.device = torch.device(device)
+        self.precision = precision
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dt = BF16 if precision == "bf16" else F32
+        self.use_tc = (precision == "bf16") if use_tc is None else bool(use_tc and precision == "bf16")
+        self.num_supports = int(cfg.get("num_supports", 11))
+        self.supports_min, self.supports_max = cfg.get("supports_min", -5), cfg.get("supports_max", 5)
+        if (self.supports_min, self.supports_max, self.num_supports) != (-5, 5, 11) and self.supports_max - self.supports_min != self.num_supports - 1:
+            raise ValueError("the fused head kernel assumes unit-spaced supports centred on 0 (config.yaml:30-32)")
+        acts = {k: ACT[cfg.get(k, {}).get("activation", "relu")] for k in ("representation_network", "dynamics_network", "prediction_network")}
+        sd = {k: v.detach().to("cpu", torch.float64) for k, v in sd.items() if v.dtype.is_floating_point}
+        self._pack(sd, acts)
+
+    # ------------------------------------------------------------------ packing
+    def _dev(self, t, dtype):
+        return t.to(self.device, dtype).contiguous()
+
+    def _conv(self, sd, conv_key, bn_key, act, cin_used=None):
+        w = sd[conv_key + ".weight"]                       # (cout, cin, k, k)
+        b = sd[conv_key + ".bias"]
+        cout, cin, k, _ = w.shape
+        if bn_key is not None:                             # eval-mode BN (eps 1e-5) folded: y = conv*a + (b - mean)*a + beta
+            a = sd[bn_key + ".weight"] / torch.sqrt(sd[bn_key + ".running_var"] + 1e-5)
+            shift = (b - sd[bn_key + ".running_mean"]) * a + sd[bn_key + ".bias"]
+        else:
+            a, shift = torch.ones(cout, dtype=torch.float64), b
+        act_bias = None
+        if cin_used is not None and cin_used < cin:        # dynamics conv_block: channels >= cin_used are the action planes
+            H, W = self.latent_hw
+            planes = []
+            for ch in range(cin_used, cin):
+                o = F.conv2d(torch.ones(1, 1, H, W, dtype=torch.float64), w[:, ch:ch + 1], padding=k // 2)   # (1,cout,H,W)
+                planes.append(o[0].permute(1, 2, 0).reshape(H * W, cout))
+            act_bias = self._dev(torch.stack(planes), torch.float32)                                          # [3][HW][cout]
+            w = w[:, :cin_used]
+        wp = w.permute(0, 2, 3, 1).reshape(cout, -1)       # [cout][(ky*k+kx)*cin + c]
+        return _Conv(self._dev(wp, self.dtype), self._dev(a, torch.float32), self._dev(shift, torch.float32), k, act, act_bias)
+
+    def _res(self, sd, prefix, act):
+        return (self._conv(sd, prefix + ".conv1", prefix + ".bn1", act), self._conv(sd, prefix + ".conv2", prefix + ".bn2", act))
+
+    def _linear(self, sd, key, C_, HW):
+        w = sd[key + ".weight"]                            # (nout, C*HW), column = c*HW + p  (Flatten of NCHW)
+        nout = w.shape[0]
+        wp = w.reshape(nout, C_, HW).permute(0, 2, 1).reshape(nout, HW * C_)   # column = p*C + c (channels-last)
+        return self._dev(wp, torch.float32), self._dev(sd[key + ".bias"], torch.float32), nout
+
+    def _pack(self, sd, acts):
+        rep_keys = sorted({int(k.split(".")[2]) for k in sd if k.startswith("rep_net.blocks.")})
+        self.latent_ch = sd["dyn_net.reward_head.0.conv.weight"].shape[1]
+        hw = sd["dyn_net.reward_head.2.weight"].shape[1] // self.latent_ch
+        self.latent_hw = {20: (4, 5)}.get(hw, None)
+        if self.latent_hw is None:
+            raise ValueError(f"unsupported latent resolution ({hw} pixels)")
+        # representation: plain convs (bias only) and residual blocks; pools sit where block indices are missing
+        self.rep = []
+        a = acts["representation_network"]
+        for i in range(max(rep_keys) + 2):
+            if f"rep_net.blocks.{i}.weight" in sd:
+                self.rep.append(("conv", self._conv(sd, f"rep_net.blocks.{i}", None, ACT["none"])))
+            elif f"rep_net.blocks.{i}.conv1.weight" in sd:
+                self.rep.append(("res", self._res(sd, f"rep_net.blocks.{i}", a)))
+            else:
+                self.rep.append(("pool", None))            # nn.AvgPool2d has no parameters (blocks.7 / blocks.11)
+        self.rep_cin = self.rep[0][1].cin
+        a = acts["dynamics_network"]
+        self.dyn_first = self._conv(sd, "dyn_net.conv_block.conv", "dyn_net.conv_block.bn", a, cin_used=self.latent_ch)
+        n_dyn = len({k.split(".")[2] for k in sd if k.startswith("dyn_net.res_blocks.")})
+        self.dyn_res = [self._res(sd, f"dyn_net.res_blocks.{i}", a) for i in range(n_dyn)]
+        self.reward_conv = self._conv(sd, "dyn_net.reward_head.0.conv", "dyn_net.reward_head.0.bn", a)
+        self.reward_lin = self._linear(sd, "dyn_net.reward_head.2", self.reward_conv.cout, hw)
+        a = acts["prediction_network"]
+        n_pred = len({k.split(".")[2] for k in sd if k.startswith("pred_net.res_blocks.")})
+        self.pred_res = [self._res(sd, f"pred_net.res_blocks.{i}", a) for i in range(n_pred)]
+        self.policy_conv = self._conv(sd, "pred_net.policy_head.0.conv", "pred_net.policy_head.0.bn", a)
+        self.policy_lin = self._linear(sd, "pred_net.policy_head.2", self.policy_conv.cout, hw)
+        self.value_conv = self._conv(sd, "pred_net.value_head.0.conv", "pred_net.value_head.0.bn", a)
+        self.value_lin = self._linear(sd, "pred_net.value_head.2", self.value_conv.cout, hw)
+        self.num_actions = self.policy_lin[2]
+
+    # ------------------------------------------------------------------ program building
+    def buf(self, n, hw, c, dtype=None):
+        return torch.empty((n, hw, c), dtype=dtype or self.dtype, device=self.device)
+
+    def _add_conv(self, prog, cv: _Conv, H, W, src, dst, res=None, dst_f32=None, act_idx=None):
+        prog.add(op=OP_CONV, dtype=self.dt, H=H, W=W, cin=cv.cin, cout=cv.cout, ksize=cv.ksize, act=cv.act,
+                 use_tc=int(self.use_tc), src=src, dst=dst, res=res, dst_f32=dst_f32, w=cv.w, scale=cv.scale, shift=cv.shift,
+                 act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx)
+
+    def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None):
+        """bufs: three same-shaped rotating buffers; cur: index of the one holding the input.  Returns
+        the index holding the output."""
+        for i, (c1, c2) in enumerate(blocks):
+            mid, out = (cur + 1) % 3, (cur + 2) % 3
+            self._add_conv(prog, c1, H, W, bufs[cur], bufs[mid])
+            self._add_conv(prog, c2, H, W, bufs[mid], bufs[out], res=bufs[cur],
+                           dst_f32=last_f32 if i == len(blocks) - 1 else None)
+            cur = out
+        return cur
+
+    def _add_head(self, prog, conv, lin, H, W, src, mid, mode, out, out_logits=None):
+        self._add_conv(prog, conv, H, W, src, mid)
+        w, b, nout = lin
+        prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=nout, head_mode=mode, src=mid, w=w, shift=b,
+                 out=out, out_logits=out_logits)
+
+    def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2):
+        """14 residual blocks + policy head + value head (networks.py:225-241) on `src` [n][20][256]."""
+        H, W = self.latent_hw
+        prog = Program(n)
+        c1, c2 = self.pred_res[0]                                   # first block reads src directly
+        self._add_conv(prog, c1, H, W, src, bufs[1])
+        self._add_conv(prog, c2, H, W, bufs[1], bufs[2], res=src)
+        cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 2)
+        self._add_head(prog, self.policy_conv, self.policy_lin, H, W, bufs[cur], mid, pi_mode, pi, policy_logits)
+        self._add_head(prog, self.value_conv, self.value_lin, H, W, bufs[cur], mid, value_mode, value, value_logits)
+        return prog
+
+    def dynamics_program(self, n, src, act_idx, bufs, mid, f32, reward, dst, dst2=None, dst2_slot=None, dst2_stride=0,
+                         reward_logits=None, reward_mode=1):
+        """ConvBlock(259->256) + 14 residual blocks + reward head + _scale_state (networks.py:151-167,
+        282-298).  src [n][20][256] parent latents, act_idx int32 [n]; scaled latent -> dst (and dst2)."""
+        H, W = self.latent_hw
+        prog = Program(n)
+        self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx)
+        cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32)
+        self._add_head(prog, self.reward_conv, self.reward_lin, H, W, bufs[cur], mid, reward_mode, reward, reward_logits)
+        prog.add(op=OP_SCALE, dtype=self.dt, H=H, W=W, cin=self.latent_ch, src=f32, dst=dst, dst2=dst2, dst2_slot=dst2_slot,
+                 dst2_stride=dst2_stride)
+        return prog
+
+    def representation_program(self, n, x_nchw, out_nchw):
+        """RepresentationNetwork.forward + _scale_state (networks.py:94-99, 271-280): float32 NCHW in/out."""
+        H, W = 16, 20
+        prog = Program(n)
+        cmax = max(cv.cout for kind, cv in self.rep if kind == "conv")
+        xin = self.buf(n, H * W, self.rep_cin)
+        bufs = [self.buf(n, H * W, cmax) for _ in range(3)]
+        f32 = self.buf(n, self.latent_hw[0] * self.latent_hw[1], cmax, torch.float32)
+        prog.add(op=OP_NCHW_IN, dtype=self.dt, H=H, W=W, cin=self.rep_cin, src=x_nchw, dst=xin)
+        src, cur = xin, None
+        n_pool = sum(1 for kind, _ in self.rep if kind == "pool")
+        pools = 0
+        for kind, item in self.rep:
+            if kind == "conv":
+                nxt = 0 if cur is None else (cur + 1) % 3
+                self._add_conv(prog, item, H, W, src, bufs[nxt])
+                cur, src = nxt, bufs[nxt]
+                ch = item.cout
+            elif kind == "res":
+                cur = self._add_res_blocks(prog, [item], H, W, bufs, cur)
+                src = bufs[cur]
+            else:
+                pools += 1
+                nxt = (cur + 1) % 3
+                prog.add(op=OP_POOL2, dtype=self.dt, H=H, W=W, cin=ch, src=src, dst=bufs[nxt],
+                         dst_f32=f32 if pools == n_pool else None)
+                H, W = H // 2, W // 2
+                cur, src = nxt, bufs[nxt]
+        lat = self.buf(n, H * W, ch)
+        prog.add(op=OP_SCALE, dtype=self.dt, H=H, W=W, cin=ch, src=f32, dst=lat)
+        prog.add(op=OP_NHWC_OUT, dtype=self.dt, H=H, W=W, cin=ch, src=lat, dst=out_nchw)
+        return prog
+
+    # ------------------------------------------------------------------ MuZeroAgent-style calls (NCHW float32 tensors)
+    def _latent_in(self, prog, h):
+        H, W = self.latent_hw
+        x = self.buf(h.shape[0], H * W, self.latent_ch)
+        prog.add(op=OP_NCHW_IN, dtype=self.dt, H=H, W=W, cin=self.latent_ch, src=h, dst=x)
+        return x
+
+    def representation(self, state: torch.Tensor) -> torch.Tensor:
+        x = state.to(self.device, torch.float32).contiguous()
+        n = x.shape[0]
+        out = torch.empty((n, self.latent_ch, *self.latent_hw), dtype=torch.float32, device=self.device)
+        self.representation_program(n, x, out).run()
+        return out
+
+    create_hidden_state_root = representation
+
+    def prediction(self, hidden: torch.Tensor):
+        """-> (policy_logits (n,3), value_logits (n,11)) raw logits, like MuZeroAgent.evaluate_state."""
+        h = hidden.to(self.device, torch.float32).contiguous()
+        n = h.shape[0]
+        H, W = self.latent_hw
+        prog = Program(n)
+        x = self._latent_in(prog, h)
+        bufs = [self.buf(n, H * W, self.latent_ch) for _ in range(3)]
+        mid = self.buf(n, H * W, self.latent_ch)
+        pol = torch.empty((n, self.num_actions), dtype=torch.float32, device=self.device)
+        val = torch.empty((n, self.num_supports), dtype=torch.float32, device=self.device)
+        prog.extend(self.prediction_program(n, x, bufs, mid, None, None, pol, val, value_mode=0, pi_mode=0))
+        prog.run()
+        return pol, val
+
+    evaluate_state = prediction
+
+    def dynamics(self, hidden: torch.Tensor, action_planes: torch.Tensor):
+        """-> (scaled latent (n,256,4,5), reward_logits (n,11)), like MuZeroAgent.hidden_state_transition."""
+        h = hidden.to(self.device, torch.float32).contiguous()
+        n = h.shape[0]
+        H, W = self.latent_hw
+        act = action_planes.to(self.device)[:, :, 0, 0].argmax(dim=1).to(torch.int32).contiguous()   # one-hot planes (mcts.py:252-268)
+        prog = Program(n)
+        x = self._latent_in(prog, h)
+        bufs = [self.buf(n, H * W, self.latent_ch) for _ in range(3)]
+        mid = self.buf(n, H * W, self.latent_ch)
+        f32 = self.buf(n, H * W, self.latent_ch, torch.float32)
+        lat = self.buf(n, H * W, self.latent_ch)
+        rew = torch.empty((n, self.num_supports), dtype=torch.float32, device=self.device)
+        out = torch.empty((n, self.latent_ch, H, W), dtype=torch.float32, device=self.device)
+        prog.extend(self.dynamics_program(n, x, act, bufs, mid, f32, None, lat, reward_logits=rew, reward_mode=0))
+        prog.add(op=OP_NHWC_OUT, dtype=self.dt, H=H, W=W, cin=self.latent_ch, src=lat, dst=out)
+        prog.run()
+        return out, rew
+
+    hidden_state_transition = dynamics
+
+    def inverted_softmax_expectation(self, logits: torch.Tensor) -> torch.Tensor:
+        """utils.py:74-81 (host-side torch ops; the search path uses the fused head kernel instead)."""
+        s = torch.linspace(self.supports_min, self.supports_max, self.num_supports, device=logits.device)
+        x = torch.sum(torch.softmax(logits, dim=-1) * s, dim=-1)
+        return torch.sign(x) * ((torch.abs(x) + (1 - 0.001)) ** 2 - 1)

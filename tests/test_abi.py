@@ -68,3 +68,24 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
                 assert "liboracle" not in text
+
+
+def test_ctypes_mirrors_match_the_c_structs():
+    from muzero_breakout_b200 import _lib
+    from muzero_breakout_b200.src.networks import MzOp
+    L = mzb.lib()
+    assert L.mzb_sizeof(0) == ctypes.sizeof(_lib.TreeArgs)
+    assert L.mzb_sizeof(1) == ctypes.sizeof(MzOp)
+
+
+def test_mcts_class_mirrors_reference_signature():
+    from muzero_breakout_b200.src.mcts import MCTSSearchVec
+    cfg = {"num_simulations": 50, "actions": [0, 1, 2], "latent_resolution": [4, 5],
+           "search": {"c1": 1.25, "c2": 19652.0, "discount_factor": 0.985}}
+    m = MCTSSearchVec(cfg, object(), None)
+    assert list(inspect.signature(MCTSSearchVec.__init__).parameters)[:4] == ["self", "cfg", "mu_zero", "scalar_transforms"]
+    assert list(inspect.signature(m.search).parameters)[:3] == ["hidden_state", "action_mask", "training_iteration"]
+    assert (m.noise_weight, m.dirchlet_alpha, m.num_simulations) == (0.175, 0.25, 50)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.search(torch.zeros(2, 256, 4, 5), torch.ones(2, 3), 0)

@@ -1,0 +1,154 @@
+"""GPU tests of the network kernels (csrc/nets.cu, csrc/conv_tc.cu through mz_run / PackedNetworks).
+
+Tolerances (max abs error / max abs reference value, i.e. relative to the tensor's range):
+  fp32 path  vs outputs of the reference networks (golden)          1e-5   (BASELINE.json north_star)
+  tcgen05 bf16 conv vs fp32 torch conv on the same bf16 operands     2e-4 on the fp32 side output
+  bf16 pipeline vs the same pipeline on CUDA cores (same bf16 rounding points)   4e-3
+  bf16 pipeline vs the fp32 reference networks (golden)              reported, bounded at 3e-2 (bf16 has an
+      8-bit mantissa and activations are rounded 29x per network: 1e-3 relative of the fp32 reference is not
+      reachable with bf16 storage; see DESIGN.md "precision")
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import perturb_bn
+from oracle.networks import OracleAgent
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().double().cpu() if hasattr(a, "detach") else torch.as_tensor(a).double()
+    b = b.detach().double().cpu() if hasattr(b, "detach") else torch.as_tensor(b).double()
+    assert a.shape == b.shape, f"{tuple(a.shape)} vs {tuple(b.shape)}"
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def agent():
+    torch.manual_seed(0)
+    a = OracleAgent()
+    perturb_bn(a, 1)
+    a.eval_mode()
+    return a
+
+
+@pytest.fixture(scope="module")
+def rec(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mcts_real.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def _planes(actions):
+    p = torch.zeros(len(actions), 3, 4, 5)
+    p[torch.arange(len(actions)), torch.as_tensor(actions)] = 1
+    return p
+
+
+def test_fp32_path_matches_reference_outputs(agent, rec):
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    nets = PackedNetworks(agent, agent.cfg, precision="f32")
+    tol = 1e-5
+    hidden = nets.representation(torch.from_numpy(rec["rep_in"]))
+    assert rel(hidden, rec["hidden"]) <= tol, f"root latent {rel(hidden, rec['hidden']):.2e}"
+    pol, val = nets.prediction(torch.from_numpy(rec["hidden"]))
+    assert rel(pol, rec["root_policy_logits"]) <= tol and rel(val, rec["root_value_logits"]) <= tol
+    h2, rew = nets.dynamics(torch.from_numpy(rec["hidden"]), _planes(rec["dyn_actions"]))
+    assert rel(h2, rec["dyn_h"]) <= tol, f"dynamics latent {rel(h2, rec['dyn_h']):.2e}"
+    assert rel(rew, rec["dyn_reward_logits"]) <= tol
+    pol2, val2 = nets.prediction(torch.from_numpy(rec["dyn_h"]))
+    assert rel(pol2, rec["pred_policy_logits"]) <= tol and rel(val2, rec["pred_value_logits"]) <= tol
+    v = nets.inverted_softmax_expectation(torch.from_numpy(rec["root_value_logits"]).cuda())
+    assert rel(v, rec["v_root"]) <= tol
+
+
+def test_fp32_path_ragged_batches(agent):
+    """batch sizes that are not multiples of any tile (1, 7, 61) against the torch fp32 oracle."""
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    nets = PackedNetworks(agent, agent.cfg, precision="f32")
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 7, 61):
+        h = torch.rand(n, 256, 4, 5, generator=g)
+        acts = torch.randint(0, 3, (n,), generator=g)
+        with torch.no_grad():
+            oh, orew = agent.hidden_state_transition(h, _planes(acts))
+            opol, oval = agent.evaluate_state(h)
+        h2, rew = nets.dynamics(h, _planes(acts))
+        pol, val = nets.prediction(h)
+        for got, want, what in ((h2, oh, "latent"), (rew, orew, "reward"), (pol, opol, "policy"), (val, oval, "value")):
+            assert rel(got, want) <= 1e-5, f"n={n} {what}: {rel(got, want):.2e}"
+
+
+CONV_CASES = [  # (n, H, W, cin, cout, ksize, residual, act_bias)
+    (1, 4, 5, 256, 256, 3, False, False), (25, 4, 5, 256, 256, 3, True, False), (26, 4, 5, 256, 256, 3, True, True),
+    (300, 4, 5, 256, 256, 3, True, False), (7, 4, 5, 256, 128, 3, False, False), (9, 4, 5, 256, 256, 1, False, False),
+    (9, 4, 5, 256, 128, 1, False, False), (5, 16, 20, 64, 128, 3, False, False), (4, 16, 20, 128, 256, 3, True, False),
+    (5, 8, 10, 256, 256, 3, True, False), (3000, 4, 5, 256, 256, 3, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n%d_%dx%d_c%d-%d_k%d_r%d_a%d" % tuple(int(x) for x in c))
+def test_tcgen05_conv_vs_torch(case):
+    """One convolution op on the tensor cores against torch's fp32 conv on the same bf16-rounded operands."""
+    from muzero_breakout_b200.src.networks import ACT, BF16, OP_CONV, Program
+    n, H, W, cin, cout, k, use_res, use_ab = case
+    g = torch.Generator().manual_seed(n * 131 + cin + cout + k)
+    x = (torch.randn(n, cin, H, W, generator=g)).bfloat16()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16()
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(n, cout, H, W, generator=g).bfloat16() if use_res else None
+    ab = torch.randn(3, H * W, cout, generator=g) * 0.2 if use_ab else None
+    idx = torch.randint(0, 3, (n,), generator=g, dtype=torch.int32)
+    want = F.conv2d(x.float(), w.float(), padding=k // 2)
+    if use_ab:
+        want = want + ab[idx.long()].view(n, H, W, cout).permute(0, 3, 1, 2)
+    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if use_res:
+        want = want + res.float()
+    want = torch.relu(want)
+
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
+    dst = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dst32 = torch.full((n, H, W, cout), float("nan"), dtype=torch.float32, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda()
+    for use_tc in (1, 0):
+        prog = Program(n)
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=cin, cout=cout, ksize=k, act=ACT["relu"], use_tc=use_tc, src=nhwc(x), dst=dst,
+                 res=nhwc(res) if use_res else None, dst_f32=dst32, w=wp, scale=scale.cuda(), shift=shift.cuda(),
+                 act_bias=ab.cuda() if use_ab else None, act_idx=idx.cuda() if use_ab else None)
+        prog.run()
+        torch.cuda.synchronize()
+        got32 = dst32.permute(0, 3, 1, 2).cpu()
+        got16 = dst.permute(0, 3, 1, 2).float().cpu()
+        assert torch.isfinite(got32).all(), f"use_tc={use_tc}: unwritten / non-finite outputs"
+        e32, e16 = rel(got32, want), rel(got16, want)
+        assert e32 <= 2e-4, f"use_tc={use_tc}: fp32 side output rel err {e32:.2e}"
+        assert e16 <= 5e-3, f"use_tc={use_tc}: bf16 output rel err {e16:.2e}"
+        dst.fill_(float("nan")); dst32.fill_(float("nan"))
+
+
+def test_bf16_pipeline_tensor_cores_vs_cuda_cores_and_reference(agent, rec):
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    tc = PackedNetworks(agent, agent.cfg, precision="bf16", use_tc=True)
+    cc = PackedNetworks(agent, agent.cfg, precision="bf16", use_tc=False)
+    h = torch.from_numpy(rec["hidden"])
+    planes = _planes(rec["dyn_actions"])
+    out = {}
+    for name, nets in (("tc", tc), ("cc", cc)):
+        h2, rew = nets.dynamics(h, planes)
+        pol, val = nets.prediction(h)
+        hid = nets.representation(torch.from_numpy(rec["rep_in"]))
+        out[name] = dict(h2=h2, rew=rew, pol=pol, val=val, hid=hid)
+    for k in out["tc"]:
+        e = rel(out["tc"][k], out["cc"][k])
+        assert e <= 4e-3, f"{k}: tensor-core vs CUDA-core bf16 pipelines differ by {e:.2e}"
+    ref = dict(h2=rec["dyn_h"], rew=rec["dyn_reward_logits"], pol=rec["root_policy_logits"], val=rec["root_value_logits"], hid=rec["hidden"])
+    errs = {k: rel(out["tc"][k], ref[k]) for k in ref}
+    print("bf16 tensor-core pipeline vs fp32 reference (rel to range):", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e <= 3e-2, f"{k}: bf16 pipeline deviates {e:.2e} from the fp32 reference"
