@@ -212,41 +212,194 @@ def cpu_env(args, sample_envs=None, budget_s=12.0):
             "sample": f"{n} steps of {B} envs, oracle/breakout_oracle.c (C restatement of parallel_breakout.py step) on {cores} threads, {el:.1f} s"}, el / n * 1e3
 
 
+
+# ------------------------------------------------------------------------------------------ mcts
+MCTS_CFG = {"num_simulations": 50, "actions": [0, 1, 2], "latent_resolution": [4, 5],
+            "search": {"c1": 1.25, "c2": 19652.0, "discount_factor": 0.985, "mcts_name": "MCTSSearchVec"}}
+# BASELINE.md section 3 (hooks on the reference modules), FLOP = 2 x MAC
+FLOP_LEAF_VALID = 984_079_360          # dynamics + prediction, zero-padding taps excluded
+FLOP_LEAF_DENSE = 1_360_988_160        # what a dense 3x3 conv executes
+FLOP_ROOT_PRED_VALID, FLOP_ROOT_PRED_DENSE = 487_004_160, 673_781_760
+FLOP_CONV_VALID = 496_962_560 + 486_932_480      # conv layers only (no Linear heads), per leaf
+FLOP_CONV_DENSE = 687_093_760 + 673_710_080
+
+
+def _time_prog(prog, reps=5):
+    prog.run(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        prog.run()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_mcts(args, rank, local, world):
+    from muzero_breakout_b200.src.mcts import MCTSSearchVec
+    from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG, OP_CONV, PackedNetworks, Program, random_state_dict
+
+    B, S, K, W = args.trees, args.sims, args.steps, args.warmup
+    dev = torch.device("cuda", local)
+    sd = random_state_dict(DEFAULT_MODEL_CFG, seed=0, bn_jitter=0.2)
+    nets = PackedNetworks(sd, DEFAULT_MODEL_CFG, precision=args.precision, device=dev)
+    cfg = dict(MCTS_CFG, num_simulations=S, model=DEFAULT_MODEL_CFG)
+    cfg["search"] = dict(MCTS_CFG["search"], precision=args.precision, output_device="cuda", cuda_device=str(dev), seed=17 + rank)
+    m = MCTSSearchVec(cfg, nets, None)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    hiddens = [torch.rand((B, 256, 4, 5), generator=g, device=dev) for _ in range(2)]    # root latents are in [0,1] (_scale_state)
+    mask = torch.ones((B, 3), device=dev)
+    for i in range(W):
+        m.search(hiddens[i & 1], mask, 0)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for i in range(K):
+            value, visits = m.search(hiddens[i & 1], mask, 0)
+        e1.record()
+        barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    assert int(visits.sum().item()) == B * S, "visit counts do not sum to num_simulations"
+    plan = next(iter(m._plans.values()))
+    launches = K * plan.kernels_per_search
+
+    # dominant kernel: the tcgen05 convolution (58 launches per simulation step); timed alone over one
+    # simulation step's conv ops with CUDA events on the launching stream
+    conv_prog = Program(B)
+    conv_prog.ops = [o for o in plan.sim_prog.ops if o.op == OP_CONV]
+    conv_prog.keep = plan.sim_prog.keep
+    conv_ms = _time_prog(conv_prog)
+    step_ms = _time_prog(plan.sim_prog)
+    n_conv = len(conv_prog.ops)
+
+    # e2e: the reference-facing call with a HOST latent tensor in and HOST results out
+    cfg2 = dict(cfg); cfg2["search"] = dict(cfg["search"], output_device="cpu")
+    m2 = MCTSSearchVec(cfg2, nets, None)
+    m2._plans = m._plans                                  # same preallocated plan / graph
+    host_hidden = hiddens[0].cpu().pin_memory()
+    host_mask = torch.ones(B, 3)
+    Ke = max(2, min(K, args.e2e_steps))
+    m2.search(host_hidden, host_mask, 0)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        v_, n_ = m2.search(host_hidden, host_mask, 0)
+    barrier_sync(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+
+    peaks = measured_peaks()
+    sims = world * B * S * K
+    achieved = FLOP_CONV_VALID * B / (conv_ms * 1e-3) / 1e12
+    out = {
+        "metric": "latent_mcts_simulations_per_s", "value": sims / (ms * 1e-3), "unit": "simulations/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"mcts: MCTSSearchVec.search, {B} roots x {S} simulations per GPU, random-init MuZero networks (config.yaml sizes), {args.precision}",
+                   "trees_per_gpu": B, "num_simulations": S, "step": "one search() call = root prediction + S x (dynamics + prediction + backup/select)",
+                   "l2": f"latent store {B * (S + 2) * 10240 * (2 if args.precision == 'bf16' else 4) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
+                   "cuda_graph": bool(m.use_graph)},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                     "kernel": f"conv_tc_kernel ({n_conv} launches per simulation step)", "flop_convention": "valid taps only (BASELINE.md section 3)",
+                     "flop_per_leaf": FLOP_CONV_VALID, "kernel_ms": conv_ms / n_conv, "achieved_dense_taps": FLOP_CONV_DENSE * B / (conv_ms * 1e-3) / 1e12,
+                     "conv_ms_per_sim_step": conv_ms, "all_kernels_ms_per_sim_step": step_ms,
+                     "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12},
+        "e2e": {"value": world * B * S * Ke / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": B * (5120 * 4 + 12), "d2h_bytes_per_step": B * (4 + 24),
+                "steps": Ke, "api": "MCTSSearchVec.search(hidden_state, action_mask, training_iteration) with host tensors in and out"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    return out, sd
+
+
+def cpu_mcts(args, sd=None, trees=24, budget_s=25.0):
+    """CPU port of the reference search (oracle/: C tree bookkeeping + fp32 torch networks on all host threads),
+    bounded sample: `trees` roots x args.sims simulations."""
+    import oracle
+    from oracle.networks import OracleAgent
+    from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG, random_state_dict
+    sd = sd or random_state_dict(DEFAULT_MODEL_CFG, seed=0, bn_jitter=0.2)
+    agent = OracleAgent()
+    agent.load_state_dict(sd, strict=False)
+    agent.eval_mode()
+    g = torch.Generator().manual_seed(1)
+    hidden = torch.rand(trees, 256, 4, 5, generator=g)
+    noise = torch.distributions.Dirichlet(torch.full((3,), 0.25)).sample((trees,))
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle.search(agent, hidden, noise, seed=n, num_simulations=args.sims)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 20:
+            break
+    cores = torch.get_num_threads()
+    return {"value": trees * args.sims * n / el, "unit": "simulations/s", "cores": cores, "kind": "port",
+            "sample": f"{n} search() calls of {trees} roots x {args.sims} simulations: oracle/mcts_oracle.c tree + fp32 torch networks "
+                      f"(oracle/networks.py) on {cores} threads of {os.cpu_count()} cpus, {el:.1f} s"}, el / n * 1e3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps of the primary workload (default: mcts 5 searches, env 200 steps)")
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="env", choices=["env"])
-    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--workload", default="both", choices=["both", "mcts", "env"],
+                    help="both: MCTS line with the env results nested under 'env' (default)")
+    ap.add_argument("--envs", type=int, default=65536, help="env workload: environments per GPU")
+    ap.add_argument("--env-steps", type=int, default=200)
+    ap.add_argument("--trees", type=int, default=4096, help="mcts workload: roots per GPU (BASELINE.json configs[2])")
+    ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    primary = "env" if args.workload == "env" else "mcts"
+    if args.steps is None:
+        args.steps = 200 if primary == "env" else 5
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        base, ms = cpu_env(args, budget_s=20.0)
-        line = {"impl": "reference", "metric": "breakout_env_steps_per_s", "value": base["value"], "unit": "env-steps/s",
+        if primary == "env":
+            base, ms = cpu_env(args, budget_s=20.0)
+            metric, unit, wl = "breakout_env_steps_per_s", "env-steps/s", "env: BreakoutEnvironment.step, reference-format outputs (fp32 (B,3,16,20) frames + reward + done + valid)"
+        else:
+            base, ms = cpu_mcts(args, budget_s=60.0)
+            metric, unit = "latent_mcts_simulations_per_s", "simulations/s"
+            wl = f"mcts: MCTSSearchVec.search, {args.trees} roots x {args.sims} simulations per GPU, random-init MuZero networks (config.yaml sizes), fp32 CPU"
+        line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "env: BreakoutEnvironment.step, reference-format outputs (fp32 (B,3,16,20) frames + reward + done + valid)",
-                           "envs_per_gpu": args.envs},
-                "cpu_baseline": base,
-                "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "config": {"workload": wl}, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if args.workload == "both":
+            env_base, _ = cpu_env(args, budget_s=15.0)
+            line["env"] = {"metric": "breakout_env_steps_per_s", "value": env_base["value"], "unit": "env-steps/s", "cpu_baseline": env_base}
         print(json.dumps(line))
         return
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
     rank, local, world = dist_setup(args.gpus)
-    out = bench_env(args, rank, local, world)
+    sd = None
+    if primary == "mcts":
+        out, sd = bench_mcts(args, rank, local, world)
+        if args.workload == "both":
+            eargs = argparse.Namespace(**vars(args)); eargs.steps = args.env_steps; eargs.warmup = max(args.warmup, 10)
+            out["env"] = bench_env(eargs, rank, local, world)
+    else:
+        out = bench_env(args, rank, local, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"], _ = cpu_env(args)
+            if primary == "mcts":
+                out["cpu_baseline"], _ = cpu_mcts(args, sd)
+                if "env" in out:
+                    out["env"]["cpu_baseline"], _ = cpu_env(args)
+            else:
+                out["cpu_baseline"], _ = cpu_env(args)
         print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist

@@ -81,6 +81,71 @@ class Program:
         return len(self.ops)
 
 
+DEFAULT_MODEL_CFG = {  # config.yaml:27-50
+    "num_supports": 11, "supports_min": -5, "supports_max": 5, "latent_channels": [128, 256], "state_history_length": 32,
+    "latent_resolution": [4, 5],
+    "representation_network": {"num_res_blocks": [2, 3, 3], "activation": "relu"},
+    "dynamics_network": {"num_res_blocks": 14, "num_actions": 3, "activation": "relu"},
+    "prediction_network": {"num_res_blocks": 14, "num_actions": 3, "activation": "relu"},
+}
+
+
+def random_state_dict(cfg: dict | None = None, seed: int = 0, bn_jitter: float = 0.0) -> dict:
+    """Random-init weights with the key names and shapes of MuZeroAgent.state_dict():
+    uniform(+-1/sqrt(fan_in)) convs / linears, BatchNorm at its defaults (optionally jittered).  For
+    benchmarks and smoke tests, where no checkpoint is available."""
+    cfg = cfg or DEFAULT_MODEL_CFG
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, cout, cin, k):
+        bound = 1.0 / (cin * k * k) ** 0.5
+        sd[key + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+        sd[key + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def bn(key, c):
+        j = bn_jitter
+        sd[key + ".weight"] = 1 + j * (torch.rand(c, generator=g) - 0.5)
+        sd[key + ".bias"] = j * (torch.rand(c, generator=g) - 0.5)
+        sd[key + ".running_mean"] = j * (torch.rand(c, generator=g) - 0.5)
+        sd[key + ".running_var"] = 1 + j * (torch.rand(c, generator=g) - 0.5)
+
+    def res(key, c):
+        conv(key + ".conv1", c, c, 3); bn(key + ".bn1", c); conv(key + ".conv2", c, c, 3); bn(key + ".bn2", c)
+
+    def lin(key, nout, nin):
+        bound = 1.0 / nin ** 0.5
+        sd[key + ".weight"] = (torch.rand(nout, nin, generator=g) * 2 - 1) * bound
+        sd[key + ".bias"] = (torch.rand(nout, generator=g) * 2 - 1) * bound
+
+    c0, c1 = cfg["latent_channels"]
+    n0, n1, n2 = cfg["representation_network"]["num_res_blocks"]
+    hw = cfg["latent_resolution"][0] * cfg["latent_resolution"][1]
+    i = 0
+    conv(f"rep_net.blocks.{i}", c0, cfg["state_history_length"] * 2, 3); i += 1
+    for _ in range(n0):
+        res(f"rep_net.blocks.{i}", c0); i += 1
+    conv(f"rep_net.blocks.{i}", c1, c0, 3); i += 1
+    for _ in range(n1):
+        res(f"rep_net.blocks.{i}", c1); i += 1
+    i += 1                                                   # AvgPool2d
+    for _ in range(n2):
+        res(f"rep_net.blocks.{i}", c1); i += 1
+    na = cfg["dynamics_network"]["num_actions"]
+    conv("dyn_net.conv_block.conv", c1, c1 + na, 3); bn("dyn_net.conv_block.bn", c1)
+    for b in range(cfg["dynamics_network"]["num_res_blocks"]):
+        res(f"dyn_net.res_blocks.{b}", c1)
+    conv("dyn_net.reward_head.0.conv", c1, c1, 1); bn("dyn_net.reward_head.0.bn", c1)
+    lin("dyn_net.reward_head.2", cfg["num_supports"], c1 * hw)
+    for b in range(cfg["prediction_network"]["num_res_blocks"]):
+        res(f"pred_net.res_blocks.{b}", c1)
+    conv("pred_net.policy_head.0.conv", c1 // 2, c1, 3); bn("pred_net.policy_head.0.bn", c1 // 2)
+    lin("pred_net.policy_head.2", cfg["prediction_network"]["num_actions"], c1 // 2 * hw)
+    conv("pred_net.value_head.0.conv", c1 // 2, c1, 1); bn("pred_net.value_head.0.bn", c1 // 2)
+    lin("pred_net.value_head.2", cfg["num_supports"], c1 // 2 * hw)
+    return sd
+
+
 class _Conv:
     """One packed convolution: w [cout][k*k*cin] (tap-major, then input channel), fp32 scale/shift."""
 
