@@ -1,7 +1,13 @@
 // 3x3 / 1x1 convolution on the B200 5th-generation tensor cores (sm_100a): implicit GEMM with
 // tcgen05.mma (bf16 x bf16 -> fp32 accumulators in TMEM), operands staged in shared memory by TMA.
 //
-//   M = output pixels: one tile = S samples x hb rows x W columns (120 rows of the 128-lane UMMA tile)
+//   M = output pixels.  Two tilings of the 128-lane UMMA tile, chosen per launch by predicted cost:
+//         "pixel"   one tile = ONE pixel position (y,x) of 128 consecutive samples.  Every row of the tile
+//                   shares the same set of in-bounds taps, so the zero-padding taps of the 3x3 conv are
+//                   skipped outright (a 4x5 latent executes 130 of the 180 (pixel,tap) pairs) and all 128
+//                   rows are used;
+//         "spatial" one tile = S samples x hb rows x W columns (<= 128 rows), for small batches of large
+//                   images (the representation network), taps fully outside the image rows skipped
 //   N = cout (128 or 256: the whole output-channel range, one UMMA N)
 //   K = taps x cin, walked as (tap, 64-channel chunk); one pipeline stage = A[128 x 64] + B[N x 64] bf16
 //
@@ -38,7 +44,8 @@ constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_
 
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
-    int S, hb, tile_rows, ytiles, ntiles;
+    int mode;          // 0 spatial tiles, 1 pixel tiles
+    int S, hb, tile_rows, ytiles, groups, ntiles;
     __nv_bfloat16 *dst;
     const __nv_bfloat16 *res;
     float *dst_f32;
@@ -143,6 +150,33 @@ __device__ __forceinline__ float activate(float v, int act)
     }
 }
 
+struct Tile {
+    int s0, y0, x0;
+    uint32_t taps;   // bit t set = tap t has in-bounds rows for this tile (others contribute exact zeros)
+};
+__device__ __forceinline__ Tile decode_tile(const ConvParams &p, int tile)
+{
+    Tile t;
+    int ny, nx;      // tile extent in y / x
+    if (p.mode == 1) {
+        const int pix = tile / p.groups, g = tile - pix * p.groups;   // group-fastest: neighbours share the pixel's cost
+        t.y0 = pix / p.W; t.x0 = pix - t.y0 * p.W; t.s0 = g * p.S;
+        ny = 1; nx = 1;
+    } else {
+        const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
+        t.s0 = sg * p.S; t.y0 = yt * p.hb; t.x0 = 0;
+        ny = p.hb; nx = p.W;
+    }
+    if (p.taps == 1) { t.taps = 1u; return t; }
+    t.taps = 0u;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if (t.y0 + dy + ny > 0 && t.y0 + dy < p.H && t.x0 + dx + nx > 0 && t.x0 + dx < p.W) t.taps |= 1u << tap;
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p)
 {
@@ -159,7 +193,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.cout;
     const int kchunks = p.cin / BLOCK_K;
-    const int ksteps = p.taps * kchunks;
     const uint32_t smem_base = smem_u32(smem);
 
     for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
@@ -186,15 +219,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
-                const int s0 = sg * p.S, y0 = yt * p.hb;
+                const Tile t = decode_tile(p, tile);
                 for (int tap = 0; tap < p.taps; ++tap) {
+                    if (!((t.taps >> tap) & 1u)) continue;
                     const int dy = p.taps == 1 ? 0 : tap / 3 - 1, dx = p.taps == 1 ? 0 : tap % 3 - 1;
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                         mbar_expect_tx(bar_full + 8 * stage, a_bytes + b_bytes);
-                        tma_load_4d(sa, &map_a, bar_full + 8 * stage, kc * BLOCK_K, dx, y0 + dy, s0);
+                        tma_load_4d(sa, &map_a, bar_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
                         tma_load_2d(sb, &map_b, bar_full + 8 * stage, tap * p.cin + kc * BLOCK_K, 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -213,6 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                const int ksteps = __popc(decode_tile(p, tile).taps) * kchunks;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(bar_full + 8 * stage, phase);                 // TMA bytes have landed
                     tc_fence_after();
@@ -236,9 +270,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
-            const int sl = r / rows_per_sample, rr = r - sl * rows_per_sample;
-            const int s = sg * p.S + sl, y = yt * p.hb + rr / p.W, x = rr % p.W;
+            const Tile t = decode_tile(p, tile);
+            int s, y, x;
+            if (p.mode == 1) { s = t.s0 + r; y = t.y0; x = t.x0; }
+            else {
+                const int sl = r / rows_per_sample, rr = r - sl * rows_per_sample;
+                s = t.s0 + sl; y = t.y0 + rr / p.W; x = rr % p.W;
+            }
             const bool valid = r < p.tile_rows && s < p.n;
             const size_t m = ((size_t)s * p.H + y) * p.W + x;            // global output row
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
@@ -251,9 +289,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(acc[j]);
-                        if (ab) t += __ldg(ab + c0 + j);
-                        v[j] = t * s_scale[c0 + j] + s_shift[c0 + j];
+                        float a = __uint_as_float(acc[j]);
+                        if (ab) a += __ldg(ab + c0 + j);
+                        v[j] = a * s_scale[c0 + j] + s_shift[c0 + j];
                     }
                     if (p.res) {
                         const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + m * N + c0);
@@ -332,19 +370,28 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
 
     ConvParams p{};
     p.n = n; p.H = o.H; p.W = o.W; p.cin = o.cin; p.cout = o.cout; p.taps = o.ksize * o.ksize; p.pad = o.ksize / 2; p.act = o.act;
-    // tile = S samples x hb rows x W columns with S*hb*W <= 128, hb | H, as many rows as possible
-    int best = 0;
+    // spatial tiling: S samples x hb rows x W columns with S*hb*W <= 128, hb | H, as many rows as possible
+    int best = 0, s_hb = 1, s_S = 1;
     for (int hb = 1; hb <= o.H; ++hb) {
         if (o.H % hb || hb * o.W > BLOCK_M) continue;
         int S = BLOCK_M / (hb * o.W);
         if (S > 256) S = 256;
         const int rows = S * hb * o.W;
-        if (rows > best || (rows == best && hb > p.hb)) { best = rows; p.hb = hb; p.S = S; }
+        if (rows > best || (rows == best && hb > s_hb)) { best = rows; s_hb = hb; s_S = S; }
     }
-    MZB_CHECK_ARG(best > 0 && o.W <= 256, "conv_tc: image row does not fit a tile");
-    p.tile_rows = best;
-    p.ytiles = o.H / p.hb;
-    p.ntiles = ((n + p.S - 1) / p.S) * p.ytiles;
+    MZB_CHECK_ARG(o.W <= 256, "conv_tc: image too wide");
+    const long long sp_tiles = best > 0 ? (long long)((n + s_S - 1) / s_S) * (o.H / s_hb) : 0;
+    // pixel tiling: 128 samples x one pixel; predicted cost = waves x average in-bounds taps
+    const long long px_groups = (n + BLOCK_M - 1) / BLOCK_M, px_tiles = px_groups * o.H * o.W;
+    double px_taps = 1.0;
+    if (o.ksize == 3) px_taps = (double)(3 * o.H - 2) * (3 * o.W - 2) / (o.H * o.W);
+    auto waves = [](long long tiles) { return (double)((tiles + kNumSMs - 1) / kNumSMs); };
+    const double cost_px = waves(px_tiles) * px_taps, cost_sp = best > 0 ? waves(sp_tiles) * p.taps : 1e30;
+    if (cost_px <= cost_sp) {
+        p.mode = 1; p.S = BLOCK_M; p.hb = 1; p.tile_rows = BLOCK_M; p.ytiles = 1; p.groups = (int)px_groups; p.ntiles = (int)px_tiles;
+    } else {
+        p.mode = 0; p.S = s_S; p.hb = s_hb; p.tile_rows = best; p.ytiles = o.H / s_hb; p.groups = 1; p.ntiles = (int)sp_tiles;
+    }
     p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
     p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
 
@@ -352,7 +399,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     {
         cuuint64_t dims[4] = {(cuuint64_t)o.cin, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)n};
         cuuint64_t strides[3] = {(cuuint64_t)o.cin * 2, (cuuint64_t)o.W * o.cin * 2, (cuuint64_t)o.H * o.W * o.cin * 2};
-        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)o.W, (cuuint32_t)p.hb, (cuuint32_t)p.S};
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(p.mode == 1 ? 1 : o.W), (cuuint32_t)p.hb, (cuuint32_t)p.S};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(o.src), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
