@@ -287,6 +287,27 @@ def bench_mcts(args, rank, local, world):
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
 
+    collectives = None
+    if world > 1:
+        # the only exchange steps of the algorithm, timed separately (device events, max over ranks)
+        import torch.distributed as dist
+        from muzero_breakout_b200 import parallel
+        def timed(fn, reps=5):
+            fn(); barrier_sync(world)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); barrier_sync(world)
+            return max_over_ranks(a.elapsed_time(b) / reps, world)
+        nbytes = parallel.broadcast_weights(nets, src=0)
+        bc_ms = timed(lambda: parallel.broadcast_weights(nets, src=0))
+        rec = torch.rand((B, parallel.RECORD_FLOATS), device=dev)
+        ag_ms = timed(lambda: parallel.all_gather_trajectory(rec))
+        collectives = {"weights_broadcast_ms": bc_ms, "weights_bytes": nbytes, "weights_broadcast_GBps": nbytes / bc_ms / 1e6,
+                       "trajectory_allgather_ms": ag_ms, "trajectory_bytes_per_rank": rec.numel() * 4,
+                       "trajectory_allgather_GBps_per_rank_in": rec.numel() * 4 * (world - 1) / ag_ms / 1e6, "backend": "nccl"}
+
     peaks = measured_peaks()
     sims = world * B * S * K
     achieved = FLOP_CONV_VALID * B / (conv_ms * 1e-3) / 1e12
@@ -309,6 +330,8 @@ def bench_mcts(args, rank, local, world):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    if collectives:
+        out["collectives"] = collectives
     return out, sd
 
 

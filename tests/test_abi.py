@@ -89,3 +89,21 @@ def test_mcts_class_mirrors_reference_signature():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             m.search(torch.zeros(2, 256, 4, 5), torch.ones(2, 3), 0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout only exists in the build container")
+def test_dropin_shadow_modules_resolve_before_the_reference():
+    """INTEGRATION.md option A: with dropin/ ahead of the reference on sys.path, the reference's own
+    get_class() loads our classes, while src.networks still comes from the reference."""
+    import subprocess
+    import sys
+    code = ("import sys, types\n"
+            "for n in ('matplotlib', 'matplotlib.pyplot'): sys.modules.setdefault(n, types.ModuleType(n))\n"
+            "from utils import get_class\n"
+            "m = get_class('src.mcts', 'MCTSSearchVec'); e = get_class('environment.parallel_breakout', 'BreakoutEnvironment')\n"
+            "n = get_class('src.networks', 'MuZeroAgent')\n"
+            "print(m.__module__, e.__module__, n.__module__)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, "/root/reference"]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["muzero_breakout_b200.src.mcts", "muzero_breakout_b200.environment.parallel_breakout", "src.networks"]
