@@ -17,8 +17,9 @@
 // unit.  Both operands are K-major with the 128-byte swizzle, so a stage is one swizzle atom wide and
 // the four K=16 MMAs of a stage advance the descriptor start address by 32 bytes.
 //
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4): tcgen05.ld ->
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2-9 = epilogue (TMEM lane quarter = warp_idx % 4, two warps per
+// quarter split the N columns; TMEM loads and residual loads are software-pipelined): tcgen05.ld ->
 // (+ per-action bias) * scale + shift (+ residual) -> activation -> bf16 (and optional fp32) stores.
 // Two TMEM accumulator buffers (2 x N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
 //
@@ -38,9 +39,10 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
 constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;        // 32 KB (N <= 256)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the N columns
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256;
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
 
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
@@ -112,7 +114,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+// tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane; asynchronous until tmem_wait().
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -123,7 +126,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for the outstanding tcgen05.ld; the registers are in/out operands so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
@@ -182,9 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float *s_scale = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
-    float *s_shift = s_scale + 256;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + 256);
+    __shared__ float s_scale[256], s_shift[256];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
@@ -200,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -263,10 +276,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter+32)
+        const int half = (warp - 2) >> 2;              // which half of the N columns this warp drains
         const int r = quarter * 32 + lane;             // row of the tile
         const int rows_per_sample = p.hb * p.W;
+        const int ncols = N / 2, col0 = half * ncols;
+        const int nchunks = ncols / 32;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -280,48 +296,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool valid = r < p.tile_rows && s < p.n;
             const size_t m = ((size_t)s * p.H + y) * p.W + x;            // global output row
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
+            const bool has_res = valid && p.res != nullptr;
+            const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + (valid ? m : 0) * N + col0);
+            uint4 res[2][4];
+            uint32_t acc[2][32];
+            if (has_res) {                                               // residual of chunk 0 is in flight while the MMAs finish
+#pragma unroll
+                for (int q = 0; q < 4; ++q) res[0][q] = __ldg(rp + q);
+            }
             mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + c0), acc);
-                if (valid) {
-                    float v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
+            tmem_ld32_async(taddr, acc[0]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float a = __uint_as_float(acc[j]);
-                        if (ab) a += __ldg(ab + c0 + j);
-                        v[j] = a * s_scale[c0 + j] + s_shift[c0 + j];
-                    }
-                    if (p.res) {
-                        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + m * N + c0);
+            for (int c = 0; c < 4; ++c) {
+                if (c < nchunks) {
+                    tmem_wait(acc[c & 1]);
+                    if (c + 1 < nchunks) {                               // next chunk: TMEM load + residual prefetch overlap this chunk's math
+                        tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
+                        if (has_res) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 u = __ldg(rp + q);
-                            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __bfloat1622float2(h[e]);
-                                v[q * 8 + e * 2] += f.x;
-                                v[q * 8 + e * 2 + 1] += f.y;
-                            }
+                            for (int q = 0; q < 4; ++q) res[(c + 1) & 1][q] = __ldg(rp + (c + 1) * 4 + q);
                         }
                     }
+                    if (valid) {
+                        const int c0 = col0 + c * 32;
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
-                    uint4 *op = reinterpret_cast<uint4 *>(p.dst + m * N + c0);
+                        for (int j = 0; j < 32; ++j) {
+                            float a = __uint_as_float(acc[c & 1][j]);
+                            if (ab) a += __ldg(ab + c0 + j);
+                            v[j] = a * s_scale[c0 + j] + s_shift[c0 + j];
+                        }
+                        if (has_res) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 u;
-                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+                            for (int q = 0; q < 4; ++q) {
+                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&res[c & 1][q]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-                        op[q] = u;
-                    }
-                    if (p.dst_f32) {
-                        float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x;
+                                    v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        }
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
+                        uint4 *op = reinterpret_cast<uint4 *>(p.dst + m * N + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                            op[q] = u;
+                        }
+                        if (p.dst_f32) {
+                            float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        }
                     }
                 }
             }
