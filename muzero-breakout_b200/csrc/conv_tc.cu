@@ -17,6 +17,11 @@
 // unit.  Both operands are K-major with the 128-byte swizzle, so a stage is one swizzle atom wide and
 // the four K=16 MMAs of a stage advance the descriptor start address by 32 bytes.
 //
+// CTA pairs (cluster of 2): the two CTAs of a pair work on two sample groups of the SAME pixel / image rows, so
+// they need the same weight tile at every k-step; each loads one half of it and TMA-multicasts it into both
+// CTAs' shared memory (halves the dominant L2 -> SM operand traffic).  Stage release is cross-CTA: a stage
+// is free when BOTH CTAs' MMAs have retired (tcgen05.commit multicast onto both CTAs' empty barriers).
+//
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
 // MMA issuer (one elected lane), warps 2-9 = epilogue (TMEM lane quarter = warp_idx % 4, two warps per
 // quarter split the N columns; TMEM loads and residual loads are software-pipelined): tcgen05.ld ->
@@ -47,7 +52,7 @@ constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
     int mode;          // 0 spatial tiles, 1 pixel tiles
-    int S, hb, tile_rows, ytiles, groups, ntiles;
+    int S, hb, tile_rows, ytiles, groups, ntiles;   // groups = sample-group PAIRS per pixel (pixel mode); ntiles = pair-tiles
     __nv_bfloat16 *dst;
     const __nv_bfloat16 *res;
     float *dst_f32;
@@ -93,12 +98,26 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, uint16_t mask)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -168,17 +187,17 @@ struct Tile {
     int s0, y0, x0;
     uint32_t taps;   // bit t set = tap t has in-bounds rows for this tile (others contribute exact zeros)
 };
-__device__ __forceinline__ Tile decode_tile(const ConvParams &p, int tile)
+__device__ __forceinline__ Tile decode_tile(const ConvParams &p, int tile, int rank)
 {
     Tile t;
     int ny, nx;      // tile extent in y / x
     if (p.mode == 1) {
         const int pix = tile / p.groups, g = tile - pix * p.groups;   // group-fastest: neighbours share the pixel's cost
-        t.y0 = pix / p.W; t.x0 = pix - t.y0 * p.W; t.s0 = g * p.S;
+        t.y0 = pix / p.W; t.x0 = pix - t.y0 * p.W; t.s0 = (2 * g + rank) * p.S;
         ny = 1; nx = 1;
     } else {
         const int sg = tile / p.ytiles, yt = tile - sg * p.ytiles;
-        t.s0 = sg * p.S; t.y0 = yt * p.hb; t.x0 = 0;
+        t.s0 = (2 * sg + rank) * p.S; t.y0 = yt * p.hb; t.x0 = 0;
         ny = p.hb; nx = p.W;
     }
     if (p.taps == 1) { t.taps = 1u; return t; }
@@ -204,6 +223,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();          // 0 / 1 inside the CTA pair
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int N = p.cout;
     const int kchunks = p.cin / BLOCK_K;
     const uint32_t smem_base = smem_u32(smem);
@@ -212,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -222,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                               // the peer's barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -231,8 +253,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t a_bytes = (uint32_t)p.tile_rows * BLOCK_K * 2, b_bytes = (uint32_t)N * BLOCK_K * 2;
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const Tile t = decode_tile(p, tile);
+            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+                const Tile t = decode_tile(p, tile, rank);
                 for (int tap = 0; tap < p.taps; ++tap) {
                     if (!((t.taps >> tap) & 1u)) continue;
                     const int dy = p.taps == 1 ? 0 : tap / 3 - 1, dx = p.taps == 1 ? 0 : tap % 3 - 1;
@@ -241,7 +263,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                         mbar_expect_tx(bar_full + 8 * stage, a_bytes + b_bytes);
                         tma_load_4d(sa, &map_a, bar_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
-                        tma_load_2d(sb, &map_b, bar_full + 8 * stage, tap * p.cin + kc * BLOCK_K, 0);
+                        // my half of the weight tile, multicast into both CTAs of the pair
+                        tma_load_2d_mc(sb + (uint32_t)(rank * (N / 2) * BLOCK_K * 2), &map_b, bar_full + 8 * stage, tap * p.cin + kc * BLOCK_K,
+                                       rank * (N / 2), (uint16_t)0x3);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -254,12 +278,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                 const int buf = it & 1;
                 mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-                const int ksteps = __popc(decode_tile(p, tile).taps) * kchunks;
+                const int ksteps = __popc(decode_tile(p, tile, rank).taps) * kchunks;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(bar_full + 8 * stage, phase);                 // TMA bytes have landed
                     tc_fence_after();
@@ -269,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
                                   (ks | k) ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * stage);                     // frees the smem slot when the MMAs retire
+                    umma_commit_mc(bar_empty + 8 * stage, (uint16_t)0x3);   // both CTAs' slot `stage` may be refilled once BOTH have retired it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(bar_tfull + 8 * buf);                           // accumulator complete -> epilogue
@@ -284,9 +308,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ncols = N / 2, col0 = half * ncols;
         const int nchunks = ncols / 32;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
             const int buf = it & 1;
-            const Tile t = decode_tile(p, tile);
+            const Tile t = decode_tile(p, tile, rank);
             int s, y, x;
             if (p.mode == 1) { s = t.s0 + r; y = t.y0; x = t.x0; }
             else {
@@ -366,6 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                               // the peer may still signal my barriers / multicast into my smem until it is done
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -414,12 +439,13 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         if (rows > best || (rows == best && hb > s_hb)) { best = rows; s_hb = hb; s_S = S; }
     }
     MZB_CHECK_ARG(o.W <= 256, "conv_tc: image too wide");
-    const long long sp_tiles = best > 0 ? (long long)((n + s_S - 1) / s_S) * (o.H / s_hb) : 0;
+    const long long sp_pairs = best > 0 ? (((n + s_S - 1) / s_S + 1) / 2) : 0;                       // sample-group pairs
+    const long long sp_tiles = sp_pairs * (best > 0 ? o.H / s_hb : 0);
     // pixel tiling: 128 samples x one pixel; predicted cost = waves x average in-bounds taps
-    const long long px_groups = (n + BLOCK_M - 1) / BLOCK_M, px_tiles = px_groups * o.H * o.W;
+    const long long px_groups = ((n + BLOCK_M - 1) / BLOCK_M + 1) / 2, px_tiles = px_groups * o.H * o.W;   // pairs of 128-sample groups
     double px_taps = 1.0;
     if (o.ksize == 3) px_taps = (double)(3 * o.H - 2) * (3 * o.W - 2) / (o.H * o.W);
-    auto waves = [](long long tiles) { return (double)((tiles + kNumSMs - 1) / kNumSMs); };
+    auto waves = [](long long tiles) { return (double)((tiles + kNumSMs / 2 - 1) / (kNumSMs / 2)); };
     const double cost_px = waves(px_tiles) * px_taps, cost_sp = best > 0 ? waves(sp_tiles) * p.taps : 1e30;
     if (cost_px <= cost_sp) {
         p.mode = 1; p.S = BLOCK_M; p.hb = 1; p.tile_rows = BLOCK_M; p.ytiles = 1; p.groups = (int)px_groups; p.ntiles = (int)px_tiles;
@@ -444,7 +470,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         const cuuint64_t K = (cuuint64_t)p.taps * o.cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)o.cout};
         cuuint64_t strides[1] = {K * 2};
-        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)o.cout};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(o.cout / 2)};     // each CTA of a pair loads half of the rows
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -456,8 +482,18 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-    conv_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    const int clusters = p.ntiles < kNumSMs / 2 ? p.ntiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, map_a, map_b, p));
     MZB_LAUNCH_CHECK();
     return 0;
 }
