@@ -17,10 +17,13 @@
 // unit.  Both operands are K-major with the 128-byte swizzle, so a stage is one swizzle atom wide and
 // the four K=16 MMAs of a stage advance the descriptor start address by 32 bytes.
 //
-// CTA pairs (cluster of 2): the two CTAs of a pair work on two sample groups of the SAME pixel / image rows, so
-// they need the same weight tile at every k-step; each loads one half of it and TMA-multicasts it into both
-// CTAs' shared memory (halves the dominant L2 -> SM operand traffic).  Stage release is cross-CTA: a stage
-// is free when BOTH CTAs' MMAs have retired (tcgen05.commit multicast onto both CTAs' empty barriers).
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): the two CTAs of a pair work on two 128-sample groups of the
+// SAME pixel / image rows, so they need the same weight tile at every k-step.  One MMA instruction issued by
+// the leader CTA computes the pair's 256 x N tile: rows 0-127 from the leader's A tile, rows 128-255 from the
+// peer's, and each CTA holds only HALF of the weight tile (N/2 rows) in its shared memory.  Per CTA and k-step
+// that is 16 KB (A) + 16 KB (B half) of TMA writes and the same of operand reads instead of 48 + 48 KB, which
+// keeps the 128 B/clk shared-memory port from capping the tensor pipe at ~2/3 (measured: 61-69 % with the
+// 1-CTA form), and the 192 KB of stages hold 6 k-steps in flight instead of 4.
 //
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 = TMA producer, warp 1 = TMEM allocator +
 // MMA issuer (one elected lane), warps 2-9 = epilogue (TMEM lane quarter = warp_idx % 4, two warps per
@@ -40,9 +43,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 per smem row = 128 bytes = one SWIZZLE_128B atom
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
-constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;        // 32 KB (N <= 256)
+constexpr int B_STAGE_BYTES = 128 * BLOCK_K * 2;        // 16 KB: this CTA's half (N/2 <= 128 rows) of the weight tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the N columns
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
@@ -71,10 +74,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
@@ -91,19 +90,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
     __trap();
 }
+// cta_group::2 TMA loads: data lands in THIS CTA's shared memory, the transaction bytes are signalled on the
+// mbarrier `bar`, a shared::cluster address that may belong to the peer (the pair leader's full barrier)
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
 {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, uint16_t mask)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -115,21 +127,18 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask)
+// commit of the pair's MMAs: arrives on the mbarrier at this offset in BOTH CTAs when they have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)0x3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -166,10 +175,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=256 (the pair), N
 __device__ __forceinline__ uint32_t instr_desc(int N)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
 }
 
 __device__ __forceinline__ float activate(float v, int act)
@@ -233,13 +242,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }   // full: both producers arrive (used in the leader)
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * NUM_EPI_WARPS); }   // both CTAs' epilogue warps (leader's copy)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -250,7 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t a_bytes = (uint32_t)p.tile_rows * BLOCK_K * 2, b_bytes = (uint32_t)N * BLOCK_K * 2;
+            const uint32_t a_bytes = (uint32_t)p.tile_rows * BLOCK_K * 2, b_bytes = (uint32_t)(N / 2) * BLOCK_K * 2;
+            const uint32_t lead_full = map_to_cta(bar_full, 0);          // the pair leader's full barriers
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
@@ -259,21 +269,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (!((t.taps >> tap) & 1u)) continue;
                     const int dy = p.taps == 1 ? 0 : tap / 3 - 1, dx = p.taps == 1 ? 0 : tap % 3 - 1;
                     for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);     // the pair's MMAs have retired this slot (in both CTAs)
                         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-                        mbar_expect_tx(bar_full + 8 * stage, a_bytes + b_bytes);
-                        tma_load_4d(sa, &map_a, bar_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
-                        // my half of the weight tile, multicast into both CTAs of the pair
-                        tma_load_2d_mc(sb + (uint32_t)(rank * (N / 2) * BLOCK_K * 2), &map_b, bar_full + 8 * stage, tap * p.cin + kc * BLOCK_K,
-                                       rank * (N / 2), (uint16_t)0x3);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));   // bytes of both CTAs
+                        else mbar_arrive_cluster(lead_full + 8 * stage);
+                        tma_load_4d(sa, &map_a, lead_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
+                        tma_load_2d(sb, &map_b, lead_full + 8 * stage, tap * p.cin + kc * BLOCK_K, rank * (N / 2));   // my half of the weight tile
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (pair leader only) =====================
+        if (lane == 0 && rank == 0) {
             const uint32_t idesc = instr_desc(N);
             int stage = 0;
             uint32_t phase = 0;
@@ -291,12 +300,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                        umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
                                   (ks | k) ? 1u : 0u);
-                    umma_commit_mc(bar_empty + 8 * stage, (uint16_t)0x3);   // both CTAs' slot `stage` may be refilled once BOTH have retired it
+                    umma_commit_pair(bar_empty + 8 * stage);                // frees slot `stage` in both CTAs when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * buf);                           // accumulator complete -> epilogue
+                umma_commit_pair(bar_tfull + 8 * buf);                      // accumulator complete -> both CTAs' epilogues
             }
         }
     } else {
@@ -307,6 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int rows_per_sample = p.hb * p.W;
         const int ncols = N / 2, col0 = half * ncols;
         const int nchunks = ncols / 32;
+        const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
         int it = 0;
         for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
             const int buf = it & 1;
@@ -385,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
         }
     }
     tc_fence_before();
@@ -394,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
