@@ -158,55 +158,97 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
     }
 }
 
-// Flatten + Linear + (softmax -> expectation -> inverse transform | softmax).  One CTA per sample.
+// Flatten + Linear + (softmax -> expectation -> inverse transform | softmax).  One CTA per HEAD_SAMPLES
+// samples: every thread owns a strided slice of the feature axis and keeps HEAD_SAMPLES x nout partial sums,
+// so each weight element is read once per CTA (not once per sample) and the reads are coalesced.
 constexpr int HEAD_MAX_OUT = 16;
-template <typename T>
-__global__ void __launch_bounds__(128)
-head_kernel(int feat, int nout, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
+constexpr int HEAD_SAMPLES = 8;
+constexpr int HEAD_THREADS = 256;
+
+template <typename T, int NOUT>
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_kernel(int n, int feat, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
             float *__restrict__ out, float *__restrict__ out_logits)
 {
-    __shared__ float s_part[4][HEAD_MAX_OUT];
-    const int i = blockIdx.x, tid = threadIdx.x;
-    const T *x = src + (size_t)i * feat;
-    float acc[HEAD_MAX_OUT];
+    __shared__ float s_part[HEAD_THREADS / 32][HEAD_SAMPLES][NOUT];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int s0 = blockIdx.x * HEAD_SAMPLES;
+    const int ns = min(HEAD_SAMPLES, n - s0);
+    float acc[HEAD_SAMPLES][NOUT];
 #pragma unroll
-    for (int o = 0; o < HEAD_MAX_OUT; ++o) acc[o] = 0.0f;
-    for (int e = tid; e < feat; e += 128) {
-        const float v = to_f(x[e]);
+    for (int s = 0; s < HEAD_SAMPLES; ++s)
 #pragma unroll
-        for (int o = 0; o < HEAD_MAX_OUT; ++o)
-            if (o < nout) acc[o] = fmaf(v, __ldg(w + (size_t)o * feat + e), acc[o]);
+        for (int o = 0; o < NOUT; ++o) acc[s][o] = 0.0f;
+    for (int e = tid; e < feat; e += HEAD_THREADS) {
+        float wv[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) wv[o] = __ldg(w + (size_t)o * feat + e);
+#pragma unroll
+        for (int s = 0; s < HEAD_SAMPLES; ++s) {
+            if (s < ns) {
+                const float v = to_f(src[(size_t)(s0 + s) * feat + e]);
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) acc[s][o] = fmaf(v, wv[o], acc[s][o]);
+            }
+        }
     }
 #pragma unroll
-    for (int o = 0; o < HEAD_MAX_OUT; ++o) {
-        float v = acc[o];
+    for (int s = 0; s < HEAD_SAMPLES; ++s)
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if ((tid & 31) == 0) s_part[tid >> 5][o] = v;
-    }
+        for (int o = 0; o < NOUT; ++o) {
+            float v = acc[s][o];
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+            if (lane == 0) s_part[wid][s][o] = v;
+        }
     __syncthreads();
-    if (tid != 0) return;
-    float logit[HEAD_MAX_OUT];
+    if (tid >= ns) return;                                       // thread s finishes sample s
+    const int i = s0 + tid;
+    float logit[NOUT];
     float mx = -INFINITY;
-    for (int o = 0; o < nout; ++o) {
-        logit[o] = ((s_part[0][o] + s_part[1][o]) + (s_part[2][o] + s_part[3][o])) + bias[o];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        float v = 0.0f;
+#pragma unroll
+        for (int q = 0; q < HEAD_THREADS / 32; ++q) v += s_part[q][tid][o];
+        logit[o] = v + bias[o];
         mx = fmaxf(mx, logit[o]);
-        if (out_logits) out_logits[(size_t)i * nout + o] = logit[o];
+        if (out_logits) out_logits[(size_t)i * NOUT + o] = logit[o];
     }
     if (mode == 0) return;
-    float den = 0.0f, e[HEAD_MAX_OUT];
-    for (int o = 0; o < nout; ++o) { e[o] = expf(logit[o] - mx); den += e[o]; }
+    float den = 0.0f, e[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) { e[o] = expf(logit[o] - mx); den += e[o]; }
     if (mode == 2) {                                                   // softmax probabilities (mcts.py:100,199)
-        for (int o = 0; o < nout; ++o) out[(size_t)i * nout + o] = e[o] / den;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) out[(size_t)i * NOUT + o] = e[o] / den;
         return;
     }
     // utils.py:66-81: supports = linspace(-5, 5, 11) (integers), x = sum p*s, y = sign(x)((|x| + 0.999)^2 - 1)
-    const float half = 0.5f * (float)(nout - 1);
+    const float half = 0.5f * (float)(NOUT - 1);
     float ex = 0.0f;
-    for (int o = 0; o < nout; ++o) ex += (e[o] / den) * ((float)o - half);
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) ex += (e[o] / den) * ((float)o - half);
     const float sg = ex > 0.0f ? 1.0f : (ex < 0.0f ? -1.0f : 0.0f);
     const float t = fabsf(ex) + 0.999f;                                  // float32(1 - epsilon), utils.py:14,28
     out[i] = sg * (t * t - 1.0f);
+}
+
+template <typename T>
+int launch_head(const mz_op &o, int n, cudaStream_t st)
+{
+    const int feat = o.H * o.W * o.cin;
+    const int grid = (n + HEAD_SAMPLES - 1) / HEAD_SAMPLES;
+#define MZB_HEAD(NO) head_kernel<T, NO><<<grid, HEAD_THREADS, 0, st>>>(n, feat, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits)
+    switch (o.nout) {
+        case 3: MZB_HEAD(3); break;
+        case 11: MZB_HEAD(11); break;
+        default:
+            mzb::set_error("head: nout=%d is not built (3 actions / 11 supports, config.yaml:6,30)", o.nout);
+            return -1;
+    }
+#undef MZB_HEAD
+    return 0;
 }
 
 template <typename T>
@@ -264,7 +306,7 @@ int run_op(const mz_op &o, int n, cudaStream_t st)
         case MZ_OP_HEAD: {
             MZB_CHECK_ARG(o.src && o.w && o.shift && o.nout > 0 && o.nout <= HEAD_MAX_OUT, "head: bad argument");
             MZB_CHECK_ARG(o.head_mode == 0 ? o.out_logits != nullptr : o.out != nullptr, "head: missing output");
-            head_kernel<T><<<n, 128, 0, st>>>(o.H * o.W * o.cin, o.nout, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits);
+            if (int rc = launch_head<T>(o, n, st)) return rc;
             break;
         }
         case MZ_OP_NCHW_IN: {
