@@ -1,5 +1,6 @@
 // Vectorised Breakout environment for B200 (sm_100a): structure-of-arrays state in HBM, one warp per
-// block of 32 environments, dense float32 frames written with coalesced 128-bit streaming stores.
+// task of 8 environments (lane = env for the game logic, then the whole warp writes the 8 frames as one contiguous
+// region), dense float32 frames written with coalesced 128-bit streaming stores.
 //
 // Replaces (behaviour, not code) environment/parallel_breakout.py of the reference:
 //   reset :107-139, get_valid_actions :141-155, step :158-254, and the caller-side
@@ -13,8 +14,8 @@ constexpr int H = MZB_ENV_H, W = MZB_ENV_W;
 constexpr int PADDLE_W = 6;
 constexpr int FRAME_V4 = MZB_ENV_FRAME_FLOATS / 4;  // 240 float4 per frame
 constexpr int GRAY_V4 = H * W / 4;                  // 80 float4 per gray frame
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int ENVS_PER_WARP = 32;
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int ENVS_PER_WARP = 8;       // envs per warp task: small tasks balance 65 536 envs over 148 SMs to ~1 %
 constexpr int WORDS = 48;         // 3 planes x 16 row bitmasks per env
 constexpr int WORDS_PAD = 49;     // +1: conflict-free when lane e writes words[e][r]
 
@@ -57,10 +58,10 @@ __device__ __forceinline__ float gray_px(uint32_t p, uint32_t b, uint32_t k)
     return fminf(fmaxf(v, 0.0f), 1.0f);
 }
 
-// Phase 2 of every frame-producing kernel: the warp's 32 frames are one contiguous 122 880 B region;
+// Phase 2 of every frame-producing kernel: the warp's ENVS_PER_WARP frames are one contiguous region;
 // every store instruction writes 512 contiguous bytes.  words = smem [32][WORDS_PAD] row bitmasks.
 // 480 float4 (= 2 frames) is the period of the (lane -> plane,row,column-group) map, so the 15
-// descriptors are computed once and reused for the 16 frame pairs.
+// descriptors are computed once and reused for the ENVS_PER_WARP/2 frame pairs.
 __device__ __forceinline__ void write_frames(const uint32_t *words, float *state_out, int env0, int B, int lane)
 {
     float4 *out = reinterpret_cast<float4 *>(state_out) + (size_t)env0 * FRAME_V4;
@@ -76,7 +77,7 @@ __device__ __forceinline__ void write_frames(const uint32_t *words, float *state
         const int sh = (rem - rr * 5) * 4;
         const int widx = plane * 16 + rr;
 #pragma unroll 4
-        for (int pair = 0; pair < 16; ++pair) {
+        for (int pair = 0; pair < ENVS_PER_WARP / 2; ++pair) {
             const int e = pair * 2 + eo;
             if (e < nenv) {
                 const uint32_t w = words[e * WORDS_PAD + widx];
@@ -98,7 +99,7 @@ __device__ __forceinline__ void write_gray(const uint32_t *words, float *gray_ou
         const int rr = i / 5;
         const int sh = (i - rr * 5) * 4;
 #pragma unroll 4
-        for (int pair = 0; pair < 16; ++pair) {
+        for (int pair = 0; pair < ENVS_PER_WARP / 2; ++pair) {
             const int e = pair * 2 + eo;
             if (e < nenv) {
                 const uint32_t *w = words + e * WORDS_PAD;
@@ -132,9 +133,9 @@ env_step_kernel(int B, uint64_t *__restrict__ hdr, uint32_t *__restrict__ bricks
     const int env0 = (blockIdx.x * WARPS_PER_BLOCK + warp) * ENVS_PER_WARP;
     if (env0 >= B) return;
     const int e = env0 + lane;
-    uint32_t *w = s_words[warp] + lane * WORDS_PAD;
+    uint32_t *w = s_words[warp] + (lane % ENVS_PER_WARP) * WORDS_PAD;
 
-    if (e < B) {
+    if (lane < ENVS_PER_WARP && e < B) {
         Hdr s = unpack(hdr[e]);
         const int a = (int)action[e];
         const int din = done[e] ? 1 : 0;
@@ -218,8 +219,8 @@ env_render_kernel(int B, const uint64_t *__restrict__ hdr, const uint32_t *__res
     const int env0 = (blockIdx.x * WARPS_PER_BLOCK + warp) * ENVS_PER_WARP;
     if (env0 >= B) return;
     const int e = env0 + lane;
-    uint32_t *w = s_words[warp] + lane * WORDS_PAD;
-    if (e < B) {
+    uint32_t *w = s_words[warp] + (lane % ENVS_PER_WARP) * WORDS_PAD;
+    if (lane < ENVS_PER_WARP && e < B) {
         Hdr s = unpack(hdr[e]);
 #pragma unroll
         for (int r = 0; r < 16; ++r) w[32 + r] = ((s.rowmask >> r) & 1u) ? bricks[(size_t)r * B + e] : 0u;
