@@ -196,6 +196,25 @@ typedef struct mz_op {
 
 int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Acting-move glue  (reference: train_torch.py _prepare_mcts_input :259-277, _encode_actions :279-293,
+ * _pad_initial_state :313-332, temperature sampling :192-198)
+ *
+ * mz_rep_input: observation history -> representation-network input, channels-last [B][16*20][64]:
+ *   channels 0..30 = the last 31 gray frames appended to the trajectory (oldest first), 31 = the current
+ *   frame, 32..63 = the last 32 actions / 3 as constant planes (oldest first).
+ *   frames float32 [slots][B][320] ring with `head` = slot of the newest appended frame; cur float32 [B][320];
+ *   acts int32 [slots][B] ring with `ahead` = slot of the newest action; slots >= 32; dtype MZ_F32 / MZ_BF16.
+ * mz_sample_actions: p_a = visits_a ** (1/temperature) / sum, one categorical draw per env with
+ *   u = u32(seed, env, step) / 2^32; writes action int64 [B] (+ optional int32 copy into an action-ring slot,
+ *   optional probabilities float32 [B][3]).
+ */
+int mz_rep_input(int B, int slots, const float *frames, int head, const float *cur, const int32_t *acts, int ahead, void *out,
+                 int dtype, void *stream);
+int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t seed, uint32_t step, int64_t *action,
+                      int32_t *act_slot, float *probs_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

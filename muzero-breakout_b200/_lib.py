@@ -80,6 +80,8 @@ def _declare(L: C.CDLL) -> None:
         "mz_tree_root": [C.POINTER(TreeArgs), vp],
         "mz_tree_step": [C.POINTER(TreeArgs), vp],
         "mz_run": [vp, i32, i32, vp],
+        "mz_rep_input": [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp],
+        "mz_sample_actions": [i32, vp, C.c_double, u64, C.c_uint32, vp, vp, vp, vp],
     })
     for name, args in sig.items():
         f = getattr(L, name)

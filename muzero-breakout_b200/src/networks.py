@@ -293,15 +293,19 @@ class PackedNetworks:
                  dst2_stride=dst2_stride)
         return prog
 
-    def representation_program(self, n, x_nchw, out_nchw):
-        """RepresentationNetwork.forward + _scale_state (networks.py:94-99, 271-280): float32 NCHW in/out."""
+    def representation_program(self, n, x_nchw, out_nchw, x_cl=None):
+        """RepresentationNetwork.forward + _scale_state (networks.py:94-99, 271-280): float32 NCHW in/out, or a
+        channels-last input buffer x_cl [n][320][64] of the activation dtype (then x_nchw is ignored)."""
         H, W = 16, 20
         prog = Program(n)
         cmax = max(cv.cout for kind, cv in self.rep if kind == "conv")
-        xin = self.buf(n, H * W, self.rep_cin)
         bufs = [self.buf(n, H * W, cmax) for _ in range(3)]
         f32 = self.buf(n, self.latent_hw[0] * self.latent_hw[1], cmax, torch.float32)
-        prog.add(op=OP_NCHW_IN, dtype=self.dt, H=H, W=W, cin=self.rep_cin, src=x_nchw, dst=xin)
+        if x_cl is None:
+            xin = self.buf(n, H * W, self.rep_cin)
+            prog.add(op=OP_NCHW_IN, dtype=self.dt, H=H, W=W, cin=self.rep_cin, src=x_nchw, dst=xin)
+        else:
+            xin = x_cl
         src, cur = xin, None
         n_pool = sum(1 for kind, _ in self.rep if kind == "pool")
         pools = 0
