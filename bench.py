@@ -332,7 +332,31 @@ def bench_mcts(args, rank, local, world):
     }
     if collectives:
         out["collectives"] = collectives
+    if not args.no_acting:
+        out["acting"] = bench_acting(args, m, dev, rank, world)
     return out, sd
+
+
+def bench_acting(args, m, dev, rank, world):
+    """Whole acting moves on the device: history ring -> rep-net input ->
+    representation network -> search -> action sampling -> env step (+ fused grayscale) -> record."""
+    from muzero_breakout_b200.acting import Actor
+    from muzero_breakout_b200.environment.parallel_breakout import BreakoutEnvironment
+    B = args.trees
+    env = BreakoutEnvironment(dict(ENV_CFG, n_parallel=B, output_device="cuda", reset_rng="device", seed=5 + rank, cuda_device=str(dev)))
+    moves = 4
+    actor = Actor(env, m, temperature=1.0, seed=rank, max_moves=moves, check_done_every=1 << 30, record_frames=False)
+    actor.run_episode()
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = actor.run_episode()
+    e1.record()
+    barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return {"metric": "acting_env_moves_per_s", "value": world * B * moves / (ms * 1e-3), "unit": "env-moves/s", "ms_per_move": ms / moves,
+            "envs_per_gpu": B, "num_simulations": args.sims, "moves_timed": moves,
+            "what": "reset + per move: mz_rep_input, representation net, MCTSSearchVec.search, mz_sample_actions, bk_env_step(+gray), record"}
 
 
 def cpu_mcts(args, sd=None, trees=24, budget_s=25.0):
@@ -377,6 +401,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-acting", action="store_true", help="skip the whole-move (rep net + search + env) aux measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     primary = "env" if args.workload == "env" else "mcts"
