@@ -130,7 +130,23 @@ __global__ void pool2_kernel(size_t total, int H, int W, int C, const T *__restr
     if (dst_f32) dst_f32[i] = v;
 }
 
-// _scale_state: one CTA per sample
+// _scale_state: one CTA per sample.  Fast path (elems == 5120: the 256x4x5 latent): each of the 256 threads
+// keeps its 20 values in registers (five float4 loads), block min/max, normalise, vectorised stores -- one read
+// of the fp32 source and one write per destination.
+template <typename T> __device__ __forceinline__ void store4(T *p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float *p, float a, float b, float c, float d)
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16 *p, float a, float b, float c, float d)
+{
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&lo);
+    u.y = *reinterpret_cast<uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst, T *__restrict__ dst2,
@@ -139,8 +155,21 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
     __shared__ float s_lo[8], s_hi[8];
     const int i = blockIdx.x, tid = threadIdx.x;
     const float *x = src + (size_t)i * elems;
+    T *d1 = dst ? dst + (size_t)i * elems : nullptr;
+    T *d2 = dst2 ? dst2 + ((size_t)i * dst2_stride + (dst2_slot ? dst2_slot[i] : 0)) * elems : nullptr;
+    const bool fast = elems == 256 * 20;
+    float4 v[5];
     float lo = INFINITY, hi = -INFINITY;
-    for (int e = tid; e < elems; e += 256) { const float v = x[e]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+    if (fast) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            v[q] = __ldcs(reinterpret_cast<const float4 *>(x) + q * 256 + tid);
+            lo = fminf(fminf(lo, fminf(v[q].x, v[q].y)), fminf(v[q].z, v[q].w));
+            hi = fmaxf(fmaxf(hi, fmaxf(v[q].x, v[q].y)), fmaxf(v[q].z, v[q].w));
+        }
+    } else {
+        for (int e = tid; e < elems; e += 256) { const float t = x[e]; lo = fminf(lo, t); hi = fmaxf(hi, t); }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
     if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
@@ -149,12 +178,21 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
 #pragma unroll
     for (int q = 1; q < 8; ++q) { lo = fminf(lo, s_lo[q]); hi = fmaxf(hi, s_hi[q]); }
     const float den = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);                 // s_max - s_min + 1e-8  (:327)
-    T *d1 = dst ? dst + (size_t)i * elems : nullptr;
-    T *d2 = dst2 ? dst2 + ((size_t)i * dst2_stride + (dst2_slot ? dst2_slot[i] : 0)) * elems : nullptr;
-    for (int e = tid; e < elems; e += 256) {
-        const T v = from_f<T>(__fdiv_rn(__fsub_rn(x[e], lo), den));
-        if (d1) d1[e] = v;
-        if (d2) d2[e] = v;
+    if (fast) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float a = __fdiv_rn(__fsub_rn(v[q].x, lo), den), b = __fdiv_rn(__fsub_rn(v[q].y, lo), den);
+            const float c = __fdiv_rn(__fsub_rn(v[q].z, lo), den), d = __fdiv_rn(__fsub_rn(v[q].w, lo), den);
+            const int e = (q * 256 + tid) * 4;
+            if (d1) store4<T>(d1 + e, a, b, c, d);
+            if (d2) store4<T>(d2 + e, a, b, c, d);
+        }
+    } else {
+        for (int e = tid; e < elems; e += 256) {
+            const T t = from_f<T>(__fdiv_rn(__fsub_rn(x[e], lo), den));
+            if (d1) d1[e] = t;
+            if (d2) d2[e] = t;
+        }
     }
 }
 
@@ -163,7 +201,21 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
 // so each weight element is read once per CTA (not once per sample) and the reads are coalesced.
 constexpr int HEAD_MAX_OUT = 16;
 constexpr int HEAD_SAMPLES = 8;
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 128;
+
+// eight consecutive features of one sample as floats (one 16-byte load for bf16, two for fp32)
+__device__ __forceinline__ void load8(const float *p, float (&f)[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16 *p, float (&f)[8])
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+}
 
 template <typename T, int NOUT>
 __global__ void __launch_bounds__(HEAD_THREADS)
@@ -179,17 +231,24 @@ head_kernel(int n, int feat, int mode, const T *__restrict__ src, const float *_
     for (int s = 0; s < HEAD_SAMPLES; ++s)
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) acc[s][o] = 0.0f;
-    for (int e = tid; e < feat; e += HEAD_THREADS) {
-        float wv[NOUT];
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) wv[o] = __ldg(w + (size_t)o * feat + e);
+    for (int e = tid * 8; e < feat; e += HEAD_THREADS * 8) {      // feat is a multiple of 8 (checked by the launcher)
+        float xv[HEAD_SAMPLES][8];
 #pragma unroll
         for (int s = 0; s < HEAD_SAMPLES; ++s) {
-            if (s < ns) {
-                const float v = to_f(src[(size_t)(s0 + s) * feat + e]);
+            if (s < ns) load8(src + (size_t)(s0 + s) * feat + e, xv[s]);
+            else {
 #pragma unroll
-                for (int o = 0; o < NOUT; ++o) acc[s][o] = fmaf(v, wv[o], acc[s][o]);
+                for (int q = 0; q < 8; ++q) xv[s][q] = 0.0f;
             }
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            float wv[8];
+            load8(w + (size_t)o * feat + e, wv);
+#pragma unroll
+            for (int s = 0; s < HEAD_SAMPLES; ++s)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[s][o] = fmaf(xv[s][q], wv[q], acc[s][o]);
         }
     }
 #pragma unroll
@@ -238,6 +297,7 @@ template <typename T>
 int launch_head(const mz_op &o, int n, cudaStream_t st)
 {
     const int feat = o.H * o.W * o.cin;
+    if (feat % 8) { mzb::set_error("head: feature count %d is not a multiple of 8", feat); return -1; }
     const int grid = (n + HEAD_SAMPLES - 1) / HEAD_SAMPLES;
 #define MZB_HEAD(NO) head_kernel<T, NO><<<grid, HEAD_THREADS, 0, st>>>(n, feat, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits)
     switch (o.nout) {
