@@ -177,7 +177,8 @@ typedef struct mz_op {
     int32_t use_tc;    /* conv, bf16: 1 = tcgen05 kernel, 0 = CUDA-core kernel */
     int32_t nout;      /* head: output features (<= 16) */
     int32_t head_mode; /* head: 0 logits, 1 scalar, 2 probabilities */
-    int32_t reserved;
+    int32_t w_layout;  /* conv: 0 = w[cout][ksize*ksize*cin]; 1 (tensor-core path only) = tile-contiguous
+                          w[tap][cin/64][cout][64], each 64-channel weight tile stored as consecutive 128-byte rows */
     const void *src;
     void *dst;
     const void *res;         /* conv: residual (same shape as dst) or NULL */

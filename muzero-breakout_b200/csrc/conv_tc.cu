@@ -55,6 +55,7 @@ constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
     int mode;          // 0 spatial tiles, 1 pixel tiles
+    int w_tiled;       // weights stored tile-contiguous [tap][cin/64][cout][64] instead of [cout][taps*cin]
     int S, hb, tile_rows, ytiles, groups, ntiles;   // groups = sample-group PAIRS per pixel (pixel mode); ntiles = pair-tiles
     __nv_bfloat16 *dst;
     const __nv_bfloat16 *res;
@@ -274,7 +275,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));   // bytes of both CTAs
                         else mbar_arrive_cluster(lead_full + 8 * stage);
                         tma_load_4d(sa, &map_a, lead_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
-                        tma_load_2d(sb, &map_b, lead_full + 8 * stage, tap * p.cin + kc * BLOCK_K, rank * (N / 2));   // my half of the weight tile
+                        if (p.w_tiled) tma_load_2d(sb, &map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + rank * (N / 2));
+                        else tma_load_2d(sb, &map_b, lead_full + 8 * stage, tap * p.cin + kc * BLOCK_K, rank * (N / 2));   // my half of the weight tile
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -357,11 +359,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int c0 = col0 + c * 32;
                         float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float a = __uint_as_float(acc[c & 1][j]);
-                            if (ab) a += __ldg(ab + c0 + j);
-                            v[j] = a * s_scale[c0 + j] + s_shift[c0 + j];
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[c & 1][j]);
+                        if (ab) {                                        // per-action bias row (dynamics first layer), 128-bit loads
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(ab + c0) + q);
+                                v[q * 4] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
+                            }
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
                         if (has_res) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -464,6 +471,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     }
     p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
     p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
+    p.w_tiled = o.w_layout == 1;
 
     CUtensorMap map_a, map_b;
     {
@@ -480,6 +488,10 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         const cuuint64_t K = (cuuint64_t)p.taps * o.cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)o.cout};
         cuuint64_t strides[1] = {K * 2};
+        if (p.w_tiled) {                                   // [tap][cin/64][cout][64]: every (tap, chunk) tile is 128-byte rows back to back
+            dims[0] = BLOCK_K; dims[1] = (cuuint64_t)p.taps * (o.cin / BLOCK_K) * o.cout;
+            strides[0] = BLOCK_K * 2;
+        }
         cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(o.cout / 2)};     // each CTA of a pair loads half of the rows
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr,

@@ -34,7 +34,7 @@ class MzOp(C.Structure):
     """mirror of struct mz_op (include/mzb200.h)"""
     _fields_ = [("op", C.c_int32), ("dtype", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cin", C.c_int32),
                 ("cout", C.c_int32), ("ksize", C.c_int32), ("act", C.c_int32), ("use_tc", C.c_int32), ("nout", C.c_int32),
-                ("head_mode", C.c_int32), ("reserved", C.c_int32),
+                ("head_mode", C.c_int32), ("w_layout", C.c_int32),
                 ("src", C.c_void_p), ("dst", C.c_void_p), ("res", C.c_void_p), ("dst_f32", C.c_void_p), ("w", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("act_bias", C.c_void_p), ("act_idx", C.c_void_p),
                 ("dst2", C.c_void_p), ("dst2_slot", C.c_void_p), ("dst2_stride", C.c_int64),
@@ -153,6 +153,7 @@ class _Conv:
         self.w, self.scale, self.shift, self.ksize, self.act, self.act_bias = w, scale, shift, ksize, act, act_bias
         self.cout = w.shape[0]
         self.cin = w.shape[1] // (ksize * ksize)
+        self.w_layout = 0
 
 
 class PackedNetworks:
@@ -198,7 +199,11 @@ class PackedNetworks:
             act_bias = self._dev(torch.stack(planes), torch.float32)                                          # [3][HW][cout]
             w = w[:, :cin_used]
         wp = w.permute(0, 2, 3, 1).reshape(cout, -1)       # [cout][(ky*k+kx)*cin + c]
-        return _Conv(self._dev(wp, self.dtype), self._dev(a, torch.float32), self._dev(shift, torch.float32), k, act, act_bias)
+        cv = _Conv(self._dev(wp, self.dtype), self._dev(a, torch.float32), self._dev(shift, torch.float32), k, act, act_bias)
+        if self.use_tc and cv.cin % 64 == 0:               # tile-contiguous copy for the TMA loads: [tap][cin/64][cout][64]
+            cv.w = self._dev(wp.reshape(cout, k * k, cv.cin // 64, 64).permute(1, 2, 0, 3), self.dtype)
+            cv.w_layout = 1
+        return cv
 
     def _res(self, sd, prefix, act):
         return (self._conv(sd, prefix + ".conv1", prefix + ".bn1", act), self._conv(sd, prefix + ".conv2", prefix + ".bn2", act))
@@ -248,7 +253,7 @@ class PackedNetworks:
 
     def _add_conv(self, prog, cv: _Conv, H, W, src, dst, res=None, dst_f32=None, act_idx=None):
         prog.add(op=OP_CONV, dtype=self.dt, H=H, W=W, cin=cv.cin, cout=cv.cout, ksize=cv.ksize, act=cv.act,
-                 use_tc=int(self.use_tc), src=src, dst=dst, res=res, dst_f32=dst_f32, w=cv.w, scale=cv.scale, shift=cv.shift,
+                 use_tc=int(self.use_tc), w_layout=cv.w_layout, src=src, dst=dst, res=res, dst_f32=dst_f32, w=cv.w, scale=cv.scale, shift=cv.shift,
                  act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx)
 
     def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None):

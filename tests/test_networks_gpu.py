@@ -116,10 +116,11 @@ def test_tcgen05_conv_vs_torch(case):
     dst = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     dst32 = torch.full((n, H, W, cout), float("nan"), dtype=torch.float32, device="cuda")
     wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda()
-    for use_tc in (1, 0):
+    wt = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin // 64, 64).permute(1, 2, 0, 3).contiguous().cuda()   # tile-contiguous
+    for use_tc, layout in ((1, 0), (1, 1), (0, 0)):
         prog = Program(n)
-        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=cin, cout=cout, ksize=k, act=ACT["relu"], use_tc=use_tc, src=nhwc(x), dst=dst,
-                 res=nhwc(res) if use_res else None, dst_f32=dst32, w=wp, scale=scale.cuda(), shift=shift.cuda(),
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=cin, cout=cout, ksize=k, act=ACT["relu"], use_tc=use_tc, w_layout=layout,
+                 src=nhwc(x), dst=dst, res=nhwc(res) if use_res else None, dst_f32=dst32, w=wt if layout else wp, scale=scale.cuda(), shift=shift.cuda(),
                  act_bias=ab.cuda() if use_ab else None, act_idx=idx.cuda() if use_ab else None)
         prog.run()
         torch.cuda.synchronize()
