@@ -257,14 +257,16 @@ class PackedNetworks:
                  act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx)
 
     def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None):
-        """bufs: three same-shaped rotating buffers; cur: index of the one holding the input.  Returns
-        the index holding the output."""
+        """bufs: same-shaped activation buffers; cur: index of the one holding the input.  Each block writes its
+        output IN PLACE over its input: conv2's epilogue reads the residual element and then writes the result to
+        the same address from the same thread, and no tile reads the block input during conv2 (its operand is the
+        mid buffer).  Two live buffers per network keep 4096 samples' activations (2 x 42 MB bf16) inside the L2.
+        Returns the index holding the output (= cur)."""
+        mid = (cur + 1) % len(bufs)
         for i, (c1, c2) in enumerate(blocks):
-            mid, out = (cur + 1) % 3, (cur + 2) % 3
             self._add_conv(prog, c1, H, W, bufs[cur], bufs[mid])
-            self._add_conv(prog, c2, H, W, bufs[mid], bufs[out], res=bufs[cur],
+            self._add_conv(prog, c2, H, W, bufs[mid], bufs[cur], res=bufs[cur],
                            dst_f32=last_f32 if i == len(blocks) - 1 else None)
-            cur = out
         return cur
 
     def _add_head(self, prog, conv, lin, H, W, src, mid, mode, out, out_logits=None):
