@@ -34,6 +34,7 @@
 // Replaces the cuDNN convolutions + separate BN / ReLU / add kernels the reference launches for
 // src/networks.py ConvBlock :7-17 and ResidualBlock :19-35 (K4-K6 of SURVEY.md section 2d).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -55,6 +56,8 @@ constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
     int mode;          // 0 spatial tiles, 1 pixel tiles
+    int debug;         // profiling experiments only (env MZB_TC_DEBUG): 1 = epilogue without memory traffic, 2 = TMA only for the
+                       // first k-step of a tile (MMAs run on stale shared memory), 4 = no MMAs
     int w_tiled;       // weights stored tile-contiguous [tap][cin/64][cout][64] instead of [cout][taps*cin]
     int S, hb, tile_rows, ytiles, groups, ntiles;   // groups = sample-group PAIRS per pixel (pixel mode); ntiles = pair-tiles
     __nv_bfloat16 *dst;
@@ -266,14 +269,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
                 const Tile t = decode_tile(p, tile, rank);
+                bool first = true;
                 for (int tap = 0; tap < p.taps; ++tap) {
                     if (!((t.taps >> tap) & 1u)) continue;
                     const int dy = p.taps == 1 ? 0 : tap / 3 - 1, dx = p.taps == 1 ? 0 : tap % 3 - 1;
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);     // the pair's MMAs have retired this slot (in both CTAs)
                         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));   // bytes of both CTAs
+                        const bool skip_tma = (p.debug & 2) && !first;
+                        first = false;
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, skip_tma ? 0u : 2 * (a_bytes + b_bytes));   // bytes of both CTAs
                         else mbar_arrive_cluster(lead_full + 8 * stage);
+                        if (skip_tma) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
                         tma_load_4d(sa, &map_a, lead_full + 8 * stage, kc * BLOCK_K, t.x0 + dx, t.y0 + dy, t.s0);
                         if (p.w_tiled) tma_load_2d(sb, &map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + rank * (N / 2));
                         else tma_load_2d(sb, &map_b, lead_full + 8 * stage, tap * p.cin + kc * BLOCK_K, rank * (N / 2));   // my half of the weight tile
@@ -302,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                        if (!(p.debug & 4)) umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
                                   (ks | k) ? 1u : 0u);
                     umma_commit_pair(bar_empty + 8 * stage);                // frees slot `stage` in both CTAs when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -329,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int sl = r / rows_per_sample, rr = r - sl * rows_per_sample;
                 s = t.s0 + sl; y = t.y0 + rr / p.W; x = rr % p.W;
             }
-            const bool valid = r < p.tile_rows && s < p.n;
+            const bool valid = r < p.tile_rows && s < p.n && !(p.debug & 1);
             const size_t m = ((size_t)s * p.H + y) * p.W + x;            // global output row
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
             const bool has_res = valid && p.res != nullptr;
@@ -472,6 +479,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
     p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
     p.w_tiled = o.w_layout == 1;
+    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("MZB_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
 
     CUtensorMap map_a, map_b;
     {
