@@ -44,14 +44,15 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 per smem row = 128 bytes = one SWIZZLE_128B atom
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
 constexpr int B_STAGE_BYTES = 128 * BLOCK_K * 2;        // 16 KB: this CTA's half (N/2 <= 128 rows) of the weight tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the N columns
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
+constexpr int EPI_STAGE_BYTES = 32 * 256;               // per epilogue warp: 32 rows x (N/2 <= 128 cols) bf16, residual in / result out
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)NUM_EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * sizeof(float) + 128;   // 226.1 KB of the 227 KB
 
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
@@ -226,10 +227,11 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams &p, int tile, int r
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ float s_scale[256], s_shift[256];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B operand tiles need 1024-byte alignment
+    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;
+    float *s_scale = reinterpret_cast<float *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);
+    float *s_shift = s_scale + 256;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + 256);
     // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
@@ -241,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int N = p.cout;
     const int kchunks = p.cin / BLOCK_K;
     const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();                  // the driver honours __align__(1024) on the dynamic segment; fail loudly if not
 
     for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
     if (warp == 0 && lane == 0) {
@@ -319,12 +322,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
+        // Thread = one row of the tile (TMEM lane).  Global traffic goes through a per-warp shared-memory
+        // staging tile so that every global instruction is coalesced (16 lanes cover one row's contiguous
+        // N/2-column segment) instead of 32 lanes touching 32 rows 10 KB apart: the residual is prefetched into
+        // the staging tile while the MMAs of this tile are still running, the result overwrites it in place
+        // (16-byte units XOR-swizzled by row: conflict-free both for row-per-lane and 16-lanes-per-row access).
         const int quarter = warp & 3;                  // TMEM lanes [32*quarter, 32*quarter+32)
         const int half = (warp - 2) >> 2;              // which half of the N columns this warp drains
         const int r = quarter * 32 + lane;             // row of the tile
         const int rows_per_sample = p.hb * p.W;
         const int ncols = N / 2, col0 = half * ncols;
         const int nchunks = ncols / 32;
+        const int units = ncols / 8;                   // 16-byte units per staged row (16 or 8)
+        const int row_bytes = ncols * 2;
+        uint8_t *stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
         const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
         int it = 0;
         for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
@@ -337,16 +348,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 s = t.s0 + sl; y = t.y0 + rr / p.W; x = rr % p.W;
             }
             const bool valid = r < p.tile_rows && s < p.n && !(p.debug & 1);
-            const size_t m = ((size_t)s * p.H + y) * p.W + x;            // global output row
+            const long long m = valid ? ((long long)s * p.H + y) * p.W + x : -1;   // global output row, -1 = nothing to write
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
-            const bool has_res = valid && p.res != nullptr;
-            const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + (valid ? m : 0) * N + col0);
-            uint4 res[2][4];
-            uint32_t acc[2][32];
-            if (has_res) {                                               // residual of chunk 0 is in flight while the MMAs finish
-#pragma unroll
-                for (int q = 0; q < 4; ++q) res[0][q] = __ldg(rp + q);
+            const bool has_res = p.res != nullptr;
+            if (has_res) {                                               // coalesced residual prefetch into the staging tile
+                for (int idx = lane; idx < 32 * units; idx += 32) {
+                    const int rr = idx / units, u = idx - rr * units;
+                    const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                    if (mr >= 0) {
+                        const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(p.res + mr * N + col0) + u);
+                        *reinterpret_cast<uint4 *>(stg + rr * row_bytes + 16 * (u ^ (rr & (units - 1)))) = v4;
+                    }
+                }
+                __syncwarp();
             }
+            uint32_t acc[2][32];
             mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
@@ -355,13 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int c = 0; c < 4; ++c) {
                 if (c < nchunks) {
                     tmem_wait(acc[c & 1]);
-                    if (c + 1 < nchunks) {                               // next chunk: TMEM load + residual prefetch overlap this chunk's math
-                        tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
-                        if (has_res) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) res[(c + 1) & 1][q] = __ldg(rp + (c + 1) * 4 + q);
-                        }
-                    }
+                    if (c + 1 < nchunks) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
                     if (valid) {
                         const int c0 = col0 + c * 32;
                         float v[32];
@@ -376,10 +386,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                        uint8_t *srow = stg + lane * row_bytes;
                         if (has_res) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&res[c & 1][q]);
+                                const uint4 u4 = *reinterpret_cast<const uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1))));
+                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u4);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const float2 f = __bfloat1622float2(h[e]);
@@ -390,14 +402,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
-                        uint4 *op = reinterpret_cast<uint4 *>(p.dst + m * N + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4 u;
-                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+                            uint4 u4;
+                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u4);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-                            op[q] = u;
+                            *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = u4;
                         }
                         if (p.dst_f32) {
                             float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
@@ -409,7 +420,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+            if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);   // accumulator drained: the next tile's MMAs may reuse it
+            // coalesced store of the staged result rows
+            for (int idx = lane; idx < 32 * units; idx += 32) {
+                const int rr = idx / units, u = idx - rr * units;
+                const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                if (mr >= 0) {
+                    const uint4 v4 = *reinterpret_cast<const uint4 *>(stg + rr * row_bytes + 16 * (u ^ (rr & (units - 1))));
+                    *(reinterpret_cast<uint4 *>(p.dst + mr * N + col0) + u) = v4;
+                }
+            }
+            __syncwarp();                                                // staging tile is reused by the next residual prefetch
         }
     }
     tc_fence_before();
