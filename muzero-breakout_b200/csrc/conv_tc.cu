@@ -197,6 +197,16 @@ __device__ __forceinline__ float activate(float v, int act)
     }
 }
 
+// profiling trace (debug & 8): per-tile timestamps of cluster 0's leader CTA, read back with mz_conv_trace()
+__device__ unsigned long long g_trace[8 * 64];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot, it) do { if ((p.debug & 8) && blockIdx.x == 0 && (it) < 64) g_trace[(slot) * 64 + (it)] = gtime(); } while (0)
+
 struct Tile {
     int s0, y0, x0;
     uint32_t taps;   // bit t set = tap t has in-bounds rows for this tile (others contribute exact zeros)
@@ -224,6 +234,7 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams &p, int tile, int r
     return t;
 }
 
+template <int N, bool kRelu>     // N = cout (one UMMA N); kRelu: the activation is ReLU (else the runtime switch)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvParams p)
 {
@@ -240,7 +251,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();          // 0 / 1 inside the CTA pair
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-    const int N = p.cout;
     const int kchunks = p.cin / BLOCK_K;
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();                  // the driver honours __align__(1024) on the dynamic segment; fail loudly if not
@@ -301,8 +311,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int it = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                 const int buf = it & 1;
+                TRACE(0, it);
                 mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
+                TRACE(1, it);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
                 const int ksteps = __popc(decode_tile(p, tile, rank).taps) * kchunks;
                 for (int ks = 0; ks < ksteps; ++ks) {
@@ -318,6 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_pair(bar_tfull + 8 * buf);                      // accumulator complete -> both CTAs' epilogues
+                TRACE(2, it);
             }
         }
     } else {
@@ -331,10 +344,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int half = (warp - 2) >> 2;              // which half of the N columns this warp drains
         const int r = quarter * 32 + lane;             // row of the tile
         const int rows_per_sample = p.hb * p.W;
-        const int ncols = N / 2, col0 = half * ncols;
-        const int nchunks = ncols / 32;
-        const int units = ncols / 8;                   // 16-byte units per staged row (16 or 8)
-        const int row_bytes = ncols * 2;
+        constexpr int ncols = N / 2, nchunks = ncols / 32;
+        constexpr int units = ncols / 8;               // 16-byte units per staged row (16 or 8)
+        constexpr int row_bytes = ncols * 2;
+        constexpr int rows_per_it = 32 / units;        // staged rows covered by one cooperative instruction (2 or 4)
+        const int col0 = half * ncols;
+        const int my_u = lane % units, my_rsub = lane / units;
         uint8_t *stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
         const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
         int it = 0;
@@ -351,20 +366,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long m = valid ? ((long long)s * p.H + y) * p.W + x : -1;   // global output row, -1 = nothing to write
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
             const bool has_res = p.res != nullptr;
-            if (has_res) {                                               // coalesced residual prefetch into the staging tile
-                for (int idx = lane; idx < 32 * units; idx += 32) {
-                    const int rr = idx / units, u = idx - rr * units;
+            if (warp == 2 && lane == 0) TRACE(3, it);
+            if (has_res) {                                               // coalesced residual prefetch into the staging tile:
+                // cp.async (global -> shared, 16 bytes each, no register staging) so that all 16 requests of a lane are
+                // in flight at once and their latency hides behind the wait for this tile's MMAs
+#pragma unroll
+                for (int k = 0; k < units; ++k) {                        // units iterations x rows_per_it rows = 32 rows
+                    const int rr = k * rows_per_it + my_rsub;
                     const long long mr = __shfl_sync(0xffffffffu, m, rr);
                     if (mr >= 0) {
-                        const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(p.res + mr * N + col0) + u);
-                        *reinterpret_cast<uint4 *>(stg + rr * row_bytes + 16 * (u ^ (rr & (units - 1)))) = v4;
+                        const uint32_t sdst = smem_u32(stg + rr * row_bytes + 16 * (my_u ^ (rr & (units - 1))));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(p.res + mr * N + col0 + my_u * 8) : "memory");
                     }
                 }
-                __syncwarp();
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             uint32_t acc[2][32];
+            if (warp == 2 && lane == 0) TRACE(4, it);
             mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
+            if (warp == 2 && lane == 0) TRACE(5, it);
+            if (has_res) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();                                            // every lane's residual pieces are visible to the whole warp
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
             tmem_ld32_async(taddr, acc[0]);
 #pragma unroll
@@ -385,7 +410,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] * s_scale[c0 + j] + s_shift[c0 + j];
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0 + q * 4), sf = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 4);
+                            v[q * 4] = v[q * 4] * sc.x + sf.x; v[q * 4 + 1] = v[q * 4 + 1] * sc.y + sf.y;
+                            v[q * 4 + 2] = v[q * 4 + 2] * sc.z + sf.z; v[q * 4 + 3] = v[q * 4 + 3] * sc.w + sf.w;
+                        }
                         uint8_t *srow = stg + lane * row_bytes;
                         if (has_res) {
 #pragma unroll
@@ -401,7 +430,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
+                        for (int j = 0; j < 32; ++j) v[j] = kRelu ? fmaxf(v[j], 0.0f) : activate(v[j], p.act);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint4 u4;
@@ -421,16 +450,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);   // accumulator drained: the next tile's MMAs may reuse it
+            if (warp == 2 && lane == 0) TRACE(6, it);
             // coalesced store of the staged result rows
-            for (int idx = lane; idx < 32 * units; idx += 32) {
-                const int rr = idx / units, u = idx - rr * units;
+#pragma unroll
+            for (int k = 0; k < units; ++k) {
+                const int rr = k * rows_per_it + my_rsub;
                 const long long mr = __shfl_sync(0xffffffffu, m, rr);
                 if (mr >= 0) {
-                    const uint4 v4 = *reinterpret_cast<const uint4 *>(stg + rr * row_bytes + 16 * (u ^ (rr & (units - 1))));
-                    *(reinterpret_cast<uint4 *>(p.dst + mr * N + col0) + u) = v4;
+                    const uint4 v4 = *reinterpret_cast<const uint4 *>(stg + rr * row_bytes + 16 * (my_u ^ (rr & (units - 1))));
+                    *(reinterpret_cast<uint4 *>(p.dst + mr * N + col0) + my_u) = v4;
                 }
             }
             __syncwarp();                                                // staging tile is reused by the next residual prefetch
+            if (warp == 2 && lane == 0) TRACE(7, it);
         }
     }
     tc_fence_before();
@@ -461,6 +493,11 @@ EncodeTiledFn encode_fn()
 }
 
 }  // namespace
+
+extern "C" int mz_conv_trace(unsigned long long *host_out)   // profiling aid: copies the 8 x 64 trace words
+{
+    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * 8 * 64) == cudaSuccess ? 0 : -2;
+}
 
 namespace mzb {
 
@@ -530,7 +567,10 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     }
     static bool attr_set = false;
     if (!attr_set) {
-        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set = true;
     }
     const int clusters = p.ntiles < kNumSMs / 2 ? p.ntiles : kNumSMs / 2;
@@ -544,7 +584,14 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, map_a, map_b, p));
+    const bool relu = o.act == MZ_ACT_RELU;
+    if (o.cout == 256) {
+        if (relu) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, map_a, map_b, p));
+        else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, false>, map_a, map_b, p));
+    } else {
+        if (relu) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, map_a, map_b, p));
+        else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false>, map_a, map_b, p));
+    }
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -17,3 +17,16 @@ for _ in range(50): p.run()
 b.record(); torch.cuda.synchronize()
 us = a.elapsed_time(b) / 50 * 1e3
 print(f"n={n} debug={os.environ.get('MZB_TC_DEBUG','0')}: {us:.1f} us per conv, {n*130*256*256*2/us/1e6:.0f} TFLOP/s valid-tap")
+
+if int(os.environ.get("MZB_TC_DEBUG", "0")) & 8:
+    import ctypes, numpy as np
+    from muzero_breakout_b200 import _lib
+    buf = np.zeros(8 * 64, np.uint64)
+    L = _lib.lib(); L.mz_conv_trace.argtypes = [ctypes.c_void_p]
+    L.mz_conv_trace(buf.ctypes.data)
+    t = buf.reshape(8, 64).astype(np.int64)
+    t0 = t[0, 0]
+    names = ["mma:wait_tempty", "mma:start_issue", "mma:issued", "epi:start", "epi:res_loaded", "epi:tfull", "epi:drained", "epi:stored"]
+    for it in range(6):
+        if t[0, it] == 0: break
+        print("tile", it, " ".join(f"{n}={(t[k, it] - t0) / 1e3:7.2f}" for k, n in enumerate(names)))
