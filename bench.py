@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 
 ENV_CFG = dict(n_parallel=24, paddle_hit_reward=0.0, brick_hit_reward=1.0, game_lost_reward=-1.0, game_won_reward=5.0)
 ENV_BYTES_PER_STEP = 3898       # 3840 frame + 4 reward + 12 valid + 2 done + 8 action + 32 SoA
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
+ENV_TRAFFIC_PER_ENV = (1.93e6 + 196.0e6) / 65536     # r1_env_step_final_full.txt, 65 536 envs per launch (the L2 keeps part of the frames)
+CONV_TRAFFIC_PER_SAMPLE = (43.2e6 + 8.8e6) / 4096    # r1_conv_tc_final_full.txt, 3x3 256->256 conv, 4096 samples per launch
 
 
 def measured_peaks():
@@ -178,7 +181,8 @@ def bench_env(args, rank, local, world):
                    "envs_per_gpu": B, "actions": "uniform random, resident in HBM", "reset_every": args.reset_every, "l2": "per-step frame output 3840*B bytes exceeds the 126 MB L2",
                    "done_fraction_at_end": done_frac},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
-                     "traffic": None, "peak_source": peaks["src"], "kernel": "env_step_kernel<frame>", "bytes_per_env_step": ENV_BYTES_PER_STEP,
+                     "traffic": ENV_TRAFFIC_PER_ENV * B, "traffic_source": "profiles/r1_env_step_final_full.txt (ncu --set full, scaled by envs per launch)",
+                     "peak_source": peaks["src"], "kernel": "env_step_kernel<frame>", "bytes_per_env_step": ENV_BYTES_PER_STEP,
                      "kernel_ms": kernel_ms},
         "e2e": {"value": world * B * Ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": B * 9, "d2h_bytes_per_step": B * (3840 + 4 + 12 + 1) + 4,
                 "steps": Ke, "api": "BreakoutEnvironment.step(state, action, done_mask) with host tensors (output_device='cpu')"},
@@ -320,9 +324,10 @@ def bench_mcts(args, rank, local, world):
                    "l2": f"latent store {B * (S + 2) * 10240 * (2 if args.precision == 'bf16' else 4) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
                    "cuda_graph": bool(m.use_graph)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": CONV_TRAFFIC_PER_SAMPLE * B,
+                     "traffic_source": "profiles/r1_conv_tc_final_full.txt (ncu --set full, one 3x3 256->256 launch, scaled by samples per launch)", "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                      "kernel": f"conv_tc_kernel ({n_conv} launches per simulation step)", "flop_convention": "valid taps only (BASELINE.md section 3)",
-                     "flop_per_leaf": FLOP_CONV_VALID, "kernel_ms": conv_ms / n_conv, "achieved_dense_taps": FLOP_CONV_DENSE * B / (conv_ms * 1e-3) / 1e12,
+                     "flop_per_leaf": FLOP_CONV_VALID, "kernel_ms": conv_ms / n_conv, 
                      "conv_ms_per_sim_step": conv_ms, "all_kernels_ms_per_sim_step": step_ms,
                      "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12},
         "e2e": {"value": world * B * S * Ke / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": B * (5120 * 4 + 12), "d2h_bytes_per_step": B * (4 + 24),
