@@ -1,0 +1,109 @@
+"""Multi-GPU plumbing: one process per GPU, environments and trees sharded by batch index.
+
+The acting path needs NO data-path collective: env i and tree i depend only on index i
+(reference parallel_breakout.py:158-254 is per-row, src/mcts.py:149,207 loop per sample), so each rank owns
+a contiguous index range and throughput scales weakly.  NCCL (torch.distributed, NVLink/NVSwitch) is used
+only where the reference has an exchange step:
+
+  broadcast_weights      target-network refresh: the reference copies the learner's state_dict into the
+                         target network every 15 iterations (train_torch.py:137-138, 361-367); here the
+                         learner rank broadcasts the PACKED weights (84 MB bf16) in one flat bucket per dtype.
+  all_gather_trajectory  per-step trajectory records (gray frame, action, reward, visit counts, value --
+                         what train_torch.py:204-208 appends to ObservationTrajectory) gathered from every
+                         rank into the replay-buffer owner's tensor, ordered by global env index.
+
+Works with any initialised process group (nccl on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+RECORD_FLOATS = 320 + 1 + 1 + 3 + 1     # gray frame 16x20, action, reward, visit counts, value
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of global indices owned by `rank`; sizes differ by at most one."""
+    base, extra = divmod(int(total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def packed_tensors(nets) -> List[torch.Tensor]:
+    """Every device tensor a PackedNetworks holds, in a deterministic order."""
+    out = []
+
+    def conv(c):
+        out.extend(t for t in (c.w, c.scale, c.shift, c.act_bias) if t is not None)
+
+    for kind, item in nets.rep:
+        if kind == "conv":
+            conv(item)
+        elif kind == "res":
+            conv(item[0]); conv(item[1])
+    conv(nets.dyn_first)
+    for a, b in nets.dyn_res + nets.pred_res:
+        conv(a); conv(b)
+    for c, lin in ((nets.reward_conv, nets.reward_lin), (nets.policy_conv, nets.policy_lin), (nets.value_conv, nets.value_lin)):
+        conv(c)
+        out.extend(lin[:2])
+    return out
+
+
+def broadcast_tensors(tensors: Iterable[torch.Tensor], src: int = 0, group=None) -> int:
+    """Broadcast a list of tensors from `src`, coalesced into one flat bucket per dtype (few large
+    messages: NVSwitch gives every peer full bandwidth, so bucket for launch latency, not link count).
+    In place.  Returns the number of bytes broadcast."""
+    tensors = list(tensors)
+    total = 0
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, ts in by_dtype.items():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in ts:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+        total += flat.numel() * flat.element_size()
+    return total
+
+
+def broadcast_weights(nets, src: int = 0, group=None) -> int:
+    return broadcast_tensors(packed_tensors(nets), src, group)
+
+
+def pack_record(gray: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, visits: torch.Tensor, value: torch.Tensor) -> torch.Tensor:
+    """(B,1,16,20) f32, (B,) i64, (B,) f32, (B,3) i64, (B,) f32 -> (B, RECORD_FLOATS) f32 (all values are small
+    integers or floats exactly representable in fp32)."""
+    B = gray.shape[0]
+    return torch.cat([gray.reshape(B, -1).float(), action.reshape(B, 1).float(), reward.reshape(B, 1).float(),
+                      visits.reshape(B, 3).float(), value.reshape(B, 1).float()], dim=1).contiguous()
+
+
+def unpack_record(rec: torch.Tensor):
+    g = rec[:, :320].reshape(-1, 1, 16, 20)
+    return g, rec[:, 320].long(), rec[:, 321], rec[:, 322:325].long(), rec[:, 325]
+
+
+def all_gather_trajectory(local: torch.Tensor, group=None) -> torch.Tensor:
+    """(B_local, F) from every rank -> (sum B_local, F), rank-major = global env index order for
+    shard_range shards.  Ranks may hold different B_local."""
+    world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    if len(set(sizes)) == 1:
+        out = torch.empty((world * sizes[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    mx = max(sizes)                                        # ragged shards: pad to the largest, gather, trim
+    padded = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
