@@ -33,23 +33,7 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 
 def packed_tensors(nets) -> List[torch.Tensor]:
     """Every device tensor a PackedNetworks holds, in a deterministic order."""
-    out = []
-
-    def conv(c):
-        out.extend(t for t in (c.w, c.scale, c.shift, c.act_bias) if t is not None)
-
-    for kind, item in nets.rep:
-        if kind == "conv":
-            conv(item)
-        elif kind == "res":
-            conv(item[0]); conv(item[1])
-    conv(nets.dyn_first)
-    for a, b in nets.dyn_res + nets.pred_res:
-        conv(a); conv(b)
-    for c, lin in ((nets.reward_conv, nets.reward_lin), (nets.policy_conv, nets.policy_lin), (nets.value_conv, nets.value_lin)):
-        conv(c)
-        out.extend(lin[:2])
-    return out
+    return [getattr(obj, attr) for obj, attr in nets.holders()]
 
 
 def broadcast_tensors(tensors: Iterable[torch.Tensor], src: int = 0, group=None) -> int:
@@ -74,7 +58,13 @@ def broadcast_tensors(tensors: Iterable[torch.Tensor], src: int = 0, group=None)
 
 
 def broadcast_weights(nets, src: int = 0, group=None) -> int:
-    return broadcast_tensors(packed_tensors(nets), src, group)
+    """Target-network refresh: one broadcast per weight arena (PackedNetworks keeps all packed tensors as views
+    into one flat buffer per dtype), in place, no staging copies."""
+    total = 0
+    for arena in nets.arenas.values():
+        dist.broadcast(arena, src=src, group=group)
+        total += arena.numel() * arena.element_size()
+    return total
 
 
 def pack_record(gray: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, visits: torch.Tensor, value: torch.Tensor) -> torch.Tensor:

@@ -156,6 +156,13 @@ class _Conv:
         self.w_layout = 0
 
 
+class _Lin:
+    """One packed Linear head: fp32 w [nout][H*W*C] in channels-last flatten order, fp32 bias."""
+
+    def __init__(self, w, b, nout):
+        self.w, self.b, self.nout = w, b, nout
+
+
 class PackedNetworks:
     def __init__(self, agent, model_cfg: dict | None = None, precision: str = "bf16", device="cuda", use_tc: bool | None = None):
         _lib.require_cuda()
@@ -212,7 +219,7 @@ class PackedNetworks:
         w = sd[key + ".weight"]                            # (nout, C*HW), column = c*HW + p  (Flatten of NCHW)
         nout = w.shape[0]
         wp = w.reshape(nout, C_, HW).permute(0, 2, 1).reshape(nout, HW * C_)   # column = p*C + c (channels-last)
-        return self._dev(wp, torch.float32), self._dev(sd[key + ".bias"], torch.float32), nout
+        return _Lin(self._dev(wp, torch.float32), self._dev(sd[key + ".bias"], torch.float32), nout)
 
     def _pack(self, sd, acts):
         rep_keys = sorted({int(k.split(".")[2]) for k in sd if k.startswith("rep_net.blocks.")})
@@ -245,7 +252,50 @@ class PackedNetworks:
         self.policy_lin = self._linear(sd, "pred_net.policy_head.2", self.policy_conv.cout, hw)
         self.value_conv = self._conv(sd, "pred_net.value_head.0.conv", "pred_net.value_head.0.bn", a)
         self.value_lin = self._linear(sd, "pred_net.value_head.2", self.value_conv.cout, hw)
-        self.num_actions = self.policy_lin[2]
+        self.num_actions = self.policy_lin.nout
+        self._consolidate()
+
+    def holders(self):
+        """(object, attribute) of every packed device tensor, in a deterministic order."""
+        out = []
+
+        def conv(c):
+            out.extend((c, a) for a in ("w", "scale", "shift", "act_bias") if getattr(c, a) is not None)
+
+        for kind, item in self.rep:
+            if kind == "conv":
+                conv(item)
+            elif kind == "res":
+                conv(item[0]); conv(item[1])
+        conv(self.dyn_first)
+        for a, b in self.dyn_res + self.pred_res:
+            conv(a); conv(b)
+        for c, lin in ((self.reward_conv, self.reward_lin), (self.policy_conv, self.policy_lin), (self.value_conv, self.value_lin)):
+            conv(c)
+            out.extend([(lin, "w"), (lin, "b")])
+        return out
+
+    def _consolidate(self):
+        """Move every packed tensor into one flat arena per dtype (256-byte aligned slices) and replace it by a
+        view: a target-network refresh is then ONE NCCL broadcast per arena, with no gather/scatter copies."""
+        self.arenas = {}
+        by_dtype = {}
+        for obj, attr in self.holders():
+            by_dtype.setdefault(getattr(obj, attr).dtype, []).append((obj, attr))
+        for dtype, items in by_dtype.items():
+            esz = torch.empty((), dtype=dtype).element_size()
+            align = 256 // esz
+            offs, total = [], 0
+            for obj, attr in items:
+                offs.append(total)
+                total += (getattr(obj, attr).numel() + align - 1) // align * align
+            arena = torch.zeros(total, dtype=dtype, device=self.device)
+            for (obj, attr), off in zip(items, offs):
+                t = getattr(obj, attr)
+                view = arena[off:off + t.numel()].view(t.shape)
+                view.copy_(t)
+                setattr(obj, attr, view)
+            self.arenas[dtype] = arena
 
     # ------------------------------------------------------------------ program building
     def buf(self, n, hw, c, dtype=None):
@@ -271,7 +321,7 @@ class PackedNetworks:
 
     def _add_head(self, prog, conv, lin, H, W, src, mid, mode, out, out_logits=None):
         self._add_conv(prog, conv, H, W, src, mid)
-        w, b, nout = lin
+        w, b, nout = lin.w, lin.b, lin.nout
         prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=nout, head_mode=mode, src=mid, w=w, shift=b,
                  out=out, out_logits=out_logits)
 
