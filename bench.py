@@ -392,6 +392,16 @@ def cpu_mcts(args, sd=None, trees=24, budget_s=25.0):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else any library prints there (NCCL's version banner,
+    # torch warnings) is sent to stderr by pointing fd 1 at fd 2 and keeping a private handle on the real stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None, help="timed steps of the primary workload (default: mcts 5 searches, env 200 steps)")
@@ -432,7 +442,7 @@ def main():
         if args.workload == "both":
             env_base, _ = cpu_env(args, budget_s=15.0)
             line["env"] = {"metric": "breakout_env_steps_per_s", "value": env_base["value"], "unit": "env-steps/s", "cpu_baseline": env_base}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -454,7 +464,7 @@ def main():
                     out["env"]["cpu_baseline"], _ = cpu_env(args)
             else:
                 out["cpu_baseline"], _ = cpu_env(args)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
