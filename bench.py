@@ -270,7 +270,7 @@ def bench_mcts(args, rank, local, world):
 
     # dominant kernel: the tcgen05 convolution (58 launches per simulation step); timed alone over one
     # simulation step's conv ops with CUDA events on the launching stream
-    conv_prog = Program(B)
+    conv_prog = Program(B, plan.sim_prog.fuse)
     conv_prog.ops = [o for o in plan.sim_prog.ops if o.op == OP_CONV]
     conv_prog.keep = plan.sim_prog.keep
     conv_ms = _time_prog(conv_prog)
@@ -327,7 +327,7 @@ def bench_mcts(args, rank, local, world):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_sustained"], "traffic": CONV_TRAFFIC_PER_SAMPLE * B,
                      "traffic_source": "profiles/r1_conv_tc_final_full.txt (ncu --set full, one 3x3 256->256 launch, scaled by samples per launch)", "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
-                     "kernel": f"conv_tc_kernel ({n_conv} launches per simulation step)", "flop_convention": "valid taps only (BASELINE.md section 3)",
+                     "kernel": f"tcgen05 convolution: {n_conv} conv layers per simulation step in {conv_prog.n_kernels} launches (conv_stack_kernel / conv_tc_kernel)", "flop_convention": "valid taps only (BASELINE.md section 3)",
                      "flop_per_leaf": FLOP_CONV_VALID, "kernel_ms": conv_ms / n_conv, 
                      "conv_ms_per_sim_step": conv_ms, "all_kernels_ms_per_sim_step": step_ms,
                      "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12},

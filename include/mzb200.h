@@ -216,6 +216,25 @@ int mz_rep_input(int B, int slots, const float *frames, int head, const float *c
 int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t seed, uint32_t step, int64_t *action,
                       int32_t *act_slot, float *probs_out, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused residual trunk: a run of consecutive MZ_OP_CONV records that are all bf16 / use_tc / w_layout 1 /
+ * 3x3 / 256 -> 256 on the 4x5 latent and touch at most three activation buffers is executed by ONE persistent
+ * launch (csrc/conv_stack.cu); layers are ordered per 128-sample group through device counters instead of
+ * kernel boundaries.
+ *   mz_stack_layer_bytes()  size of one device-resident layer descriptor
+ *   mz_stack_build          fills a HOST blob (64-byte aligned, n_ops * mz_stack_layer_bytes() bytes) from the op
+ *                           records; bufs[n_bufs] (<= 3) are the activation buffers the ops' src/dst/res point to.
+ *                           The caller copies the blob to device memory once.
+ *   mz_stack_run            runs the trunk: blob_dev = the uploaded blob, bufs = the same buffers in the same order,
+ *                           act_idx as in mz_op, done = int32 [n_layers * ceil(nsamples/128)] scratch (zeroed here,
+ *                           on the stream).
+ */
+size_t mz_stack_layer_bytes(void);
+int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs);
+int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,12 +75,15 @@ def _declare(L: C.CDLL) -> None:
     }
     L.mz_tree_bytes.argtypes, L.mz_tree_bytes.restype = [i32], C.c_size_t
     L.mz_tree_nodes.argtypes, L.mz_tree_nodes.restype = [i32], i32
+    L.mz_stack_layer_bytes.argtypes, L.mz_stack_layer_bytes.restype = [], C.c_size_t
     sig.update({
         "mz_puct_tables": [i32, C.c_double, C.c_double, vp, vp],
         "mz_tree_root": [C.POINTER(TreeArgs), vp],
         "mz_tree_step": [C.POINTER(TreeArgs), vp],
         "mz_run": [vp, i32, i32, vp],
         "mz_rep_input": [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp],
+        "mz_stack_build": [vp, i32, vp, C.c_size_t, vp, i32],
+        "mz_stack_run": [vp, i32, i32, vp, i32, vp, vp, vp],
         "mz_sample_actions": [i32, vp, C.c_double, u64, C.c_uint32, vp, vp, vp, vp],
     })
     for name, args in sig.items():

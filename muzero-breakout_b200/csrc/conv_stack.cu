@@ -1,0 +1,394 @@
+// A whole residual trunk (a run of 3x3 256->256 convolutions on the 4x5 latent: the dynamics network's
+// ConvBlock + 14 ResidualBlocks, or the prediction network's 14 ResidualBlocks) in ONE persistent launch.
+//
+// Same tile kernel as conv_tc.cu (per-pixel tiles that skip the zero-padding taps, cta_group::2 pair MMAs,
+// TMA-fed 5-stage ring, two TMEM accumulators, coalesced staging epilogue), but the CTA pairs walk the layers
+// back to back instead of returning to the host between them.  A layer only needs the previous layer's output for
+// the SAME 128-sample group (a 3x3 conv mixes pixels, never samples), so there is no grid-wide barrier:
+// done[layer][group] counts the epilogue warps that have stored (and fenced) their part of the 20 pixel tiles of
+// a group, and the TMA producer of a tile of layer L+1 waits for done[L][its group] == 20 x 8 before it issues
+// the first load.  This removes, per convolution, the launch gap, the prologue (barrier init, TMEM allocation,
+// cluster sync), the exposed last epilogue and the tail of the wave -- about 10 of 55 us at 4096 samples, and
+// most of the time at small batches (60 launches of ~20 us at 24 samples).
+//
+// Residual blocks run in place on two activation buffers (conv1: X -> Y, conv2: Y + X -> X): every reader of a
+// group's buffer belongs to the previous layer of that group and has finished before the counter completes.
+// Cross-proxy ordering: epilogue stores are generic-proxy writes that a later TMA (async proxy) reads, so the writer
+// does st.global -> __threadfence -> fence.proxy.async -> red.release and the reader ld.acquire -> fence.proxy.async.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int MAX_BUFS = 3;
+constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
+
+struct alignas(64) StackLayer {          // device-resident descriptor of one convolution of the trunk
+    CUtensorMap map_b;                   // tile-contiguous weights [9][4][256][64]
+    const float *scale, *shift;          // [256]
+    const float *act_bias;               // [3][20][256] or NULL
+    float *dst_f32;                      // optional fp32 copy of the output or NULL
+    int src, dst, res;                   // activation buffer ids; res = -1: no residual
+    int act;
+};
+
+struct StackParams {
+    CUtensorMap map_act[MAX_BUFS];       // activation buffers as (channel, x, y, sample) TMA tensors
+    __nv_bfloat16 *act[MAX_BUFS];
+    const StackLayer *layers;
+    int nlayers;
+    int *done;                           // [nlayers][groups], zeroed by the caller before the launch
+    const int *act_idx;
+    int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs)
+};
+
+__device__ __forceinline__ uint32_t tap_mask(int y, int x)
+{
+    uint32_t m = 0u;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        if (y + dy >= 0 && y + dy < LAT_H && x + dx >= 0 && x + dx < LAT_W) m |= 1u << tap;
+    }
+    return m;
+}
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
+{
+    constexpr int N = CH;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;
+    float *s_scale = reinterpret_cast<float *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);   // [scale 256 | shift 256] of the current layer
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_scale + 2 * 256);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    constexpr int kchunks = CH / BLOCK_K;
+    const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();
+
+    if (warp == 0 && lane == 0) {
+        for (int b = 0; b < MAX_BUFS; ++b) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_act[b]) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            constexpr uint32_t a_bytes = BLOCK_M * BLOCK_K * 2, b_bytes = (N / 2) * BLOCK_K * 2;
+            const uint32_t lead_full = map_to_cta(bar_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int layer = 0; layer < p.nlayers; ++layer) {
+                const StackLayer *L = p.layers + layer;
+                const int src = L->src;
+                for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+                    const int pix = tile / p.pairs, g = 2 * (tile - pix * p.pairs) + rank;
+                    const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                    const uint32_t taps = tap_mask(y0, x0);
+                    if (layer > 0 && g < p.groups) {
+                        // the previous layer's output for this sample group: all 20 pixel tiles x 8 epilogue warps stored
+                        const int *flag = p.done + (size_t)(layer - 1) * p.groups + g;
+                        uint32_t spins = 0;
+                        while (ld_acquire(flag) < HW * NUM_EPI_WARPS) {
+                            if (++spins > (1u << 26)) __trap();
+                            __nanosleep(32);
+                        }
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!((taps >> tap) & 1u)) continue;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                            if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));
+                            else mbar_arrive_cluster(lead_full + 8 * stage);
+                            tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
+                            tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + rank * (N / 2));
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (pair leader only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = instr_desc(N);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int layer = 0; layer < p.nlayers; ++layer) {
+                for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+                    const int buf = it & 1;
+                    const int pix = tile / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                    mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                    const int ksteps = __popc(tap_mask(y0, x0)) * kchunks;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                        const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                           (ks | k) ? 1u : 0u);
+                        umma_commit_pair(bar_empty + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(bar_tfull + 8 * buf);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;
+        constexpr int ncols = N / 2, nchunks = ncols / 32, units = ncols / 8, row_bytes = ncols * 2, rows_per_it = 32 / units;
+        const int col0 = half * ncols;
+        const int my_u = lane % units, my_rsub = lane / units;
+        const int etid = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
+        uint8_t *stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
+        const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
+        int it = 0;
+        for (int layer = 0; layer < p.nlayers; ++layer) {
+            const StackLayer *L = p.layers + layer;
+            // per-layer BN scale/shift: the first barrier proves every epilogue warp has finished the previous layer
+            // (nobody reads the old values any more), the second that the new ones are in place
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float *sc = s_scale, *sf = sc + 256;
+            sc[etid] = L->scale[etid];
+            sf[etid] = L->shift[etid];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const __nv_bfloat16 *res_base = L->res >= 0 ? p.act[L->res] : nullptr;
+            __nv_bfloat16 *dst_base = p.act[L->dst];
+            const float *act_bias = L->act_bias;
+            float *dst_f32 = L->dst_f32;
+            const int act = L->act;
+            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+                const int buf = it & 1;
+                const int pix = tile / p.pairs, g = 2 * (tile - pix * p.pairs) + rank;
+                const int s = g * BLOCK_M + r;
+                const bool valid = s < p.n;
+                const long long m = valid ? (long long)s * HW + pix : -1;        // global output row
+                const float *ab = (valid && act_bias) ? act_bias + ((size_t)p.act_idx[s] * HW + pix) * N : nullptr;
+                if (res_base) {
+#pragma unroll
+                    for (int k = 0; k < units; ++k) {
+                        const int rr = k * rows_per_it + my_rsub;
+                        const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                        if (mr >= 0) {
+                            const uint32_t sdst = smem_u32(stg + rr * row_bytes + 16 * (my_u ^ (rr & (units - 1))));
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(res_base + mr * N + col0 + my_u * 8) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                uint32_t acc[2][32];
+                mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+                tc_fence_after();
+                if (res_base) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
+                tmem_ld32_async(taddr, acc[0]);
+#pragma unroll
+                for (int c = 0; c < nchunks; ++c) {
+                    tmem_wait(acc[c & 1]);
+                    if (c + 1 < nchunks) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
+                    if (valid) {
+                        const int c0 = col0 + c * 32;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[c & 1][j]);
+                        if (ab) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(ab + c0) + q);
+                                v[q * 4] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 a4 = *reinterpret_cast<const float4 *>(sc + c0 + q * 4), b4 = *reinterpret_cast<const float4 *>(sf + c0 + q * 4);
+                            v[q * 4] = v[q * 4] * a4.x + b4.x; v[q * 4 + 1] = v[q * 4 + 1] * a4.y + b4.y;
+                            v[q * 4 + 2] = v[q * 4 + 2] * a4.z + b4.z; v[q * 4 + 3] = v[q * 4 + 3] * a4.w + b4.w;
+                        }
+                        uint8_t *srow = stg + lane * row_bytes;
+                        if (res_base) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 u4 = *reinterpret_cast<const uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1))));
+                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u4);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __bfloat1622float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x;
+                                    v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (act == MZ_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = activate(v[j], act);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u4;
+                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u4);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                            *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = u4;
+                        }
+                        if (dst_f32) {
+                            float4 *fp = reinterpret_cast<float4 *>(dst_f32 + m * N + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+#pragma unroll
+                for (int k = 0; k < units; ++k) {
+                    const int rr = k * rows_per_it + my_rsub;
+                    const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                    if (mr >= 0) {
+                        const uint4 v4 = *reinterpret_cast<const uint4 *>(stg + rr * row_bytes + 16 * (my_u ^ (rr & (units - 1))));
+                        *(reinterpret_cast<uint4 *>(dst_base + mr * N + col0) + my_u) = v4;
+                    }
+                }
+                // publish: this warp's part of (layer, group g, pixel pix) is in global memory
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && g < p.groups) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + (size_t)layer * p.groups + g) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+constexpr size_t STACK_SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)NUM_EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * sizeof(float) + 128;
+
+}  // namespace
+
+extern "C" {
+
+size_t mz_stack_layer_bytes(void) { return sizeof(StackLayer); }
+
+int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs)
+{
+    MZB_CHECK_ARG(ops && n_ops > 0 && blob_host && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS, "bad argument");
+    MZB_CHECK_ARG(blob_bytes >= (size_t)n_ops * sizeof(StackLayer), "blob too small");
+    MZB_CHECK_ARG((reinterpret_cast<uintptr_t>(blob_host) & 63) == 0, "blob must be 64-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+    StackLayer *L = reinterpret_cast<StackLayer *>(blob_host);
+    auto buf_id = [&](const void *ptr) { for (int i = 0; i < n_bufs; ++i) if (bufs[i] == ptr) return i; return -1; };
+    for (int i = 0; i < n_ops; ++i) {
+        const mz_op &o = ops[i];
+        MZB_CHECK_ARG(o.op == MZ_OP_CONV && o.dtype == MZ_BF16 && o.use_tc && o.w_layout == 1 && o.ksize == 3 && o.cin == CH && o.cout == CH &&
+                          o.H == LAT_H && o.W == LAT_W, "op is not a stackable 3x3 256->256 convolution on the 4x5 latent");
+        StackLayer &l = L[i];
+        l.src = buf_id(o.src); l.dst = buf_id(o.dst); l.res = o.res ? buf_id(o.res) : -1;
+        MZB_CHECK_ARG(l.src >= 0 && l.dst >= 0 && (!o.res || l.res >= 0), "op buffer is not one of the stack's activation buffers");
+        MZB_CHECK_ARG(l.src != l.dst, "a convolution cannot run in place on its own input");
+        l.scale = o.scale; l.shift = o.shift; l.act_bias = o.act_bias; l.dst_f32 = o.dst_f32; l.act = o.act;
+        cuuint64_t dims[2] = {BLOCK_K, (cuuint64_t)9 * (CH / BLOCK_K) * CH};
+        cuuint64_t strides[1] = {BLOCK_K * 2};
+        cuuint32_t box[2] = {BLOCK_K, CH / 2};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&l.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
+    }
+    return 0;
+}
+
+int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
+                 void *stream)
+{
+    MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS && done, "bad argument");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    StackParams p{};
+    for (int b = 0; b < MAX_BUFS; ++b) {
+        void *ptr = bufs[b < n_bufs ? b : 0];
+        p.act[b] = (__nv_bfloat16 *)ptr;
+        cuuint64_t dims[4] = {CH, LAT_W, LAT_H, (cuuint64_t)nsamples};
+        cuuint64_t strides[3] = {CH * 2, LAT_W * CH * 2, HW * CH * 2};
+        cuuint32_t box[4] = {BLOCK_K, 1, 1, BLOCK_M};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p.map_act[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return -2; }
+    }
+    p.layers = reinterpret_cast<const StackLayer *>(blob_dev);
+    p.nlayers = n_layers;
+    p.done = done;
+    p.act_idx = act_idx;
+    p.n = nsamples;
+    p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
+    p.pairs = (p.groups + 1) / 2;
+    p.ntiles = HW * p.pairs;
+    MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = STACK_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel, p));
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

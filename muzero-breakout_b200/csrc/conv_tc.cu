@@ -33,26 +33,9 @@
 //
 // Replaces the cuDNN convolutions + separate BN / ReLU / add kernels the reference launches for
 // src/networks.py ConvBlock :7-17 and ResidualBlock :19-35 (K4-K6 of SURVEY.md section 2d).
-#include <cuda.h>
-#include <stdlib.h>
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;          // bf16 per smem row = 128 bytes = one SWIZZLE_128B atom
-constexpr int UMMA_K = 16;
-constexpr int STAGES = 5;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
-constexpr int B_STAGE_BYTES = 128 * BLOCK_K * 2;        // 16 KB: this CTA's half (N/2 <= 128 rows) of the weight tile
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_EPI_WARPS = 8;                        // two per TMEM lane quarter, each takes half of the N columns
-constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
-constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_BYTES = 32 * 256;               // per epilogue warp: 32 rows x (N/2 <= 128 cols) bf16, residual in / result out
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)NUM_EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * sizeof(float) + 128;   // 226.1 KB of the 227 KB
 
 struct ConvParams {
     int n, H, W, cin, cout, taps, pad, act;
@@ -67,135 +50,6 @@ struct ConvParams {
     const float *scale, *shift, *act_bias;
     const int *act_idx;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    // bounded spin: a protocol bug traps (launch error reported to the host) instead of hanging the GPU
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.b32 %0, 1, 0, p;\n}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-// cta_group::2 TMA loads: data lands in THIS CTA's shared memory, the transaction bytes are signalled on the
-// mbarrier `bar`, a shared::cluster address that may belong to the peer (the pair leader's full barrier)
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// commit of the pair's MMAs: arrives on the mbarrier at this offset in BOTH CTAs when they have retired
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)0x3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// tcgen05.ld of 32 consecutive fp32 columns of this thread's TMEM lane; asynchronous until tmem_wait().
-__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-// wait for the outstanding tcgen05.ld; the registers are in/out operands so that no use of them can be
-// scheduled above the wait
-__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
-// 8-row groups 1024 bytes apart (SBO), LBO unused (=1), version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=256 (the pair), N
-__device__ __forceinline__ uint32_t instr_desc(int N)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
-}
-
-__device__ __forceinline__ float activate(float v, int act)
-{
-    switch (act) {
-        case MZ_ACT_RELU: return fmaxf(v, 0.0f);
-        case MZ_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
-        case MZ_ACT_SILU: return v / (1.0f + __expf(-v));
-        case MZ_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-        default: return v;
-    }
-}
 
 // profiling trace (debug & 8): per-tile timestamps of cluster 0's leader CTA, read back with mz_conv_trace()
 __device__ unsigned long long g_trace[8 * 64];
@@ -473,23 +327,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
-}
-
-// ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
 }
 
 }  // namespace

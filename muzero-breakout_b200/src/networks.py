@@ -19,6 +19,7 @@ There is no CPU path: everything here needs a CUDA device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as F
@@ -45,14 +46,53 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-class Program:
-    """A list of mz_op records with every pointer resolved; run() enqueues it on the current stream."""
+def _stackable(o) -> bool:
+    """3x3 256->256 tensor-core convolution on the 4x5 latent with tile-contiguous weights (csrc/conv_stack.cu)."""
+    return (o.op == OP_CONV and o.dtype == BF16 and o.use_tc == 1 and o.w_layout == 1 and o.ksize == 3 and o.cin == 256
+            and o.cout == 256 and o.H == 4 and o.W == 5)
 
-    def __init__(self, n: int):
+
+class _Stack:
+    """A run of stackable convolutions executed by one persistent launch (mz_stack_run)."""
+
+    def __init__(self, ops, n, device):
+        L = _lib.lib()
+        self.n, self.nlayers = n, len(ops)
+        bufs = []
+        for o in ops:
+            for ptr in (o.src, o.dst, o.res):
+                if ptr and ptr not in bufs:
+                    bufs.append(ptr)
+        self.ok = len(bufs) <= 3
+        if not self.ok:
+            return
+        lb = L.mz_stack_layer_bytes()
+        raw = (C.c_uint8 * (self.nlayers * lb + 64))()
+        host = (C.addressof(raw) + 63) & ~63
+        arr = (MzOp * self.nlayers)(*ops)
+        self.bufs = (C.c_void_p * len(bufs))(*bufs)
+        self.nbufs = len(bufs)
+        _lib.check(L.mz_stack_build(arr, self.nlayers, host, self.nlayers * lb, self.bufs, self.nbufs))
+        blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone()
+        self.blob = blob.to(device)
+        self.done = torch.zeros(self.nlayers * ((n + 127) // 128), dtype=torch.int32, device=device)
+        self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
+
+    def run(self, st):
+        _lib.check(_lib.lib().mz_stack_run(self.blob.data_ptr(), self.nlayers, self.n, self.bufs, self.nbufs, self.act_idx,
+                                           self.done.data_ptr(), st))
+
+
+class Program:
+    """A list of mz_op records with every pointer resolved; run() enqueues it on the current stream.  With
+    fuse=True, runs of two or more stackable convolutions become one persistent launch each."""
+
+    def __init__(self, n: int, fuse: bool = False):
         self.n = n
         self.ops = []
         self.keep = []            # tensors the ops point into
-        self._arr = None
+        self.fuse = fuse
+        self._segs = None
 
     def add(self, **kw):
         op = MzOp()
@@ -62,23 +102,54 @@ class Program:
                 v = v.data_ptr()
             setattr(op, k, v)
         self.ops.append(op)
-        self._arr = None
+        self._segs = None
         return op
 
     def extend(self, other: "Program"):
         self.ops += other.ops
         self.keep += other.keep
-        self._arr = None
+        self.fuse = self.fuse or other.fuse
+        self._segs = None
+
+    def _build(self):
+        segs, plain, i = [], [], 0
+        device = next((t.device for t in self.keep if t.is_cuda), torch.device("cuda"))
+
+        def flush():
+            if plain:
+                segs.append(("ops", (MzOp * len(plain))(*plain), len(plain)))
+                plain.clear()
+
+        while i < len(self.ops):
+            j = i
+            while self.fuse and j < len(self.ops) and _stackable(self.ops[j]):
+                j += 1
+            stack = _Stack(self.ops[i:j], self.n, device) if j - i >= 2 else None
+            if stack is not None and stack.ok:
+                flush()
+                segs.append(("stack", stack, j - i))
+                i = j
+            else:
+                plain.append(self.ops[i])
+                i += 1
+        flush()
+        self._segs = segs
 
     def run(self, stream=None):
-        if self._arr is None:
-            self._arr = (MzOp * len(self.ops))(*self.ops)
+        if self._segs is None:
+            self._build()
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        _lib.check(_lib.lib().mz_run(self._arr, len(self.ops), self.n, st))
+        for kind, item, cnt in self._segs:
+            if kind == "ops":
+                _lib.check(_lib.lib().mz_run(item, cnt, self.n, st))
+            else:
+                item.run(st)
 
     @property
     def n_kernels(self) -> int:
-        return len(self.ops)
+        if self._segs is None:
+            self._build()
+        return sum(cnt if kind == "ops" else 1 for kind, _, cnt in self._segs)
 
 
 DEFAULT_MODEL_CFG = {  # config.yaml:27-50
@@ -175,6 +246,7 @@ class PackedNetworks:
         self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.dt = BF16 if precision == "bf16" else F32
         self.use_tc = (precision == "bf16") if use_tc is None else bool(use_tc and precision == "bf16")
+        self.fuse_stacks = self.use_tc and os.environ.get("MZB_NO_STACK", "0") != "1"   # whole trunks in one persistent launch
         self.num_supports = int(cfg.get("num_supports", 11))
         self.supports_min, self.supports_max = cfg.get("supports_min", -5), cfg.get("supports_max", 5)
         if (self.supports_min, self.supports_max, self.num_supports) != (-5, 5, 11) and self.supports_max - self.supports_min != self.num_supports - 1:
@@ -306,13 +378,13 @@ class PackedNetworks:
                  use_tc=int(self.use_tc), w_layout=cv.w_layout, src=src, dst=dst, res=res, dst_f32=dst_f32, w=cv.w, scale=cv.scale, shift=cv.shift,
                  act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx)
 
-    def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None):
+    def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None, mid=None):
         """bufs: same-shaped activation buffers; cur: index of the one holding the input.  Each block writes its
         output IN PLACE over its input: conv2's epilogue reads the residual element and then writes the result to
         the same address from the same thread, and no tile reads the block input during conv2 (its operand is the
         mid buffer).  Two live buffers per network keep 4096 samples' activations (2 x 42 MB bf16) inside the L2.
         Returns the index holding the output (= cur)."""
-        mid = (cur + 1) % len(bufs)
+        mid = (cur + 1) % len(bufs) if mid is None else mid
         for i, (c1, c2) in enumerate(blocks):
             self._add_conv(prog, c1, H, W, bufs[cur], bufs[mid])
             self._add_conv(prog, c2, H, W, bufs[mid], bufs[cur], res=bufs[cur],
@@ -328,11 +400,11 @@ class PackedNetworks:
     def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2):
         """14 residual blocks + policy head + value head (networks.py:225-241) on `src` [n][20][256]."""
         H, W = self.latent_hw
-        prog = Program(n)
-        c1, c2 = self.pred_res[0]                                   # first block reads src directly
-        self._add_conv(prog, c1, H, W, src, bufs[1])
-        self._add_conv(prog, c2, H, W, bufs[1], bufs[2], res=src)
-        cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 2)
+        prog = Program(n, self.fuse_stacks)
+        c1, c2 = self.pred_res[0]                                   # first block reads src directly (src, bufs[0], bufs[1]: three buffers)
+        self._add_conv(prog, c1, H, W, src, bufs[0])
+        self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=src)
+        cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 1, mid=0)
         self._add_head(prog, self.policy_conv, self.policy_lin, H, W, bufs[cur], mid, pi_mode, pi, policy_logits)
         self._add_head(prog, self.value_conv, self.value_lin, H, W, bufs[cur], mid, value_mode, value, value_logits)
         return prog
@@ -342,7 +414,7 @@ class PackedNetworks:
         """ConvBlock(259->256) + 14 residual blocks + reward head + _scale_state (networks.py:151-167,
         282-298).  src [n][20][256] parent latents, act_idx int32 [n]; scaled latent -> dst (and dst2)."""
         H, W = self.latent_hw
-        prog = Program(n)
+        prog = Program(n, self.fuse_stacks)
         self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx)
         cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32)
         self._add_head(prog, self.reward_conv, self.reward_lin, H, W, bufs[cur], mid, reward_mode, reward, reward_logits)

@@ -154,3 +154,24 @@ def test_bf16_pipeline_tensor_cores_vs_cuda_cores_and_reference(agent, rec):
         assert e <= 2e-2, f"{k}: tensor-core vs CUDA-core bf16 pipelines differ by {e:.2e}"
     for k, e in errs.items():
         assert e <= 3e-2, f"{k}: bf16 pipeline deviates {e:.2e} from the fp32 reference"
+
+
+@pytest.mark.parametrize("n", [5, 130, 3000])
+def test_fused_trunk_launch_equals_layer_by_layer(agent, n):
+    """csrc/conv_stack.cu (whole residual trunk in one persistent launch, layers ordered by per-group device
+    counters) must give bit-identical results to one launch per convolution: same tiles, same arithmetic."""
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    fused = PackedNetworks(agent, agent.cfg, precision="bf16")
+    plain = PackedNetworks(agent, agent.cfg, precision="bf16")
+    plain.fuse_stacks = False
+    assert fused.fuse_stacks
+    g = torch.Generator().manual_seed(n)
+    h = torch.rand(n, 256, 4, 5, generator=g)
+    acts = torch.randint(0, 3, (n,), generator=g)
+    for rep in range(2):                       # twice: the done-counters are re-zeroed on the stream each run
+        a_h, a_r = fused.dynamics(h, _planes(acts))
+        b_h, b_r = plain.dynamics(h, _planes(acts))
+        a_p, a_v = fused.prediction(h)
+        b_p, b_v = plain.prediction(h)
+        for x, y, what in ((a_h, b_h, "latent"), (a_r, b_r, "reward"), (a_p, b_p, "policy"), (a_v, b_v, "value")):
+            assert torch.equal(x, y), f"n={n} rep={rep} {what}: fused and per-layer launches differ (max {float((x - y).abs().max()):.3e})"
