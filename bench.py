@@ -229,7 +229,9 @@ FLOP_CONV_VALID = 496_962_560 + 486_932_480      # conv layers only (no Linear h
 FLOP_CONV_DENSE = 687_093_760 + 673_710_080
 
 
-def _time_prog(prog, reps=5):
+def _time_prog(prog, reps=50):
+    """mean duration over `reps` back-to-back runs: long enough (~0.2 s) that the clocks settle under the power cap,
+    like inside a search and like the sustained cuBLAS figure the roofline divides by"""
     prog.run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -145,7 +145,7 @@ __device__ __forceinline__ void select_leaf(const Params &p, const TreeView &t, 
             continue;
         }
         if (c == NO_CHILD) {                                          // placeholder -> new slot :167-175
-            c = nslots++;
+            c = nslots < p.lay.nodes ? nslots++ : p.lay.nodes - 1;    // a search allocates at most S+1 slots; stay in bounds if misused
             if (lane == 0) { set3i(nc, a, (pick3i(nc, a) & 0xFFFF) | (c << 16)); *t.row(3, cur) = nc; }
         }
         __syncwarp();
