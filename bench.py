@@ -171,6 +171,23 @@ def bench_env(args, rank, local, world):
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
 
+    aux24 = None
+    if rank == 0 and not getattr(args, "no_aux", False):
+        # BASELINE.json configs[0]: config.yaml default env count (24), reference-facing call with host tensors
+        env24 = BreakoutEnvironment(dict(ENV_CFG, n_parallel=24))
+        torch.manual_seed(42)
+        s24, _ = env24.reset()
+        d24 = torch.zeros(24, dtype=torch.bool)
+        acts24 = torch.randint(0, 3, (1000, 24))
+        for i in range(20):
+            s24, *_ = env24.step(s24, acts24[i], d24)
+        t0 = time.perf_counter()
+        for i in range(20, 1000):
+            s24, r24, d24, v24 = env24.step(s24, acts24[i], d24)
+        el = time.perf_counter() - t0
+        aux24 = {"workload": "BreakoutEnvironment.step, 24 envs (config.yaml default), host tensors in and out (BASELINE.json configs[0])",
+                 "us_per_step": el / 980 * 1e6, "value": 24 * 980 / el, "unit": "env-steps/s", "note": "launch- and copy-latency-bound"}
+
     peaks = measured_peaks()
     kernel_ms = ms / K
     achieved = ENV_BYTES_PER_STEP * B / (kernel_ms * 1e-3) / 1e9
@@ -190,6 +207,8 @@ def bench_env(args, rank, local, world):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    if aux24:
+        out["config_defaults"] = aux24
     return out
 
 
@@ -342,6 +361,22 @@ def bench_mcts(args, rank, local, world):
         out["collectives"] = collectives
     if not args.no_acting:
         out["acting"] = bench_acting(args, m, dev, rank, world)
+    if rank == 0 and not args.no_aux:
+        # BASELINE.json configs[1]: config.yaml defaults (24 roots x 50 simulations), same weights, one GPU
+        cfg24 = dict(cfg); cfg24["search"] = dict(cfg["search"], seed=3)
+        m24 = MCTSSearchVec(cfg24, nets, None)
+        h24 = hiddens[0][:24].contiguous()
+        for _ in range(3):
+            m24.search(h24, None, 0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            m24.search(h24, None, 0)
+        b.record(); torch.cuda.synchronize()
+        t24 = a.elapsed_time(b) / 5
+        out["config_defaults"] = {"workload": "MCTSSearchVec.search, config.yaml defaults: 24 roots x 50 simulations (BASELINE.json configs[1])",
+                                  "ms_per_search": t24, "value": 24 * S / (t24 * 1e-3), "unit": "simulations/s", "note": "latency-bound: 20 pixel tiles per layer"}
     return out, sd
 
 
@@ -420,6 +455,7 @@ def main():
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-acting", action="store_true", help="skip the whole-move (rep net + search + env) aux measurement")
+    ap.add_argument("--no-aux", action="store_true", help="skip the config.yaml-default (24 envs / roots) aux measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     primary = "env" if args.workload == "env" else "mcts"
