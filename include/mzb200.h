@@ -227,7 +227,7 @@ int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t
  *                           records; bufs[n_bufs] (<= 3) are the activation buffers the ops' src/dst/res point to.
  *                           The caller copies the blob to device memory once.
  *   mz_stack_run            runs the trunk: blob_dev = the uploaded blob, bufs = the same buffers in the same order,
- *                           act_idx as in mz_op, done = int32 [n_layers * ceil(nsamples/128)] scratch (zeroed here,
+ *                           act_idx as in mz_op, done = int32 [n_layers * ceil(nsamples/128) * 20] scratch (zeroed here,
  *                           on the stream).
  */
 size_t mz_stack_layer_bytes(void);

@@ -4,15 +4,17 @@
 // Same tile kernel as conv_tc.cu (per-pixel tiles that skip the zero-padding taps, cta_group::2 pair MMAs,
 // TMA-fed 5-stage ring, two TMEM accumulators, coalesced staging epilogue), but the CTA pairs walk the layers
 // back to back instead of returning to the host between them.  A layer only needs the previous layer's output for
-// the SAME 128-sample group (a 3x3 conv mixes pixels, never samples), so there is no grid-wide barrier:
-// done[layer][group] counts the epilogue warps that have stored (and fenced) their part of the 20 pixel tiles of
-// a group, and the TMA producer of a tile of layer L+1 waits for done[L][its group] == 20 x 8 before it issues
-// the first load.  This removes, per convolution, the launch gap, the prologue (barrier init, TMEM allocation,
+// the SAME 128-sample group (a 3x3 conv mixes pixels, never samples) at the tile's 3x3 pixel neighbourhood, so
+// there is no grid-wide barrier: done[layer][group][pixel] counts the epilogue warps that have stored (and fenced)
+// their part of that pixel tile, and the TMA producer of tile (pixel p, group g) of layer L+1 waits for
+// done[L][g][q] == 8 for the in-bounds neighbours q of p before it issues the first load.  The CTA pairs therefore
+// flow from one layer into the next without draining their pipelines.  This removes, per convolution, the launch gap, the prologue (barrier init, TMEM allocation,
 // cluster sync), the exposed last epilogue and the tail of the wave -- about 10 of 55 us at 4096 samples, and
 // most of the time at small batches (60 launches of ~20 us at 24 samples).
 //
-// Residual blocks run in place on two activation buffers (conv1: X -> Y, conv2: Y + X -> X): every reader of a
-// group's buffer belongs to the previous layer of that group and has finished before the counter completes.
+// Residual blocks run in place on two activation buffers (conv1: X -> Y, conv2: Y + X -> X).  The neighbour wait
+// also covers the write-after-read hazards: the tiles of the previous layer that READ buffer[g][p] are exactly the
+// neighbours q of p (p is in N(q) iff q is in N(p)), the same tiles whose outputs tile p needs.
 // Cross-proxy ordering: epilogue stores are generic-proxy writes that a later TMA (async proxy) reads, so the writer
 // does st.global -> __threadfence -> fence.proxy.async -> red.release and the reader ld.acquire -> fence.proxy.async.
 #include "tc_common.cuh"
@@ -36,7 +38,7 @@ struct StackParams {
     __nv_bfloat16 *act[MAX_BUFS];
     const StackLayer *layers;
     int nlayers;
-    int *done;                           // [nlayers][groups], zeroed by the caller before the launch
+    int *done;                           // [nlayers][groups][20 pixels], zeroed before the launch
     const int *act_idx;
     int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs)
 };
@@ -108,12 +110,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0);
                     if (layer > 0 && g < p.groups) {
-                        // the previous layer's output for this sample group: all 20 pixel tiles x 8 epilogue warps stored
-                        const int *flag = p.done + (size_t)(layer - 1) * p.groups + g;
-                        uint32_t spins = 0;
-                        while (ld_acquire(flag) < HW * NUM_EPI_WARPS) {
-                            if (++spins > (1u << 26)) __trap();
-                            __nanosleep(32);
+                        // the previous layer's output of this sample group at the in-bounds neighbour pixels (= the taps):
+                        // all 8 epilogue warps of each of those tiles have stored and fenced
+                        const int *flags = p.done + ((size_t)(layer - 1) * p.groups + g) * HW;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!((taps >> tap) & 1u)) continue;
+                            const int *flag = flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1);
+                            uint32_t spins = 0;
+                            while (ld_acquire(flag) < NUM_EPI_WARPS) {
+                                if (++spins > (1u << 26)) __trap();
+                                __nanosleep(32);
+                            }
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 __threadfence();
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __syncwarp();
-                if (lane == 0 && g < p.groups) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + (size_t)layer * p.groups + g) : "memory");
+                if (lane == 0 && g < p.groups) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + ((size_t)layer * p.groups + g) * HW + pix) : "memory");
             }
         }
     }
@@ -369,7 +376,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.pairs = (p.groups + 1) / 2;
     p.ntiles = HW * p.pairs;
-    MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups, st));
+    MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups * HW, st));
     static bool attr_set = false;
     if (!attr_set) {
         MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));

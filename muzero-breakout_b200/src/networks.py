@@ -75,7 +75,7 @@ class _Stack:
         _lib.check(L.mz_stack_build(arr, self.nlayers, host, self.nlayers * lb, self.bufs, self.nbufs))
         blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone()
         self.blob = blob.to(device)
-        self.done = torch.zeros(self.nlayers * ((n + 127) // 128), dtype=torch.int32, device=device)
+        self.done = torch.zeros(self.nlayers * ((n + 127) // 128) * 20, dtype=torch.int32, device=device)
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
 
     def run(self, st):
