@@ -40,6 +40,7 @@ struct StackParams {
     int nlayers;
     int *done;                           // [nlayers][groups][20 pixels], zeroed before the launch
     const int *act_idx;
+    int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
     int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs)
 };
 
@@ -113,15 +114,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                         // the previous layer's output of this sample group at the in-bounds neighbour pixels (= the taps):
                         // all 8 epilogue warps of each of those tiles have stored and fenced
                         const int *flags = p.done + ((size_t)(layer - 1) * p.groups + g) * HW;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            if (!((taps >> tap) & 1u)) continue;
-                            const int *flag = flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1);
-                            uint32_t spins = 0;
-                            while (ld_acquire(flag) < NUM_EPI_WARPS) {
-                                if (++spins > (1u << 26)) __trap();
-                                __nanosleep(32);
+                        uint32_t spins = 0;
+                        for (;;) {                                       // all neighbour flags are read in parallel (one L2 round trip)
+                            int ready = 1;
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                if (p.fine && ((taps >> tap) & 1u)) {
+                                    const int v = *reinterpret_cast<const volatile int *>(flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1));
+                                    ready &= v >= NUM_EPI_WARPS;
+                                }
                             }
+                            if (!p.fine) {
+#pragma unroll
+                                for (int q = 0; q < HW; ++q) ready &= *reinterpret_cast<const volatile int *>(flags + q) >= NUM_EPI_WARPS;
+                            }
+                            if (ready) break;
+                            if (++spins > (1u << 26)) __trap();
+                            __nanosleep(32);
                         }
+                        asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: pairs with the epilogues' red.release
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     for (int tap = 0; tap < 9; ++tap) {
@@ -372,6 +383,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.nlayers = n_layers;
     p.done = done;
     p.act_idx = act_idx;
+    { static int fine = -1; if (fine < 0) { const char *e = getenv("MZB_STACK_FINE"); fine = e ? atoi(e) : 1; } p.fine = fine; }
     p.n = nsamples;
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.pairs = (p.groups + 1) / 2;
