@@ -164,12 +164,12 @@ int mz_tree_step(const mz_tree_args *args, void *stream);
  *   MZ_OP_NHWC_OUT  channels-last src -> float32 NCHW dst
  */
 enum { MZ_OP_CONV = 0, MZ_OP_POOL2 = 1, MZ_OP_SCALE = 2, MZ_OP_HEAD = 3, MZ_OP_NCHW_IN = 4, MZ_OP_NHWC_OUT = 5 };
-enum { MZ_F32 = 0, MZ_BF16 = 1 };
+enum { MZ_F32 = 0, MZ_BF16 = 1, MZ_F16 = 2 };   /* MZ_F16: same tensor-core path and rate as bf16, 11-bit mantissa */
 enum { MZ_ACT_NONE = 0, MZ_ACT_RELU = 1, MZ_ACT_LEAKY_RELU = 2, MZ_ACT_SILU = 3, MZ_ACT_GELU = 4 }; /* utils.py:99-108 */
 
 typedef struct mz_op {
     int32_t op;        /* MZ_OP_* */
-    int32_t dtype;     /* MZ_F32 / MZ_BF16: element type of src / dst / res / w */
+    int32_t dtype;     /* MZ_F32 / MZ_BF16 / MZ_F16: element type of src / dst / res / w */
     int32_t H, W;      /* spatial size of src */
     int32_t cin, cout; /* channels of src / dst */
     int32_t ksize;     /* conv: 1 or 3 */
@@ -233,7 +233,7 @@ int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t
 size_t mz_stack_layer_bytes(void);
 int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs);
 int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
-                 void *stream);
+                 int dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -75,7 +75,7 @@ class Actor:
         cur = gray0
         rec = {k: [] for k in ("action", "reward", "value", "visits", "recorded", "frames")}
         initial_state, initial_dx = state.clone(), env.ball_dx
-        dt = BF16 if nets.dt == BF16 else F32
+        dt = nets.dt
         ep_seed = (self.seed * 0x9E3779B97F4A7C15 + self._episodes * 0xC2B2AE3D27D4EB4F + 7) & 0xFFFFFFFFFFFFFFFF
         self._episodes += 1
         for move in range(self.max_moves):

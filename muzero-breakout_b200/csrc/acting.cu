@@ -5,6 +5,7 @@
 //   _prepare_mcts_input :259-277 + _encode_actions :279-293 + _pad_initial_state :313-332  (rep-net input)
 //   temperature sampling :192-198 (visit_counts ** (1/T), normalise, Categorical.sample per env)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,7 @@ namespace {
 template <typename T> __device__ __forceinline__ T cvt(float v);
 template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
 
 // One thread per (env, pixel): writes the 64 channels of that pixel contiguously (channels-last).
 //   channels 0..30  the last 31 frames appended to the trajectory, oldest first (ObservationTrajectory.get_states()[-31:])
@@ -77,6 +79,7 @@ int mz_rep_input(int B, int slots, const float *frames, int head, const float *c
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dtype == MZ_F32) rep_input_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(B, slots, frames, head, cur, acts, ahead, (float *)out);
     else if (dtype == MZ_BF16) rep_input_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(B, slots, frames, head, cur, acts, ahead, (__nv_bfloat16 *)out);
+    else if (dtype == MZ_F16) rep_input_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(B, slots, frames, head, cur, acts, ahead, (__half *)out);
     else { mzb::set_error("mz_rep_input: unknown dtype %d", dtype); return -1; }
     MZB_LAUNCH_CHECK();
     return 0;

@@ -40,6 +40,7 @@ struct StackParams {
     int nlayers;
     int *done;                           // [nlayers][groups][20 pixels], zeroed before the launch
     const int *act_idx;
+    int f16;                             // 16-bit element type: 0 = bf16, 1 = fp16
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
     int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs)
 };
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc(N);
+            const uint32_t idesc = instr_desc(N, p.f16 != 0);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
@@ -262,10 +263,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 u4 = *reinterpret_cast<const uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1))));
-                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u4);
+                                const uint32_t *h = reinterpret_cast<const uint32_t *>(&u4);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    const float2 f = __bfloat1622float2(h[e]);
+                                    const float2 f = unpack2(h[e], p.f16);
                                     v[q * 8 + e * 2] += f.x;
                                     v[q * 8 + e * 2 + 1] += f.y;
                                 }
@@ -281,9 +282,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint4 u4;
-                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u4);
+                            uint32_t *h = reinterpret_cast<uint32_t *>(&u4);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                            for (int e = 0; e < 4; ++e) h[e] = pack2(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1], p.f16);
                             *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = u4;
                         }
                         if (dst_f32) {
@@ -342,7 +343,7 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
     auto buf_id = [&](const void *ptr) { for (int i = 0; i < n_bufs; ++i) if (bufs[i] == ptr) return i; return -1; };
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
-        MZB_CHECK_ARG(o.op == MZ_OP_CONV && o.dtype == MZ_BF16 && o.use_tc && o.w_layout == 1 && o.ksize == 3 && o.cin == CH && o.cout == CH &&
+        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.use_tc && o.w_layout == 1 && o.ksize == 3 && o.cin == CH && o.cout == CH &&
                           o.H == LAT_H && o.W == LAT_W, "op is not a stackable 3x3 256->256 convolution on the 4x5 latent");
         StackLayer &l = L[i];
         l.src = buf_id(o.src); l.dst = buf_id(o.dst); l.res = o.res ? buf_id(o.res) : -1;
@@ -353,7 +354,7 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
         cuuint64_t strides[1] = {BLOCK_K * 2};
         cuuint32_t box[2] = {BLOCK_K, CH / 2};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&l.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&l.map_b, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
@@ -361,9 +362,9 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
 }
 
 int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
-                 void *stream)
+                 int dtype, void *stream)
 {
-    MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS && done, "bad argument");
+    MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
     EncodeTiledFn enc = encode_fn();
     if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -375,10 +376,11 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
         cuuint64_t strides[3] = {CH * 2, LAT_W * CH * 2, HW * CH * 2};
         cuuint32_t box[4] = {BLOCK_K, 1, 1, BLOCK_M};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&p.map_act[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&p.map_act[b], dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return -2; }
     }
+    p.f16 = dtype == MZ_F16;
     p.layers = reinterpret_cast<const StackLayer *>(blob_dev);
     p.nlayers = n_layers;
     p.done = done;

@@ -42,6 +42,7 @@ struct ConvParams {
     int mode;          // 0 spatial tiles, 1 pixel tiles
     int debug;         // profiling experiments only (env MZB_TC_DEBUG): 1 = epilogue without memory traffic, 2 = TMA only for the
                        // first k-step of a tile (MMAs run on stale shared memory), 4 = no MMAs
+    int f16;           // 16-bit element type: 0 = bf16, 1 = fp16
     int w_tiled;       // weights stored tile-contiguous [tap][cin/64][cout][64] instead of [cout][taps*cin]
     int S, hb, tile_rows, ytiles, groups, ntiles;   // groups = sample-group PAIRS per pixel (pixel mode); ntiles = pair-tiles
     __nv_bfloat16 *dst;
@@ -159,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc(N);
+            const uint32_t idesc = instr_desc(N, p.f16 != 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -274,10 +275,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 u4 = *reinterpret_cast<const uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1))));
-                                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u4);
+                                const uint32_t *h = reinterpret_cast<const uint32_t *>(&u4);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    const float2 f = __bfloat1622float2(h[e]);
+                                    const float2 f = unpack2(h[e], p.f16);
                                     v[q * 8 + e * 2] += f.x;
                                     v[q * 8 + e * 2 + 1] += f.y;
                                 }
@@ -288,9 +289,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint4 u4;
-                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u4);
+                            uint32_t *h = reinterpret_cast<uint32_t *>(&u4);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                            for (int e = 0; e < 4; ++e) h[e] = pack2(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1], p.f16);
                             *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = u4;
                         }
                         if (p.dst_f32) {
@@ -374,6 +375,8 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
     p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
     p.w_tiled = o.w_layout == 1;
+    p.f16 = o.dtype == MZ_F16;
+    const CUtensorMapDataType tm_type = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("MZB_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
 
     CUtensorMap map_a, map_b;
@@ -382,7 +385,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         cuuint64_t strides[3] = {(cuuint64_t)o.cin * 2, (cuuint64_t)o.W * o.cin * 2, (cuuint64_t)o.H * o.W * o.cin * 2};
         cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(p.mode == 1 ? 1 : o.W), (cuuint32_t)p.hb, (cuuint32_t)p.S};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(o.src), dims, strides, box, estr,
+        CUresult r = enc(&map_a, tm_type, 4, const_cast<void *>(o.src), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return -2; }
@@ -397,7 +400,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
         }
         cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(o.cout / 2)};     // each CTA of a pair loads half of the rows
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr,
+        CUresult r = enc(&map_b, tm_type, 2, const_cast<void *>(o.w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return -2; }

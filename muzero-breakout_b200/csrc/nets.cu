@@ -7,6 +7,7 @@
 // network forwards :94-99,151-167,225-241, MuZeroAgent._scale_state :314-328 and
 // utils.py ScalarTransforms.inverted_softmax_expectation :74-81 of the reference.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -19,9 +20,11 @@ namespace {
 
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 __device__ __forceinline__ float activate(float v, int act)
 {
@@ -147,6 +150,15 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16 
     *reinterpret_cast<uint2 *>(p) = u;
 }
 
+template <> __device__ __forceinline__ void store4<__half>(__half *p, float a, float b, float c, float d)
+{
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&lo);
+    u.y = *reinterpret_cast<uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst, T *__restrict__ dst2,
@@ -215,6 +227,14 @@ __device__ __forceinline__ void load8(const __nv_bfloat16 *p, float (&f)[8])
     const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
     for (int q = 0; q < 4; ++q) { const float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+}
+
+__device__ __forceinline__ void load8(const __half *p, float (&f)[8])
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t = __half22float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
 }
 
 template <typename T, int NOUT>
@@ -400,9 +420,10 @@ extern "C" int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream)
         const mz_op &o = ops[i];
         int rc;
         if (o.dtype == MZ_F32) rc = run_op<float>(o, nsamples, st);
-        else if (o.dtype == MZ_BF16) {
+        else if (o.dtype == MZ_BF16 || o.dtype == MZ_F16) {
             if (o.op == MZ_OP_CONV && o.use_tc) rc = mzb::conv_tc_launch(o, nsamples, st);
-            else rc = run_op<__nv_bfloat16>(o, nsamples, st);
+            else if (o.dtype == MZ_BF16) rc = run_op<__nv_bfloat16>(o, nsamples, st);
+            else rc = run_op<__half>(o, nsamples, st);
         } else {
             mzb::set_error("mz_run: op %d has unknown dtype %d", i, o.dtype);
             return -1;

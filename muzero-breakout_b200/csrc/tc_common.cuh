@@ -5,6 +5,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -136,10 +137,24 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=256 (the pair), N
-__device__ __forceinline__ uint32_t instr_desc(int N)
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both
+// K-major, M=256 (the pair), N
+__device__ __forceinline__ uint32_t instr_desc(int N, bool f16 = false)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+}
+// two packed 16-bit activations <-> floats; `f16` is uniform per launch
+__device__ __forceinline__ float2 unpack2(uint32_t u, bool f16)
+{
+    if (f16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16)
+{
+    if (f16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t *>(&h); }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
 }
 
 __device__ __forceinline__ float activate(float v, int act)

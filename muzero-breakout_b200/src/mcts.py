@@ -97,7 +97,7 @@ class _SearchPlan:
         dev = nets.device
         H, W = nets.latent_hw
         ch, hw = nets.latent_ch, H * W
-        esz = 2 if nets.dt == BF16 else 4
+        esz = 4 if nets.dt == F32 else 2
         self.tree = TreeBuffers(B, S, c1, c2, discount, dev, latent_bytes=hw * ch * esz)
         self.noise_weight = noise_weight
         t = self.tree

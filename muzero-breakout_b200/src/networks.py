@@ -9,8 +9,9 @@ evaluate the representation / dynamics / prediction networks.
         .prediction(hidden)                    <-> MuZeroAgent.evaluate_state            :300-312
         .inverted_softmax_expectation(logits)  <-> ScalarTransforms (utils.py:74-81)
 
-precision "bf16": bf16 weights and activations, tcgen05 tensor-core convolutions (csrc/conv_tc.cu),
-fp32 accumulation and epilogues; "f32": fp32 everything on CUDA cores (the 1e-5 parity path).
+precision "bf16": bf16 weights and activations, tcgen05 tensor-core convolutions (csrc/conv_tc.cu, conv_stack.cu),
+fp32 accumulation and epilogues; "f16": the same path and speed with fp16 storage (11-bit mantissa: ~8x closer to
+the fp32 reference, range 65504); "f32": fp32 everything on CUDA cores (the 1e-5 parity path).
 Eval-mode BatchNorm and the conv bias are folded into a per-channel fp32 (scale, shift) applied in the
 convolution epilogue; the three one-hot action planes of the dynamics input become a per-action bias
 table (they are spatially constant, so their convolution is a [3][20][256] lookup).
@@ -27,7 +28,7 @@ import torch.nn.functional as F
 from .. import _lib
 
 OP_CONV, OP_POOL2, OP_SCALE, OP_HEAD, OP_NCHW_IN, OP_NHWC_OUT = range(6)
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT = {"none": 0, "relu": 1, "leaky_relu": 2, "silu": 3, "gelu": 4}   # utils.py:99-108
 
 
@@ -48,7 +49,7 @@ def _p(t):
 
 def _stackable(o) -> bool:
     """3x3 256->256 tensor-core convolution on the 4x5 latent with tile-contiguous weights (csrc/conv_stack.cu)."""
-    return (o.op == OP_CONV and o.dtype == BF16 and o.use_tc == 1 and o.w_layout == 1 and o.ksize == 3 and o.cin == 256
+    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize == 3 and o.cin == 256
             and o.cout == 256 and o.H == 4 and o.W == 5)
 
 
@@ -77,10 +78,11 @@ class _Stack:
         self.blob = blob.to(device)
         self.done = torch.zeros(self.nlayers * ((n + 127) // 128) * 20, dtype=torch.int32, device=device)
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
+        self.dtype = ops[0].dtype
 
     def run(self, st):
         _lib.check(_lib.lib().mz_stack_run(self.blob.data_ptr(), self.nlayers, self.n, self.bufs, self.nbufs, self.act_idx,
-                                           self.done.data_ptr(), st))
+                                           self.done.data_ptr(), self.dtype, st))
 
 
 class Program:
@@ -237,15 +239,16 @@ class _Lin:
 class PackedNetworks:
     def __init__(self, agent, model_cfg: dict | None = None, precision: str = "bf16", device="cuda", use_tc: bool | None = None):
         _lib.require_cuda()
-        if precision not in ("bf16", "f32"):
-            raise ValueError("precision must be 'bf16' or 'f32'")
+        if precision not in ("bf16", "f16", "f32"):
+            raise ValueError("precision must be 'bf16', 'f16' or 'f32'")
         sd = agent if isinstance(agent, dict) else agent.state_dict()
         cfg = model_cfg or getattr(agent, "cfg", None) or {}
         self.device = torch.device(device)
         self.precision = precision
-        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.dt = BF16 if precision == "bf16" else F32
-        self.use_tc = (precision == "bf16") if use_tc is None else bool(use_tc and precision == "bf16")
+        self.dtype = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[precision]
+        self.dt = {"bf16": BF16, "f16": F16, "f32": F32}[precision]
+        half = precision in ("bf16", "f16")
+        self.use_tc = half if use_tc is None else bool(use_tc and half)
         self.fuse_stacks = self.use_tc and os.environ.get("MZB_NO_STACK", "0") != "1"   # whole trunks in one persistent launch
         self.num_supports = int(cfg.get("num_supports", 11))
         self.supports_min, self.supports_max = cfg.get("supports_min", -5), cfg.get("supports_max", 5)

@@ -175,3 +175,19 @@ def test_fused_trunk_launch_equals_layer_by_layer(agent, n):
         b_p, b_v = plain.prediction(h)
         for x, y, what in ((a_h, b_h, "latent"), (a_r, b_r, "reward"), (a_p, b_p, "policy"), (a_v, b_v, "value")):
             assert torch.equal(x, y), f"n={n} rep={rep} {what}: fused and per-layer launches differ (max {float((x - y).abs().max()):.3e})"
+
+
+def test_f16_pipeline_vs_reference(agent, rec):
+    """precision="f16": same tensor-core kernels with fp16 storage.  Measured here against the fp32 reference outputs;
+    bound 2.5e-3 relative to range (emulation of the rounding points on the CPU predicts ~1.2e-3)."""
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    nets = PackedNetworks(agent, agent.cfg, precision="f16")
+    h = torch.from_numpy(rec["hidden"])
+    h2, rew = nets.dynamics(h, _planes(rec["dyn_actions"]))
+    pol, val = nets.prediction(h)
+    hid = nets.representation(torch.from_numpy(rec["rep_in"]))
+    errs = dict(h2=rel(h2, rec["dyn_h"]), rew=rel(rew, rec["dyn_reward_logits"]), pol=rel(pol, rec["root_policy_logits"]),
+                val=rel(val, rec["root_value_logits"]), hid=rel(hid, rec["hidden"]))
+    print("f16 tensor-core pipeline vs fp32 reference (rel to range):", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, e in errs.items():
+        assert e <= 2.5e-3, f"{k}: f16 pipeline deviates {e:.2e} from the fp32 reference"

@@ -56,7 +56,7 @@ def _stepped(m, hidden, noise, seed):
     return t.out_value.cpu().numpy().copy(), t.out_visits.cpu().numpy().copy(), rec, plan
 
 
-@pytest.mark.parametrize("precision,B", [("f32", 5), ("bf16", 24), ("bf16", 333)])
+@pytest.mark.parametrize("precision,B", [("f32", 5), ("bf16", 24), ("bf16", 333), ("f16", 40)])
 def test_search_lockstep_identical_visits(agent, precision, B):
     m = make(agent, precision)
     g = torch.Generator().manual_seed(B)
