@@ -343,7 +343,7 @@ def bench_mcts(args, rank, local, world):
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"mcts: MCTSSearchVec.search, {B} roots x {S} simulations per GPU, random-init MuZero networks (config.yaml sizes), {args.precision}",
                    "trees_per_gpu": B, "num_simulations": S, "step": "one search() call = root prediction + S x (dynamics + prediction + backup/select)",
-                   "l2": f"latent store {B * (S + 2) * 10240 * (2 if args.precision == 'bf16' else 4) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
+                   "l2": f"latent store {B * (S + 2) * 10240 * (4 if args.precision == 'f32' else 2) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
                    "cuda_graph": bool(m.use_graph)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_sustained"], "traffic": CONV_TRAFFIC_PER_SAMPLE * B,
@@ -450,7 +450,7 @@ def main():
     ap.add_argument("--env-steps", type=int, default=200)
     ap.add_argument("--trees", type=int, default=4096, help="mcts workload: roots per GPU (BASELINE.json configs[2])")
     ap.add_argument("--sims", type=int, default=50)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
