@@ -173,8 +173,10 @@ class MCTSSearchVec:
         self.device = torch.device(s.get("cuda_device", "cuda"))
         self._model_cfg = cfg.get("model", {})
         self._nets = None
+        self._nets_external = False
         self._nets_key = None
         self._plans = {}
+        self.max_plans = int(s.get("max_plans", 3))
         self._calls = 0
 
     # ------------------------------------------------------------------ weights
@@ -190,9 +192,22 @@ class MCTSSearchVec:
         key = self._weights_key()
         if key != self._nets_key:
             m = self.mu_zero
-            self._nets = m if isinstance(m, PackedNetworks) else PackedNetworks(m, self._model_cfg, self.precision, self.device)
+            if isinstance(m, PackedNetworks):
+                self._nets, self._plans = m, {}
+            else:
+                fresh = PackedNetworks(m, self._model_cfg, self.precision, self.device)
+                old = self._nets
+                same = (old is not None and not self._nets_external and old.arenas.keys() == fresh.arenas.keys()
+                        and all(old.arenas[k].shape == fresh.arenas[k].shape for k in fresh.arenas))
+                if same:
+                    # target refresh (train_torch.py:361-367): same architecture -> overwrite the weight arenas in place;
+                    # every op program and captured CUDA graph keeps pointing at the same addresses
+                    for k, a in fresh.arenas.items():
+                        old.arenas[k].copy_(a)
+                else:
+                    self._nets, self._plans = fresh, {}
+            self._nets_external = isinstance(m, PackedNetworks)
             self._nets_key = key
-            self._plans = {}
         return self._nets
 
     # ------------------------------------------------------------------ search
@@ -205,7 +220,13 @@ class MCTSSearchVec:
         plan = self._plans.get(key)
         if plan is None:
             plan = _SearchPlan(nets, B, self.num_simulations, self.c1, self.c2, self.discount, float(self.noise_weight), self.use_graph)
-            self._plans = {key: plan}                       # one live plan: its buffers are the big allocation
+            # keep the few most recent plans: train_torch.py alternates between n_parallel roots (acting) and 2 roots
+            # (test rollout, :448-452) every iteration, and a plan is a graph capture plus its buffers
+            self._plans[key] = plan
+            while len(self._plans) > self.max_plans:
+                self._plans.pop(next(iter(self._plans)))
+        else:
+            self._plans[key] = self._plans.pop(key)         # most recently used last
         if noise is None:                                   # Dirichlet(0.25 * ones(3)) per tree, mcts.py:114
             conc = torch.full((B, len(self.actions)), self.dirchlet_alpha, device=self.device)
             noise = torch._sample_dirichlet(conc)
