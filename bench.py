@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 ENV_CFG = dict(n_parallel=24, paddle_hit_reward=0.0, brick_hit_reward=1.0, game_lost_reward=-1.0, game_won_reward=5.0)
 ENV_BYTES_PER_STEP = 3898       # 3840 frame + 4 reward + 12 valid + 2 done + 8 action + 32 SoA
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
-ENV_TRAFFIC_PER_ENV = (1.93e6 + 196.0e6) / 65536     # r1_env_step_final_full.txt, 65 536 envs per launch (the L2 keeps part of the frames)
+ENV_TRAFFIC_PER_ENV = (1.92e6 + 196.2e6) / 65536     # r1_env_step_final_full.txt, 65 536 envs per launch (the L2 keeps part of the frames)
 CONV_TRAFFIC_PER_SAMPLE = (43.2e6 + 8.8e6) / 4096    # r1_conv_tc_final_full.txt, 3x3 256->256 conv, 4096 samples per launch
 
 

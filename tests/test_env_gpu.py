@@ -213,3 +213,23 @@ def test_errors_are_loud():
     bad = torch.zeros(2, 3, 16, 20)                                        # no ball pixel
     with pytest.raises(IndexError):
         env.step(bad, torch.tensor([1, 1]), torch.zeros(2, dtype=torch.bool))
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 31, 33])
+def test_tiny_batches_vs_oracle(B):
+    """batch sizes below one warp task / one block, host tensors (the reference-facing call)."""
+    env = make_env(B)
+    orc = oracle.EnvOracle(B)
+    torch.manual_seed(B)
+    state, _ = env.reset()
+    torch.manual_seed(B)
+    ostate = orc.reset()
+    _eq(state, ostate, "reset")
+    done, odone = torch.zeros(B, dtype=torch.bool), np.zeros(B, np.uint8)
+    g = torch.Generator().manual_seed(B)
+    for t in range(70):
+        a = torch.randint(0, 3, (B,), generator=g)
+        state, reward, done, valid = env.step(state, a, done)
+        ostate, oreward, odone, ovalid = orc.step(ostate, a, odone)
+        _eq(state, ostate, f"step {t} state"); _eq(reward, oreward, f"step {t} reward")
+        _eq(done.to(torch.uint8), odone, f"step {t} done"); _eq(valid, ovalid, f"step {t} valid")

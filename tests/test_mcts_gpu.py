@@ -51,7 +51,8 @@ def test_tree_lockstep_vs_reference_golden(golden_dir):
         assert np.array_equal(value.view(np.uint32), rec["value"].view(np.uint32)), f"{name}: root value not bit-identical"
 
 
-@pytest.mark.parametrize("B,S,mode", [(3000, 50, "mild"), (777, 100, "optimistic"), (4096, 50, "ties")])
+@pytest.mark.parametrize("B,S,mode", [(3000, 50, "mild"), (777, 100, "optimistic"), (4096, 50, "ties"), (1, 1, "mild"), (2, 2, "ties"),
+                                      (33, 300, "optimistic")])
 def test_tree_large_batch_vs_oracle(B, S, mode):
     """Thousands of trees, random network outputs, S=100 exercises node slots beyond the shared-memory
     stage; 'ties' feeds constant outputs so that every pUCT call is an exact tie."""
