@@ -89,4 +89,4 @@ def test_tree_large_batch_vs_oracle(B, S, mode):
     assert np.array_equal(t.out_value.cpu().numpy().view(np.uint32), ovalue.view(np.uint32))
     assert np.all(ovisits.sum(1) == S)
     hist = t.depth_hist.cpu().numpy()
-    assert hist.sum() == B * S and (hist[1:].sum() > 0)
+    assert hist.sum() == B * S and (S < 3 or hist[1:].sum() > 0)
