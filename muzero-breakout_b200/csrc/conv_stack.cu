@@ -25,7 +25,8 @@ constexpr int MAX_BUFS = 3;
 constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
 
 struct alignas(64) StackLayer {          // device-resident descriptor of one convolution of the trunk
-    CUtensorMap map_b;                   // tile-contiguous weights [9][4][256][64]
+    CUtensorMap map_b;                   // tile-contiguous weights [9][4][256][64], box = 128 rows (half of N = 256)
+    CUtensorMap map_b_half;              // same tensor, box = 64 rows (half of an N = 128 slice: small-batch mode)
     const float *scale, *shift;          // [256]
     const float *act_bias;               // [3][20][256] or NULL
     float *dst_f32;                      // optional fp32 copy of the output or NULL
@@ -42,7 +43,7 @@ struct StackParams {
     const int *act_idx;
     int f16;                             // 16-bit element type: 0 = bf16, 1 = fp16
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
-    int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs)
+    int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs * N/NT)
 };
 
 __device__ __forceinline__ uint32_t tap_mask(int y, int x)
@@ -56,16 +57,13 @@ __device__ __forceinline__ uint32_t tap_mask(int y, int x)
     return m;
 }
 
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
+// NT = output channels per tile: 256 (one tile per pixel and group pair) or 128 (two tiles: small batches have too few
+// pixel tiles to fill the chip, so the N dimension is split to halve the per-layer latency and double the busy SMs)
+template <int NT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
 {
     constexpr int N = CH;
+    constexpr int nsplit = CH / NT;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;
     float *s_scale = reinterpret_cast<float *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);   // [scale 256 | shift 256] of the current layer
@@ -100,15 +98,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            constexpr uint32_t a_bytes = BLOCK_M * BLOCK_K * 2, b_bytes = (N / 2) * BLOCK_K * 2;
+            constexpr uint32_t a_bytes = BLOCK_M * BLOCK_K * 2, b_bytes = (NT / 2) * BLOCK_K * 2;
             const uint32_t lead_full = map_to_cta(bar_full, 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
                 const StackLayer *L = p.layers + layer;
                 const int src = L->src;
+                const CUtensorMap *map_b = NT == CH ? &L->map_b : &L->map_b_half;
                 for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
-                    const int pix = tile / p.pairs, g = 2 * (tile - pix * p.pairs) + rank;
+                    const int ns = tile % nsplit, t2 = tile / nsplit;
+                    const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0);
                     if (layer > 0 && g < p.groups) {
@@ -122,12 +122,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                             for (int tap = 0; tap < 9; ++tap) {
                                 if (p.fine && ((taps >> tap) & 1u)) {
                                     const int v = *reinterpret_cast<const volatile int *>(flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1));
-                                    ready &= v >= NUM_EPI_WARPS;
+                                    ready &= v >= NUM_EPI_WARPS * nsplit;
                                 }
                             }
                             if (!p.fine) {
 #pragma unroll
-                                for (int q = 0; q < HW; ++q) ready &= *reinterpret_cast<const volatile int *>(flags + q) >= NUM_EPI_WARPS;
+                                for (int q = 0; q < HW; ++q) ready &= *reinterpret_cast<const volatile int *>(flags + q) >= NUM_EPI_WARPS * nsplit;
                             }
                             if (ready) break;
                             if (++spins > (1u << 26)) __trap();
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                             if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));
                             else mbar_arrive_cluster(lead_full + 8 * stage);
                             tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
-                            tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + rank * (N / 2));
+                            tma_load_2d(sb, map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + ns * NT + rank * (NT / 2));
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -156,16 +156,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc(N, p.f16 != 0);
+            const uint32_t idesc = instr_desc(NT, p.f16 != 0);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
                 for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
-                    const int pix = tile / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                    const int pix = (tile / nsplit) / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NT);
                     const int ksteps = __popc(tap_mask(y0, x0)) * kchunks;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
@@ -187,8 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
         // ===================== epilogue (warps 2..9) =====================
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int r = quarter * 32 + lane;
-        constexpr int ncols = N / 2, nchunks = ncols / 32, units = ncols / 8, row_bytes = ncols * 2, rows_per_it = 32 / units;
-        const int col0 = half * ncols;
+        constexpr int ncols = NT / 2, nchunks = ncols / 32, units = ncols / 8, row_bytes = ncols * 2, rows_per_it = 32 / units;
         const int my_u = lane % units, my_rsub = lane / units;
         const int etid = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
         uint8_t *stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
@@ -210,7 +209,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
             const int act = L->act;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                 const int buf = it & 1;
-                const int pix = tile / p.pairs, g = 2 * (tile - pix * p.pairs) + rank;
+                const int ns = tile % nsplit, t2 = tile / nsplit;
+                const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
+                const int col0 = ns * NT + half * ncols;
                 const int s = g * BLOCK_M + r;
                 const bool valid = s < p.n;
                 const long long m = valid ? (long long)s * HW + pix : -1;        // global output row
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     __syncwarp();
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NT + half * ncols);
                 tmem_ld32_async(taddr, acc[0]);
 #pragma unroll
                 for (int c = 0; c < nchunks; ++c) {
@@ -357,6 +358,10 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
         CUresult r = enc(&l.map_b, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
+        cuuint32_t box_half[2] = {BLOCK_K, CH / 4};
+        r = enc(&l.map_b_half, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides,
+                box_half, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled(weights, half box) failed: %d", (int)r); return -2; }
     }
     return 0;
 }
@@ -389,11 +394,14 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.n = nsamples;
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.pairs = (p.groups + 1) / 2;
-    p.ntiles = HW * p.pairs;
+    // few pixel tiles (<= half of the 74 CTA pairs): split N in two so that twice as many pairs work on half-size tiles
+    const bool split = HW * p.pairs * 2 <= mzb::kNumSMs / 2;
+    p.ntiles = HW * p.pairs * (split ? 2 : 1);
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups * HW, st));
     static bool attr_set = false;
     if (!attr_set) {
-        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
         attr_set = true;
     }
     const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
@@ -407,7 +415,8 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel, p));
+    if (split) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<128>, p));
+    else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<256>, p));
     MZB_LAUNCH_CHECK();
     return 0;
 }
