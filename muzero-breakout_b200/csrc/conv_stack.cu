@@ -42,9 +42,19 @@ struct StackParams {
     int *done;                           // [nlayers][groups][20 pixels], zeroed before the launch
     const int *act_idx;
     int f16;                             // 16-bit element type: 0 = bf16, 1 = fp16
+    int trace;                           // profiling (env MZB_STACK_TRACE=1): cluster 0's leader records per-layer timestamps
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
     int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs * N/NT)
 };
+
+__device__ unsigned long long g_stack_trace[6 * 64];
+__device__ __forceinline__ unsigned long long gtime_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define STRACE(slot, layer) do { if (p.trace && blockIdx.x == 0 && (layer) < 64) g_stack_trace[(slot) * 64 + (layer)] = gtime_ns(); } while (0)
 
 __device__ __forceinline__ uint32_t tap_mask(int y, int x)
 {
@@ -57,17 +67,42 @@ __device__ __forceinline__ uint32_t tap_mask(int y, int x)
     return m;
 }
 
+// Shared-memory geometry of one kernel variant: A ring (AROWS x 128 B per k-step; the UMMA always reads 128 rows, the rows
+// past AROWS alias the following slots / the tail pad and only feed output rows that are discarded), B ring (this CTA's
+// NT/2 weight rows per k-step), the epilogue staging tiles, scale/shift, barriers.  Smaller slots = more k-steps in flight:
+// a k-step's TMA round trip is ~1.4 us regardless of its size, so a small batch is bound by stages / latency.
+template <int NT, int AROWS>
+struct Geo {
+    static constexpr int A_SLOT = AROWS * BLOCK_K * 2;
+    static constexpr int B_SLOT = (NT / 2) * BLOCK_K * 2;
+    static constexpr int A_PAD = BLOCK_M * BLOCK_K * 2 - A_SLOT;
+    static constexpr int EPI_WARP = 32 * (NT / 2) * 2;
+    static constexpr int FIXED = A_PAD + NUM_EPI_WARPS * EPI_WARP + 2 * 256 * (int)sizeof(float) + 384;
+    static constexpr int RAW = (232448 - FIXED) / (A_SLOT + B_SLOT);
+    static constexpr int STAGES = RAW > 16 ? 16 : RAW;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_SLOT + A_PAD;
+    static constexpr int EPI_OFF = B_OFF + STAGES * B_SLOT;
+    static constexpr int SS_OFF = EPI_OFF + NUM_EPI_WARPS * EPI_WARP;
+    static constexpr int BAR_OFF = SS_OFF + 2 * 256 * (int)sizeof(float);
+    static constexpr size_t SMEM = BAR_OFF + 384;
+    static_assert(STAGES >= 4 && SMEM <= 232448, "shared-memory budget");
+    static_assert(B_OFF % 1024 == 0 && A_SLOT % 1024 == 0 && B_SLOT % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+};
+
 // NT = output channels per tile: 256 (one tile per pixel and group pair) or 128 (two tiles: small batches have too few
 // pixel tiles to fill the chip, so the N dimension is split to halve the per-layer latency and double the busy SMs)
-template <int NT>
+template <int NT, int AROWS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
 {
     constexpr int N = CH;
     constexpr int nsplit = CH / NT;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *epi_stage = smem + STAGES * STAGE_BYTES;
-    float *s_scale = reinterpret_cast<float *>(epi_stage + NUM_EPI_WARPS * EPI_STAGE_BYTES);   // [scale 256 | shift 256] of the current layer
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_scale + 2 * 256);
+    using G = Geo<NT, AROWS>;
+    constexpr int STAGES = G::STAGES;                 // shadows the one-layer kernel's constant
+    uint8_t *epi_stage = smem + G::EPI_OFF;
+    float *s_scale = reinterpret_cast<float *>(smem + G::SS_OFF);   // [scale 256 | shift 256] of the current layer
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::BAR_OFF);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
@@ -98,7 +133,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            constexpr uint32_t a_bytes = BLOCK_M * BLOCK_K * 2, b_bytes = (NT / 2) * BLOCK_K * 2;
+            constexpr uint32_t a_bytes = G::A_SLOT, b_bytes = G::B_SLOT;
             const uint32_t lead_full = map_to_cta(bar_full, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -111,6 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0);
+                    if (tile == cluster_id) STRACE(0, layer);
                     if (layer > 0 && g < p.groups) {
                         // the previous layer's output of this sample group at the in-bounds neighbour pixels (= the taps):
                         // all 8 epilogue warps of each of those tiles have stored and fenced
@@ -136,13 +172,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                         asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: pairs with the epilogues' red.release
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
+                    if (tile == cluster_id) STRACE(1, layer);
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((taps >> tap) & 1u)) continue;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
 #pragma unroll
                         for (int kc = 0; kc < kchunks; ++kc) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                            const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                             if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));
                             else mbar_arrive_cluster(lead_full + 8 * stage);
                             tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
@@ -170,7 +207,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                        if (ks == 0 && tile == cluster_id) STRACE(2, layer);
+                        const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
@@ -180,6 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit_pair(bar_tfull + 8 * buf);
+                    if (tile == cluster_id) STRACE(3, layer);
                 }
             }
         }
@@ -190,7 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
         constexpr int ncols = NT / 2, nchunks = ncols / 32, units = ncols / 8, row_bytes = ncols * 2, rows_per_it = 32 / units;
         const int my_u = lane % units, my_rsub = lane / units;
         const int etid = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
-        uint8_t *stg = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
+        uint8_t *stg = epi_stage + (warp - 2) * G::EPI_WARP;
         const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
         int it = 0;
         for (int layer = 0; layer < p.nlayers; ++layer) {
@@ -231,6 +270,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 uint32_t acc[2][32];
                 mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
                 tc_fence_after();
+                if (warp == 2 && lane == 0 && tile == cluster_id) STRACE(4, layer);
                 if (res_base) {
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     __syncwarp();
@@ -312,6 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __syncwarp();
                 if (lane == 0 && g < p.groups) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + ((size_t)layer * p.groups + g) * HW + pix) : "memory");
+                if (warp == 2 && lane == 0 && tile == cluster_id) STRACE(5, layer);
             }
         }
     }
@@ -325,13 +366,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     }
 }
 
-constexpr size_t STACK_SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + (size_t)NUM_EPI_WARPS * EPI_STAGE_BYTES + 2 * 256 * sizeof(float) + 128;
 
 }  // namespace
 
 extern "C" {
 
 size_t mz_stack_layer_bytes(void) { return sizeof(StackLayer); }
+
+int mz_stack_trace(unsigned long long *host_out)   // profiling aid: copies the 6 x 64 trace words
+{
+    return cudaMemcpyFromSymbol(host_out, g_stack_trace, sizeof(unsigned long long) * 6 * 64) == cudaSuccess ? 0 : -2;
+}
 
 int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs)
 {
@@ -374,12 +419,13 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     cudaStream_t st = (cudaStream_t)stream;
     StackParams p{};
+    const int arows = nsamples <= 32 ? 32 : BLOCK_M;      // rows of the activation box: tiny batches load only what exists
     for (int b = 0; b < MAX_BUFS; ++b) {
         void *ptr = bufs[b < n_bufs ? b : 0];
         p.act[b] = (__nv_bfloat16 *)ptr;
         cuuint64_t dims[4] = {CH, LAT_W, LAT_H, (cuuint64_t)nsamples};
         cuuint64_t strides[3] = {CH * 2, LAT_W * CH * 2, HW * CH * 2};
-        cuuint32_t box[4] = {BLOCK_K, 1, 1, BLOCK_M};
+        cuuint32_t box[4] = {BLOCK_K, 1, 1, (cuuint32_t)arows};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p.map_act[b], dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -390,6 +436,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.nlayers = n_layers;
     p.done = done;
     p.act_idx = act_idx;
+    { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_STACK_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
     { static int fine = -1; if (fine < 0) { const char *e = getenv("MZB_STACK_FINE"); fine = e ? atoi(e) : 1; } p.fine = fine; }
     p.n = nsamples;
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
@@ -400,23 +447,25 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups * HW, st));
     static bool attr_set = false;
     if (!attr_set) {
-        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
-        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<256, 128>::SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<128, 128>::SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<128, 32>::SMEM));
         attr_set = true;
     }
     const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = STACK_SMEM_BYTES;
+    cfg.dynamicSmemBytes = !split ? Geo<256, 128>::SMEM : (arows == 32 ? Geo<128, 32>::SMEM : Geo<128, 128>::SMEM);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (split) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<128>, p));
-    else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<256>, p));
+    if (!split) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<256, 128>, p));
+    else if (arows == 32) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<128, 32>, p));
+    else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<128, 128>, p));
     MZB_LAUNCH_CHECK();
     return 0;
 }
