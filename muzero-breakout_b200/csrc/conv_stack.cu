@@ -54,7 +54,7 @@ __device__ __forceinline__ unsigned long long gtime_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define STRACE(slot, layer) do { if (p.trace && blockIdx.x == 0 && (layer) < 64) g_stack_trace[(slot) * 64 + (layer)] = gtime_ns(); } while (0)
+#define STRACE(slot, layer) do { if (p.trace == 1 && blockIdx.x == 0 && (layer) < 64) g_stack_trace[(slot) * 64 + (layer)] = gtime_ns(); } while (0)
 
 __device__ __forceinline__ uint32_t tap_mask(int y, int x)
 {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
         if (lane == 0) {
             constexpr uint32_t a_bytes = G::A_SLOT, b_bytes = G::B_SLOT;
             const uint32_t lead_full = map_to_cta(bar_full, 0);
-            int stage = 0;
+            int stage = 0, nks = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
                 const StackLayer *L = p.layers + layer;
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                             const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                             if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));
                             else mbar_arrive_cluster(lead_full + 8 * stage);
+                            if (p.trace == 2 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && nks < 64) g_stack_trace[nks++] = gtime_ns();
                             tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
                             tma_load_2d(sb, map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + ns * NT + rank * (NT / 2));
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         if (ks == 0 && tile == cluster_id) STRACE(2, layer);
+                        if (p.trace == 3 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && ks < 64) g_stack_trace[ks] = gtime_ns();
                         const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
@@ -419,7 +421,9 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     cudaStream_t st = (cudaStream_t)stream;
     StackParams p{};
-    const int arows = nsamples <= 32 ? 32 : BLOCK_M;      // rows of the activation box: tiny batches load only what exists
+    static int want_split0 = -1;
+    if (want_split0 < 0) { const char *e = getenv("MZB_STACK_SPLIT"); want_split0 = e ? atoi(e) : 0; }
+    const int arows = (want_split0 && nsamples <= 32) ? 32 : BLOCK_M;   // rows of the activation box (split mode: tiny batches load only what exists)
     for (int b = 0; b < MAX_BUFS; ++b) {
         void *ptr = bufs[b < n_bufs ? b : 0];
         p.act[b] = (__nv_bfloat16 *)ptr;
@@ -441,8 +445,13 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.n = nsamples;
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.pairs = (p.groups + 1) / 2;
-    // few pixel tiles (<= half of the 74 CTA pairs): split N in two so that twice as many pairs work on half-size tiles
-    const bool split = HW * p.pairs * 2 <= mzb::kNumSMs / 2;
+    // Few pixel tiles (<= half of the 74 CTA pairs): N can be split in two so that twice as many pairs work on half-size
+    // tiles with a deeper pipeline.  Measured at 24 samples: no gain (51 ms per 50-simulation search either way) -- a
+    // k-step costs the single MMA-issuing thread ~300 ns (barrier wait + fence + 4 tcgen05.mma + commit, traced with
+    // MZB_STACK_TRACE=3) whatever N is, so small batches are issue-bound, not tensor-bound.  Off unless MZB_STACK_SPLIT=1.
+    static int want_split = -1;
+    if (want_split < 0) { const char *e = getenv("MZB_STACK_SPLIT"); want_split = e ? atoi(e) : 0; }
+    const bool split = want_split && HW * p.pairs * 2 <= mzb::kNumSMs / 2;
     p.ntiles = HW * p.pairs * (split ? 2 : 1);
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups * HW, st));
     static bool attr_set = false;
