@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = instr_desc(NT, p.f16 != 0);
             int stage = 0, it = 0;
-            uint32_t phase = 0, ready = 0;
+            uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
                 for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
@@ -206,26 +206,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NT);
                     const int ksteps = __popc(tap_mask(y0, x0)) * kchunks;
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const bool tr4 = p.trace == 4 && layer == 1 && tile == cluster_id && blockIdx.x == 0 && ks >= 4 && ks < 12;
-                        if (tr4) g_stack_trace[(ks - 4) * 4 + 0] = clock64();
-                        if (!ready) mbar_wait(bar_full + 8 * stage, phase);     // usually already seen complete by the early probe
+                        mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        if (tr4) g_stack_trace[(ks - 4) * 4 + 1] = clock64();
                         if (ks == 0 && tile == cluster_id) STRACE(2, layer);
                         if (p.trace == 3 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && ks < 64) g_stack_trace[ks] = gtime_ns();
-                        const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
-                        const uint32_t nphase = nstage == 0 ? phase ^ 1 : phase;
-                        const uint32_t nready = mbar_test(bar_full + 8 * nstage, nphase);   // probe the next stage while the MMAs issue
                         const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
                                            (ks | k) ? 1u : 0u);
-                        if (tr4) g_stack_trace[(ks - 4) * 4 + 2] = clock64();
                         umma_commit_pair(bar_empty + 8 * stage);
-                        if (tr4) g_stack_trace[(ks - 4) * 4 + 3] = clock64();
-                        stage = nstage; phase = nphase; ready = nready;
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit_pair(bar_tfull + 8 * buf);
                     if (tile == cluster_id) STRACE(3, layer);

@@ -162,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0 && rank == 0) {
             const uint32_t idesc = instr_desc(N, p.f16 != 0);
             int stage = 0;
-            uint32_t phase = 0, ready = 0;
+            uint32_t phase = 0;
             int it = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                 const int buf = it & 1;
@@ -173,11 +173,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
                 const int ksteps = __popc(decode_tile(p, tile, rank).taps) * kchunks;
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    if (!ready) mbar_wait(bar_full + 8 * stage, phase);     // TMA bytes have landed (usually already seen by the early probe)
+                    mbar_wait(bar_full + 8 * stage, phase);                 // TMA bytes have landed
                     tc_fence_after();
-                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
-                    const uint32_t nphase = nstage == 0 ? phase ^ 1 : phase;
-                    const uint32_t nready = mbar_test(bar_full + 8 * nstage, nphase);   // probe the next stage while the MMAs issue
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
@@ -185,7 +182,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (!(p.debug & 4)) umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
                                   (ks | k) ? 1u : 0u);
                     umma_commit_pair(bar_empty + 8 * stage);                // frees slot `stage` in both CTAs when the MMAs retire
-                    stage = nstage; phase = nphase; ready = nready;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_pair(bar_tfull + 8 * buf);                      // accumulator complete -> both CTAs' epilogues
                 TRACE(2, it);

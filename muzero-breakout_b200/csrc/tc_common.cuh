@@ -36,20 +36,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// non-blocking probe of a phase; used to start looking at the NEXT stage's barrier before the MMAs of the current one are
-// issued, so that its ~100-cycle latency overlaps them instead of sitting on the issuing thread's critical path
-__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.b32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done;
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;

@@ -14,8 +14,3 @@ L = _lib.lib(); L.mz_stack_trace.argtypes = [ctypes.c_void_p]
 L.mz_stack_trace(buf.ctypes.data)
 t = buf[:16].astype(np.int64)
 print("mode", os.environ.get("MZB_STACK_TRACE"), "n", n, "k-step timestamps (ns since first):", (t - t[0]).tolist())
-
-if os.environ.get("MZB_STACK_TRACE") == "4":
-    c = buf[:32].astype(np.int64).reshape(8, 4)
-    for k in range(8):
-        print(f"k-step {k+4}: wait+fence {c[k,1]-c[k,0]:5d}  4xMMA issue {c[k,2]-c[k,1]:5d}  commit {c[k,3]-c[k,2]:5d}  loop tail {(c[k+1,0]-c[k,3]) if k < 7 else 0:5d}  cycles")
