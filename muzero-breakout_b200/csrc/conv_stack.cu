@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int MAX_BUFS = 4;
+constexpr int MAX_BUFS = 3;
 constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
 
 struct alignas(64) StackLayer {          // device-resident descriptor of one convolution of the trunk
@@ -32,7 +32,6 @@ struct alignas(64) StackLayer {          // device-resident descriptor of one co
     float *dst_f32;                      // optional fp32 copy of the output or NULL
     int src, dst, res;                   // activation buffer ids; res = -1: no residual
     int act;
-    int ksize;                           // 3, or 1 (only as the last layer of a stack: a 1x1 head convolution)
 };
 
 struct StackParams {
@@ -142,12 +141,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 const StackLayer *L = p.layers + layer;
                 const int src = L->src;
                 const CUtensorMap *map_b = NT == CH ? &L->map_b : &L->map_b_half;
-                const bool one = L->ksize == 1;                  // 1x1: centre tap only, weight tiles indexed as tap 0
                 for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
                     const int ns = tile % nsplit, t2 = tile / nsplit;
                     const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
-                    const uint32_t taps = one ? (1u << 4) : tap_mask(y0, x0);
+                    const uint32_t taps = tap_mask(y0, x0);
                     if (tile == cluster_id) STRACE(0, layer);
                     if (layer > 0 && g < p.groups) {
                         // the previous layer's output of this sample group at the in-bounds neighbour pixels (= the taps):
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                             else mbar_arrive_cluster(lead_full + 8 * stage);
                             if (p.trace == 2 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && nks < 64) g_stack_trace[nks++] = gtime_ns();
                             tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
-                            tma_load_2d(sb, map_b, lead_full + 8 * stage, 0, ((one ? 0 : tap) * kchunks + kc) * N + ns * NT + rank * (NT / 2));
+                            tma_load_2d(sb, map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + ns * NT + rank * (NT / 2));
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -200,14 +198,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
-                const bool one = p.layers[layer].ksize == 1;
                 for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
                     const int pix = (tile / nsplit) / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NT);
-                    const int ksteps = (one ? 1 : __popc(tap_mask(y0, x0))) * kchunks;
+                    const int ksteps = __popc(tap_mask(y0, x0)) * kchunks;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
@@ -394,15 +391,14 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
     auto buf_id = [&](const void *ptr) { for (int i = 0; i < n_bufs; ++i) if (bufs[i] == ptr) return i; return -1; };
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
-        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.use_tc && o.w_layout == 1 && (o.ksize == 3 || o.ksize == 1) && o.cin == CH && o.cout == CH &&
-                          o.H == LAT_H && o.W == LAT_W, "op is not a stackable 256->256 convolution on the 4x5 latent");
-        MZB_CHECK_ARG(o.ksize == 3 || i == n_ops - 1, "a 1x1 convolution can only be the last layer of a stack");
+        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.use_tc && o.w_layout == 1 && o.ksize == 3 && o.cin == CH && o.cout == CH &&
+                          o.H == LAT_H && o.W == LAT_W, "op is not a stackable 3x3 256->256 convolution on the 4x5 latent");
         StackLayer &l = L[i];
         l.src = buf_id(o.src); l.dst = buf_id(o.dst); l.res = o.res ? buf_id(o.res) : -1;
         MZB_CHECK_ARG(l.src >= 0 && l.dst >= 0 && (!o.res || l.res >= 0), "op buffer is not one of the stack's activation buffers");
         MZB_CHECK_ARG(l.src != l.dst, "a convolution cannot run in place on its own input");
-        l.scale = o.scale; l.shift = o.shift; l.act_bias = o.act_bias; l.dst_f32 = o.dst_f32; l.act = o.act; l.ksize = o.ksize;
-        cuuint64_t dims[2] = {BLOCK_K, (cuuint64_t)(o.ksize * o.ksize) * (CH / BLOCK_K) * CH};
+        l.scale = o.scale; l.shift = o.shift; l.act_bias = o.act_bias; l.dst_f32 = o.dst_f32; l.act = o.act;
+        cuuint64_t dims[2] = {BLOCK_K, (cuuint64_t)9 * (CH / BLOCK_K) * CH};
         cuuint64_t strides[1] = {BLOCK_K * 2};
         cuuint32_t box[2] = {BLOCK_K, CH / 2};
         cuuint32_t estr[2] = {1, 1};

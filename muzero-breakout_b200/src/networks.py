@@ -49,7 +49,7 @@ def _p(t):
 
 def _stackable(o) -> bool:
     """3x3 256->256 tensor-core convolution on the 4x5 latent with tile-contiguous weights (csrc/conv_stack.cu)."""
-    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize in (1, 3) and o.cin == 256
+    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize == 3 and o.cin == 256
             and o.cout == 256 and o.H == 4 and o.W == 5)
 
 
@@ -64,7 +64,7 @@ class _Stack:
             for ptr in (o.src, o.dst, o.res):
                 if ptr and ptr not in bufs:
                     bufs.append(ptr)
-        self.ok = len(bufs) <= 4
+        self.ok = len(bufs) <= 3
         if not self.ok:
             return
         lb = L.mz_stack_layer_bytes()
@@ -126,8 +126,6 @@ class Program:
             j = i
             while self.fuse and j < len(self.ops) and _stackable(self.ops[j]):
                 j += 1
-                if self.ops[j - 1].ksize == 1:      # a 1x1 head convolution may only close a stack
-                    break
             stack = _Stack(self.ops[i:j], self.n, device) if j - i >= 2 else None
             if stack is not None and stack.ok:
                 flush()
@@ -292,27 +290,6 @@ class PackedNetworks:
     def _res(self, sd, prefix, act):
         return (self._conv(sd, prefix + ".conv1", prefix + ".bn1", act), self._conv(sd, prefix + ".conv2", prefix + ".bn2", act))
 
-    def _policy_value(self, sd, act, hw):
-        wp, wv = sd["pred_net.policy_head.0.conv.weight"], sd["pred_net.value_head.0.conv.weight"]     # (128,256,3,3), (128,256,1,1)
-        cp, cv = wp.shape[0], wv.shape[0]
-        w = torch.zeros(cp + cv, wp.shape[1], 3, 3, dtype=torch.float64)
-        w[:cp] = wp
-        w[cp:, :, 1, 1] = wv[:, :, 0, 0]
-        merged = {"pv.conv.weight": w, "pv.conv.bias": torch.cat([sd["pred_net.policy_head.0.conv.bias"], sd["pred_net.value_head.0.conv.bias"]])}
-        for k in ("weight", "bias", "running_mean", "running_var"):
-            merged["pv.bn." + k] = torch.cat([sd["pred_net.policy_head.0.bn." + k], sd["pred_net.value_head.0.bn." + k]])
-        conv = self._conv(merged, "pv.conv", "pv.bn", act)
-        C_ = cp + cv
-
-        def widen(key, lo, n):                              # Linear over (c, p) of ITS head -> over (p, c) of the merged 256 channels
-            lw = sd[key + ".weight"]
-            nout = lw.shape[0]
-            full = torch.zeros(nout, hw, C_, dtype=torch.float64)
-            full[:, :, lo:lo + n] = lw.reshape(nout, n, hw).permute(0, 2, 1)
-            return _Lin(self._dev(full.reshape(nout, hw * C_), torch.float32), self._dev(sd[key + ".bias"], torch.float32), nout)
-
-        return conv, widen("pred_net.policy_head.2", 0, cp), widen("pred_net.value_head.2", cp, cv)
-
     def _linear(self, sd, key, C_, HW):
         w = sd[key + ".weight"]                            # (nout, C*HW), column = c*HW + p  (Flatten of NCHW)
         nout = w.shape[0]
@@ -346,11 +323,10 @@ class PackedNetworks:
         a = acts["prediction_network"]
         n_pred = len({k.split(".")[2] for k in sd if k.startswith("pred_net.res_blocks.")})
         self.pred_res = [self._res(sd, f"pred_net.res_blocks.{i}", a) for i in range(n_pred)]
-        # policy head (3x3, 256->128) and value head (1x1, 256->128) read the same trunk output: one 3x3 256->256
-        # convolution computes both (value weights on the centre tap, exact zeros elsewhere), so it can ride at the end of
-        # the prediction trunk's persistent launch; the two Linear layers see the 256-channel result with zero weights on
-        # the other head's channels
-        self.pv_conv, self.policy_lin, self.value_lin = self._policy_value(sd, a, hw)
+        self.policy_conv = self._conv(sd, "pred_net.policy_head.0.conv", "pred_net.policy_head.0.bn", a)
+        self.policy_lin = self._linear(sd, "pred_net.policy_head.2", self.policy_conv.cout, hw)
+        self.value_conv = self._conv(sd, "pred_net.value_head.0.conv", "pred_net.value_head.0.bn", a)
+        self.value_lin = self._linear(sd, "pred_net.value_head.2", self.value_conv.cout, hw)
         self.num_actions = self.policy_lin.nout
         self._consolidate()
 
@@ -369,9 +345,8 @@ class PackedNetworks:
         conv(self.dyn_first)
         for a, b in self.dyn_res + self.pred_res:
             conv(a); conv(b)
-        conv(self.reward_conv)
-        conv(self.pv_conv)
-        for lin in (self.reward_lin, self.policy_lin, self.value_lin):
+        for c, lin in ((self.reward_conv, self.reward_lin), (self.policy_conv, self.policy_lin), (self.value_conv, self.value_lin)):
+            conv(c)
             out.extend([(lin, "w"), (lin, "b")])
         return out
 
@@ -419,8 +394,10 @@ class PackedNetworks:
                            dst_f32=last_f32 if i == len(blocks) - 1 else None)
         return cur
 
-    def _add_linear_head(self, prog, lin, H, W, cin, mid, mode, out, out_logits=None):
-        prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=cin, nout=lin.nout, head_mode=mode, src=mid, w=lin.w, shift=lin.b,
+    def _add_head(self, prog, conv, lin, H, W, src, mid, mode, out, out_logits=None):
+        self._add_conv(prog, conv, H, W, src, mid)
+        w, b, nout = lin.w, lin.b, lin.nout
+        prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=nout, head_mode=mode, src=mid, w=w, shift=b,
                  out=out, out_logits=out_logits)
 
     def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2):
@@ -431,9 +408,8 @@ class PackedNetworks:
         self._add_conv(prog, c1, H, W, src, bufs[0])
         self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=src)
         cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 1, mid=0)
-        self._add_conv(prog, self.pv_conv, H, W, bufs[cur], mid)             # both head convolutions, closes the trunk's launch
-        self._add_linear_head(prog, self.policy_lin, H, W, self.pv_conv.cout, mid, pi_mode, pi, policy_logits)
-        self._add_linear_head(prog, self.value_lin, H, W, self.pv_conv.cout, mid, value_mode, value, value_logits)
+        self._add_head(prog, self.policy_conv, self.policy_lin, H, W, bufs[cur], mid, pi_mode, pi, policy_logits)
+        self._add_head(prog, self.value_conv, self.value_lin, H, W, bufs[cur], mid, value_mode, value, value_logits)
         return prog
 
     def dynamics_program(self, n, src, act_idx, bufs, mid, f32, reward, dst, dst2=None, dst2_slot=None, dst2_stride=0,
@@ -444,8 +420,7 @@ class PackedNetworks:
         prog = Program(n, self.fuse_stacks)
         self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx)
         cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32)
-        self._add_conv(prog, self.reward_conv, H, W, bufs[cur], mid)         # 1x1 reward-head convolution, closes the trunk's launch
-        self._add_linear_head(prog, self.reward_lin, H, W, self.reward_conv.cout, mid, reward_mode, reward, reward_logits)
+        self._add_head(prog, self.reward_conv, self.reward_lin, H, W, bufs[cur], mid, reward_mode, reward, reward_logits)
         prog.add(op=OP_SCALE, dtype=self.dt, H=H, W=W, cin=self.latent_ch, src=f32, dst=dst, dst2=dst2, dst2_slot=dst2_slot,
                  dst2_stride=dst2_stride)
         return prog
