@@ -29,6 +29,7 @@ from .. import _lib
 
 OP_CONV, OP_POOL2, OP_SCALE, OP_HEAD, OP_NCHW_IN, OP_NHWC_OUT = range(6)
 F32, BF16, F16 = 0, 1, 2
+FUSE_MAX_SAMPLES = int(os.environ.get("MZB_FUSE_MAX_SAMPLES", "3072"))
 ACT = {"none": 0, "relu": 1, "leaky_relu": 2, "silu": 3, "gelu": 4}   # utils.py:99-108
 
 
@@ -124,7 +125,11 @@ class Program:
 
         while i < len(self.ops):
             j = i
-            while self.fuse and j < len(self.ops) and _stackable(self.ops[j]):
+            # measured (1 B200, 50-simulation searches): the persistent trunk launch wins below ~3000 samples (24: 51 vs 60 ms,
+            # 2048: +2 %), one launch per layer wins above (4096: +2 %, 8192: +8 %: per-tile fences and flag traffic cost more
+            # than the launch gaps they replace once every CTA pair has 5+ tiles per layer)
+            fuse = self.fuse and self.n <= FUSE_MAX_SAMPLES
+            while fuse and j < len(self.ops) and _stackable(self.ops[j]):
                 j += 1
             stack = _Stack(self.ops[i:j], self.n, device) if j - i >= 2 else None
             if stack is not None and stack.ok:
