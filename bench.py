@@ -361,6 +361,8 @@ def bench_mcts(args, rank, local, world):
         out["collectives"] = collectives
     if not args.no_acting:
         out["acting"] = bench_acting(args, m, dev, rank, world)
+    if not args.no_aux:
+        out["replay"] = bench_replay(args, dev, rank, world, cpu=not args.no_cpu_baseline)
     if rank == 0 and not args.no_aux:
         # BASELINE.json configs[1]: config.yaml defaults (24 roots x 50 simulations), same weights, one GPU
         cfg24 = dict(cfg); cfg24["search"] = dict(cfg["search"], seed=3)
@@ -400,6 +402,70 @@ def bench_acting(args, m, dev, rank, world):
     return {"metric": "acting_env_moves_per_s", "value": world * B * moves / (ms * 1e-3), "unit": "env-moves/s", "ms_per_move": ms / moves,
             "envs_per_gpu": B, "num_simulations": args.sims, "moves_timed": moves,
             "what": "reset + per move: mz_rep_input, representation net, MCTSSearchVec.search, mz_sample_actions, bk_env_step(+gray), record"}
+
+
+def bench_replay(args, dev, rank, world, cpu=True):
+    """Device replay buffer: one rb_append of a whole acting batch (4096 trajectories x 64
+    moves into a 60 000-sample buffer, config.yaml replay_buffer_max) and rb_gather of config.yaml's 512-sample minibatch."""
+    from muzero_breakout_b200.replay_buffer import ReplayBuffer
+    B, T, K, cap, mb = 4096, 64, 5, 60000, 512
+    g = torch.Generator(device=dev).manual_seed(3 + rank)
+    lens = torch.randint(40, T + 1, (B,), device=dev, generator=g)
+    rec = dict(action=torch.randint(0, 3, (T, B), device=dev, generator=g), reward=torch.randint(-1, 2, (T, B), device=dev, generator=g).float(),
+               value=torch.rand((T, B), device=dev, generator=g), visits=torch.randint(0, 51, (T, B, 3), device=dev, generator=g),
+               frames=torch.rand((T, B, 1, 16, 20), device=dev, generator=g), recorded=torch.arange(T, device=dev)[:, None] < lens[None, :],
+               initial_gray=torch.rand((B, 1, 16, 20), device=dev, generator=g))
+    rb = ReplayBuffer(32, K, cap, 0.985, 512, device=dev, max_moves=261)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    app_ms = timed(lambda: rb.save_episode(rec), 10)
+    moves = int(lens.sum().item())
+    idxs = [torch.randperm(cap, device=dev, generator=g)[:mb] for _ in range(8)]
+    it = [0]
+
+    def gather():
+        it[0] += 1
+        return rb.minibatch(idxs[it[0] % 8])
+
+    ga_ms = timed(gather, 50)
+    app_bytes = (moves + B) * 1304 * 2 + moves * 8          # entries read + written (frame + scalars), targets
+    ga_bytes = mb * (32 * 1280 * 2 + 32 * 8 + K * 40)       # 32 frames read + written per sample, actions, K-step rows
+    peaks = measured_peaks()
+    out = {"append": {"ms": app_ms, "trajectories": B, "moves": moves, "moves_per_s": moves / (app_ms * 1e-3), "GBps": app_bytes / app_ms / 1e6,
+                      "what": "ReplayBuffer.save_episode: rb_len + rb_scan + rb_store + rb_sample (value targets), no host sync"},
+           "minibatch": {"ms": ga_ms, "samples": mb, "samples_per_s": mb / (ga_ms * 1e-3), "GBps": ga_bytes / ga_ms / 1e6,
+                         "frac_of_hbm_peak": ga_bytes / ga_ms / 1e6 / peaks["hbm"],
+                         "what": "ReplayBuffer.minibatch(512 random indices): one rb_gather launch + 6 output allocations"},
+           "buffer": {"samples": rb.length, "max_length": cap, "entry_ring_MB": rb._t["frame"].numel() * 4 / 1e6}}
+    if cpu and rank == 0 and world == 1:
+        from oracle.replay_oracle import ReplayOracle
+        c = {k: v[:, :6].cpu().numpy() for k, v in rec.items() if k != "initial_gray"}
+        ig = rec["initial_gray"][:6].cpu().numpy()
+        orc = ReplayOracle(32, K, cap, 0.985, 512)
+        t0 = time.perf_counter()
+        n_moves = 0
+        for b in range(6):
+            n = int(lens[b])
+            orc.save(ig[b], c["frames"][:n, b], c["action"][:n, b], c["reward"][:n, b], c["visits"][:n, b], c["value"][:n, b])
+            n_moves += n
+        t1 = time.perf_counter()
+        ii = np.random.RandomState(0).randint(0, len(orc), mb)
+        for f in ("past_actions", "states", "visit_counts", "future_actions", "rewards", "values"):
+            orc.batch(f, ii)
+        t2 = time.perf_counter()
+        out["cpu_baseline"] = {"append_moves_per_s": n_moves / (t1 - t0), "minibatch_samples_per_s": mb / (t2 - t1), "cores": 1, "kind": "port",
+                               "sample": f"oracle/replay_oracle.py (numpy restatement of replay_buffer.py): 6 trajectories / {n_moves} moves saved, one 512-sample minibatch"}
+    return out
 
 
 def cpu_mcts(args, sd=None, trees=24, budget_s=25.0):

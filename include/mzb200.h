@@ -30,7 +30,7 @@ int mzb_version(void);
 const char *mzb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 uint64_t mzb_launch_count(void);
-/* ABI check for foreign-language bindings: sizeof(mz_tree_args) (which=0), sizeof(mz_op) (which=1) */
+/* ABI check for foreign-language bindings: sizeof(mz_tree_args) (which=0), sizeof(mz_op) (which=1), sizeof(rb_ring) (2) */
 size_t mzb_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------------
@@ -234,6 +234,62 @@ size_t mz_stack_layer_bytes(void);
 int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs);
 int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
                  int dtype, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Replay buffer  (reference: replay_buffer.py)
+ *
+ * A trajectory of T moves is stored once, as T+1 consecutive entries of an entry ring (entry 0 = the
+ * initial gray frame; entry m+1 = move m: gray frame after the move, action, reward, visit counts,
+ * search value -- the tuple train_torch.py:205-207 appends), instead of one materialised 32-frame
+ * window per sample (replay_buffer.py:116-119).  A sample is 8 bytes of metadata
+ * (ring index of entry 0 | start s << 32 | T << 48) + K value targets + the trajectory's reward sum, in a
+ * FIFO sample ring of cap_samples = ReplayBuffer.max_length (:154-163).  state[0] = entries ever written,
+ * state[1] = samples ever appended (device-resident: appends need no host sync); live samples are the last
+ * min(state[1], cap_samples), logical index 0 = oldest (the reference's list order).
+ * gpow[k] = (float)(discount ** k) for k = 0..15, computed by the host in double like the reference's
+ * Python `self.discount**k` (:142-148).
+ * status int32[1]: sticky error bits OR-ed by kernels: */
+#define MZB_RB_ERR_BAD_LENGTH 1 /* a trajectory length outside [0, min(T, max_moves)] */
+#define MZB_RB_ERR_BAD_INDEX 2  /* rb_gather index outside [-length, length): the reference raises IndexError */
+
+typedef struct rb_ring {
+    int32_t cap_samples, cap_entries, K, hist; /* hist = seq_len = 32 (config.yaml:37) */
+    float *frame;                              /* [cap_entries][320] */
+    int32_t *action;                           /* [cap_entries] */
+    float *reward, *value;                     /* [cap_entries] */
+    float *visits;                             /* [cap_entries][3]  (float: the reference's stack promotes to fp32) */
+    uint64_t *meta;                            /* [cap_samples] */
+    float *reward_sum;                         /* [cap_samples] */
+    float *target;                             /* [cap_samples][K]  value targets (:136-152) */
+    uint64_t *state;                           /* [2] */
+    float gpow[16];
+} rb_ring;
+
+/* bytes of the per-call placement scratch of rb_append for B trajectories */
+size_t rb_plan_bytes(int B);
+/* entries the entry ring needs so that no live sample's trajectory is ever overwritten */
+long long rb_entries_for(int cap_samples, int K, int max_moves);
+
+/* save_observation_trajectory (:96-165) for B trajectories at once, recorded move-major by the acting loop:
+ * action int64[T][B], reward/value float[T][B], visits int64[T][B][3], frames float[T][B][320] (gray frame after
+ * the move), init_frame float[B][320]; pad_action = the action the 32 padding rows hold (0 in
+ * _pad_initial_state, train_torch.py:324).  Trajectory b has lengths[b] moves if lengths != NULL, else the number of
+ * set bytes in recorded[.][b] (uint8 [T][B], "not done before the move", train_torch.py:205).  Trajectories
+ * shorter than min_length are skipped (train_torch.py:224 passes K+2; the raw method corresponds to 0);
+ * the rest give length-K+1 samples each, appended in env order, evicting the oldest beyond cap_samples. */
+int rb_append(const rb_ring *ring, int B, int T, const int64_t *action, const float *reward, const float *value,
+              const int64_t *visits, const float *frames, const float *init_frame, int pad_action,
+              const uint8_t *recorded, const int32_t *lengths, int min_length, int max_moves, void *plan,
+              int32_t *status, void *stream);
+
+/* get_batched_past_actions / future_actions / states / rewards / visit_counts / values (:167-210) for the n
+ * logical sample indices idx (device int64; negative = from the newest, like a Python list); any output may be
+ * NULL.  past_actions int64[n][hist], future_actions int64[n][K], states float[n][hist][320],
+ * rewards float[n][K], visit_counts float[n][K][3], values float[n][K] (the value TARGETS, :152),
+ * value_buffer float[n][K] (the raw search values, :131-133), reward_sums float[n] (:122). */
+int rb_gather(const rb_ring *ring, int n, const int64_t *idx, int64_t *past_actions, int64_t *future_actions,
+              float *states, float *rewards, float *visit_counts, float *values, float *value_buffer,
+              float *reward_sums, int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

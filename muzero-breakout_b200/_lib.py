@@ -86,6 +86,12 @@ def _declare(L: C.CDLL) -> None:
         "mz_stack_run": [vp, i32, i32, vp, i32, vp, vp, i32, vp],
         "mz_sample_actions": [i32, vp, C.c_double, u64, C.c_uint32, vp, vp, vp, vp],
     })
+    L.rb_plan_bytes.argtypes, L.rb_plan_bytes.restype = [i32], C.c_size_t
+    L.rb_entries_for.argtypes, L.rb_entries_for.restype = [i32, i32, i32], C.c_longlong
+    sig.update({
+        "rb_append": [vp, i32, i32] + [vp] * 6 + [i32, vp, vp, i32, i32, vp, vp, vp],
+        "rb_gather": [vp, i32] + [vp] * 11,
+    })
     for name, args in sig.items():
         f = getattr(L, name)
         f.argtypes, f.restype = args, i32

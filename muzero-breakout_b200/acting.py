@@ -59,7 +59,8 @@ class Actor:
     def run_episode(self):
         """-> dict of device tensors, T = number of moves played:
         action (T,B) i64, reward (T,B) f32, value (T,B) f32, visits (T,B,3) i64, recorded (T,B) bool
-        (= not done before the move, train_torch.py:205), done (B,) bool, frames (T,B,1,16,20) f32 (optional)."""
+        (= not done before the move, train_torch.py:205), done (B,) bool, frames (T,B,1,16,20) f32 (optional),
+        initial_gray (B,1,16,20).  replay_buffer.ReplayBuffer.save_episode(record) stores it without a host round trip."""
         _lib.require_cuda()
         env, L = self.env, _lib.lib()
         B = int(env.batch)
@@ -102,6 +103,7 @@ class Actor:
         out = {k: torch.stack(v) for k, v in rec.items() if v}
         out["done"] = done
         out["initial_state"], out["initial_dx"] = initial_state, initial_dx
+        out["initial_gray"] = gray0.clone().view(B, 1, 16, 20)                    # the 31 padding frames (:313-332), for ReplayBuffer.save_episode
         return out
 
     def _step_into(self, action, done, gray_out):

@@ -26,5 +26,5 @@ extern "C" {
 int mzb_version(void) { return MZB_VERSION; }
 const char *mzb_last_error(void) { return mzb::g_err; }
 uint64_t mzb_launch_count(void) { return mzb::g_launches.load(std::memory_order_relaxed); }
-size_t mzb_sizeof(int which) { return which == 0 ? sizeof(mz_tree_args) : (which == 1 ? sizeof(mz_op) : 0); }
+size_t mzb_sizeof(int which) { return which == 0 ? sizeof(mz_tree_args) : (which == 1 ? sizeof(mz_op) : (which == 2 ? sizeof(rb_ring) : 0)); }
 }

@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by RUNNING THE UNMODIFIED REFERENCE (/root/reference).
 
 Build container only (the reference is not on the GPU box):
-    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|all]
+    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|replay|all]
 
 Outputs (np.savez_compressed, all small):
     env_config1.npz  BASELINE.json configs[0]: B=24, torch.manual_seed(42), 10 000 steps, episode
@@ -11,6 +11,8 @@ Outputs (np.savez_compressed, all small):
     mcts_fake.npz    MCTSSearchVec.search with injected RNG + deterministic fake networks
     mcts_real.npz    same with the real fp32 MuZeroAgent (seed 0, perturbed BN), B=4; doubles as the
                      network golden (rep-net output, per-simulation dynamics/prediction outputs)
+    replay.npz       replay_buffer.py ObservationTrajectory + ReplayBuffer fed the way train_torch.py:204-208,
+                     223-225,313-332 feeds them (synthetic trajectories of 3..261 moves, FIFO eviction at 150 samples)
 """
 from __future__ import annotations
 
@@ -236,6 +238,78 @@ def gen_mcts_real(B=4, S=50, seed=7):
     print("mcts_real: visits", rec["visits"].tolist(), "value", rec["value"].tolist())
 
 
+def synth_trajectories(lengths, seed=11):
+    """Per trajectory: initial gray frame (1,16,20) and per move (action i64, gray frame, reward f32 from the env's
+    reward set, visit counts i64 summing to 50, value f32) -- the tuple train_torch.py:205-207 appends."""
+    g = torch.Generator().manual_seed(seed)
+    levels = torch.tensor([0.0, 0.3, 0.6, 1.0])
+    rset = torch.tensor([0.0, 0.0, 0.0, 1.0, 1.0, -1.0, 5.0, 6.0, 4.0])
+    out = []
+    for T in lengths:
+        def frame():
+            f = torch.zeros(320)
+            idx = torch.randint(0, 320, (12,), generator=g)
+            f[idx] = levels[torch.randint(1, 4, (12,), generator=g)]
+            return f.view(1, 16, 20)
+        init = frame()
+        frames = torch.stack([frame() for _ in range(T)]) if T else torch.zeros(0, 1, 16, 20)
+        action = torch.randint(0, 3, (T,), generator=g)
+        reward = rset[torch.randint(0, len(rset), (T,), generator=g)]
+        v0 = torch.randint(0, 51, (T,), generator=g)
+        v1 = (torch.rand(T, generator=g) * (51 - v0)).long()
+        visits = torch.stack([v0, v1, 50 - v0 - v1], 1)
+        value = (torch.rand(T, generator=g) * 8 - 2).float()
+        out.append(dict(init=init, frames=frames, action=action, reward=reward, visits=visits, value=value))
+    return out
+
+
+def gen_replay(cap=150, K=5, hist=32, discount=0.985, n_sum=24):
+    from replay_buffer import ObservationTrajectory, ReplayBuffer   # the reference
+
+    lengths = [3, 5, 6, 7, 8, 14, 15, 16, 17, 40, 100, 261, 9, 33]
+    trajs = synth_trajectories(lengths)
+    rb = ReplayBuffer(hist, K, cap, discount, n_sum)
+    snaps, snap_after, snap_out = [], [9, len(lengths) - 1], {}
+
+    def snapshot(tag):
+        n = rb.length
+        idx = torch.arange(n)
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(3))[:40]
+        o = {"perm": perm.numpy()}
+        for name, fn in (("past_actions", rb.get_batched_past_actions), ("future_actions", rb.get_batched_future_actions),
+                         ("states", rb.get_batched_states), ("rewards", rb.get_batched_rewards),
+                         ("visit_counts", rb.get_batched_visit_counts), ("values", rb.get_batched_values)):
+            full = fn(idx)
+            o[name] = full.numpy()
+            o[name + "_dtype"] = np.array(str(full.dtype))
+            assert torch.equal(fn(perm), full[perm])
+        o["value_buffer"] = torch.stack(rb.value_buffer).numpy()
+        o["reward_sums"] = np.array(rb.get_reward_sums(), np.float64)
+        o["reward_sums_all"] = np.array(rb.reward_sums, np.float64)
+        snap_out.update({f"s{tag}_{k}": v for k, v in o.items()})
+
+    for ti, tr in enumerate(trajs):
+        ot = ObservationTrajectory(                                   # train_torch.py:313-332 _pad_initial_state
+            actions=[0 for _ in range(hist)], states=[tr["init"] for _ in range(hist - 1)],
+            rewards=[0 for _ in range(hist)], visit_counts=[torch.zeros(3) for _ in range(hist)],
+            values=[0.0 for _ in range(hist)], length=0, reward_sum=0)
+        for t in range(len(tr["action"])):                            # train_torch.py:204-208
+            ot.add_observation(tr["action"][t], tr["frames"][t], tr["reward"][t], tr["visits"][t], tr["value"][t])
+        rb.save_observation_trajectory(ot)                            # every length, not only > K+1 (:224 is the caller's filter)
+        snaps.append(rb.length)
+        if ti in snap_after:
+            snapshot(snap_after.index(ti))
+    out = dict(meta=np.array([cap, K, hist, n_sum], np.int64), discount=np.array(discount), lengths=np.array(lengths),
+               length_after=np.array(snaps), snap_after=np.array(snap_after))
+    for i, tr in enumerate(trajs):
+        for k, v in tr.items():
+            out[f"t{i}_{k}"] = v.numpy()
+    out.update(snap_out)
+    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    print("replay: lengths after each save", snaps, {k: (out["s1_" + k].shape, str(out["s1_" + k + "_dtype"])) for k in
+          ("past_actions", "future_actions", "states", "rewards", "visit_counts", "values")})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.chdir("/tmp")
@@ -244,3 +318,4 @@ if __name__ == "__main__":
     if what in ("play", "all"): gen_env_play()
     if what in ("mcts", "all"): gen_mcts_fake()
     if what in ("net", "all"): gen_mcts_real()
+    if what in ("replay", "all"): gen_replay()

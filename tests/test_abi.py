@@ -18,7 +18,7 @@ ENV_CFG = dict(n_parallel=24, paddle_hit_reward=0.0, brick_hit_reward=1.0, game_
 def _declared():
     src = open(os.path.join(ROOT, "include", "mzb200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:bk|mz|mzb)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:bk|mz|mzb|rb)_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():
@@ -76,6 +76,30 @@ def test_ctypes_mirrors_match_the_c_structs():
     L = mzb.lib()
     assert L.mzb_sizeof(0) == ctypes.sizeof(_lib.TreeArgs)
     assert L.mzb_sizeof(1) == ctypes.sizeof(MzOp)
+    from muzero_breakout_b200.replay_buffer import RbRing
+    assert L.mzb_sizeof(2) == ctypes.sizeof(RbRing)
+
+
+def test_replay_buffer_mirrors_reference_signature():
+    """replay_buffer.py:76-94 constructor and the methods train_torch.py calls (:101,147,225,230,377,469-476)."""
+    from muzero_breakout_b200.replay_buffer import ObservationTrajectory, ReplayBuffer
+    assert list(inspect.signature(ReplayBuffer.__init__).parameters)[:6] == ["self", "seq_len", "K", "max_length", "discount", "num_rewards_to_sum"]
+    rb = ReplayBuffer(32, 5, 60000, 0.985, 24)
+    for m in ("save_observation_trajectory", "get_batched_past_actions", "get_batched_future_actions", "get_batched_states",
+              "get_batched_rewards", "get_batched_visit_counts", "get_batched_values", "get_reward_sums", "empty_buffer"):
+        assert callable(getattr(rb, m))
+    assert (rb.length, len(rb), rb.max_length, rb.K, rb.hist_seq_len) == (0, 0, 60000, 5, 32)
+    ot = ObservationTrajectory(actions=[0] * 32, states=[torch.zeros(1, 16, 20)] * 31, rewards=[0] * 32,
+                               visit_counts=[torch.zeros(3)] * 32, values=[0.0] * 32, length=0, reward_sum=0)
+    ot.add_observation(torch.tensor(2), torch.ones(1, 16, 20), torch.tensor(1.0), torch.tensor([10, 20, 20]), torch.tensor(0.5))
+    assert ot.length == 1 and float(ot.get_reward_sum()) == 1.0 and ot.get_actions().shape == (33,) and ot.get_states().shape == (32, 1, 16, 20)
+    L = mzb.lib()
+    assert L.rb_entries_for(60000, 5, 512) == (60000 + 512) * 6 + 513 and L.rb_entries_for(0, 5, 512) < 0
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            rb.save_observation_trajectory(ot)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            rb.get_batched_states(torch.tensor([0]))
 
 
 def test_mcts_class_mirrors_reference_signature():
@@ -102,8 +126,10 @@ def test_dropin_shadow_modules_resolve_before_the_reference():
             "from utils import get_class\n"
             "m = get_class('src.mcts', 'MCTSSearchVec'); e = get_class('environment.parallel_breakout', 'BreakoutEnvironment')\n"
             "n = get_class('src.networks', 'MuZeroAgent')\n"
-            "print(m.__module__, e.__module__, n.__module__)\n")
+            "import replay_buffer as r\n"
+            "print(m.__module__, e.__module__, n.__module__, r.ReplayBuffer.__module__)\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, "/root/reference"]))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0, out.stderr
-    assert out.stdout.split() == ["muzero_breakout_b200.src.mcts", "muzero_breakout_b200.environment.parallel_breakout", "src.networks"]
+    assert out.stdout.split() == ["muzero_breakout_b200.src.mcts", "muzero_breakout_b200.environment.parallel_breakout", "src.networks",
+                                  "muzero_breakout_b200.replay_buffer"]
