@@ -97,3 +97,31 @@ def all_gather_trajectory(local: torch.Tensor, group=None) -> torch.Tensor:
     out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+EPISODE_FIELDS = ("action", "reward", "value", "visits", "frames", "recorded")
+
+
+def all_gather_episode(record: dict, group=None) -> dict:
+    """Whole-episode form of the trajectory exchange: every rank's acting.Actor.run_episode record (move-major
+    (T_r, B_r, ...) tensors + initial_gray (B_r,1,16,20)) -> one record over all environments in global env order,
+    ready for replay_buffer.ReplayBuffer.save_episode on the replay-buffer owner (reference analogue: the per-step
+    appends of train_torch.py:204-208 followed by :223-225).  Ranks may have played different numbers of moves
+    (their games ended at different times): shorter records are padded with recorded = False moves, which
+    save_episode ignores."""
+    dev = record["action"].device
+    t = torch.tensor([record["action"].shape[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    T = int(t.item())
+    out = {}
+    for k in EPISODE_FIELDS:
+        x = record[k]
+        if x.shape[0] < T:
+            x = torch.cat([x, torch.zeros((T - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)], dim=0)
+        flat = x.transpose(0, 1).contiguous()                                   # env-major so that ranks concatenate along dim 0
+        if flat.dtype == torch.bool:
+            flat = flat.to(torch.uint8)
+        g = all_gather_trajectory(flat, group=group)
+        out[k] = (g.bool() if record[k].dtype == torch.bool else g).transpose(0, 1).contiguous()
+    out["initial_gray"] = all_gather_trajectory(record["initial_gray"].contiguous(), group=group)
+    return out

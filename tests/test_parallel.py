@@ -53,6 +53,30 @@ def _worker(rank, world, port, q):
             full = torch.arange(total)
             assert torch.equal(a2, full % 3) and torch.equal(r2, full.float() * 0.5) and torch.equal(n2[:, 0], full)
             assert torch.equal(g2[:, 0, 0, 0], (full % 2).float()) and torch.allclose(v2, full.float() / 7)
+        # whole-episode exchange: ranks played different numbers of moves with different shard sizes
+        lo, hi = parallel.shard_range(7, rank, world)
+        B, T = hi - lo, 5 + 3 * rank
+
+        def episode(lo, hi, T):
+            e = torch.arange(lo, hi)
+            mv = torch.arange(T)
+            return dict(action=(mv[:, None] + e[None, :]) % 3, reward=(mv[:, None] * 10 + e[None, :]).float(),
+                        value=(mv[:, None] - e[None, :]).float() / 4, visits=torch.stack([mv[:, None] + e[None, :]] * 3, -1),
+                        frames=(mv[:, None, None, None, None] + e[None, :, None, None, None]).float().expand(T, hi - lo, 1, 16, 20).contiguous(),
+                        recorded=mv[:, None] < (2 + e[None, :]), initial_gray=e.float().view(-1, 1, 1, 1).expand(hi - lo, 1, 16, 20).contiguous())
+
+        merged = parallel.all_gather_episode(episode(lo, hi, T))
+        Tm = 5 + 3 * (world - 1)
+        for r in range(world):
+            a, b = parallel.shard_range(7, r, world)
+            want = episode(a, b, 5 + 3 * r)
+            for k, v in want.items():
+                if k == "initial_gray":
+                    assert torch.equal(merged[k][a:b], v)
+                else:
+                    assert merged[k].shape[0] == Tm and merged[k].dtype == v.dtype
+                    assert torch.equal(merged[k][:v.shape[0], a:b], v), k
+                    assert not merged[k][v.shape[0]:, a:b].any(), k            # padding moves: zeros, recorded = False
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
