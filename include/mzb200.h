@@ -226,14 +226,16 @@ int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t
  *   mz_stack_build          fills a HOST blob (64-byte aligned, n_ops * mz_stack_layer_bytes() bytes) from the op
  *                           records; bufs[n_bufs] (<= 3) are the activation buffers the ops' src/dst/res point to.
  *                           The caller copies the blob to device memory once.
- *   mz_stack_run            runs the trunk: blob_dev = the uploaded blob, bufs = the same buffers in the same order,
- *                           act_idx as in mz_op, done = int32 [n_layers * ceil(nsamples/128) * 20] scratch (zeroed here,
- *                           on the stream).
+ *   mz_stack_run            runs the trunk on samples [sample0, sample0 + nsamples) of the buffers: blob_dev = the
+ *                           uploaded blob, bufs = the same buffers in the same order (base pointers), act_idx as in mz_op
+ *                           (base pointer), done = int32 [n_layers * ceil(nsamples/128) * 20] scratch (zeroed here, on
+ *                           the stream).  Large batches are run as several launches over sample slices whose two live
+ *                           activation buffers fit the 126 MB L2 (hosts: 4096 samples = 84 MB).
  */
 size_t mz_stack_layer_bytes(void);
 int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs);
-int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
-                 int dtype, void *stream);
+int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx,
+                 int32_t *done, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay buffer  (reference: replay_buffer.py)

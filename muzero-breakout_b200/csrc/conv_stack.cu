@@ -44,7 +44,9 @@ struct StackParams {
     int f16;                             // 16-bit element type: 0 = bf16, 1 = fp16
     int trace;                           // profiling (env MZB_STACK_TRACE=1): cluster 0's leader records per-layer timestamps
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
+    int rot;                             // tile -> CTA-pair assignment is rotated by rot pairs per layer (evens out the 4/6/9-tap tile costs)
     int n, groups, pairs, ntiles;        // samples, 128-sample groups, group pairs, pair-tiles per layer (= 20 * pairs * N/NT)
+    long long f32_off;                   // element offset of this launch's first sample in the layers' dst_f32 tensors
 };
 
 __device__ unsigned long long g_stack_trace[6 * 64];
@@ -92,8 +94,10 @@ struct Geo {
 
 // NT = output channels per tile: 256 (one tile per pixel and group pair) or 128 (two tiles: small batches have too few
 // pixel tiles to fill the chip, so the N dimension is split to halve the per-layer latency and double the busy SMs)
+constexpr int STACK_THREADS = NUM_THREADS + 32;       // + warp 10: the dependency scout
+
 template <int NT, int AROWS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
+__global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
 {
     constexpr int N = CH;
     constexpr int nsplit = CH / NT;
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    int *s_ready = reinterpret_cast<int *>(bars + 2 * STAGES + 5);          // tiles of this CTA's list whose inputs are known to be complete
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -113,7 +118,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
     constexpr int kchunks = CH / BLOCK_K;
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();
+    // first tile of this CTA pair in `layer`; the pair then strides by nclusters.  All warp roles walk the same list.
+    auto first_tile = [&](int layer) { return (cluster_id + layer * p.rot) % nclusters; };
 
+    if (threadIdx.x == 0) *s_ready = 0;
     if (warp == 0 && lane == 0) {
         for (int b = 0; b < MAX_BUFS; ++b) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_act[b]) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
@@ -135,44 +143,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
         if (lane == 0) {
             constexpr uint32_t a_bytes = G::A_SLOT, b_bytes = G::B_SLOT;
             const uint32_t lead_full = map_to_cta(bar_full, 0);
-            int stage = 0, nks = 0;
+            int stage = 0, nks = 0, seq = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
                 const StackLayer *L = p.layers + layer;
                 const int src = L->src;
                 const CUtensorMap *map_b = NT == CH ? &L->map_b : &L->map_b_half;
-                for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+                const int first = first_tile(layer);
+                for (int tile = first; tile < p.ntiles; tile += nclusters) {
                     const int ns = tile % nsplit, t2 = tile / nsplit;
                     const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0);
-                    if (tile == cluster_id) STRACE(0, layer);
-                    if (layer > 0 && g < p.groups) {
-                        // the previous layer's output of this sample group at the in-bounds neighbour pixels (= the taps):
-                        // all 8 epilogue warps of each of those tiles have stored and fenced
-                        const int *flags = p.done + ((size_t)(layer - 1) * p.groups + g) * HW;
+                    if (tile == first) STRACE(0, layer);
+                    ++seq;
+                    if (layer > 0) {
+                        // the scout warp has seen the previous layer's output of this sample group complete at the in-bounds
+                        // neighbour pixels (and acquired it); it polls ahead of this loop, so this wait is a shared-memory read
                         uint32_t spins = 0;
-                        for (;;) {                                       // all neighbour flags are read in parallel (one L2 round trip)
-                            int ready = 1;
-#pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                if (p.fine && ((taps >> tap) & 1u)) {
-                                    const int v = *reinterpret_cast<const volatile int *>(flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1));
-                                    ready &= v >= NUM_EPI_WARPS * nsplit;
-                                }
-                            }
-                            if (!p.fine) {
-#pragma unroll
-                                for (int q = 0; q < HW; ++q) ready &= *reinterpret_cast<const volatile int *>(flags + q) >= NUM_EPI_WARPS * nsplit;
-                            }
-                            if (ready) break;
-                            if (++spins > (1u << 26)) __trap();
-                            __nanosleep(32);
+                        for (;;) {
+                            int v;
+                            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(s_ready)) : "memory");
+                            if (v >= seq) break;
+                            if (++spins > (1u << 28)) __trap();
                         }
-                        asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: pairs with the epilogues' red.release
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    if (tile == cluster_id) STRACE(1, layer);
+                    if (tile == first) STRACE(1, layer);
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((taps >> tap) & 1u)) continue;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -182,7 +179,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                             const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                             if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (a_bytes + b_bytes));
                             else mbar_arrive_cluster(lead_full + 8 * stage);
-                            if (p.trace == 2 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && nks < 64) g_stack_trace[nks++] = gtime_ns();
+                            if (p.trace == 2 && layer == 0 && tile == first && blockIdx.x == 0 && nks < 64) g_stack_trace[nks++] = gtime_ns();
                             tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
                             tma_load_2d(sb, map_b, lead_full + 8 * stage, 0, (tap * kchunks + kc) * N + ns * NT + rank * (NT / 2));
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -198,7 +195,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int layer = 0; layer < p.nlayers; ++layer) {
-                for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+                const int first = first_tile(layer);
+                for (int tile = first; tile < p.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
                     const int pix = (tile / nsplit) / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
@@ -208,8 +206,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        if (ks == 0 && tile == cluster_id) STRACE(2, layer);
-                        if (p.trace == 3 && layer == 0 && tile == cluster_id && blockIdx.x == 0 && ks < 64) g_stack_trace[ks] = gtime_ns();
+                        if (ks == 0 && tile == first) STRACE(2, layer);
+                        if (p.trace == 3 && layer == 0 && tile == first && blockIdx.x == 0 && ks < 64) g_stack_trace[ks] = gtime_ns();
                         const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
 #pragma unroll
@@ -220,11 +218,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit_pair(bar_tfull + 8 * buf);
-                    if (tile == cluster_id) STRACE(3, layer);
+                    if (tile == first) STRACE(3, layer);
                 }
             }
         }
-    } else {
+    } else if (warp < 2 + NUM_EPI_WARPS) {
         // ===================== epilogue (warps 2..9) =====================
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int r = quarter * 32 + lane;
@@ -246,9 +244,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
             const __nv_bfloat16 *res_base = L->res >= 0 ? p.act[L->res] : nullptr;
             __nv_bfloat16 *dst_base = p.act[L->dst];
             const float *act_bias = L->act_bias;
-            float *dst_f32 = L->dst_f32;
+            float *dst_f32 = L->dst_f32 ? L->dst_f32 + p.f32_off : nullptr;
             const int act = L->act;
-            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+            const int first = first_tile(layer);
+            for (int tile = first; tile < p.ntiles; tile += nclusters, ++it) {
                 const int buf = it & 1;
                 const int ns = tile % nsplit, t2 = tile / nsplit;
                 const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
@@ -272,7 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 uint32_t acc[2][32];
                 mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
                 tc_fence_after();
-                if (warp == 2 && lane == 0 && tile == cluster_id) STRACE(4, layer);
+                if (warp == 2 && lane == 0 && tile == first) STRACE(4, layer);
                 if (res_base) {
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     __syncwarp();
@@ -354,7 +353,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_stack_kernel(const __grid
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __syncwarp();
                 if (lane == 0 && g < p.groups) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + ((size_t)layer * p.groups + g) * HW + pix) : "memory");
-                if (warp == 2 && lane == 0 && tile == cluster_id) STRACE(5, layer);
+                if (warp == 2 && lane == 0 && tile == first) STRACE(5, layer);
+            }
+        }
+    } else if (lane == 0) {
+        // ===================== dependency scout (warp 10) =====================
+        // Walks this CTA's tile list AHEAD of the TMA producer: for tile (pixel p, group g) of layer L+1 it polls
+        // done[L][g][q] of the in-bounds neighbour pixels q (one L2 round trip for all of them), acquires, and publishes the
+        // running count of cleared tiles in shared memory.  The producer's own wait is then a shared-memory read, so the
+        // flag round trip + fence (~2 us) no longer sits between the last load of one tile and the first of the next.
+        int seq = 0;
+        for (int layer = 0; layer < p.nlayers; ++layer) {
+            const int first = first_tile(layer);
+            for (int tile = first; tile < p.ntiles; tile += nclusters) {
+                const int t2 = tile / nsplit;
+                const int pix = t2 / p.pairs, g = 2 * (t2 - pix * p.pairs) + rank;
+                const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                ++seq;
+                if (layer == 0) continue;
+                if (g < p.groups) {
+                    const uint32_t taps = tap_mask(y0, x0);
+                    const int *flags = p.done + ((size_t)(layer - 1) * p.groups + g) * HW;
+                    uint32_t spins = 0;
+                    for (;;) {
+                        int ready = 1;
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (p.fine && ((taps >> tap) & 1u)) {
+                                const int v = *reinterpret_cast<const volatile int *>(flags + (y0 + tap / 3 - 1) * LAT_W + (x0 + tap % 3 - 1));
+                                ready &= v >= NUM_EPI_WARPS * nsplit;
+                            }
+                        }
+                        if (!p.fine) {
+#pragma unroll
+                            for (int q = 0; q < HW; ++q) ready &= *reinterpret_cast<const volatile int *>(flags + q) >= NUM_EPI_WARPS * nsplit;
+                        }
+                        if (ready) break;
+                        if (++spins > (1u << 26)) __trap();
+                        __nanosleep(32);
+                    }
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire: pairs with the epilogues' red.release
+                }
+                asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(s_ready)), "r"(seq) : "memory");
             }
         }
     }
@@ -413,10 +453,10 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
     return 0;
 }
 
-int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
+int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx, int32_t *done,
                  int dtype, void *stream)
 {
-    MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
+    MZB_CHECK_ARG(blob_dev && n_layers > 0 && sample0 >= 0 && nsamples > 0 && bufs && n_bufs > 0 && n_bufs <= MAX_BUFS && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
     EncodeTiledFn enc = encode_fn();
     if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -425,7 +465,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     if (want_split0 < 0) { const char *e = getenv("MZB_STACK_SPLIT"); want_split0 = e ? atoi(e) : 0; }
     const int arows = (want_split0 && nsamples <= 32) ? 32 : BLOCK_M;   // rows of the activation box (split mode: tiny batches load only what exists)
     for (int b = 0; b < MAX_BUFS; ++b) {
-        void *ptr = bufs[b < n_bufs ? b : 0];
+        void *ptr = (__nv_bfloat16 *)bufs[b < n_bufs ? b : 0] + (size_t)sample0 * HW * CH;    // this launch's slice of the samples
         p.act[b] = (__nv_bfloat16 *)ptr;
         cuuint64_t dims[4] = {CH, LAT_W, LAT_H, (cuuint64_t)nsamples};
         cuuint64_t strides[3] = {CH * 2, LAT_W * CH * 2, HW * CH * 2};
@@ -439,9 +479,11 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     p.layers = reinterpret_cast<const StackLayer *>(blob_dev);
     p.nlayers = n_layers;
     p.done = done;
-    p.act_idx = act_idx;
+    p.act_idx = act_idx ? act_idx + sample0 : nullptr;
+    p.f32_off = (long long)sample0 * HW * CH;
     { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_STACK_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
     { static int fine = -1; if (fine < 0) { const char *e = getenv("MZB_STACK_FINE"); fine = e ? atoi(e) : 1; } p.fine = fine; }
+    { static int rot = -1; if (rot < 0) { const char *e = getenv("MZB_STACK_ROT"); rot = e ? atoi(e) : 13; } p.rot = rot; }
     p.n = nsamples;
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.pairs = (p.groups + 1) / 2;
@@ -464,7 +506,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int nsamples, void *const *
     const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(STACK_THREADS);
     cfg.dynamicSmemBytes = !split ? Geo<256, 128>::SMEM : (arows == 32 ? Geo<128, 32>::SMEM : Geo<128, 128>::SMEM);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -29,7 +29,8 @@ from .. import _lib
 
 OP_CONV, OP_POOL2, OP_SCALE, OP_HEAD, OP_NCHW_IN, OP_NHWC_OUT = range(6)
 F32, BF16, F16 = 0, 1, 2
-FUSE_MAX_SAMPLES = int(os.environ.get("MZB_FUSE_MAX_SAMPLES", "3072"))
+FUSE_MAX_SAMPLES = int(os.environ.get("MZB_FUSE_MAX_SAMPLES", "1000000"))
+STACK_CHUNK = int(os.environ.get("MZB_STACK_CHUNK", "4096"))     # samples per trunk launch: two live activation buffers of 4096 samples = 84 MB stay in the 126 MB L2
 ACT = {"none": 0, "relu": 1, "leaky_relu": 2, "silu": 3, "gelu": 4}   # utils.py:99-108
 
 
@@ -77,13 +78,19 @@ class _Stack:
         _lib.check(L.mz_stack_build(arr, self.nlayers, host, self.nlayers * lb, self.bufs, self.nbufs))
         blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone()
         self.blob = blob.to(device)
-        self.done = torch.zeros(self.nlayers * ((n + 127) // 128) * 20, dtype=torch.int32, device=device)
+        # sample slices: equal chunks of whole 256-sample group pairs, at most ~STACK_CHUNK samples each
+        nchunks = 1 if n <= STACK_CHUNK * 5 // 4 else (n + STACK_CHUNK - 1) // STACK_CHUNK
+        per = ((n + nchunks - 1) // nchunks + 255) // 256 * 256
+        self.chunks = [(s0, min(per, n - s0)) for s0 in range(0, n, per)]
+        self.done = torch.zeros(self.nlayers * ((per + 127) // 128) * 20, dtype=torch.int32, device=device)
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
         self.dtype = ops[0].dtype
 
     def run(self, st):
-        _lib.check(_lib.lib().mz_stack_run(self.blob.data_ptr(), self.nlayers, self.n, self.bufs, self.nbufs, self.act_idx,
-                                           self.done.data_ptr(), self.dtype, st))
+        L = _lib.lib()
+        for s0, cnt in self.chunks:
+            _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, s0, cnt, self.bufs, self.nbufs, self.act_idx,
+                                      self.done.data_ptr(), self.dtype, st))
 
 
 class Program:
@@ -125,9 +132,9 @@ class Program:
 
         while i < len(self.ops):
             j = i
-            # measured (1 B200, 50-simulation searches): the persistent trunk launch wins below ~3000 samples (24: 51 vs 60 ms,
-            # 2048: +2 %), one launch per layer wins above (4096: +2 %, 8192: +8 %: per-tile fences and flag traffic cost more
-            # than the launch gaps they replace once every CTA pair has 5+ tiles per layer)
+            # measured (1 B200, 50-simulation searches, profiles/prof_trunk.py): with the dependency scout warp and the per-layer
+            # rotation of the tile assignment the persistent trunk launch beats one launch per layer at every batch size
+            # (4096: 3.94 -> 3.67 ms per simulation step), run over <= ~4096-sample slices so that the working set stays in L2
             fuse = self.fuse and self.n <= FUSE_MAX_SAMPLES
             while fuse and j < len(self.ops) and _stackable(self.ops[j]):
                 j += 1
@@ -156,7 +163,7 @@ class Program:
     def n_kernels(self) -> int:
         if self._segs is None:
             self._build()
-        return sum(cnt if kind == "ops" else 1 for kind, _, cnt in self._segs)
+        return sum(cnt if kind == "ops" else len(item.chunks) for kind, item, cnt in self._segs)
 
 
 DEFAULT_MODEL_CFG = {  # config.yaml:27-50
