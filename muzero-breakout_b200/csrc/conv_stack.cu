@@ -199,14 +199,17 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 for (int tile = first; tile < p.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
                     const int pix = (tile / nsplit) / p.pairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4] = gtime_ns();
                     mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 1] = gtime_ns();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NT);
                     const int ksteps = __popc(tap_mask(y0, x0)) * kchunks;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         if (ks == 0 && tile == first) STRACE(2, layer);
+                        if (p.trace == 4 && ks == 0 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 2] = gtime_ns();
                         if (p.trace == 3 && layer == 0 && tile == first && blockIdx.x == 0 && ks < 64) g_stack_trace[ks] = gtime_ns();
                         const uint32_t sa = smem_base + G::A_OFF + stage * G::A_SLOT, sb = smem_base + G::B_OFF + stage * G::B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     }
                     umma_commit_pair(bar_tfull + 8 * buf);
                     if (tile == first) STRACE(3, layer);
+                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 3] = (gtime_ns() - g_stack_trace[it * 4 + 2]) | ((unsigned long long)ksteps << 40);   // issue time | k-steps
                 }
             }
         }
