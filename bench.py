@@ -31,7 +31,10 @@ ENV_CFG = dict(n_parallel=24, paddle_hit_reward=0.0, brick_hit_reward=1.0, game_
 ENV_BYTES_PER_STEP = 3898       # 3840 frame + 4 reward + 12 valid + 2 done + 8 action + 32 SoA
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/):
 ENV_TRAFFIC_PER_ENV = (1.92e6 + 196.2e6) / 65536     # r1_env_step_final_full.txt, 65 536 envs per launch (the L2 keeps part of the frames)
-CONV_TRAFFIC_PER_SAMPLE = (43.2e6 + 8.8e6) / 4096    # r1_conv_tc_final_full.txt, 3x3 256->256 conv, 4096 samples per launch
+# DRAM bytes per (sample, trunk layer) of conv_stack_kernel: profiles/r1_conv_stack_scout_full.txt, the 28-layer prediction trunk at
+# 4096 samples per launch read 801.7 MB and wrote 1078.1 MB
+TRUNK_TRAFFIC_PER_SAMPLE_LAYER = (801.693952e6 + 1078.071e6) / (28 * 4096)
+FLOP_TRUNK_LAYER_VALID = 130 * 256 * 256 * 2           # one 3x3 256->256 conv on the 4x5 latent, in-bounds taps only, per sample
 
 
 def measured_peaks():
@@ -297,6 +300,15 @@ def bench_mcts(args, rank, local, world):
     conv_ms = _time_prog(conv_prog)
     step_ms = _time_prog(plan.sim_prog)
     n_conv = len(conv_prog.ops)
+    # the dominant kernel alone: the residual-trunk launches (conv_stack_kernel) of one simulation step
+    from muzero_breakout_b200.src.networks import _stackable
+    trunk_prog = Program(B, plan.sim_prog.fuse)
+    trunk_prog.ops = [o for o in conv_prog.ops if _stackable(o)]
+    trunk_prog.keep = plan.sim_prog.keep
+    if not trunk_prog.ops:                                  # fp32 parity path: no tensor-core trunk, report all convolutions
+        trunk_prog = conv_prog
+    trunk_ms = _time_prog(trunk_prog)
+    n_trunk, trunk_launches = len(trunk_prog.ops), trunk_prog.n_kernels
 
     # e2e: the reference-facing call with a HOST latent tensor in and HOST results out
     cfg2 = dict(cfg); cfg2["search"] = dict(cfg["search"], output_device="cpu")
@@ -336,7 +348,7 @@ def bench_mcts(args, rank, local, world):
 
     peaks = measured_peaks()
     sims = world * B * S * K
-    achieved = FLOP_CONV_VALID * B / (conv_ms * 1e-3) / 1e12
+    achieved = FLOP_TRUNK_LAYER_VALID * n_trunk * B / (trunk_ms * 1e-3) / 1e12
     out = {
         "metric": "latent_mcts_simulations_per_s", "value": sims / (ms * 1e-3), "unit": "simulations/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -346,10 +358,12 @@ def bench_mcts(args, rank, local, world):
                    "l2": f"latent store {B * (S + 2) * 10240 * (4 if args.precision == 'f32' else 2) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
                    "cuda_graph": bool(m.use_graph)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": CONV_TRAFFIC_PER_SAMPLE * B,
-                     "traffic_source": "profiles/r1_conv_tc_final_full.txt (ncu --set full, one 3x3 256->256 launch, scaled by samples per launch)", "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
-                     "kernel": f"tcgen05 convolution: {n_conv} conv layers per simulation step in {conv_prog.n_kernels} launches (conv_stack_kernel / conv_tc_kernel)", "flop_convention": "valid taps only (BASELINE.md section 3)",
-                     "flop_per_leaf": FLOP_CONV_VALID, "kernel_ms": conv_ms / n_conv, 
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": TRUNK_TRAFFIC_PER_SAMPLE_LAYER * n_trunk * B / trunk_launches,
+                     "traffic_source": "profiles/r1_conv_stack_scout_full.txt (ncu --set full, the 28-layer trunk launch at 4096 samples, scaled by layers x samples per launch)", "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                     "kernel": f"conv_stack_kernel (tcgen05 residual trunk): {n_trunk} 3x3 256->256 conv layers of one simulation step in {trunk_launches} launches", "flop_convention": "valid taps only (BASELINE.md section 3)",
+                     "flop_per_launch": FLOP_TRUNK_LAYER_VALID * n_trunk * B / trunk_launches, "kernel_ms": trunk_ms / trunk_launches,
+                     "all_convs": {"layers": n_conv, "launches": conv_prog.n_kernels, "ms_per_sim_step": conv_ms, "achieved": FLOP_CONV_VALID * B / (conv_ms * 1e-3) / 1e12,
+                                   "flop_per_leaf": FLOP_CONV_VALID},
                      "conv_ms_per_sim_step": conv_ms, "all_kernels_ms_per_sim_step": step_ms,
                      "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12},
         "e2e": {"value": world * B * S * Ke / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": B * (5120 * 4 + 12), "d2h_bytes_per_step": B * (4 + 24),

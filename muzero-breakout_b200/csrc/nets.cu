@@ -191,10 +191,20 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
     for (int q = 1; q < 8; ++q) { lo = fminf(lo, s_lo[q]); hi = fmaxf(hi, s_hi[q]); }
     const float den = __fadd_rn(__fsub_rn(hi, lo), 1e-8f);                 // s_max - s_min + 1e-8  (:327)
     if (fast) {
+        // fp32 outputs (the 1e-5 parity path): the reference's correctly rounded division.  16-bit outputs: one reciprocal per
+        // sample and a multiply -- the <= 1.5 ulp(fp32) difference disappears in the rounding to bf16 / fp16, and the IEEE
+        // division sequence was what bound this kernel (ncu: SM 72 % busy at 30 % of the DRAM rate)
+        const float inv = __frcp_rn(den);
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const float a = __fdiv_rn(__fsub_rn(v[q].x, lo), den), b = __fdiv_rn(__fsub_rn(v[q].y, lo), den);
-            const float c = __fdiv_rn(__fsub_rn(v[q].z, lo), den), d = __fdiv_rn(__fsub_rn(v[q].w, lo), den);
+            float a, b, c, d;
+            if (sizeof(T) == 4) {
+                a = __fdiv_rn(__fsub_rn(v[q].x, lo), den); b = __fdiv_rn(__fsub_rn(v[q].y, lo), den);
+                c = __fdiv_rn(__fsub_rn(v[q].z, lo), den); d = __fdiv_rn(__fsub_rn(v[q].w, lo), den);
+            } else {
+                a = __fmul_rn(__fsub_rn(v[q].x, lo), inv); b = __fmul_rn(__fsub_rn(v[q].y, lo), inv);
+                c = __fmul_rn(__fsub_rn(v[q].z, lo), inv); d = __fmul_rn(__fsub_rn(v[q].w, lo), inv);
+            }
             const int e = (q * 256 + tid) * 4;
             if (d1) store4<T>(d1 + e, a, b, c, d);
             if (d2) store4<T>(d2 + e, a, b, c, d);
@@ -212,7 +222,7 @@ scale_state_kernel(int elems, const float *__restrict__ src, T *__restrict__ dst
 // samples: every thread owns a strided slice of the feature axis and keeps HEAD_SAMPLES x nout partial sums,
 // so each weight element is read once per CTA (not once per sample) and the reads are coalesced.
 constexpr int HEAD_MAX_OUT = 16;
-constexpr int HEAD_SAMPLES = 8;
+constexpr int HEAD_SAMPLES = 4;      // 4096 samples = 1024 CTAs, 4 per SM: 8 samples per CTA gave 512 CTAs on 444 slots, a half-empty second wave
 constexpr int HEAD_THREADS = 128;
 
 // eight consecutive features of one sample as floats (one 16-byte load for bf16, two for fp32)
@@ -238,7 +248,7 @@ __device__ __forceinline__ void load8(const __half *p, float (&f)[8])
 }
 
 template <typename T, int NOUT>
-__global__ void __launch_bounds__(HEAD_THREADS)
+__global__ void __launch_bounds__(HEAD_THREADS, 4)
 head_kernel(int n, int feat, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
             float *__restrict__ out, float *__restrict__ out_logits)
 {
