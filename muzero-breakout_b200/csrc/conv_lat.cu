@@ -1,0 +1,320 @@
+// Latency-mode residual trunk for SMALL leaf batches (config.yaml's default acting stage: 24 roots): the same run of
+// 3x3 256->256 convolutions on the 4x5 latent as conv_stack.cu, one persistent launch, but tiled for latency instead of
+// throughput.
+//
+// Why a second kernel.  The tcgen05 trunk works on pixel tiles of 128 samples x 256 output channels: at 24 samples a layer
+// is 20 tiles (20 of the 148 SMs), each of which streams the whole 1.18 MB weight tensor through one SM's TMA port and
+// issues 256x256x16 MMAs with 24 useful rows -- ~20 us per layer, 57 dependent layers per simulation step.  Here a layer
+// is cut into (3-sample row tile) x (16-output-channel slice) work items, 16 * ceil(n/3) of them (128 CTAs at n = 24): every
+// SM streams only its 72 KB slice of the weights (prefetched with cp.async while the previous layer computes), the 60
+// activation rows of its samples stay in shared memory for all 9 taps, and the math is warp-level mma.sync m16n8k16
+// (bf16/fp16 in, fp32 accumulate) with the K dimension split over the 8 warps.  tcgen05 needs M = 128 rows per instruction;
+// at 60 rows x 16 channels per CTA the legacy warp MMA is the unit that fits.
+//
+// Layer ordering without kernel boundaries: a 3x3 convolution never mixes samples, so item (layer L, row tile r) needs
+// exactly the 16 channel slices of (L-1, r).  done[L][r] counts finished items (stores -> __threadfence -> bar ->
+// red.release); the consumer's thread 0 spins on ld.acquire, then the CTA loads the rows with cp.async.cg (L2).  The same
+// wait covers the write-after-read hazards of the in-place residual blocks (the readers of buffer[r] in layer L-1 are the
+// 16 items that have to be finished).  Every CTA walks its items in (layer, tile) order and the grid never exceeds the SM
+// count (1 CTA per SM by shared memory), so a dependency always points at an item that is running or finished.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
+constexpr int RS = 3;                    // samples per row tile
+constexpr int ROWS = RS * HW;            // 60 real rows, padded to 4 m16 tiles
+constexpr int MT = 4;
+constexpr int NS = 16;                   // output channels per item (two n8 tiles)
+constexpr int NSLICES = CH / NS;         // 16
+constexpr int KSTEPS = 9 * CH / 16;      // 144 k16 steps per item
+constexpr int WARPS = 8, THREADS = WARPS * 32;
+constexpr int STEPS_PER_WARP = KSTEPS / WARPS;   // 18
+constexpr int ZROW = 63;                 // an all-zero activation row (padding taps, padding rows)
+constexpr int A_BYTES = 64 * CH * 2;     // 32 KB: [64 rows][512 B], 16-byte chunks XOR-swizzled by (row & 7)
+constexpr int W_UNITS = 9 * (CH / 64);   // 36 (tap, 64-channel chunk) units of [16 rows][128 B]
+constexpr int W_BYTES = W_UNITS * NS * 128;      // 72 KB per item, double-buffered
+constexpr int RED_BYTES = WARPS * 32 * 32 * 4;   // 32 KB: per-warp partial accumulators in fragment order
+constexpr int SMEM_BYTES = A_BYTES + 2 * W_BYTES + RED_BYTES;   // 208 KB
+static_assert(KSTEPS % WARPS == 0, "K split");
+
+struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
+    const void *w;                       // tile-contiguous weights [9][4][256][64] (w_layout 1)
+    const float *scale, *shift;          // [256]
+    const float *act_bias;               // [3][20][256] or NULL
+    float *dst_f32;                      // optional fp32 copy of the output or NULL
+    const void *src;                     // activations [n][20][256], 16-bit
+    void *dst;
+    const void *res;                     // or NULL
+    int act, pad;
+};
+
+struct LatParams {
+    const LatLayer *layers;
+    int nlayers, n, rtiles, f16;
+    int *done;                           // [nlayers][rtiles], zeroed before the launch
+    const int *act_idx;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <bool F16>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    if (F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack2(uint32_t u)
+{
+    if (F16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b)
+{
+    if (F16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t *>(&h); }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ float activate(float v, int act)
+{
+    switch (act) {
+        case MZ_ACT_RELU: return fmaxf(v, 0.0f);
+        case MZ_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
+        case MZ_ACT_SILU: return v / (1.0f + __expf(-v));
+        case MZ_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        default: return v;
+    }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sA = smem, *sW = smem + A_BYTES;
+    float *sRed = reinterpret_cast<float *>(smem + A_BYTES + 2 * W_BYTES);
+    const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = p.rtiles * NSLICES;
+    const int tpc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA per layer (>= 1)
+    const int total = p.nlayers * tpc;
+
+    // the zero rows 60..63 are never overwritten
+    for (int i = tid; i < 4 * CH * 2 / 16; i += THREADS) reinterpret_cast<uint4 *>(sA + ROWS * CH * 2)[i] = make_uint4(0u, 0u, 0u, 0u);
+
+    auto weights_async = [&](int seq) {          // the item's [36 units][16 rows][128 B] weight slice -> buffer seq & 1
+        const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
+        const uint8_t *w = reinterpret_cast<const uint8_t *>(p.layers[layer].w);
+        const uint32_t dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
+        for (int i = tid; i < W_UNITS * NS * 8; i += THREADS) {
+            const int u = i >> 7, row = (i >> 3) & 15, c = i & 7;
+            cp_async16(dst0 + u * (NS * 128) + row * 128 + ((c ^ (row & 7)) << 4), w + ((size_t)(u * CH + ns * NS + row) * 64 + c * 8) * 2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // ldmatrix source rows of this lane: A matrices (m16 x k16, row-major) are [rows 0-7 | rows 8-15] x [k 0-7 | k 8-15]
+    const int mj = lane >> 3;
+    int a_row[MT];                    // row inside the tile, or -1
+    uint32_t a_taps[MT];              // in-bounds taps of that row's pixel
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r = mt * 16 + (mj & 1) * 8 + (lane & 7);
+        a_row[mt] = r;
+        uint32_t m = 0u;
+        if (r < ROWS) {
+            const int pix = r % HW, y = pix / LAT_W, x = pix - y * LAT_W;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                if (y + dy >= 0 && y + dy < LAT_H && x + dx >= 0 && x + dx < LAT_W) m |= 1u << tap;
+            }
+        }
+        a_taps[mt] = m;
+    }
+    const int a_khalf = mj >> 1;
+    // B matrices (k16 x n8, "col"): [n 0-7 | n 8-15] x [k 0-7 | k 8-15] -> {b0, b1} of n-tile 0, {b0, b1} of n-tile 1
+    const int b_n = (mj >> 1) * 8 + (lane & 7), b_khalf = mj & 1;
+    // epilogue ownership: warp -> (m-tile, n-tile), thread -> rows g and g+8, two adjacent channels
+    const int e_mt = warp >> 1, e_nt = warp & 1;
+    const int e_r0 = e_mt * 16 + (lane >> 2), e_c = e_nt * 8 + (lane & 3) * 2;
+
+    if (total > 0) weights_async(0);
+    __syncthreads();
+
+    for (int seq = 0; seq < total; ++seq) {
+        const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
+        const int rt = tile / NSLICES, ns = tile - rt * NSLICES;
+        const LatLayer *L = p.layers + layer;
+        const int s0 = rt * RS;                                   // first sample of the row tile
+        const int nrows = min(RS, p.n - s0) * HW;                 // rows that exist
+
+        if (layer > 0) {
+            if (tid == 0) {
+                const int *flag = p.done + (size_t)(layer - 1) * p.rtiles + rt;
+                uint32_t spins = 0;
+                for (;;) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                    if (v >= NSLICES) break;
+                    if (++spins > (1u << 26)) __trap();           // a protocol bug traps instead of hanging the GPU
+                }
+            }
+            __syncthreads();
+        }
+        {   // this tile's activation rows -> shared memory (all 256 channels; reused by the 9 taps)
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(L->src) + (size_t)s0 * HW * CH * 2;
+            for (int i = tid; i < nrows * 32; i += THREADS) {
+                const int row = i >> 5, c = i & 31;
+                cp_async16(sA_u + row * (CH * 2) + ((c ^ (row & 7)) << 4), src + (size_t)row * (CH * 2) + c * 16);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        // epilogue operands that do not depend on the math: fetched now, used after the reduction
+        const int co = ns * NS + e_c;
+        const float2 sc = __ldg(reinterpret_cast<const float2 *>(L->scale + co)), sf = __ldg(reinterpret_cast<const float2 *>(L->shift + co));
+        float2 ab[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = e_r0 + h * 8;
+            if (r < nrows) {
+                const int s = s0 + r / HW, pix = r % HW;
+                if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * CH + co));
+                if (L->res) rs[h] = unpack2<F16>(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * CH + co)));
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");          // this item's weights (issued one item ago) and rows
+        __syncthreads();
+        if (seq + 1 < total) weights_async(seq + 1);              // overlaps the math below
+
+        float acc[MT][2][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.0f;
+
+        const uint32_t wbuf = sW_u + (uint32_t)(seq & 1) * W_BYTES;
+#pragma unroll 2
+        for (int t = warp * STEPS_PER_WARP; t < (warp + 1) * STEPS_PER_WARP; ++t) {
+            const int tap = t >> 4, k16 = t & 15;
+            const int doff = (tap / 3 - 1) * LAT_W + (tap % 3 - 1);
+            uint32_t b[4];
+            {
+                const int u = tap * 4 + (k16 >> 2), c = (k16 & 3) * 2 + b_khalf;
+                ldmatrix_x4(wbuf + u * (NS * 128) + b_n * 128 + ((c ^ (b_n & 7)) << 4), b);
+            }
+            const int ca = k16 * 2 + a_khalf;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                int row = a_row[mt] + doff;
+                if (!((a_taps[mt] >> tap) & 1u) || row >= nrows) row = ZROW;   // zero padding, padding rows, samples past n
+                uint32_t a[4];
+                ldmatrix_x4(sA_u + row * (CH * 2) + ((ca ^ (row & 7)) << 4), a);
+                mma16816<F16>(acc[mt][0], a, b[0], b[1]);
+                mma16816<F16>(acc[mt][1], a, b[2], b[3]);
+            }
+        }
+        // K reduction over the warps: partials in fragment order (conflict-free), summed in warp order (deterministic)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sRed[(warp * 32 + (mt * 2 + nt) * 4 + q) * 32 + lane] = acc[mt][nt][q];
+        __syncthreads();
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s += sRed[(w * 32 + (e_mt * 2 + e_nt) * 4 + q) * 32 + lane];
+            v[q] = s;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = e_r0 + h * 8;
+            if (r < nrows) {
+                float x0 = (v[h * 2] + ab[h].x) * sc.x + sf.x + rs[h].x;
+                float x1 = (v[h * 2 + 1] + ab[h].y) * sc.y + sf.y + rs[h].y;
+                x0 = activate(x0, L->act);
+                x1 = activate(x1, L->act);
+                const size_t o = ((size_t)s0 * HW + r) * CH + co;
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(L->dst) + o) = pack2<F16>(x0, x1);
+                if (L->dst_f32) *reinterpret_cast<float2 *>(L->dst_f32 + o) = make_float2(x0, x1);
+            }
+        }
+        // publish: this item's part of (layer, row tile) is in global memory
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + (size_t)layer * p.rtiles + rt) : "memory");
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mz_lat_layer_bytes(void) { return sizeof(LatLayer); }
+
+int mz_lat_max_samples(void) { return RS * (mzb::kNumSMs / NSLICES); }      // one wave of items: 27 samples
+
+int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes)
+{
+    MZB_CHECK_ARG(ops && n_ops > 0 && blob_host, "bad argument");
+    MZB_CHECK_ARG(blob_bytes >= (size_t)n_ops * sizeof(LatLayer), "blob too small");
+    LatLayer *L = reinterpret_cast<LatLayer *>(blob_host);
+    for (int i = 0; i < n_ops; ++i) {
+        const mz_op &o = ops[i];
+        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.dtype == ops[0].dtype && o.w_layout == 1 && o.ksize == 3 && o.cin == CH &&
+                          o.cout == CH && o.H == LAT_H && o.W == LAT_W, "op is not a 3x3 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights");
+        MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
+        MZB_CHECK_ARG(!o.act_bias || o.act_idx, "act_bias without act_idx");
+        L[i] = LatLayer{o.w, o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, 0};
+    }
+    return 0;
+}
+
+int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
+{
+    MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    LatParams p{};
+    p.layers = reinterpret_cast<const LatLayer *>(blob_dev);
+    p.nlayers = n_layers;
+    p.n = nsamples;
+    p.rtiles = (nsamples + RS - 1) / RS;
+    p.f16 = dtype == MZ_F16;
+    p.done = done;
+    p.act_idx = act_idx;
+    MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.rtiles, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int ntiles = p.rtiles * NSLICES;
+    const int grid = ntiles < mzb::kNumSMs ? ntiles : mzb::kNumSMs;     // all CTAs co-resident (see the header comment)
+    if (p.f16) conv_lat_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    else conv_lat_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -55,12 +55,33 @@ def _stackable(o) -> bool:
             and o.cout == 256 and o.H == 4 and o.W == 5)
 
 
-class _Stack:
-    """A run of stackable convolutions executed by one persistent launch (mz_stack_run)."""
+def lat_max_samples() -> int:
+    """Batches up to this size run their trunks in latency mode (csrc/conv_lat.cu: a single wave of 16 x ceil(n/3) work
+    items); larger ones on the tcgen05 trunk (csrc/conv_stack.cu).  MZB_LAT_MAX_SAMPLES overrides (0 = never)."""
+    e = os.environ.get("MZB_LAT_MAX_SAMPLES")
+    return int(e) if e is not None else int(_lib.lib().mz_lat_max_samples())
 
-    def __init__(self, ops, n, device):
+
+class _Stack:
+    """A run of stackable convolutions executed by one persistent launch (mz_stack_run, or mz_lat_run for small batches)."""
+
+    def __init__(self, ops, n, device, lat_max=None):
         L = _lib.lib()
         self.n, self.nlayers = n, len(ops)
+        self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
+        self.dtype = ops[0].dtype
+        arr = (MzOp * self.nlayers)(*ops)
+        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max)
+        if self.lat:
+            self.ok = True
+            lb = L.mz_lat_layer_bytes()
+            raw = (C.c_uint8 * (self.nlayers * lb + 64))()
+            host = (C.addressof(raw) + 63) & ~63
+            _lib.check(L.mz_lat_build(arr, self.nlayers, host, self.nlayers * lb))
+            self.blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone().to(device)
+            self.chunks = [(0, n)]
+            self.done = torch.zeros(self.nlayers * ((n + 2) // 3), dtype=torch.int32, device=device)
+            return
         bufs = []
         for o in ops:
             for ptr in (o.src, o.dst, o.res):
@@ -72,7 +93,6 @@ class _Stack:
         lb = L.mz_stack_layer_bytes()
         raw = (C.c_uint8 * (self.nlayers * lb + 64))()
         host = (C.addressof(raw) + 63) & ~63
-        arr = (MzOp * self.nlayers)(*ops)
         self.bufs = (C.c_void_p * len(bufs))(*bufs)
         self.nbufs = len(bufs)
         _lib.check(L.mz_stack_build(arr, self.nlayers, host, self.nlayers * lb, self.bufs, self.nbufs))
@@ -83,11 +103,12 @@ class _Stack:
         per = ((n + nchunks - 1) // nchunks + 255) // 256 * 256
         self.chunks = [(s0, min(per, n - s0)) for s0 in range(0, n, per)]
         self.done = torch.zeros(self.nlayers * ((per + 127) // 128) * 20, dtype=torch.int32, device=device)
-        self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
-        self.dtype = ops[0].dtype
 
     def run(self, st):
         L = _lib.lib()
+        if self.lat:
+            _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
+            return
         for s0, cnt in self.chunks:
             _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, s0, cnt, self.bufs, self.nbufs, self.act_idx,
                                       self.done.data_ptr(), self.dtype, st))
@@ -97,11 +118,12 @@ class Program:
     """A list of mz_op records with every pointer resolved; run() enqueues it on the current stream.  With
     fuse=True, runs of two or more stackable convolutions become one persistent launch each."""
 
-    def __init__(self, n: int, fuse: bool = False):
+    def __init__(self, n: int, fuse: bool = False, lat_max: int | None = None):
         self.n = n
         self.ops = []
         self.keep = []            # tensors the ops point into
         self.fuse = fuse
+        self.lat_max = lat_max    # None: lat_max_samples(); 0: tcgen05 trunk at every batch size
         self._segs = None
 
     def add(self, **kw):
@@ -119,6 +141,7 @@ class Program:
         self.ops += other.ops
         self.keep += other.keep
         self.fuse = self.fuse or other.fuse
+        self.lat_max = other.lat_max if self.lat_max is None else self.lat_max
         self._segs = None
 
     def _build(self):
@@ -138,7 +161,7 @@ class Program:
             fuse = self.fuse and self.n <= FUSE_MAX_SAMPLES
             while fuse and j < len(self.ops) and _stackable(self.ops[j]):
                 j += 1
-            stack = _Stack(self.ops[i:j], self.n, device) if j - i >= 2 else None
+            stack = _Stack(self.ops[i:j], self.n, device, self.lat_max) if j - i >= 2 else None
             if stack is not None and stack.ok:
                 flush()
                 segs.append(("stack", stack, j - i))
@@ -262,6 +285,7 @@ class PackedNetworks:
         half = precision in ("bf16", "f16")
         self.use_tc = half if use_tc is None else bool(use_tc and half)
         self.fuse_stacks = self.use_tc and os.environ.get("MZB_NO_STACK", "0") != "1"   # whole trunks in one persistent launch
+        self.lat_max = None        # None: trunks of batches <= lat_max_samples() run in latency mode; 0: always the tcgen05 trunk
         self.num_supports = int(cfg.get("num_supports", 11))
         self.supports_min, self.supports_max = cfg.get("supports_min", -5), cfg.get("supports_max", 5)
         if (self.supports_min, self.supports_max, self.num_supports) != (-5, 5, 11) and self.supports_max - self.supports_min != self.num_supports - 1:
@@ -415,7 +439,7 @@ class PackedNetworks:
     def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2):
         """14 residual blocks + policy head + value head (networks.py:225-241) on `src` [n][20][256]."""
         H, W = self.latent_hw
-        prog = Program(n, self.fuse_stacks)
+        prog = Program(n, self.fuse_stacks, self.lat_max)
         c1, c2 = self.pred_res[0]                                   # first block reads src directly (src, bufs[0], bufs[1]: three buffers)
         self._add_conv(prog, c1, H, W, src, bufs[0])
         self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=src)
@@ -429,7 +453,7 @@ class PackedNetworks:
         """ConvBlock(259->256) + 14 residual blocks + reward head + _scale_state (networks.py:151-167,
         282-298).  src [n][20][256] parent latents, act_idx int32 [n]; scaled latent -> dst (and dst2)."""
         H, W = self.latent_hw
-        prog = Program(n, self.fuse_stacks)
+        prog = Program(n, self.fuse_stacks, self.lat_max)
         self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx)
         cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32)
         self._add_head(prog, self.reward_conv, self.reward_lin, H, W, bufs[cur], mid, reward_mode, reward, reward_logits)
