@@ -254,6 +254,8 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  */
 size_t mz_lat_layer_bytes(void);
 int mz_lat_max_samples(void);
+int mz_lat_max_layers(void);    /* layer descriptors of one launch are staged in shared memory: at most this many (32) */
+int mz_lat_trace(unsigned long long *host_out_8x64);   /* profiling aid (MZB_LAT_TRACE=1): per-layer phase timestamps of CTA 0 */
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes);
 int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
 

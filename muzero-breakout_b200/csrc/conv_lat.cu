@@ -12,7 +12,7 @@
 // at 60 rows x 16 channels per CTA the legacy warp MMA is the unit that fits.
 //
 // Layer ordering without kernel boundaries: a 3x3 convolution never mixes samples, so item (layer L, row tile r) needs
-// exactly the 16 channel slices of (L-1, r).  done[L][r] counts finished items (stores -> __threadfence -> bar ->
+// exactly the 16 channel slices of (L-1, r).  done[L][r] counts finished items (stores -> bar -> thread 0: fence +
 // red.release); the consumer's thread 0 spins on ld.acquire, then the CTA loads the rows with cp.async.cg (L2).  The same
 // wait covers the write-after-read hazards of the in-place residual blocks (the readers of buffer[r] in layer L-1 are the
 // 16 items that have to be finished).  Every CTA walks its items in (layer, tile) order and the grid never exceeds the SM
@@ -35,12 +35,13 @@ constexpr int KSTEPS = 9 * CH / 16;      // 144 k16 steps per item
 constexpr int WARPS = 8, THREADS = WARPS * 32;
 constexpr int STEPS_PER_WARP = KSTEPS / WARPS;   // 18
 constexpr int ZROW = 63;                 // an all-zero activation row (padding taps, padding rows)
-constexpr int A_BYTES = 64 * CH * 2;     // 32 KB: [64 rows][512 B], 16-byte chunks XOR-swizzled by (row & 7)
+constexpr int A_PITCH = CH * 2 + 16;     // 528 B: consecutive rows start 16 bytes apart modulo 128 -> conflict-free ldmatrix without an XOR
+constexpr int A_BYTES = 64 * A_PITCH;    // 33 KB: [64 rows][528 B]
 constexpr int W_UNITS = 9 * (CH / 64);   // 36 (tap, 64-channel chunk) units of [16 rows][128 B]
 constexpr int W_BYTES = W_UNITS * NS * 128;      // 72 KB per item, double-buffered
 constexpr int RED_BYTES = WARPS * 32 * 32 * 4;   // 32 KB: per-warp partial accumulators in fragment order
-constexpr int SMEM_BYTES = A_BYTES + 2 * W_BYTES + RED_BYTES;   // 208 KB
-static_assert(KSTEPS % WARPS == 0, "K split");
+constexpr int MAX_LAYERS = 32;           // descriptors are staged in shared memory (a trunk has 28-29 layers)
+static_assert(KSTEPS % WARPS == 0 && STEPS_PER_WARP == 18 && WARPS * 32 == CH, "K split: two k16 steps of each of the 9 taps per warp");
 
 struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
     const void *w;                       // tile-contiguous weights [9][4][256][64] (w_layout 1)
@@ -53,12 +54,19 @@ struct alignas(64) LatLayer {            // device-resident descriptor of one co
     int act, pad;
 };
 
+constexpr int SMEM_BYTES = A_BYTES + 2 * W_BYTES + RED_BYTES + MAX_LAYERS * (int)sizeof(LatLayer);   // 212 KB
+static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
+
 struct LatParams {
     const LatLayer *layers;
     int nlayers, n, rtiles, f16;
     int *done;                           // [nlayers][rtiles], zeroed before the launch
     const int *act_idx;
+    int trace;                           // profiling (env MZB_LAT_TRACE=1): CTA 0's thread 0 records phase timestamps per layer
 };
+
+__device__ unsigned long long g_lat_trace[8 * 64];
+#define LTRACE(slot) do { if (p.trace && blockIdx.x == 0 && tid == 0 && seq < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_lat_trace[(slot) * 64 + seq] = t_; } } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
@@ -109,18 +117,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem, *sW = smem + A_BYTES;
     float *sRed = reinterpret_cast<float *>(smem + A_BYTES + 2 * W_BYTES);
+    const LatLayer *sLayers = reinterpret_cast<const LatLayer *>(smem + A_BYTES + 2 * W_BYTES + RED_BYTES);   // no pointer chase through L2 per layer
     const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = p.rtiles * NSLICES;
     const int tpc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA per layer (>= 1)
     const int total = p.nlayers * tpc;
 
+    for (int i = tid; i < p.nlayers * (int)(sizeof(LatLayer) / 16); i += THREADS)
+        reinterpret_cast<uint4 *>(smem + A_BYTES + 2 * W_BYTES + RED_BYTES)[i] = __ldg(reinterpret_cast<const uint4 *>(p.layers) + i);
     // the zero rows 60..63 are never overwritten
-    for (int i = tid; i < 4 * CH * 2 / 16; i += THREADS) reinterpret_cast<uint4 *>(sA + ROWS * CH * 2)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 4 * A_PITCH / 16; i += THREADS) reinterpret_cast<uint4 *>(sA + ROWS * A_PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
 
     auto weights_async = [&](int seq) {          // the item's [36 units][16 rows][128 B] weight slice -> buffer seq & 1
         const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
-        const uint8_t *w = reinterpret_cast<const uint8_t *>(p.layers[layer].w);
+        const uint8_t *w = reinterpret_cast<const uint8_t *>(sLayers[layer].w);
         const uint32_t dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
         for (int i = tid; i < W_UNITS * NS * 8; i += THREADS) {
             const int u = i >> 7, row = (i >> 3) & 15, c = i & 7;
@@ -153,16 +164,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     const int e_mt = warp >> 1, e_nt = warp & 1;
     const int e_r0 = e_mt * 16 + (lane >> 2), e_c = e_nt * 8 + (lane & 3) * 2;
 
-    if (total > 0) weights_async(0);
     __syncthreads();
+    if (total > 0) weights_async(0);
 
     for (int seq = 0; seq < total; ++seq) {
         const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
         const int rt = tile / NSLICES, ns = tile - rt * NSLICES;
-        const LatLayer *L = p.layers + layer;
+        const LatLayer *L = sLayers + layer;
         const int s0 = rt * RS;                                   // first sample of the row tile
         const int nrows = min(RS, p.n - s0) * HW;                 // rows that exist
 
+        LTRACE(0);
         if (layer > 0) {
             if (tid == 0) {
                 const int *flag = p.done + (size_t)(layer - 1) * p.rtiles + rt;
@@ -176,11 +188,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             }
             __syncthreads();
         }
+        LTRACE(1);
         {   // this tile's activation rows -> shared memory (all 256 channels; reused by the 9 taps)
             const uint8_t *src = reinterpret_cast<const uint8_t *>(L->src) + (size_t)s0 * HW * CH * 2;
             for (int i = tid; i < nrows * 32; i += THREADS) {
                 const int row = i >> 5, c = i & 31;
-                cp_async16(sA_u + row * (CH * 2) + ((c ^ (row & 7)) << 4), src + (size_t)row * (CH * 2) + c * 16);
+                cp_async16(sA_u + row * A_PITCH + c * 16, src + (size_t)row * (CH * 2) + c * 16);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
@@ -199,7 +212,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         }
         asm volatile("cp.async.wait_all;" ::: "memory");          // this item's weights (issued one item ago) and rows
         __syncthreads();
+        LTRACE(2);
         if (seq + 1 < total) weights_async(seq + 1);              // overlaps the math below
+        LTRACE(6);
 
         float acc[MT][2][4];
 #pragma unroll
@@ -210,26 +225,43 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.0f;
 
         const uint32_t wbuf = sW_u + (uint32_t)(seq & 1) * W_BYTES;
-#pragma unroll 2
-        for (int t = warp * STEPS_PER_WARP; t < (warp + 1) * STEPS_PER_WARP; ++t) {
-            const int tap = t >> 4, k16 = t & 15;
-            const int doff = (tap / 3 - 1) * LAT_W + (tap % 3 - 1);
-            uint32_t b[4];
-            {
-                const int u = tap * 4 + (k16 >> 2), c = (k16 & 3) * 2 + b_khalf;
-                ldmatrix_x4(wbuf + u * (NS * 128) + b_n * 128 + ((c ^ (b_n & 7)) << 4), b);
+        uint32_t a_mask[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) a_mask[mt] = a_row[mt] < nrows ? a_taps[mt] : 0u;
+        // K split: warp w owns input channels [32 w, 32 w + 32) = two k16 steps of every tap, so everything that depends on the
+        // warp (channel offsets, swizzled weight addresses) is loop-invariant and everything that depends on the tap is a
+        // compile-time constant of the unrolled loop.  Software-pipelined: the fragments of step i+1 are in flight while step
+        // i's 8 MMAs issue (two warps per scheduler cannot hide the ldmatrix -> mma latency by themselves).
+        uint32_t af[2][MT][4], bf[2][4];
+        uint32_t rowa[MT];
+        const uint32_t a_base = sA_u + (uint32_t)(warp * 4 + a_khalf) * 16;                         // + row * A_PITCH (+ 32 for the second k16)
+        const uint32_t b_base0 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
+        const uint32_t b_base1 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2 + 1) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
+        auto load_frags = [&](int i, uint32_t (&a)[MT][4], uint32_t (&b)[4]) {       // i = tap * 2 + j, compile-time after unrolling
+            const int tap = i >> 1, j = i & 1;
+            if (j == 0) {
+                const int doff = (tap / 3 - 1) * LAT_W + (tap % 3 - 1);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = ((a_mask[mt] >> tap) & 1u) ? a_row[mt] + doff : ZROW;        // zero padding, padding rows, samples past n
+                    rowa[mt] = a_base + row * A_PITCH;
+                }
             }
-            const int ca = k16 * 2 + a_khalf;
+            ldmatrix_x4((j ? b_base1 : b_base0) + tap * 4 * (NS * 128), b);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) ldmatrix_x4(rowa[mt] + j * 32, a[mt]);
+        };
+        load_frags(0, af[0], bf[0]);
+#pragma unroll
+        for (int i = 0; i < STEPS_PER_WARP; ++i) {
+            if (i + 1 < STEPS_PER_WARP) load_frags(i + 1, af[(i + 1) & 1], bf[(i + 1) & 1]);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                int row = a_row[mt] + doff;
-                if (!((a_taps[mt] >> tap) & 1u) || row >= nrows) row = ZROW;   // zero padding, padding rows, samples past n
-                uint32_t a[4];
-                ldmatrix_x4(sA_u + row * (CH * 2) + ((ca ^ (row & 7)) << 4), a);
-                mma16816<F16>(acc[mt][0], a, b[0], b[1]);
-                mma16816<F16>(acc[mt][1], a, b[2], b[3]);
+                mma16816<F16>(acc[mt][0], af[i & 1][mt], bf[i & 1][0], bf[i & 1][1]);
+                mma16816<F16>(acc[mt][1], af[i & 1][mt], bf[i & 1][2], bf[i & 1][3]);
             }
         }
+        LTRACE(7);
         // K reduction over the warps: partials in fragment order (conflict-free), summed in warp order (deterministic)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -237,6 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) sRed[(warp * 32 + (mt * 2 + nt) * 4 + q) * 32 + lane] = acc[mt][nt][q];
+        LTRACE(3);
         __syncthreads();
         float v[4];
 #pragma unroll
@@ -260,9 +293,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             }
         }
         // publish: this item's part of (layer, row tile) is in global memory
-        __threadfence();
+        // (bar.sync orders every thread's stores before thread 0's fence + release, which are cumulative: the
+        // cooperative-groups grid-barrier pattern)
+        LTRACE(4);
         __syncthreads();
-        if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + (size_t)layer * p.rtiles + rt) : "memory");
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + (size_t)layer * p.rtiles + rt) : "memory");
+        }
+        LTRACE(5);
     }
 }
 
@@ -272,7 +311,14 @@ extern "C" {
 
 size_t mz_lat_layer_bytes(void) { return sizeof(LatLayer); }
 
+int mz_lat_max_layers(void) { return MAX_LAYERS; }
+
 int mz_lat_max_samples(void) { return RS * (mzb::kNumSMs / NSLICES); }      // one wave of items: 27 samples
+
+int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 x 64 trace words
+{
+    return cudaMemcpyFromSymbol(host_out, g_lat_trace, sizeof(unsigned long long) * 8 * 64) == cudaSuccess ? 0 : -2;
+}
 
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes)
 {
@@ -292,6 +338,7 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
 
 int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
 {
+    MZB_CHECK_ARG(n_layers <= MAX_LAYERS, "too many layers for one launch");
     MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     LatParams p{};
@@ -302,6 +349,7 @@ int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *
     p.f16 = dtype == MZ_F16;
     p.done = done;
     p.act_idx = act_idx;
+    { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_LAT_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.rtiles, st));
     static bool attr_set = false;
     if (!attr_set) {

@@ -71,7 +71,7 @@ class _Stack:
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
         self.dtype = ops[0].dtype
         arr = (MzOp * self.nlayers)(*ops)
-        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max)
+        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max) and self.nlayers <= L.mz_lat_max_layers()
         if self.lat:
             self.ok = True
             lb = L.mz_lat_layer_bytes()
