@@ -241,14 +241,14 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  * Latency-mode residual trunk (csrc/conv_lat.cu): the same run of stackable convolutions as mz_stack_*, for SMALL
  * leaf batches (config.yaml's default acting stage, train_torch.py:164-258 with n_parallel = 24: every network call of
  * src/mcts.py:95,194-198 has 24 samples).  One persistent launch of 16 * ceil(nsamples/3) work items
- * (3-sample row tile x 16-output-channel slice; warp-level mma.sync, weights prefetched per layer, layers ordered by
+ * (3-sample row tile x 16-output-channel slice; warp-level mma.sync, weights streamed by TMA one item ahead, layers ordered by
  * device counters per row tile).  Results are the same convolution on the same 16-bit operands with fp32
  * accumulation; the accumulation ORDER differs from the tcgen05 kernels, so outputs agree to fp32 rounding, not bit
  * for bit.
  *   mz_lat_layer_bytes()   size of one device-resident layer descriptor
- *   mz_lat_max_samples()   largest batch that is a single wave of work items (27); hosts use the tcgen05 trunk above it
+ *   mz_lat_max_samples()   largest batch hosts run here (81 = three waves of work items; measured crossover with the tcgen05 trunk)
  *   mz_lat_build           fills a HOST blob (64-byte aligned, n_ops * mz_lat_layer_bytes() bytes) from the op records
- *                          (raw pointers, no tensor maps); the caller copies it to device memory once
+ *                          (a weight tensor map + operand pointers per layer); the caller copies it to device memory once
  *   mz_lat_run             runs the trunk on samples [0, nsamples): act_idx as in mz_op, done = int32
  *                          [n_layers * ceil(nsamples/3)] scratch (zeroed here, on the stream)
  */

@@ -6,10 +6,16 @@
 // is 20 tiles (20 of the 148 SMs), each of which streams the whole 1.18 MB weight tensor through one SM's TMA port and
 // issues 256x256x16 MMAs with 24 useful rows -- ~20 us per layer, 57 dependent layers per simulation step.  Here a layer
 // is cut into (3-sample row tile) x (16-output-channel slice) work items, 16 * ceil(n/3) of them (128 CTAs at n = 24): every
-// SM streams only its 72 KB slice of the weights (prefetched with cp.async while the previous layer computes), the 60
-// activation rows of its samples stay in shared memory for all 9 taps, and the math is warp-level mma.sync m16n8k16
-// (bf16/fp16 in, fp32 accumulate) with the K dimension split over the 8 warps.  tcgen05 needs M = 128 rows per instruction;
-// at 60 rows x 16 channels per CTA the legacy warp MMA is the unit that fits.
+// SM streams only its 72 KB slice of the weights (4 TMA boxes of 9 [16 channels][64 inputs] units, SWIZZLE_128B = the layout
+// ldmatrix wants, requested one item ahead by one thread, double-buffered, mbarrier-tracked), the 60 activation rows of its
+// samples stay in shared memory for all 9 taps, and the math is warp-level mma.sync m16n8k16 (bf16/fp16 in, fp32
+// accumulate) with the K dimension split over the 8 warps (warp w owns input channels [32 w, 32 w + 32) of every tap).
+// tcgen05 needs M = 128 rows per instruction; at 60 rows x 16 channels per CTA the legacy warp MMA is the unit that fits.
+// Measured on this B200 (profiles/micro/hmma_rate.cu): 1 HMMA.16816 per 2 cycles per SM, 1 LDSM.x4 per 4.06 cycles per SM;
+// an item is 1152 HMMA + 720 LDSM.x4, i.e. shared-memory-read-bound at 2900 cycles = 1.5 us (the math phase takes 2.2 us).
+// Tried and backed out (profiles/experiments/conv_lat_cluster16.cu.txt): one 16-CTA cluster per row tile with the layer
+// hand-off through distributed shared memory -- only 7 such clusters fit on the chip at once (24 roots need 8), and the
+// 16 x 16 slice broadcast + barrier.cluster cost 2.7 us per layer against 2.1 us for the global-memory hand-off below.
 //
 // Layer ordering without kernel boundaries: a 3x3 convolution never mixes samples, so item (layer L, row tile r) needs
 // exactly the 16 channel slices of (L-1, r).  done[L][r] counts finished items (stores -> bar -> thread 0: fence +
@@ -17,11 +23,7 @@
 // wait covers the write-after-read hazards of the in-place residual blocks (the readers of buffer[r] in layer L-1 are the
 // 16 items that have to be finished).  Every CTA walks its items in (layer, tile) order and the grid never exceeds the SM
 // count (1 CTA per SM by shared memory), so a dependency always points at an item that is running or finished.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <stdlib.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -43,8 +45,7 @@ constexpr int RED_BYTES = WARPS * 32 * 32 * 4;   // 32 KB: per-warp partial accu
 constexpr int MAX_LAYERS = 32;           // descriptors are staged in shared memory (a trunk has 28-29 layers)
 static_assert(KSTEPS % WARPS == 0 && STEPS_PER_WARP == 18 && WARPS * 32 == CH, "K split: two k16 steps of each of the 9 taps per warp");
 
-struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
-    const void *w;                       // tile-contiguous weights [9][4][256][64] (w_layout 1)
+struct LatOperands {                     // 64 bytes; staged in shared memory
     const float *scale, *shift;          // [256]
     const float *act_bias;               // [3][20][256] or NULL
     float *dst_f32;                      // optional fp32 copy of the output or NULL
@@ -53,9 +54,15 @@ struct alignas(64) LatLayer {            // device-resident descriptor of one co
     const void *res;                     // or NULL
     int act, pad;
 };
-
-constexpr int SMEM_BYTES = A_BYTES + 2 * W_BYTES + RED_BYTES + MAX_LAYERS * (int)sizeof(LatLayer);   // 212 KB
-static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
+struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
+    CUtensorMap map_w;                   // tile-contiguous weights [9][4][256][64] as 3-D (64, 256, 36) with box (64, 16, 9), SWIZZLE_128B
+    LatOperands o;
+};
+static_assert(sizeof(LatLayer) == 192 && sizeof(LatOperands) == 64, "layout");
+constexpr int W_BOX = 9;                 // units per TMA box: 4 boxes of 18 KB per item (36 boxes of 2 KB took 6.5 us to land: the TMA unit is per-box-latency-bound)
+constexpr int OFF_W = 0, OFF_A = 2 * W_BYTES, OFF_RED = OFF_A + A_BYTES, OFF_OPS = OFF_RED + RED_BYTES, OFF_BAR = OFF_OPS + MAX_LAYERS * 64;
+constexpr int LAT_SMEM = OFF_BAR + 16;   // 210 KB
+static_assert(LAT_SMEM <= 232448 && OFF_A % 1024 == 0 && OFF_OPS % 16 == 0 && OFF_BAR % 8 == 0, "shared-memory map (weight units are SWIZZLE_128B atoms: 1024-byte aligned)");
 
 struct LatParams {
     const LatLayer *layers;
@@ -63,12 +70,12 @@ struct LatParams {
     int *done;                           // [nlayers][rtiles], zeroed before the launch
     const int *act_idx;
     int trace;                           // profiling (env MZB_LAT_TRACE=1): CTA 0's thread 0 records phase timestamps per layer
+    int w_early;                         // 1 (default): the next item's weights are requested before this item's math, 0: right after it
 };
 
 __device__ unsigned long long g_lat_trace[8 * 64];
 #define LTRACE(slot) do { if (p.trace && blockIdx.x == 0 && tid == 0 && seq < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_lat_trace[(slot) * 64 + seq] = t_; } } while (0)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -87,57 +94,47 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-template <bool F16>
-__device__ __forceinline__ float2 unpack2(uint32_t u)
+// W_BOX weight units [16 output channels][64 input channels] -> shared memory, bytes signalled on `bar`
+__device__ __forceinline__ void tma_load_units(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
 {
-    if (F16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
-}
-template <bool F16>
-__device__ __forceinline__ uint32_t pack2(float a, float b)
-{
-    if (F16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t *>(&h); }
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
-__device__ __forceinline__ float activate(float v, int act)
-{
-    switch (act) {
-        case MZ_ACT_RELU: return fmaxf(v, 0.0f);
-        case MZ_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
-        case MZ_ACT_SILU: return v / (1.0f + __expf(-v));
-        case MZ_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-        default: return v;
-    }
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 template <bool F16>
 __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *sA = smem, *sW = smem + A_BYTES;
-    float *sRed = reinterpret_cast<float *>(smem + A_BYTES + 2 * W_BYTES);
-    const LatLayer *sLayers = reinterpret_cast<const LatLayer *>(smem + A_BYTES + 2 * W_BYTES + RED_BYTES);   // no pointer chase through L2 per layer
-    const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+    uint8_t *sA = smem + OFF_A;
+    float *sRed = reinterpret_cast<float *>(smem + OFF_RED);
+    const LatOperands *sOps = reinterpret_cast<const LatOperands *>(smem + OFF_OPS);   // no pointer chase through L2 per layer
+    const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(smem + OFF_W), bar_w = smem_u32(smem + OFF_BAR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = p.rtiles * NSLICES;
     const int tpc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA per layer (>= 1)
     const int total = p.nlayers * tpc;
+    if (sW_u & 1023u) __trap();
 
-    for (int i = tid; i < p.nlayers * (int)(sizeof(LatLayer) / 16); i += THREADS)
-        reinterpret_cast<uint4 *>(smem + A_BYTES + 2 * W_BYTES + RED_BYTES)[i] = __ldg(reinterpret_cast<const uint4 *>(p.layers) + i);
+    for (int i = tid; i < p.nlayers * 4; i += THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_OPS)[i] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(p.layers + (i >> 2)) + 128) + (i & 3));
     // the zero rows 60..63 are never overwritten
     for (int i = tid; i < 4 * A_PITCH / 16; i += THREADS) reinterpret_cast<uint4 *>(sA + ROWS * A_PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_w + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
-    auto weights_async = [&](int seq) {          // the item's [36 units][16 rows][128 B] weight slice -> buffer seq & 1
-        const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
-        const uint8_t *w = reinterpret_cast<const uint8_t *>(sLayers[layer].w);
-        const uint32_t dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
-        for (int i = tid; i < W_UNITS * NS * 8; i += THREADS) {
-            const int u = i >> 7, row = (i >> 3) & 15, c = i & 7;
-            cp_async16(dst0 + u * (NS * 128) + row * 128 + ((c ^ (row & 7)) << 4), w + ((size_t)(u * CH + ns * NS + row) * 64 + c * 8) * 2);
+    // an item's [36 units][16 rows][128 B] weight slice -> buffer seq & 1: 4 TMA boxes issued by one thread; the buffer's
+    // previous readers (ldmatrix of item seq - 2) are behind a __syncthreads
+    auto weights_async = [&](int seq) {
+        if (tid == 0) {
+            const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
+            const uint32_t bar = bar_w + 8 * (seq & 1), dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
+            mbar_expect_tx(bar, W_BYTES);
+#pragma unroll
+            for (int b = 0; b < W_UNITS / W_BOX; ++b) tma_load_units(dst0 + b * W_BOX * NS * 128, &p.layers[layer].map_w, bar, 0, ns * NS, b * W_BOX);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     // ldmatrix source rows of this lane: A matrices (m16 x k16, row-major) are [rows 0-7 | rows 8-15] x [k 0-7 | k 8-15]
@@ -170,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     for (int seq = 0; seq < total; ++seq) {
         const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
         const int rt = tile / NSLICES, ns = tile - rt * NSLICES;
-        const LatLayer *L = sLayers + layer;
+        const LatOperands *L = sOps + layer;
         const int s0 = rt * RS;                                   // first sample of the row tile
         const int nrows = min(RS, p.n - s0) * HW;                 // rows that exist
 
@@ -207,13 +204,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             if (r < nrows) {
                 const int s = s0 + r / HW, pix = r % HW;
                 if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * CH + co));
-                if (L->res) rs[h] = unpack2<F16>(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * CH + co)));
+                if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * CH + co)), F16);
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");          // this item's weights (issued one item ago) and rows
+        asm volatile("cp.async.wait_all;" ::: "memory");          // this item's rows
+        mbar_wait(bar_w + 8 * (seq & 1), (seq >> 1) & 1);         // and weights (requested one item ago)
         __syncthreads();
         LTRACE(2);
-        if (seq + 1 < total) weights_async(seq + 1);              // overlaps the math below
+        if (p.w_early && seq + 1 < total) weights_async(seq + 1);      // default: lands while this item's math runs
         LTRACE(6);
 
         float acc[MT][2][4];
@@ -271,6 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 for (int q = 0; q < 4; ++q) sRed[(warp * 32 + (mt * 2 + nt) * 4 + q) * 32 + lane] = acc[mt][nt][q];
         LTRACE(3);
         __syncthreads();
+        if (!p.w_early && seq + 1 < total) weights_async(seq + 1);    // MZB_LAT_W_EARLY=0: requested after the math instead (measured: no gain)
         float v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 x0 = activate(x0, L->act);
                 x1 = activate(x1, L->act);
                 const size_t o = ((size_t)s0 * HW + r) * CH + co;
-                *reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(L->dst) + o) = pack2<F16>(x0, x1);
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(L->dst) + o) = pack2(x0, x1, F16);
                 if (L->dst_f32) *reinterpret_cast<float2 *>(L->dst_f32 + o) = make_float2(x0, x1);
             }
         }
@@ -313,7 +312,9 @@ size_t mz_lat_layer_bytes(void) { return sizeof(LatLayer); }
 
 int mz_lat_max_layers(void) { return MAX_LAYERS; }
 
-int mz_lat_max_samples(void) { return RS * (mzb::kNumSMs / NSLICES); }      // one wave of items: 27 samples
+// Measured crossover (profiles/README.md, ms per simulation step, latency mode vs tcgen05 trunk): 27 samples (one wave of 144 items)
+// 0.40 vs 1.20, 48 (two waves) 0.69 vs 1.22, 60 (three) 0.97 vs 1.23, 96 (four) 1.26 vs 1.25 -> up to three waves
+int mz_lat_max_samples(void) { return 3 * RS * (mzb::kNumSMs / NSLICES); }    // 81
 
 int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 x 64 trace words
 {
@@ -322,8 +323,11 @@ int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 
 
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes)
 {
-    MZB_CHECK_ARG(ops && n_ops > 0 && blob_host, "bad argument");
+    MZB_CHECK_ARG(ops && n_ops > 0 && n_ops <= MAX_LAYERS && blob_host, "bad argument (at most 32 layers per launch)");
     MZB_CHECK_ARG(blob_bytes >= (size_t)n_ops * sizeof(LatLayer), "blob too small");
+    MZB_CHECK_ARG((reinterpret_cast<uintptr_t>(blob_host) & 63) == 0, "blob must be 64-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     LatLayer *L = reinterpret_cast<LatLayer *>(blob_host);
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
@@ -331,7 +335,14 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
                           o.cout == CH && o.H == LAT_H && o.W == LAT_W, "op is not a 3x3 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights");
         MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
         MZB_CHECK_ARG(!o.act_bias || o.act_idx, "act_bias without act_idx");
-        L[i] = LatLayer{o.w, o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, 0};
+        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, 0};
+        cuuint64_t dims[3] = {64, CH, W_UNITS};
+        cuuint64_t strides[2] = {128, (cuuint64_t)CH * 128};
+        cuuint32_t box[3] = {64, NS, W_BOX};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&L[i].map_w, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(o.w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
     return 0;
 }
@@ -350,17 +361,18 @@ int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *
     p.done = done;
     p.act_idx = act_idx;
     { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_LAT_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
+    { static int we = -1; if (we < 0) { const char *e = getenv("MZB_LAT_W_EARLY"); we = e ? atoi(e) : 1; } p.w_early = we; }
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.rtiles, st));
     static bool attr_set = false;
     if (!attr_set) {
-        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));
         attr_set = true;
     }
     const int ntiles = p.rtiles * NSLICES;
     const int grid = ntiles < mzb::kNumSMs ? ntiles : mzb::kNumSMs;     // all CTAs co-resident (see the header comment)
-    if (p.f16) conv_lat_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
-    else conv_lat_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    if (p.f16) conv_lat_kernel<true><<<grid, THREADS, LAT_SMEM, st>>>(p);
+    else conv_lat_kernel<false><<<grid, THREADS, LAT_SMEM, st>>>(p);
     MZB_LAUNCH_CHECK();
     return 0;
 }
