@@ -108,7 +108,7 @@ def agent():
     return a
 
 
-@pytest.mark.parametrize("n", [2, 24, 27])
+@pytest.mark.parametrize("n", [2, 24, 27, 61])
 def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
     """dynamics + prediction with the trunks in latency mode against the same networks on the tcgen05 trunk (lat_max = 0)
     and against the fp32 torch oracle; run twice (the done-counters are re-zeroed on the stream each run)."""
