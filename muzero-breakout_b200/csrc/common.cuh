@@ -53,4 +53,15 @@ __host__ __device__ __forceinline__ uint32_t mz_rng_u32(uint64_t seed, uint32_t 
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute applies to the current device's copy of a kernel: per-device "already done" flags (a host process may
+// drive several GPUs even though the usual deployment is one process per GPU)
+inline bool first_use_on_device(bool (&seen)[64])
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+}
+
 }  // namespace mzb

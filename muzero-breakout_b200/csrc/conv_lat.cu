@@ -363,11 +363,10 @@ int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *
     { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_LAT_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
     { static int we = -1; if (we < 0) { const char *e = getenv("MZB_LAT_W_EARLY"); we = e ? atoi(e) : 1; } p.w_early = we; }
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.rtiles, st));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (mzb::first_use_on_device(attr_set)) {
         MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));
         MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));
-        attr_set = true;
     }
     const int ntiles = p.rtiles * NSLICES;
     const int grid = ntiles < mzb::kNumSMs ? ntiles : mzb::kNumSMs;     // all CTAs co-resident (see the header comment)

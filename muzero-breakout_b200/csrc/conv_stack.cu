@@ -500,12 +500,11 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     const bool split = want_split && HW * p.pairs * 2 <= mzb::kNumSMs / 2;
     p.ntiles = HW * p.pairs * (split ? 2 : 1);
     MZB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)n_layers * p.groups * HW, st));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (mzb::first_use_on_device(attr_set)) {
         MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<256, 128>::SMEM));
         MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<128, 128>::SMEM));
         MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<128, 32>::SMEM));
-        attr_set = true;
     }
     const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
     cudaLaunchConfig_t cfg{};

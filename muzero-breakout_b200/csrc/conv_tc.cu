@@ -405,13 +405,12 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return -2; }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (mzb::first_use_on_device(attr_set)) {
         MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         MZB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_set = true;
     }
     const int clusters = p.ntiles < kNumSMs / 2 ? p.ntiles : kNumSMs / 2;
     cudaLaunchConfig_t cfg{};
