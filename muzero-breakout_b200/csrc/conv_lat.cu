@@ -52,7 +52,7 @@ struct LatOperands {                     // 64 bytes; staged in shared memory
     const void *src;                     // activations [n][20][256], 16-bit
     void *dst;
     const void *res;                     // or NULL
-    int act, pad;
+    int act, k1;                         // k1: 1x1 convolution (centre tap only, 4 weight units) -- the reward head's ConvBlock (networks.py:138-146)
 };
 struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
     CUtensorMap map_w;                   // tile-contiguous weights [9][4][256][64] as 3-D (64, 256, 36) with box (64, 16, 9), SWIZZLE_128B
@@ -131,9 +131,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         if (tid == 0) {
             const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
             const uint32_t bar = bar_w + 8 * (seq & 1), dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
-            mbar_expect_tx(bar, W_BYTES);
+            if (sOps[layer].k1) {                                  // one box of 4 units (the map's box is (64, 16, 4))
+                mbar_expect_tx(bar, 4 * NS * 128);
+                tma_load_units(dst0, &p.layers[layer].map_w, bar, 0, ns * NS, 0);
+            } else {
+                mbar_expect_tx(bar, W_BYTES);
 #pragma unroll
-            for (int b = 0; b < W_UNITS / W_BOX; ++b) tma_load_units(dst0 + b * W_BOX * NS * 128, &p.layers[layer].map_w, bar, 0, ns * NS, b * W_BOX);
+                for (int b = 0; b < W_UNITS / W_BOX; ++b) tma_load_units(dst0 + b * W_BOX * NS * 128, &p.layers[layer].map_w, bar, 0, ns * NS, b * W_BOX);
+            }
         }
     };
 
@@ -235,7 +240,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         const uint32_t a_base = sA_u + (uint32_t)(warp * 4 + a_khalf) * 16;                         // + row * A_PITCH (+ 32 for the second k16)
         const uint32_t b_base0 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
         const uint32_t b_base1 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2 + 1) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
-        auto load_frags = [&](int i, uint32_t (&a)[MT][4], uint32_t (&b)[4]) {       // i = tap * 2 + j, compile-time after unrolling
+        // i = tap * 2 + j (compile-time after unrolling); wtap = the tap's index in the weight tensor
+        auto load_frags = [&](int i, int wtap, uint32_t (&a)[MT][4], uint32_t (&b)[4]) {
             const int tap = i >> 1, j = i & 1;
             if (j == 0) {
                 const int doff = (tap / 3 - 1) * LAT_W + (tap % 3 - 1);
@@ -245,18 +251,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                     rowa[mt] = a_base + row * A_PITCH;
                 }
             }
-            ldmatrix_x4((j ? b_base1 : b_base0) + tap * 4 * (NS * 128), b);
+            ldmatrix_x4((j ? b_base1 : b_base0) + wtap * 4 * (NS * 128), b);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) ldmatrix_x4(rowa[mt] + j * 32, a[mt]);
         };
-        load_frags(0, af[0], bf[0]);
-#pragma unroll
-        for (int i = 0; i < STEPS_PER_WARP; ++i) {
-            if (i + 1 < STEPS_PER_WARP) load_frags(i + 1, af[(i + 1) & 1], bf[(i + 1) & 1]);
+        auto mma_step = [&](const uint32_t (&a)[MT][4], const uint32_t (&b)[4]) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                mma16816<F16>(acc[mt][0], af[i & 1][mt], bf[i & 1][0], bf[i & 1][1]);
-                mma16816<F16>(acc[mt][1], af[i & 1][mt], bf[i & 1][2], bf[i & 1][3]);
+                mma16816<F16>(acc[mt][0], a[mt], b[0], b[1]);
+                mma16816<F16>(acc[mt][1], a[mt], b[2], b[3]);
+            }
+        };
+        if (L->k1) {                                                // centre tap only: this warp's two k16 steps
+            load_frags(8, 0, af[0], bf[0]);
+            load_frags(9, 0, af[1], bf[1]);
+            mma_step(af[0], bf[0]);
+            mma_step(af[1], bf[1]);
+        } else {
+            load_frags(0, 0, af[0], bf[0]);
+#pragma unroll
+            for (int i = 0; i < STEPS_PER_WARP; ++i) {
+                if (i + 1 < STEPS_PER_WARP) load_frags(i + 1, (i + 1) >> 1, af[(i + 1) & 1], bf[(i + 1) & 1]);
+                mma_step(af[i & 1], bf[i & 1]);
             }
         }
         LTRACE(7);
@@ -331,14 +347,14 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
     LatLayer *L = reinterpret_cast<LatLayer *>(blob_host);
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
-        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.dtype == ops[0].dtype && o.w_layout == 1 && o.ksize == 3 && o.cin == CH &&
-                          o.cout == CH && o.H == LAT_H && o.W == LAT_W, "op is not a 3x3 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights");
+        MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.dtype == ops[0].dtype && o.w_layout == 1 && (o.ksize == 3 || o.ksize == 1) && o.cin == CH &&
+                          o.cout == CH && o.H == LAT_H && o.W == LAT_W, "op is not a 3x3 / 1x1 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights");
         MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
         MZB_CHECK_ARG(!o.act_bias || o.act_idx, "act_bias without act_idx");
-        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, 0};
-        cuuint64_t dims[3] = {64, CH, W_UNITS};
+        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, o.ksize == 1};
+        cuuint64_t dims[3] = {64, CH, (cuuint64_t)(o.ksize == 1 ? CH / 64 : W_UNITS)};
         cuuint64_t strides[2] = {128, (cuuint64_t)CH * 128};
-        cuuint32_t box[3] = {64, NS, W_BOX};
+        cuuint32_t box[3] = {64, NS, (cuuint32_t)(o.ksize == 1 ? CH / 64 : W_BOX)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&L[i].map_w, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(o.w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -62,6 +62,12 @@ def lat_max_samples() -> int:
     return int(e) if e is not None else int(_lib.lib().mz_lat_max_samples())
 
 
+def _lat_stackable(o) -> bool:
+    """what the latency-mode trunk (csrc/conv_lat.cu) takes: 3x3 or 1x1 256->256 convolutions on the 4x5 latent."""
+    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize in (1, 3) and o.cin == 256
+            and o.cout == 256 and o.H == 4 and o.W == 5)
+
+
 class _Stack:
     """A run of stackable convolutions executed by one persistent launch (mz_stack_run, or mz_lat_run for small batches)."""
 
@@ -71,7 +77,7 @@ class _Stack:
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
         self.dtype = ops[0].dtype
         arr = (MzOp * self.nlayers)(*ops)
-        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max) and self.nlayers <= L.mz_lat_max_layers()
+        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max) and self.nlayers <= L.mz_lat_max_layers() and all(_lat_stackable(o) for o in ops)
         if self.lat:
             self.ok = True
             lb = L.mz_lat_layer_bytes()
@@ -159,8 +165,17 @@ class Program:
             # rotation of the tile assignment the persistent trunk launch beats one launch per layer at every batch size
             # (4096: 3.94 -> 3.67 ms per simulation step), run over <= ~4096-sample slices so that the working set stays in L2
             fuse = self.fuse and self.n <= FUSE_MAX_SAMPLES
-            while fuse and j < len(self.ops) and _stackable(self.ops[j]):
-                j += 1
+            lat = self.n <= (lat_max_samples() if self.lat_max is None else self.lat_max)
+            if lat:
+                # latency mode also takes 1x1 256->256 layers (the reward head's ConvBlock) and needs a chain: each layer reads
+                # the previous one's output
+                max_layers = _lib.lib().mz_lat_max_layers()
+                while (fuse and j < len(self.ops) and j - i < max_layers and _lat_stackable(self.ops[j])
+                       and (j == i or self.ops[j].src == self.ops[j - 1].dst)):
+                    j += 1
+            else:
+                while fuse and j < len(self.ops) and _stackable(self.ops[j]):
+                    j += 1
             stack = _Stack(self.ops[i:j], self.n, device, self.lat_max) if j - i >= 2 else None
             if stack is not None and stack.ok:
                 flush()

@@ -50,28 +50,30 @@ def _run_layers(ops, n, dtype):
     return done.cpu()
 
 
-LAYER_CASES = [  # (n, residual, act_bias, act, dtype)
+LAYER_CASES = [  # (n, residual, act_bias, act, dtype[, ksize])
+    (24, False, False, "relu", "bf16", 1), (7, True, False, "relu", "f16", 1),
     (1, False, False, "relu", "bf16"), (3, True, False, "relu", "bf16"), (24, True, True, "relu", "bf16"), (25, True, False, "none", "bf16"),
     (27, False, True, "silu", "bf16"), (61, True, True, "relu", "bf16"), (200, True, False, "relu", "bf16"), (24, True, True, "relu", "f16"),
 ]
 
 
-@pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: "n%d_r%d_a%d_%s_%s" % (c[0], c[1], c[2], c[3], c[4]))
+@pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: "n%d_r%d_a%d_%s_%s_k%d" % (c[0], c[1], c[2], c[3], c[4], c[5] if len(c) > 5 else 3))
 def test_one_layer_vs_torch(case):
-    """One 3x3 256->256 convolution (+ action bias, folded BN, residual, activation) against torch's fp32 conv on the same
+    """One 3x3 (or 1x1) 256->256 convolution (+ action bias, folded BN, residual, activation) against torch's fp32 conv on the same
     16-bit operands; every output element compared, buffers NaN-prefilled.  n = 61 / 200 need several items per CTA."""
     from muzero_breakout_b200.src.networks import ACT, BF16, F16, OP_CONV, MzOp
-    n, use_res, use_ab, act, prec = case
+    n, use_res, use_ab, act, prec = case[:5]
+    k = case[5] if len(case) > 5 else 3
     td, dt = (torch.bfloat16, BF16) if prec == "bf16" else (torch.float16, F16)
     g = torch.Generator().manual_seed(n * 7 + use_res + 2 * use_ab)
     x = torch.randn(n, 256, 4, 5, generator=g).to(td)
-    w = (torch.randn(256, 256, 3, 3, generator=g) / 48.0).to(td)
+    w = (torch.randn(256, 256, k, k, generator=g) / (16.0 * k)).to(td)
     scale = torch.rand(256, generator=g) + 0.5
     shift = torch.randn(256, generator=g) * 0.1
     res = torch.randn(n, 256, 4, 5, generator=g).to(td) if use_res else None
     ab = torch.randn(3, 20, 256, generator=g) * 0.2 if use_ab else None
     idx = torch.randint(0, 3, (n,), generator=g, dtype=torch.int32)
-    want = F.conv2d(x.float(), w.float(), padding=1)
+    want = F.conv2d(x.float(), w.float(), padding=k // 2)
     if use_ab:
         want = want + ab[idx.long()].view(n, 4, 5, 256).permute(0, 3, 1, 2)
     want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
@@ -81,11 +83,11 @@ def test_one_layer_vs_torch(case):
 
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
     keep = dict(src=nhwc(x), res=nhwc(res) if use_res else None, scale=scale.cuda(), shift=shift.cuda(), ab=ab.cuda() if use_ab else None,
-                idx=idx.cuda(), w=w.permute(0, 2, 3, 1).reshape(256, 9, 4, 64).permute(1, 2, 0, 3).contiguous().cuda(),
+                idx=idx.cuda(), w=w.permute(0, 2, 3, 1).reshape(256, k * k, 4, 64).permute(1, 2, 0, 3).contiguous().cuda(),
                 dst=torch.full((n, 4, 5, 256), float("nan"), dtype=td, device="cuda"),
                 dst32=torch.full((n, 4, 5, 256), float("nan"), dtype=torch.float32, device="cuda"))
     op = MzOp()
-    for k, v in dict(op=OP_CONV, dtype=dt, H=4, W=5, cin=256, cout=256, ksize=3, act=ACT[act], use_tc=1, w_layout=1, src=keep["src"], dst=keep["dst"],
+    for k, v in dict(op=OP_CONV, dtype=dt, H=4, W=5, cin=256, cout=256, ksize=k, act=ACT[act], use_tc=1, w_layout=1, src=keep["src"], dst=keep["dst"],
                      res=keep["res"], dst_f32=keep["dst32"], w=keep["w"], scale=keep["scale"], shift=keep["shift"], act_bias=keep["ab"],
                      act_idx=keep["idx"] if use_ab else None).items():
         setattr(op, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
@@ -129,7 +131,7 @@ def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
         a = lat.dynamics(h, _planes(acts)) + lat.prediction(h)
         n1 = _lib.launch_count()
         b = tc.dynamics(h, _planes(acts)) + tc.prediction(h)
-        assert n1 - n0 == _lib.launch_count() - n1, "both forms are one launch per trunk"
+        assert n1 - n0 == _lib.launch_count() - n1 - 1, "one launch per trunk in both forms; the latency form also takes the reward head's 1x1 conv"
         for x, y, o, what in zip(a, b, (oh, orew, opol, oval), ("latent", "reward", "policy", "value")):
             assert torch.isfinite(x).all()
             assert rel(x, y) <= 2e-2, f"n={n} {what}: latency trunk vs tcgen05 trunk {rel(x, y):.2e}"
