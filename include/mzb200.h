@@ -248,16 +248,21 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  *   mz_lat_layer_bytes()   size of one device-resident layer descriptor
  *   mz_lat_max_samples()   largest batch hosts run here (81 = three waves of work items; measured crossover with the tcgen05 trunk)
  *   mz_lat_build           fills a HOST blob (64-byte aligned, n_ops * mz_lat_layer_bytes() bytes) from the op records
- *                          (a weight tensor map + operand pointers per layer); the caller copies it to device memory once
- *   mz_lat_run             runs the trunk on samples [0, nsamples): act_idx as in mz_op, done = int32
- *                          [n_layers * ceil(nsamples/3)] scratch (zeroed here, on the stream)
+ *                          (a weight tensor map + operand pointers per record); the caller copies it to device memory once.
+ *                          Records: 3x3 or 1x1 256->256 convolutions forming a chain (ops[i].src == ops[i-1].dst; the 1x1 is the
+ *                          reward head's ConvBlock, networks.py:138-146), optionally followed by ONE pair of 256->128
+ *                          convolutions that both read the last 256-channel output and write different buffers (the policy
+ *                          3x3 and value 1x1 ConvBlocks, networks.py:200-218): the pair runs as one split layer, 8 + 8
+ *                          channel slices.  Returns 1 when the records end with such a pair, 0 otherwise, < 0 on error.
+ *   mz_lat_run             runs the n_ops records on samples [0, nsamples): split_last = mz_lat_build's return value,
+ *                          act_idx as in mz_op, done = int32 [n_ops * ceil(nsamples/3)] scratch (zeroed here, on the stream)
  */
 size_t mz_lat_layer_bytes(void);
 int mz_lat_max_samples(void);
 int mz_lat_max_layers(void);    /* layer descriptors of one launch are staged in shared memory: at most this many (32) */
 int mz_lat_trace(unsigned long long *host_out_8x64);   /* profiling aid (MZB_LAT_TRACE=1): per-layer phase timestamps of CTA 0 */
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes);
-int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
+int mz_lat_run(const void *blob_dev, int n_ops, int split_last, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay buffer  (reference: replay_buffer.py)

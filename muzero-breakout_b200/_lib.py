@@ -88,7 +88,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_stack_build": [vp, i32, vp, C.c_size_t, vp, i32],
         "mz_stack_run": [vp, i32, i32, i32, vp, i32, vp, vp, i32, vp],
         "mz_lat_build": [vp, i32, vp, C.c_size_t],
-        "mz_lat_run": [vp, i32, i32, vp, vp, i32, vp],
+        "mz_lat_run": [vp, i32, i32, i32, vp, vp, i32, vp],
         "mz_sample_actions": [i32, vp, C.c_double, u64, C.c_uint32, vp, vp, vp, vp],
     })
     L.rb_plan_bytes.argtypes, L.rb_plan_bytes.restype = [i32], C.c_size_t

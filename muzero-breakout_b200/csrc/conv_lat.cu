@@ -52,7 +52,9 @@ struct LatOperands {                     // 64 bytes; staged in shared memory
     const void *src;                     // activations [n][20][256], 16-bit
     void *dst;
     const void *res;                     // or NULL
-    int act, k1;                         // k1: 1x1 convolution (centre tap only, 4 weight units) -- the reward head's ConvBlock (networks.py:138-146)
+    int act;
+    short k1;                            // 1x1 convolution (centre tap only, 4 weight units): the reward / value heads' ConvBlocks (networks.py:138-146, 212-218)
+    short cout;                          // 256, or 128 for the two halves of a split last layer (policy + value head convolutions)
 };
 struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
     CUtensorMap map_w;                   // tile-contiguous weights [9][4][256][64] as 3-D (64, 256, 36) with box (64, 16, 9), SWIZZLE_128B
@@ -69,6 +71,7 @@ struct LatParams {
     int nlayers, n, rtiles, f16;
     int *done;                           // [nlayers][rtiles], zeroed before the launch
     const int *act_idx;
+    int split_last;                      // the last layer is two 128-channel convolutions of the same input (records nlayers-1 and nlayers): slices 0-7 / 8-15
     int trace;                           // profiling (env MZB_LAT_TRACE=1): CTA 0's thread 0 records phase timestamps per layer
     int w_early;                         // 1 (default): the next item's weights are requested before this item's math, 0: right after it
 };
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     const int total = p.nlayers * tpc;
     if (sW_u & 1023u) __trap();
 
-    for (int i = tid; i < p.nlayers * 4; i += THREADS)
+    for (int i = tid; i < (p.nlayers + p.split_last) * 4; i += THREADS)
         reinterpret_cast<uint4 *>(smem + OFF_OPS)[i] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(p.layers + (i >> 2)) + 128) + (i & 3));
     // the zero rows 60..63 are never overwritten
     for (int i = tid; i < 4 * A_PITCH / 16; i += THREADS) reinterpret_cast<uint4 *>(sA + ROWS * A_PITCH)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -129,15 +132,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     // previous readers (ldmatrix of item seq - 2) are behind a __syncthreads
     auto weights_async = [&](int seq) {
         if (tid == 0) {
-            const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x, ns = tile % NSLICES;
+            const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
+            int ns = tile % NSLICES, rec = layer;
+            if (p.split_last && layer == p.nlayers - 1 && ns >= NSLICES / 2) { rec = layer + 1; ns -= NSLICES / 2; }
             const uint32_t bar = bar_w + 8 * (seq & 1), dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
-            if (sOps[layer].k1) {                                  // one box of 4 units (the map's box is (64, 16, 4))
+            if (sOps[rec].k1) {                                    // one box of 4 units (the map's box is (64, 16, 4))
                 mbar_expect_tx(bar, 4 * NS * 128);
-                tma_load_units(dst0, &p.layers[layer].map_w, bar, 0, ns * NS, 0);
+                tma_load_units(dst0, &p.layers[rec].map_w, bar, 0, ns * NS, 0);
             } else {
                 mbar_expect_tx(bar, W_BYTES);
 #pragma unroll
-                for (int b = 0; b < W_UNITS / W_BOX; ++b) tma_load_units(dst0 + b * W_BOX * NS * 128, &p.layers[layer].map_w, bar, 0, ns * NS, b * W_BOX);
+                for (int b = 0; b < W_UNITS / W_BOX; ++b) tma_load_units(dst0 + b * W_BOX * NS * 128, &p.layers[rec].map_w, bar, 0, ns * NS, b * W_BOX);
             }
         }
     };
@@ -171,8 +176,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
 
     for (int seq = 0; seq < total; ++seq) {
         const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
-        const int rt = tile / NSLICES, ns = tile - rt * NSLICES;
-        const LatOperands *L = sOps + layer;
+        const int rt = tile / NSLICES;
+        int ns = tile - rt * NSLICES, rec = layer;                // ns: 16-channel slice of this item's convolution
+        if (p.split_last && layer == p.nlayers - 1 && ns >= NSLICES / 2) { rec = layer + 1; ns -= NSLICES / 2; }
+        const LatOperands *L = sOps + rec;
+        const int cout = L->cout;
         const int s0 = rt * RS;                                   // first sample of the row tile
         const int nrows = min(RS, p.n - s0) * HW;                 // rows that exist
 
@@ -208,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             const int r = e_r0 + h * 8;
             if (r < nrows) {
                 const int s = s0 + r / HW, pix = r % HW;
-                if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * CH + co));
-                if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * CH + co)), F16);
+                if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * cout + co));
+                if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * cout + co)), F16);
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");          // this item's rows
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 float x1 = (v[h * 2 + 1] + ab[h].y) * sc.y + sf.y + rs[h].y;
                 x0 = activate(x0, L->act);
                 x1 = activate(x1, L->act);
-                const size_t o = ((size_t)s0 * HW + r) * CH + co;
+                const size_t o = ((size_t)s0 * HW + r) * cout + co;
                 *reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(L->dst) + o) = pack2(x0, x1, F16);
                 if (L->dst_f32) *reinterpret_cast<float2 *>(L->dst_f32 + o) = make_float2(x0, x1);
             }
@@ -339,38 +347,48 @@ int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 
 
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes)
 {
-    MZB_CHECK_ARG(ops && n_ops > 0 && n_ops <= MAX_LAYERS && blob_host, "bad argument (at most 32 layers per launch)");
+    MZB_CHECK_ARG(ops && n_ops > 0 && n_ops <= MAX_LAYERS && blob_host, "bad argument (at most 32 records per launch)");
     MZB_CHECK_ARG(blob_bytes >= (size_t)n_ops * sizeof(LatLayer), "blob too small");
     MZB_CHECK_ARG((reinterpret_cast<uintptr_t>(blob_host) & 63) == 0, "blob must be 64-byte aligned");
     EncodeTiledFn enc = encode_fn();
     if (!enc) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     LatLayer *L = reinterpret_cast<LatLayer *>(blob_host);
+    const bool split = n_ops >= 3 && ops[n_ops - 1].cout == CH / 2 && ops[n_ops - 2].cout == CH / 2;
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
+        const bool half = split && i >= n_ops - 2;
         MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.dtype == ops[0].dtype && o.w_layout == 1 && (o.ksize == 3 || o.ksize == 1) && o.cin == CH &&
-                          o.cout == CH && o.H == LAT_H && o.W == LAT_W, "op is not a 3x3 / 1x1 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights");
+                          o.cout == (half ? CH / 2 : CH) && o.H == LAT_H && o.W == LAT_W,
+                      "op is not a 3x3 / 1x1 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights (or one of two final 256->128 ones)");
         MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
         MZB_CHECK_ARG(!o.act_bias || o.act_idx, "act_bias without act_idx");
-        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, o.ksize == 1};
-        cuuint64_t dims[3] = {64, CH, (cuuint64_t)(o.ksize == 1 ? CH / 64 : W_UNITS)};
-        cuuint64_t strides[2] = {128, (cuuint64_t)CH * 128};
+        // every layer reads the previous layer's output (the layer counters order exactly that); the two halves of a split last layer
+        // both read the output of the layer before them and write different buffers
+        const int prev = half ? n_ops - 3 : i - 1;
+        MZB_CHECK_ARG(i == 0 || o.src == ops[prev].dst, "the layers must form a chain: each one reads the previous one's output");
+        MZB_CHECK_ARG(!half || (!o.res && !o.act_bias && ops[n_ops - 1].dst != ops[n_ops - 2].dst), "split last layer: no residual / action bias, two destinations");
+        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, (short)(o.ksize == 1), (short)o.cout};
+        cuuint64_t dims[3] = {64, (cuuint64_t)o.cout, (cuuint64_t)(o.ksize == 1 ? CH / 64 : W_UNITS)};
+        cuuint64_t strides[2] = {128, (cuuint64_t)o.cout * 128};
         cuuint32_t box[3] = {64, NS, (cuuint32_t)(o.ksize == 1 ? CH / 64 : W_BOX)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&L[i].map_w, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(o.w), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
-    return 0;
+    return split ? 1 : 0;       // 1: the last two records are the halves of a split layer (pass n_ops and split_last = 1 to mz_lat_run)
 }
 
-int mz_lat_run(const void *blob_dev, int n_layers, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
+int mz_lat_run(const void *blob_dev, int n_ops, int split_last, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
 {
-    MZB_CHECK_ARG(n_layers <= MAX_LAYERS, "too many layers for one launch");
+    MZB_CHECK_ARG(n_ops <= MAX_LAYERS && (!split_last || n_ops >= 3), "too many layers for one launch");
+    const int n_layers = n_ops - (split_last ? 1 : 0);
     MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     LatParams p{};
     p.layers = reinterpret_cast<const LatLayer *>(blob_dev);
     p.nlayers = n_layers;
+    p.split_last = split_last ? 1 : 0;
     p.n = nsamples;
     p.rtiles = (nsamples + RS - 1) / RS;
     p.f16 = dtype == MZ_F16;

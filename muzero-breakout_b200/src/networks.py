@@ -63,9 +63,10 @@ def lat_max_samples() -> int:
 
 
 def _lat_stackable(o) -> bool:
-    """what the latency-mode trunk (csrc/conv_lat.cu) takes: 3x3 or 1x1 256->256 convolutions on the 4x5 latent."""
+    """what the latency-mode trunk (csrc/conv_lat.cu) takes: 3x3 or 1x1 256->256 convolutions on the 4x5 latent, and a final pair
+    of 256->128 ones that read the same input (the policy and value heads' ConvBlocks)."""
     return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize in (1, 3) and o.cin == 256
-            and o.cout == 256 and o.H == 4 and o.W == 5)
+            and o.cout in (128, 256) and o.H == 4 and o.W == 5)
 
 
 class _Stack:
@@ -83,7 +84,10 @@ class _Stack:
             lb = L.mz_lat_layer_bytes()
             raw = (C.c_uint8 * (self.nlayers * lb + 64))()
             host = (C.addressof(raw) + 63) & ~63
-            _lib.check(L.mz_lat_build(arr, self.nlayers, host, self.nlayers * lb))
+            rc = L.mz_lat_build(arr, self.nlayers, host, self.nlayers * lb)
+            if rc < 0:
+                _lib.check(rc)
+            self.split_last = int(rc == 1)               # the last two records are the two halves of one layer
             self.blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone().to(device)
             self.chunks = [(0, n)]
             self.done = torch.zeros(self.nlayers * ((n + 2) // 3), dtype=torch.int32, device=device)
@@ -113,7 +117,7 @@ class _Stack:
     def run(self, st):
         L = _lib.lib()
         if self.lat:
-            _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
+            _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.split_last, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
             return
         for s0, cnt in self.chunks:
             _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, s0, cnt, self.bufs, self.nbufs, self.act_idx,
@@ -170,9 +174,16 @@ class Program:
                 # latency mode also takes 1x1 256->256 layers (the reward head's ConvBlock) and needs a chain: each layer reads
                 # the previous one's output
                 max_layers = _lib.lib().mz_lat_max_layers()
-                while (fuse and j < len(self.ops) and j - i < max_layers and _lat_stackable(self.ops[j])
-                       and (j == i or self.ops[j].src == self.ops[j - 1].dst)):
-                    j += 1
+                ops = self.ops
+                while fuse and j < len(ops) and j - i < max_layers and _lat_stackable(ops[j]) and (j == i or ops[j].src == ops[j - 1].dst):
+                    if ops[j].cout == 256:
+                        j += 1
+                        continue
+                    # 256 -> 128: only as the final pair of a run, both halves reading the previous layer's output
+                    if (j > i and j + 1 < len(ops) and j - i + 2 <= max_layers and _lat_stackable(ops[j + 1]) and ops[j + 1].cout == 128
+                            and ops[j + 1].src == ops[j].src and ops[j + 1].dst != ops[j].dst and not ops[j].res and not ops[j + 1].res):
+                        j += 2
+                    break
             else:
                 while fuse and j < len(self.ops) and _stackable(self.ops[j]):
                     j += 1
@@ -459,8 +470,18 @@ class PackedNetworks:
         self._add_conv(prog, c1, H, W, src, bufs[0])
         self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=src)
         cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 1, mid=0)
-        self._add_head(prog, self.policy_conv, self.policy_lin, H, W, bufs[cur], mid, pi_mode, pi, policy_logits)
-        self._add_head(prog, self.value_conv, self.value_lin, H, W, bufs[cur], mid, value_mode, value, value_logits)
+        # both head ConvBlocks first (they read the same trunk output and write the two halves of `mid`), then the two Linear heads:
+        # in latency mode the pair rides as the last, split layer of the trunk launch
+        half = n * H * W * self.policy_conv.cout
+        assert self.policy_conv.cout + self.value_conv.cout <= mid.shape[-1], "mid holds both heads' feature maps"
+        mid_p = mid.view(-1)[:half].view(n, H * W, self.policy_conv.cout)
+        mid_v = mid.view(-1)[half:half + n * H * W * self.value_conv.cout].view(n, H * W, self.value_conv.cout)
+        self._add_conv(prog, self.policy_conv, H, W, bufs[cur], mid_p)
+        self._add_conv(prog, self.value_conv, H, W, bufs[cur], mid_v)
+        for lin, conv, src_, mode, out, logits in ((self.policy_lin, self.policy_conv, mid_p, pi_mode, pi, policy_logits),
+                                                   (self.value_lin, self.value_conv, mid_v, value_mode, value, value_logits)):
+            prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=lin.nout, head_mode=mode, src=src_, w=lin.w, shift=lin.b,
+                     out=out, out_logits=logits)
         return prog
 
     def dynamics_program(self, n, src, act_idx, bufs, mid, f32, reward, dst, dst2=None, dst2_slot=None, dst2_stride=0,

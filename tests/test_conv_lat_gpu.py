@@ -41,11 +41,12 @@ def _run_layers(ops, n, dtype):
     lb = L.mz_lat_layer_bytes()
     raw = (C.c_uint8 * (len(ops) * lb + 64))()
     host = (C.addressof(raw) + 63) & ~63
-    _lib.check(L.mz_lat_build((MzOp * len(ops))(*ops), len(ops), host, len(ops) * lb))
+    split = L.mz_lat_build((MzOp * len(ops))(*ops), len(ops), host, len(ops) * lb)
+    assert split in (0, 1), _lib.lib().mzb_last_error().decode()
     blob = torch.frombuffer((C.c_uint8 * (len(ops) * lb)).from_address(host), dtype=torch.uint8).clone().cuda()
     done = torch.full((len(ops) * ((n + 2) // 3),), 77, dtype=torch.int32, device="cuda")       # the call zeroes it
     act_idx = next((o.act_idx for o in ops if o.act_idx), None)
-    _lib.check(L.mz_lat_run(blob.data_ptr(), len(ops), n, act_idx, done.data_ptr(), dtype, torch.cuda.current_stream().cuda_stream))
+    _lib.check(L.mz_lat_run(blob.data_ptr(), len(ops), split, n, act_idx, done.data_ptr(), dtype, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return done.cpu()
 
@@ -131,7 +132,7 @@ def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
         a = lat.dynamics(h, _planes(acts)) + lat.prediction(h)
         n1 = _lib.launch_count()
         b = tc.dynamics(h, _planes(acts)) + tc.prediction(h)
-        assert n1 - n0 == _lib.launch_count() - n1 - 1, "one launch per trunk in both forms; the latency form also takes the reward head's 1x1 conv"
+        assert n1 - n0 == _lib.launch_count() - n1 - 3, "one launch per trunk in both forms; the latency form also takes the three head ConvBlocks"
         for x, y, o, what in zip(a, b, (oh, orew, opol, oval), ("latent", "reward", "policy", "value")):
             assert torch.isfinite(x).all()
             assert rel(x, y) <= 2e-2, f"n={n} {what}: latency trunk vs tcgen05 trunk {rel(x, y):.2e}"
