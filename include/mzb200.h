@@ -253,8 +253,10 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  *                          reward head's ConvBlock, networks.py:138-146), optionally followed by ONE pair of 256->128
  *                          convolutions that both read the last 256-channel output and write different buffers (the policy
  *                          3x3 and value 1x1 ConvBlocks, networks.py:200-218): the pair runs as one split layer, 8 + 8
- *                          channel slices.  Returns 1 when the records end with such a pair, 0 otherwise, < 0 on error.
- *   mz_lat_run             runs the n_ops records on samples [0, nsamples): split_last = mz_lat_build's return value,
+ *                          channel slices.  Up to two trailing MZ_OP_HEAD / MZ_OP_SCALE records (3 or 11 head outputs; 5120-element
+ *                          _scale_state) become tail ops: they run per sample at the end of the same launch.  Returns flags >= 0
+ *                          (bit 0: the convolutions end with a split pair; bits 1-2: number of tail ops), < 0 on error.
+ *   mz_lat_run             runs the n_ops records on samples [0, nsamples): flags = mz_lat_build's return value,
  *                          act_idx as in mz_op, done = int32 [n_ops * ceil(nsamples/3)] scratch (zeroed here, on the stream)
  */
 size_t mz_lat_layer_bytes(void);
@@ -262,7 +264,7 @@ int mz_lat_max_samples(void);
 int mz_lat_max_layers(void);    /* layer descriptors of one launch are staged in shared memory: at most this many (32) */
 int mz_lat_trace(unsigned long long *host_out_8x64);   /* profiling aid (MZB_LAT_TRACE=1): per-layer phase timestamps of CTA 0 */
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes);
-int mz_lat_run(const void *blob_dev, int n_ops, int split_last, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
+int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay buffer  (reference: replay_buffer.py)

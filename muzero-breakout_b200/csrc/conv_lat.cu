@@ -23,6 +23,8 @@
 // wait covers the write-after-read hazards of the in-place residual blocks (the readers of buffer[r] in layer L-1 are the
 // 16 items that have to be finished).  Every CTA walks its items in (layer, tile) order and the grid never exceeds the SM
 // count (1 CTA per SM by shared memory), so a dependency always points at an item that is running or finished.
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -61,6 +63,21 @@ struct alignas(64) LatLayer {            // device-resident descriptor of one co
     LatOperands o;
 };
 static_assert(sizeof(LatLayer) == 192 && sizeof(LatOperands) == 64, "layout");
+// A tail op: per-sample work that follows the last convolution and would otherwise be two more launches per trunk -- the heads'
+// Flatten + Linear + softmax / support expectation (networks.py:147-149,207-209,221-223; utils.py:74-81) and _scale_state
+// (networks.py:314-328).  Stored in the blob slot that follows the convolution records (one LatLayer-sized slot per op).
+struct LatTail {
+    int kind;                            // MZ_OP_HEAD or MZ_OP_SCALE
+    int mode, nout, feat;                // head: head_mode, outputs (3 / 11), features per sample; scale: feat = elements per sample (5120)
+    const void *src;                     // head: 16-bit [n][feat]; scale: float32 [n][feat]
+    const float *w, *bias;               // head: [nout][feat], [nout]
+    float *out, *out_logits;             // head
+    void *dst, *dst2;                    // scale: 16-bit outputs (dst2: the tree's latent store)
+    const int *dst2_slot;
+    long long dst2_stride;
+};
+static_assert(sizeof(LatTail) <= sizeof(LatLayer), "a tail op fits a blob slot");
+constexpr int MAX_TAILS = 2;
 constexpr int W_BOX = 9;                 // units per TMA box: 4 boxes of 18 KB per item (36 boxes of 2 KB took 6.5 us to land: the TMA unit is per-box-latency-bound)
 constexpr int OFF_W = 0, OFF_A = 2 * W_BYTES, OFF_RED = OFF_A + A_BYTES, OFF_OPS = OFF_RED + RED_BYTES, OFF_BAR = OFF_OPS + MAX_LAYERS * 64;
 constexpr int LAT_SMEM = OFF_BAR + 16;   // 210 KB
@@ -71,6 +88,7 @@ struct LatParams {
     int nlayers, n, rtiles, f16;
     int *done;                           // [nlayers][rtiles], zeroed before the launch
     const int *act_idx;
+    int ntails;                          // tail ops in the blob slots nlayers + split_last ...
     int split_last;                      // the last layer is two 128-channel convolutions of the same input (records nlayers-1 and nlayers): slices 0-7 / 8-15
     int trace;                           // profiling (env MZB_LAT_TRACE=1): CTA 0's thread 0 records phase timestamps per layer
     int w_early;                         // 1 (default): the next item's weights are requested before this item's math, 0: right after it
@@ -102,6 +120,111 @@ __device__ __forceinline__ void tma_load_units(uint32_t dst, const CUtensorMap *
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// ---------------------------------------------------------------- tail ops (one sample, the whole CTA)
+template <bool F16>
+__device__ __forceinline__ void load8_16(const void *p, float (&f)[8])
+{
+    const uint4 u = __ldcg(reinterpret_cast<const uint4 *>(p));          // written by other CTAs of this launch: L2, never L1
+    const uint32_t h[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 t = unpack2(h[q], F16); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+}
+
+// Flatten + Linear, then head_mode 0: raw logits; 1: inverted_softmax_expectation (utils.py:74-81); 2: softmax probabilities
+// (same arithmetic as nets.cu:head_kernel; the summation order over the features differs)
+template <bool F16, int NOUT>
+__device__ void tail_head(const LatTail &t, int s, float *scratch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = 0.0f;
+    const uint16_t *x = reinterpret_cast<const uint16_t *>(t.src) + (size_t)s * t.feat;
+    for (int e = tid * 8; e < t.feat; e += THREADS * 8) {
+        float xv[8];
+        load8_16<F16>(x + e, xv);
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(t.w + (size_t)o * t.feat + e)), w1 = __ldg(reinterpret_cast<const float4 *>(t.w + (size_t)o * t.feat + e) + 1);
+            acc[o] = fmaf(xv[0], w0.x, acc[o]); acc[o] = fmaf(xv[1], w0.y, acc[o]); acc[o] = fmaf(xv[2], w0.z, acc[o]); acc[o] = fmaf(xv[3], w0.w, acc[o]);
+            acc[o] = fmaf(xv[4], w1.x, acc[o]); acc[o] = fmaf(xv[5], w1.y, acc[o]); acc[o] = fmaf(xv[6], w1.z, acc[o]); acc[o] = fmaf(xv[7], w1.w, acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+        float v = acc[o];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0) scratch[wid * NOUT + o] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float logit[NOUT], mx = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            float v = 0.0f;
+#pragma unroll
+            for (int q = 0; q < WARPS; ++q) v += scratch[q * NOUT + o];
+            logit[o] = v + t.bias[o];
+            mx = fmaxf(mx, logit[o]);
+            if (t.out_logits) t.out_logits[(size_t)s * NOUT + o] = logit[o];
+        }
+        if (t.mode != 0) {
+            float den = 0.0f, e[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) { e[o] = expf(logit[o] - mx); den += e[o]; }
+            if (t.mode == 2) {                                                 // softmax probabilities (mcts.py:100,199)
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) t.out[(size_t)s * NOUT + o] = e[o] / den;
+            } else {                                                           // utils.py:66-81
+                const float half = 0.5f * (float)(NOUT - 1);
+                float ex = 0.0f;
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) ex += (e[o] / den) * ((float)o - half);
+                const float sg = ex > 0.0f ? 1.0f : (ex < 0.0f ? -1.0f : 0.0f);
+                const float a = fabsf(ex) + 0.999f;                            // float32(1 - epsilon), utils.py:14,28
+                t.out[s] = sg * (a * a - 1.0f);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// MuZeroAgent._scale_state (networks.py:314-328) of one sample's 5120 fp32 values -> 16-bit dst / dst2 (as nets.cu:scale_state_kernel)
+template <bool F16>
+__device__ void tail_scale(const LatTail &t, int s, float *scratch)
+{
+    const int tid = threadIdx.x;
+    const float *x = t.src ? reinterpret_cast<const float *>(t.src) + (size_t)s * t.feat : nullptr;
+    float4 v[5];
+    float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        v[q] = __ldcg(reinterpret_cast<const float4 *>(x) + q * THREADS + tid);
+        lo = fminf(fminf(lo, fminf(v[q].x, v[q].y)), fminf(v[q].z, v[q].w));
+        hi = fmaxf(fmaxf(hi, fmaxf(v[q].x, v[q].y)), fmaxf(v[q].z, v[q].w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((tid & 31) == 0) { scratch[tid >> 5] = lo; scratch[8 + (tid >> 5)] = hi; }
+    __syncthreads();
+    lo = scratch[0]; hi = scratch[8];
+#pragma unroll
+    for (int q = 1; q < WARPS; ++q) { lo = fminf(lo, scratch[q]); hi = fmaxf(hi, scratch[8 + q]); }
+    const float inv = __frcp_rn(__fadd_rn(__fsub_rn(hi, lo), 1e-8f));          // 1 / (s_max - s_min + 1e-8)  (:327)
+    uint16_t *d1 = t.dst ? reinterpret_cast<uint16_t *>(t.dst) + (size_t)s * t.feat : nullptr;
+    uint16_t *d2 = t.dst2 ? reinterpret_cast<uint16_t *>(t.dst2) + ((size_t)s * t.dst2_stride + (t.dst2_slot ? t.dst2_slot[s] : 0)) * t.feat : nullptr;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const uint2 o = make_uint2(pack2(__fmul_rn(__fsub_rn(v[q].x, lo), inv), __fmul_rn(__fsub_rn(v[q].y, lo), inv), F16),
+                                   pack2(__fmul_rn(__fsub_rn(v[q].z, lo), inv), __fmul_rn(__fsub_rn(v[q].w, lo), inv), F16));
+        const int e = (q * THREADS + tid) * 4;
+        if (d1) *reinterpret_cast<uint2 *>(d1 + e) = o;
+        if (d2) *reinterpret_cast<uint2 *>(d2 + e) = o;
+    }
+    __syncthreads();
 }
 
 template <bool F16>
@@ -326,6 +449,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         }
         LTRACE(5);
     }
+
+    // Tail ops, after this CTA's last convolution item (they wait on convolution items only, which never wait on a tail): the CTAs
+    // that computed channel slices 0..2 of the last layer of a row tile take one of its three samples each.
+    if (p.ntails) {
+        const LatLayer *tail_slots = p.layers + p.nlayers + p.split_last;      // one LatLayer-sized blob slot per tail op
+        for (int k = 0; k < tpc; ++k) {
+            const int tile = (int)blockIdx.x + k * (int)gridDim.x, rt = tile / NSLICES, j = tile - rt * NSLICES, s = rt * RS + j;
+            if (j >= RS || s >= p.n) continue;
+            if (tid == 0) {
+                const int *flag = p.done + (size_t)(p.nlayers - 1) * p.rtiles + rt;
+                uint32_t spins = 0;
+                for (;;) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                    if (v >= NSLICES) break;
+                    if (++spins > (1u << 26)) __trap();
+                }
+            }
+            __syncthreads();
+            for (int i = 0; i < p.ntails; ++i) {
+                const LatTail t = *reinterpret_cast<const LatTail *>(tail_slots + i);
+                if (t.kind == MZ_OP_SCALE) tail_scale<F16>(t, s, sRed);
+                else if (t.nout == 3) tail_head<F16, 3>(t, s, sRed);
+                else tail_head<F16, 11>(t, s, sRed);
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -347,12 +497,37 @@ int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 
 
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes)
 {
-    MZB_CHECK_ARG(ops && n_ops > 0 && n_ops <= MAX_LAYERS && blob_host, "bad argument (at most 32 records per launch)");
+    // (n_ops is reduced to the number of convolution records below)
+    MZB_CHECK_ARG(ops && n_ops > 0 && n_ops <= MAX_LAYERS + MAX_TAILS && blob_host, "bad argument (at most 32 convolution records + 2 tail ops per launch)");
     MZB_CHECK_ARG(blob_bytes >= (size_t)n_ops * sizeof(LatLayer), "blob too small");
     MZB_CHECK_ARG((reinterpret_cast<uintptr_t>(blob_host) & 63) == 0, "blob must be 64-byte aligned");
     EncodeTiledFn enc = encode_fn();
     if (!enc) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     LatLayer *L = reinterpret_cast<LatLayer *>(blob_host);
+    // trailing tail ops (heads, _scale_state): one blob slot each after the convolution records
+    int ntails = 0;
+    while (ntails < MAX_TAILS && n_ops - ntails > 1 && (ops[n_ops - 1 - ntails].op == MZ_OP_HEAD || ops[n_ops - 1 - ntails].op == MZ_OP_SCALE)) ++ntails;
+    const int n_all = n_ops;
+    n_ops -= ntails;
+    for (int i = 0; i < ntails; ++i) {
+        const mz_op &o = ops[n_ops + i];
+        MZB_CHECK_ARG(o.dtype == ops[0].dtype && o.src, "tail op: element type / source");
+        LatTail t{};
+        t.kind = o.op;
+        t.feat = o.H * o.W * o.cin;
+        t.src = o.src;
+        if (o.op == MZ_OP_HEAD) {
+            MZB_CHECK_ARG(o.w && o.shift && (o.nout == 3 || o.nout == 11) && t.feat % 8 == 0, "tail head: 3 or 11 outputs, features a multiple of 8");
+            MZB_CHECK_ARG(o.head_mode == 0 ? o.out_logits != nullptr : o.out != nullptr, "tail head: missing output");
+            t.mode = o.head_mode; t.nout = o.nout; t.w = reinterpret_cast<const float *>(o.w); t.bias = o.shift; t.out = o.out; t.out_logits = o.out_logits;
+        } else {
+            MZB_CHECK_ARG(t.feat == HW * CH && (o.dst || o.dst2), "tail scale: 5120 elements per sample, a destination");
+            t.dst = o.dst; t.dst2 = o.dst2; t.dst2_slot = o.dst2_slot; t.dst2_stride = o.dst2_stride;
+        }
+        memcpy(reinterpret_cast<uint8_t *>(L + n_ops + i), &t, sizeof(t));
+    }
+    (void)n_all;
+    MZB_CHECK_ARG(n_ops <= MAX_LAYERS, "at most 32 convolution records per launch");
     const bool split = n_ops >= 3 && ops[n_ops - 1].cout == CH / 2 && ops[n_ops - 2].cout == CH / 2;
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
@@ -376,11 +551,13 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
-    return split ? 1 : 0;       // 1: the last two records are the halves of a split layer (pass n_ops and split_last = 1 to mz_lat_run)
+    return (split ? 1 : 0) | (ntails << 1);       // flags for mz_lat_run: bit 0 = the last two convolution records are the halves of a split layer, bits 1-2 = tail ops
 }
 
-int mz_lat_run(const void *blob_dev, int n_ops, int split_last, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
+int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream)
 {
+    const int split_last = flags & 1, ntails = (flags >> 1) & 3;
+    n_ops -= ntails;                         // convolution records
     MZB_CHECK_ARG(n_ops <= MAX_LAYERS && (!split_last || n_ops >= 3), "too many layers for one launch");
     const int n_layers = n_ops - (split_last ? 1 : 0);
     MZB_CHECK_ARG(blob_dev && n_layers > 0 && nsamples > 0 && done && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
@@ -389,6 +566,7 @@ int mz_lat_run(const void *blob_dev, int n_ops, int split_last, int nsamples, co
     p.layers = reinterpret_cast<const LatLayer *>(blob_dev);
     p.nlayers = n_layers;
     p.split_last = split_last ? 1 : 0;
+    p.ntails = ntails;
     p.n = nsamples;
     p.rtiles = (nsamples + RS - 1) / RS;
     p.f16 = dtype == MZ_F16;

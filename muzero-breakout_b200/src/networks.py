@@ -72,13 +72,16 @@ def _lat_stackable(o) -> bool:
 class _Stack:
     """A run of stackable convolutions executed by one persistent launch (mz_stack_run, or mz_lat_run for small batches)."""
 
-    def __init__(self, ops, n, device, lat_max=None):
+    def __init__(self, ops, n, device, lat_max=None, n_tail=0):
+        """ops: the convolutions, followed (latency mode only) by n_tail head / scale ops that run at the end of the same launch."""
         L = _lib.lib()
         self.n, self.nlayers = n, len(ops)
         self.act_idx = next((o.act_idx for o in ops if o.act_idx), None)
         self.dtype = ops[0].dtype
         arr = (MzOp * self.nlayers)(*ops)
-        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max) and self.nlayers <= L.mz_lat_max_layers() and all(_lat_stackable(o) for o in ops)
+        convs = ops[:len(ops) - n_tail]
+        self.lat = n <= (lat_max_samples() if lat_max is None else lat_max) and len(convs) <= L.mz_lat_max_layers() and all(_lat_stackable(o) for o in convs)
+        assert self.lat or n_tail == 0
         if self.lat:
             self.ok = True
             lb = L.mz_lat_layer_bytes()
@@ -87,7 +90,7 @@ class _Stack:
             rc = L.mz_lat_build(arr, self.nlayers, host, self.nlayers * lb)
             if rc < 0:
                 _lib.check(rc)
-            self.split_last = int(rc == 1)               # the last two records are the two halves of one layer
+            self.flags = rc                              # bit 0: the last two convolutions are the halves of one layer; bits 1-2: tail ops
             self.blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone().to(device)
             self.chunks = [(0, n)]
             self.done = torch.zeros(self.nlayers * ((n + 2) // 3), dtype=torch.int32, device=device)
@@ -117,7 +120,7 @@ class _Stack:
     def run(self, st):
         L = _lib.lib()
         if self.lat:
-            _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.split_last, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
+            _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.flags, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
             return
         for s0, cnt in self.chunks:
             _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, s0, cnt, self.bufs, self.nbufs, self.act_idx,
@@ -187,10 +190,18 @@ class Program:
             else:
                 while fuse and j < len(self.ops) and _stackable(self.ops[j]):
                     j += 1
-            stack = _Stack(self.ops[i:j], self.n, device, self.lat_max) if j - i >= 2 else None
+            n_tail = 0
+            if lat and j - i >= 2:
+                # the heads (Flatten + Linear + softmax / expectation) and _scale_state that follow run at the end of the same launch
+                while (n_tail < 2 and j + n_tail < len(self.ops) and self.ops[j + n_tail].dtype == self.ops[i].dtype
+                       and (self.ops[j + n_tail].op == OP_HEAD and self.ops[j + n_tail].nout in (3, 11)
+                            or self.ops[j + n_tail].op == OP_SCALE and self.ops[j + n_tail].H * self.ops[j + n_tail].W * self.ops[j + n_tail].cin == 5120)):
+                    n_tail += 1
+            stack = _Stack(self.ops[i:j + n_tail], self.n, device, self.lat_max, n_tail) if j - i >= 2 else None
+            j += n_tail if stack is not None and stack.ok else 0
             if stack is not None and stack.ok:
                 flush()
-                segs.append(("stack", stack, j - i))
+                segs.append(("stack", stack, j - i))          # j - i: ops covered by the launch
                 i = j
             else:
                 plain.append(self.ops[i])

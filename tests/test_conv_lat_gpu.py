@@ -132,7 +132,9 @@ def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
         a = lat.dynamics(h, _planes(acts)) + lat.prediction(h)
         n1 = _lib.launch_count()
         b = tc.dynamics(h, _planes(acts)) + tc.prediction(h)
-        assert n1 - n0 == _lib.launch_count() - n1 - 3, "one launch per trunk in both forms; the latency form also takes the three head ConvBlocks"
+        # latency form: layout in, ONE launch for the dynamics network (trunk + reward ConvBlock + reward head + _scale_state), layout out;
+        # layout in, ONE launch for the prediction network (trunk + policy / value ConvBlocks + both heads)
+        assert n1 - n0 == 5 and _lib.launch_count() - n1 == 12, (n1 - n0, _lib.launch_count() - n1)
         for x, y, o, what in zip(a, b, (oh, orew, opol, oval), ("latent", "reward", "policy", "value")):
             assert torch.isfinite(x).all()
             assert rel(x, y) <= 2e-2, f"n={n} {what}: latency trunk vs tcgen05 trunk {rel(x, y):.2e}"
