@@ -241,8 +241,8 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  * Latency-mode residual trunk (csrc/conv_lat.cu): the same run of stackable convolutions as mz_stack_*, for SMALL
  * leaf batches (config.yaml's default acting stage, train_torch.py:164-258 with n_parallel = 24: every network call of
  * src/mcts.py:95,194-198 has 24 samples).  One persistent launch of 16 * ceil(nsamples/3) work items
- * (3-sample row tile x 16-output-channel slice; warp-level mma.sync, weights streamed by TMA one item ahead, layers ordered by
- * device counters per row tile).  Results are the same convolution on the same 16-bit operands with fp32
+ * (3-sample row tile x 16-output-channel slice; warp-level mma.sync, weights streamed by TMA one item ahead, layers handed over
+ * through flag-in-data words in L2).  Results are the same convolution on the same 16-bit operands with fp32
  * accumulation; the accumulation ORDER differs from the tcgen05 kernels, so outputs agree to fp32 rounding, not bit
  * for bit.
  *   mz_lat_layer_bytes()   size of one device-resident layer descriptor
@@ -256,15 +256,19 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  *                          channel slices.  Up to two trailing MZ_OP_HEAD / MZ_OP_SCALE records (3 or 11 head outputs; 5120-element
  *                          _scale_state) become tail ops: they run per sample at the end of the same launch.  Returns flags >= 0
  *                          (bit 0: the convolutions end with a split pair; bits 1-2: number of tail ops), < 0 on error.
+ *   mz_lat_scratch_bytes   size of the launch's scratch (layer hand-off buffers + epoch / counters) for nsamples
  *   mz_lat_run             runs the n_ops records on samples [0, nsamples): flags = mz_lat_build's return value,
- *                          act_idx as in mz_op, done = int32 [n_ops * ceil(nsamples/3)] scratch (zeroed here, on the stream)
+ *                          act_idx as in mz_op, scratch = mz_lat_scratch_bytes(nsamples) bytes, 16-byte aligned, ZEROED ONCE by
+ *                          the caller and then owned by this trunk's launches (they keep a launch epoch in it, so a
+ *                          CUDA-graph replay needs no reset; one scratch per concurrently running trunk)
  */
 size_t mz_lat_layer_bytes(void);
 int mz_lat_max_samples(void);
 int mz_lat_max_layers(void);    /* layer descriptors of one launch are staged in shared memory: at most this many (32) */
 int mz_lat_trace(unsigned long long *host_out_8x64);   /* profiling aid (MZB_LAT_TRACE=1): per-layer phase timestamps of CTA 0 */
 int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes);
-int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const int32_t *act_idx, int32_t *done, int dtype, void *stream);
+size_t mz_lat_scratch_bytes(int nsamples);
+int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const int32_t *act_idx, void *scratch, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay buffer  (reference: replay_buffer.py)

@@ -79,6 +79,7 @@ def _declare(L: C.CDLL) -> None:
     L.mz_lat_layer_bytes.argtypes, L.mz_lat_layer_bytes.restype = [], C.c_size_t
     L.mz_lat_max_samples.argtypes, L.mz_lat_max_samples.restype = [], i32
     L.mz_lat_max_layers.argtypes, L.mz_lat_max_layers.restype = [], i32
+    L.mz_lat_scratch_bytes.argtypes, L.mz_lat_scratch_bytes.restype = [i32], C.c_size_t
     sig.update({
         "mz_puct_tables": [i32, C.c_double, C.c_double, vp, vp],
         "mz_tree_root": [C.POINTER(TreeArgs), vp],

@@ -93,7 +93,7 @@ class _Stack:
             self.flags = rc                              # bit 0: the last two convolutions are the halves of one layer; bits 1-2: tail ops
             self.blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone().to(device)
             self.chunks = [(0, n)]
-            self.done = torch.zeros(self.nlayers * ((n + 2) // 3), dtype=torch.int32, device=device)
+            self.done = torch.zeros((L.mz_lat_scratch_bytes(n) + 3) // 4, dtype=torch.int32, device=device)   # zeroed once; the launches keep their epoch in it
             return
         bufs = []
         for o in ops:

@@ -1,7 +1,7 @@
 """Per-layer phase timeline of the latency-mode trunk (csrc/conv_lat.cu), CTA 0, from globaltimer stamps:
     MZB_LAT_TRACE=1 python profiles/prof_lat_trace.py 24
-phases per layer: wait (spin on the previous layer's counter) | load (activation rows + this layer's weights landed) |
-math (18 k16 steps per warp) | reduce+epilogue (partials through shared memory, stores) | publish (fence, barrier, red.release)"""
+phases per layer: poll+load (the previous layer's flag-in-data words polled into the row buffer + this layer's weights landed) |
+w-issue (next item's TMA boxes) | math (18 k16 steps per warp) | to-smem (partials) | reduce+epilogue (stores) | end (barrier)"""
 import ctypes
 import os
 import sys
@@ -26,7 +26,7 @@ L.mz_lat_trace(buf.ctypes.data)
 t = buf.reshape(8, 64).astype(np.int64)
 t = t[[0, 1, 2, 6, 7, 3, 4, 5]]      # program order: slot 6 = next layer's weight prefetch issued, 7 = MMAs done
 nl = 28
-names = ["wait", "load", "w-issue", "math", "to-smem", "reduce+epi", "publish"]
+names = ["-", "poll+load", "w-issue", "math", "to-smem", "reduce+epi", "end"]
 d = np.stack([t[i + 1, :nl] - t[i, :nl] for i in range(7)])
 for l in range(nl):
     print(f"layer {l:2d}: " + "  ".join(f"{names[i]} {d[i, l]:6d}" for i in range(7)) + f"   total {t[7, l] - t[0, l]:6d} ns")
