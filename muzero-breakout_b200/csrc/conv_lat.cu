@@ -6,7 +6,7 @@
 // is 20 tiles (20 of the 148 SMs), each of which streams the whole 1.18 MB weight tensor through one SM's TMA port and
 // issues 256x256x16 MMAs with 24 useful rows -- ~20 us per layer, 57 dependent layers per simulation step.  Here a layer
 // is cut into (3-sample row tile) x (16-output-channel slice) work items, 16 * ceil(n/3) of them (128 CTAs at n = 24): every
-// SM streams only its 72 KB slice of the weights (4 TMA boxes of 9 [16 channels][64 inputs] units, SWIZZLE_128B = the layout
+// SM streams only its 72 KB slice of the weights (one TMA box of 36 [16 channels][64 inputs] units, SWIZZLE_128B = the layout
 // ldmatrix wants, requested one item ahead by one thread, double-buffered, mbarrier-tracked), the 60 activation rows of its
 // samples stay in shared memory for all 9 taps, and the math is warp-level mma.sync m16n8k16 (bf16/fp16 in, fp32
 // accumulate) with the K dimension split over the 8 warps (warp w owns input channels [32 w, 32 w + 32) of every tap).
@@ -84,7 +84,7 @@ static_assert(sizeof(LatTail) <= sizeof(LatLayer), "a tail op fits a blob slot")
 constexpr int MAX_TAILS = 2;
 constexpr int LL_PER_THREAD = ROWS * (CH / 4) / THREADS;       // 15 16-byte hand-off loads per thread and item
 static_assert(LL_PER_THREAD * THREADS == ROWS * CH / 4, "hand-off loads");
-constexpr int W_BOX = 9;                 // units per TMA box: 4 boxes of 18 KB per item (36 boxes of 2 KB took 6.5 us to land: the TMA unit is per-box-latency-bound)
+constexpr int W_BOX = 36;                // units per TMA box: the whole 72 KB slice in one instruction (each cp.async.bulk.tensor issue holds its thread ~0.1-0.15 us; 36 boxes of 2 KB took 6.5 us to land)
 constexpr int OFF_W = 0, OFF_A = 2 * W_BYTES, OFF_RED = OFF_A + A_BYTES, OFF_OPS = OFF_RED + RED_BYTES, OFF_BAR = OFF_OPS + MAX_LAYERS * 64;
 constexpr int LAT_SMEM = OFF_BAR + 16;   // 210 KB
 static_assert(LAT_SMEM <= 232448 && OFF_A % 1024 == 0 && OFF_OPS % 16 == 0 && OFF_BAR % 8 == 0, "shared-memory map (weight units are SWIZZLE_128B atoms: 1024-byte aligned)");
