@@ -265,7 +265,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) tree_kernel(Params p)
         if (selecting && p.dyn_in) {
             const uint4 *src = p.latent_store + ((size_t)tree * p.lay.nodes + parent) * p.latent_vec;
             uint4 *dst = p.dyn_in + (size_t)tree * p.latent_vec;
-            for (int i = lane; i < p.latent_vec; i += 32) dst[i] = src[i];
+            // batches of 8 loads in flight per lane before the stores (src and dst may alias as far as the compiler knows, so a plain
+            // copy loop is one dependent L2 round trip per 512 bytes: 20 of them for a 10 KB latent, most of a small batch's tree step)
+            for (int i0 = lane; i0 < p.latent_vec; i0 += 32 * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (i0 + 32 * k < p.latent_vec) v[k] = __ldcs(src + i0 + 32 * k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (i0 + 32 * k < p.latent_vec) dst[i0 + 32 * k] = v[k];
+            }
         }
         __syncwarp();
     }
