@@ -246,7 +246,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
  * accumulation; the accumulation ORDER differs from the tcgen05 kernels, so outputs agree to fp32 rounding, not bit
  * for bit.
  *   mz_lat_layer_bytes()   size of one device-resident layer descriptor
- *   mz_lat_max_samples()   largest batch hosts run here (81 = three waves of work items; measured crossover with the tcgen05 trunk)
+ *   mz_lat_max_samples()   largest batch hosts run here (108 = four waves of work items; measured crossover with the tcgen05 trunk)
  *   mz_lat_build           fills a HOST blob (64-byte aligned, n_ops * mz_lat_layer_bytes() bytes) from the op records
  *                          (a weight tensor map + operand pointers per record); the caller copies it to device memory once.
  *                          Records: 3x3 or 1x1 256->256 convolutions forming a chain (ops[i].src == ops[i-1].dst; the 1x1 is the

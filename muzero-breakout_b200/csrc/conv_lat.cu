@@ -531,8 +531,8 @@ size_t mz_lat_layer_bytes(void) { return sizeof(LatLayer); }
 int mz_lat_max_layers(void) { return MAX_LAYERS; }
 
 // Measured crossover (profiles/README.md, ms per simulation step, latency mode vs tcgen05 trunk): 27 samples (one wave of 144 items)
-// 0.40 vs 1.20, 48 (two waves) 0.69 vs 1.22, 60 (three) 0.97 vs 1.23, 96 (four) 1.26 vs 1.25 -> up to three waves
-int mz_lat_max_samples(void) { return 3 * RS * (mzb::kNumSMs / NSLICES); }    // 81
+// 0.32 vs 1.20, 81 (three waves) 0.88 vs 1.23, 108 (four) 1.16 vs 1.26, 135 (five) 1.46 vs 1.27 -> up to four waves
+int mz_lat_max_samples(void) { return 4 * RS * (mzb::kNumSMs / NSLICES); }    // 108
 
 int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 x 64 trace words
 {
