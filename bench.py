@@ -393,8 +393,9 @@ def bench_mcts(args, rank, local, world):
         t24 = a.elapsed_time(b) / 5
         out["config_defaults"] = {"workload": "MCTSSearchVec.search, config.yaml defaults: 24 roots x 50 simulations (BASELINE.json configs[1])",
                                   "ms_per_search": t24, "value": 24 * S / (t24 * 1e-3), "unit": "simulations/s",
-                                  "note": "latency-bound (57 dependent trunk layers per simulation): trunks run in latency mode, csrc/conv_lat.cu, 128 work items "
-                                          "of 3 samples x 16 output channels per layer on mma.sync, ~5.5 us per layer against ~20 us on the tcgen05 trunk"}
+                                  "note": "latency-bound (57 dependent trunk layers per simulation): the networks run in latency mode, csrc/conv_lat.cu -- 128 work items "
+                                          "of 3 samples x 16 output channels per layer on mma.sync, flag-in-data layer hand-off, head convolutions / heads / _scale_state "
+                                          "inside the same launch: 3 launches per simulation step, ~4.8 us per layer against ~20 us on the tcgen05 trunk"}
     return out, sd
 
 
