@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             asm volatile("cp.async.wait_all;" ::: "memory");
         } else {
             // Layer hand-off, flag in data (the NCCL "LL" idea): the previous layer's 16 items wrote every pair of output channels as one
-            // 8-byte word {2 x 16-bit, flag}, flag = (launch epoch, layer).  An 8-byte store is indivisible, so a word that carries this
+            // 8-byte word {2 x 16-bit, flag}, flag = (launch epoch, layer).  A 64-bit store is indivisible, so a word that carries this
             // layer's flag carries this layer's data: no fence on the producer side, no counter, no second round trip -- the consumer
             // polls the data itself (16-byte loads = 2 words) and moves what has arrived into the row buffer.
             const uint32_t want = flag_base + (uint32_t)layer;                     // = flag of layer - 1's outputs
@@ -360,7 +360,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 for (int k = 0; k < LL_PER_THREAD; ++k)
                     if ((pending >> k) & 1u) {
                         const uint4 *q = llp + tid + k * THREADS;
-                        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(q) : "memory");
+                        // two 64-bit elements: a naturally aligned 64-bit access is single-copy atomic in the PTX memory model, so data and
+                        // flag of a word are always from the same store
+                        unsigned long long w0, w1;
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(q) : "memory");
+                        v[k] = make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
                     }
 #pragma unroll
                 for (int k = 0; k < LL_PER_THREAD; ++k)
@@ -465,7 +469,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 const uint32_t packed = pack2(x0, x1, F16);
                 if (layer + 1 < p.nlayers) {                      // the next layer's items poll this word
                     uint2 *w = p.ll + ((size_t)(layer & 1) * p.rtiles + rt) * (ROWS * CH / 2) + (size_t)r * (CH / 2) + (co >> 1);
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(packed), "r"(flag_base + (uint32_t)layer + 1u) : "memory");
+                    const unsigned long long word = (unsigned long long)packed | ((unsigned long long)(flag_base + (uint32_t)layer + 1u) << 32);
+                    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w), "l"(word) : "memory");          // one indivisible 64-bit store
                 }
                 *reinterpret_cast<uint32_t *>(reinterpret_cast<uint16_t *>(L->dst) + o) = packed;
                 if (L->dst_f32) *reinterpret_cast<float2 *>(L->dst_f32 + o) = make_float2(x0, x1);
