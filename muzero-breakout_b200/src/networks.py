@@ -484,9 +484,12 @@ class PackedNetworks:
         # both head ConvBlocks first (they read the same trunk output and write the two halves of `mid`), then the two Linear heads:
         # in latency mode the pair rides as the last, split layer of the trunk launch
         half = n * H * W * self.policy_conv.cout
-        assert self.policy_conv.cout + self.value_conv.cout <= mid.shape[-1], "mid holds both heads' feature maps"
         mid_p = mid.view(-1)[:half].view(n, H * W, self.policy_conv.cout)
-        mid_v = mid.view(-1)[half:half + n * H * W * self.value_conv.cout].view(n, H * W, self.value_conv.cout)
+        if self.policy_conv.cout + self.value_conv.cout <= mid.shape[-1]:
+            mid_v = mid.view(-1)[half:half + n * H * W * self.value_conv.cout].view(n, H * W, self.value_conv.cout)
+        else:                                                      # head ConvBlocks wider than half the latent: a buffer of its own
+            mid_v = self.buf(n, H * W, self.value_conv.cout)
+            prog.keep.append(mid_v)
         self._add_conv(prog, self.policy_conv, H, W, bufs[cur], mid_p)
         self._add_conv(prog, self.value_conv, H, W, bufs[cur], mid_v)
         for lin, conv, src_, mode, out, logits in ((self.policy_lin, self.policy_conv, mid_p, pi_mode, pi, policy_logits),
