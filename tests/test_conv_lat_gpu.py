@@ -115,7 +115,7 @@ def agent():
 @pytest.mark.parametrize("n", [2, 24, 27, 61])
 def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
     """dynamics + prediction with the trunks in latency mode against the same networks on the tcgen05 trunk (lat_max = 0)
-    and against the fp32 torch oracle; run twice (the done-counters are re-zeroed on the stream each run)."""
+    and against the fp32 torch oracle; run twice (the second run is the next launch epoch on the same hand-off buffers)."""
     from muzero_breakout_b200.src.networks import PackedNetworks, lat_max_samples
     assert n <= lat_max_samples()
     lat = PackedNetworks(agent, agent.cfg, precision="bf16")
