@@ -130,3 +130,22 @@ def test_mutable_attributes_and_repacking(agent):
     other.load_state_dict(agent.state_dict())
     v4, n4 = m.search(hidden, None, 0, noise=noise, seed=5)
     assert np.array_equal(v4.numpy(), v1.numpy()) and np.array_equal(n4.numpy(), n1.numpy())
+
+
+@pytest.mark.parametrize("B", [24, 70])
+def test_repeated_graph_replays_are_deterministic(agent, B):
+    """The latency-mode networks keep a launch epoch in their hand-off buffers instead of resetting them (csrc/conv_lat.cu):
+    many replays of the same captured search with the same noise and seed must return bit-identical results, and a replay
+    after a different input must not see anything stale."""
+    m = make(agent, "bf16", output_device="cuda")
+    g = torch.Generator().manual_seed(B)
+    h1, h2 = torch.rand(B, 256, 4, 5, generator=g), torch.rand(B, 256, 4, 5, generator=g)
+    noise = dirichlet_noise(B, seed=3)
+    v1, n1 = m.search(h1, None, 0, noise=noise, seed=11)
+    v2, n2 = m.search(h2, None, 0, noise=noise, seed=11)
+    assert int(n1.sum()) == B * CFG["num_simulations"] and not torch.equal(v1, v2)
+    for rep in range(12):
+        va, na = m.search(h1, None, 0, noise=noise, seed=11)
+        assert torch.equal(va, v1) and torch.equal(na, n1), f"replay {rep} of input 1 differs"
+        vb, nb = m.search(h2, None, 0, noise=noise, seed=11)
+        assert torch.equal(vb, v2) and torch.equal(nb, n2), f"replay {rep} of input 2 differs"
