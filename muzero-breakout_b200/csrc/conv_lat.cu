@@ -15,12 +15,14 @@
 // an item is 1152 HMMA + 720 LDSM.x4, i.e. shared-memory-read-bound at 2900 cycles = 1.5 us (the math phase takes 2.2 us).
 // Tried and backed out (profiles/experiments/conv_lat_cluster16.cu.txt): one 16-CTA cluster per row tile with the layer
 // hand-off through distributed shared memory -- only 7 such clusters fit on the chip at once (24 roots need 8), and the
-// 16 x 16 slice broadcast + barrier.cluster cost 2.7 us per layer against 2.1 us for the global-memory hand-off below.
+// 16 x 16 slice broadcast + barrier.cluster cost 2.7 us per layer against 2.1 us for the first global-memory hand-off below.
+// The network's other pieces ride in the same launch: 1x1 256->256 layers (the reward head's ConvBlock), a split last layer
+// (policy 3x3 + value 1x1 256->128 ConvBlocks) and per-sample tail ops (heads, _scale_state) -- 3 launches per simulation step.
 //
 // Layer ordering without kernel boundaries: a 3x3 convolution never mixes samples, so item (layer L, row tile r) needs
 // exactly the 16 channel slices of (L-1, r).  The hand-off is "flag in data" (the idea of NCCL's LL protocol): every pair of
 // output channels is stored as one 8-byte word {2 x 16-bit, flag = (launch epoch, layer)} into a per-row-tile buffer (two buffers,
-// by layer parity); an 8-byte store is indivisible, so a consumer that polls the words and finds this layer's flag has this
+// by layer parity); a 64-bit store is indivisible, so a consumer that polls the words and finds this layer's flag has this
 // layer's data -- no fence, no counter, no second round trip.  A buffer is overwritten two layers later, by items that have
 // consumed the layer in between, which exists only when all consumers of the older data were done with it.  The launch epoch
 // lives in device memory and is advanced by the last CTA to finish, so a CUDA-graph replay needs no reset of the buffers.
