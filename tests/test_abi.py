@@ -80,6 +80,21 @@ def test_ctypes_mirrors_match_the_c_structs():
     assert L.mzb_sizeof(2) == ctypes.sizeof(RbRing)
 
 
+def test_latency_trunk_host_queries():
+    """host-side entry points of the latency-mode trunk (csrc/conv_lat.cu) that need no GPU: sizes, limits, argument checks."""
+    from muzero_breakout_b200.src.networks import MzOp, lat_max_samples
+    L = mzb.lib()
+    assert L.mz_lat_layer_bytes() == 192 and L.mz_lat_max_layers() == 32
+    assert L.mz_lat_max_samples() == 108 and lat_max_samples() == 108          # four waves of 27 samples
+    for n, rtiles in ((1, 1), (24, 8), (25, 9), (108, 36)):
+        assert L.mz_lat_scratch_bytes(n) == 2 * rtiles * 60 * 128 * 8 + 4 * (2 + 2 * rtiles)
+    ops = (MzOp * 1)()
+    raw = (ctypes.c_uint8 * 512)()
+    host = (ctypes.addressof(raw) + 63) & ~63
+    assert L.mz_lat_build(ops, 0, host, 192) < 0 and b"bad argument" in L.mzb_last_error()       # no records
+    assert L.mz_lat_run(None, 1, 0, 24, None, None, 1, None) < 0                                  # null blob / scratch: refused before any launch
+
+
 def test_replay_buffer_mirrors_reference_signature():
     """replay_buffer.py:76-94 constructor and the methods train_torch.py calls (:101,147,225,230,377,469-476)."""
     from muzero_breakout_b200.replay_buffer import ObservationTrajectory, ReplayBuffer
