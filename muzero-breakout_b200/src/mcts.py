@@ -175,16 +175,25 @@ class MCTSSearchVec:
         self._nets = None
         self._nets_external = False
         self._nets_key = None
+        self._key_refs = None          # (module, its parameter / buffer tensors, their ids): see _weights_key
         self._plans = {}
         self.max_plans = int(s.get("max_plans", 3))
         self._calls = 0
 
     # ------------------------------------------------------------------ weights
     def _weights_key(self):
+        """Identity of the module + the version counters of its parameters and buffers (load_state_dict and optimizer steps bump
+        them in place, train_torch.py:137-138,361-367; :449-451 swaps the module).  Walking the module tree costs ~1.2 ms per call
+        (542 tensors) -- 7 % of a 24-root search -- so the tensor list is cached per module object and only the version counters are
+        read per call (0.07 ms); the full walk is repeated every 16th call in case a Parameter object itself was replaced."""
         m = self.mu_zero
         if isinstance(m, PackedNetworks):
             return ("packed", id(m))
-        return (id(m),) + tuple((id(p), p._version) for p in m.state_dict(keep_vars=True).values())
+        refs = self._key_refs
+        if refs is None or refs[0] is not m or self._calls % 16 == 0:
+            tensors = list(m.state_dict(keep_vars=True).values())
+            self._key_refs = refs = (m, tensors, tuple(id(t) for t in tensors))
+        return (id(m), refs[2]) + tuple(t._version for t in refs[1])
 
     def packed_networks(self) -> PackedNetworks:
         """(Re)pack when the module object or any parameter/buffer version changed

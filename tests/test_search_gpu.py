@@ -130,6 +130,11 @@ def test_mutable_attributes_and_repacking(agent):
     other.load_state_dict(agent.state_dict())
     v4, n4 = m.search(hidden, None, 0, noise=noise, seed=5)
     assert np.array_equal(v4.numpy(), v1.numpy()) and np.array_equal(n4.numpy(), n1.numpy())
+    # an in-place update of one parameter of the same module (an optimizer step): seen through its version counter on the next call
+    with torch.no_grad():
+        other.pred_net.value_head[2].bias[:3].add_(4.0)
+    v5, n5 = m.search(hidden, None, 0, noise=noise, seed=5)
+    assert np.array_equal(v5.numpy(), v3.numpy()) and not np.allclose(v5.numpy(), v1.numpy())
 
 
 @pytest.mark.parametrize("B", [24, 70])
