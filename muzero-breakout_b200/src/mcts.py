@@ -124,6 +124,7 @@ class _SearchPlan:
         self.keep = [store, dyn_in, bufs, mid, f32]
         self.use_graph = use_graph
         self.graph = None
+        self.conc = None              # (alpha, device tensor of concentrations) of the root noise, allocated on first use
         self.kernels_per_search = self.root_prog.n_kernels + 1 + S * (self.sim_prog.n_kernels + 1)
 
     def _enqueue(self, seed, use_seed_dev):
@@ -237,8 +238,9 @@ class MCTSSearchVec:
         else:
             self._plans[key] = self._plans.pop(key)         # most recently used last
         if noise is None:                                   # Dirichlet(0.25 * ones(3)) per tree, mcts.py:114
-            conc = torch.full((B, len(self.actions)), self.dirchlet_alpha, device=self.device)
-            noise = torch._sample_dirichlet(conc)
+            if plan.conc is None or plan.conc[0] != self.dirchlet_alpha:          # (alpha on the host, its device tensor)
+                plan.conc = (self.dirchlet_alpha, torch.full((B, len(self.actions)), self.dirchlet_alpha, device=self.device))
+            noise = torch._sample_dirichlet(plan.conc[1])
         if seed is None:
             seed = (self.seed * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03 + 1) & 0xFFFFFFFFFFFFFFFF
         self._calls += 1

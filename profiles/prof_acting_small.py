@@ -23,10 +23,11 @@ actor = Actor(env, m, temperature=1.0, seed=0, max_moves=moves, check_done_every
 actor.run_episode()
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-actor.run_episode()
-b.record(); torch.cuda.synchronize()
-print(f"n={B}: acting move {a.elapsed_time(b) / moves:.2f} ms (rep input + representation net + search + sampling + env step + record)")
+for rep in range(3):
+    a.record()
+    actor.run_episode()
+    b.record(); torch.cuda.synchronize()
+    print(f"n={B}: acting move {a.elapsed_time(b) / moves:.2f} ms (rep input + representation net + search + sampling + env step + record)")
 x = torch.rand(B, 64, 16, 20, device="cuda")
 out = torch.empty(B, 256, 4, 5, device="cuda")
 prog = nets.representation_program(B, x, out)
