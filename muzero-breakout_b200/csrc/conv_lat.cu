@@ -44,7 +44,6 @@ constexpr int NSLICES = CH / NS;         // 16
 constexpr int KSTEPS = 9 * CH / 16;      // 144 k16 steps per item
 constexpr int WARPS = 8, THREADS = WARPS * 32;
 constexpr int STEPS_PER_WARP = KSTEPS / WARPS;   // 18
-constexpr int ZROW = 63;                 // an all-zero activation row (padding taps, padding rows)
 constexpr int A_PITCH = CH * 2 + 16;     // 528 B: consecutive rows start 16 bytes apart modulo 128 -> conflict-free ldmatrix without an XOR
 constexpr int A_BYTES = 64 * A_PITCH;    // 33 KB: [64 rows][528 B]
 constexpr int W_UNITS = 9 * (CH / 64);   // 36 (tap, 64-channel chunk) units of [16 rows][128 B]
@@ -403,6 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         uint32_t af[2][MT][4], bf[2][4];
         uint32_t rowa[MT];
         const uint32_t a_base = sA_u + (uint32_t)(warp * 4 + a_khalf) * 16;                         // + row * A_PITCH (+ 32 for the second k16)
+        const uint32_t zero_base = sA_u + ROWS * A_PITCH;                                           // rows 60..63: 2112 bytes of zeros; [0, 160) are used
         const uint32_t b_base0 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
         const uint32_t b_base1 = wbuf + (warp >> 1) * (NS * 128) + b_n * 128 + (((((warp * 2 + 1) & 3) * 2 + b_khalf) ^ (b_n & 7)) << 4);
         // i = tap * 2 + j (compile-time after unrolling); wtap = the tap's index in the weight tensor
@@ -412,8 +412,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 const int doff = (tap / 3 - 1) * LAT_W + (tap % 3 - 1);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    const int row = ((a_mask[mt] >> tap) & 1u) ? a_row[mt] + doff : ZROW;        // zero padding, padding rows, samples past n
-                    rowa[mt] = a_base + row * A_PITCH;
+                    // zero padding, padding rows, samples past n: a 16-byte chunk of the zero rows IN THE BANK GROUP of the row it
+                    // replaces -- a fixed zero chunk collides with whichever valid row of the same 8x16-byte matrix shares its
+                    // bank group (border pixels are 14 of 20: ncu showed 24 % extra shared-memory wavefronts from bank conflicts)
+                    const uint32_t addr = a_base + (uint32_t)((a_row[mt] + doff) * A_PITCH);
+                    rowa[mt] = ((a_mask[mt] >> tap) & 1u) ? addr : zero_base + ((addr - zero_base) & 127u);
                 }
             }
             ldmatrix_x4((j ? b_base1 : b_base0) + wtap * 4 * (NS * 128), b);
