@@ -377,6 +377,7 @@ def bench_mcts(args, rank, local, world):
         out["acting"] = bench_acting(args, m, dev, rank, world)
     if not args.no_aux:
         out["replay"] = bench_replay(args, dev, rank, world, cpu=not args.no_cpu_baseline)
+        out["train_ends"] = bench_train_ends(dev, rank, world, cpu=not args.no_cpu_baseline)
     if rank == 0 and not args.no_aux:
         # BASELINE.json configs[1]: config.yaml defaults (24 roots x 50 simulations), same weights, one GPU
         cfg24 = dict(cfg); cfg24["search"] = dict(cfg["search"], seed=3)
@@ -482,6 +483,62 @@ def bench_replay(args, dev, rank, world, cpu=True):
         t2 = time.perf_counter()
         out["cpu_baseline"] = {"append_moves_per_s": n_moves / (t1 - t0), "minibatch_samples_per_s": mb / (t2 - t1), "cores": 1, "kind": "port",
                                "sample": f"oracle/replay_oracle.py (numpy restatement of replay_buffer.py): 6 trajectories / {n_moves} moves saved, one 512-sample minibatch"}
+    return out
+
+
+def bench_train_ends(dev, rank, world, cpu=True):
+    """Loss and optimizer ends of the training step (first slice): mz_adam over the 42 205 081 parameters of
+    the three networks (28 B per parameter: HBM-bound) and mz_loss on config.yaml's minibatch (512 x K=5 rows, launch-bound)."""
+    from muzero_breakout_b200 import _lib
+    from muzero_breakout_b200.train import loss_fn
+    L = _lib.lib()
+    n = 42_205_081
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    p = torch.randn(n, device=dev, generator=g) * 0.05
+    grad = torch.randn(n, device=dev, generator=g) * 1e-3
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    step = [0]
+
+    def adam():
+        step[0] += 1
+        _lib.check(L.mz_adam(n, p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, step[0], stream))
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    adam_ms = timed(adam, 20)
+    B, K = 512, 5
+    pr, pv = (torch.randn(B, K, 11, device=dev, generator=g) for _ in range(2))
+    pp = torch.randn(B, K, 3, device=dev, generator=g)
+    obs = torch.randint(-1, 2, (B, K), device=dev, generator=g).float()
+    val = (torch.rand(B, K, device=dev, generator=g) - 0.5) * 20
+    vis = torch.randint(1, 30, (B, K, 3), device=dev, generator=g).float()
+    sup = torch.linspace(-5, 5, 11, device=dev)
+    loss_ms = timed(lambda: loss_fn(obs, pr, val, pv, vis, pp, sup, K), 50)
+    peaks = measured_peaks()
+    out = {"adam": {"ms": adam_ms, "parameters": n, "GBps": n * 28 / adam_ms / 1e6, "frac_of_hbm_peak": n * 28 / adam_ms / 1e6 / peaks["hbm"],
+                    "bytes_per_parameter": 28, "what": "mz_adam: one launch over the flat fp32 parameter / gradient / moment buffers (1.18 GB of traffic, larger than L2)"},
+           "loss": {"ms": loss_ms, "rows": B * K, "what": "train.loss_fn: one mz_loss launch (3 KL divergences + total + gradients w.r.t. the logits) + output allocations"}}
+    if cpu and rank == 0 and world == 1:
+        from oracle import train_oracle as T
+        ns = 2_000_000
+        cp, cg = p[:ns].cpu().numpy(), grad[:ns].cpu().numpy()
+        t0 = time.perf_counter()
+        T.adam_step(cp, cg, np.zeros(ns, np.float32), np.zeros(ns, np.float32), 1)
+        t1 = time.perf_counter()
+        T.loss_fn(obs.cpu().numpy(), pr.cpu().numpy(), val.cpu().numpy(), pv.cpu().numpy(), vis.cpu().numpy(), pp.cpu().numpy(), sup.cpu().numpy(), K)
+        t2 = time.perf_counter()
+        out["cpu_baseline"] = {"adam_parameters_per_s": ns / (t1 - t0), "loss_ms": (t2 - t1) * 1e3, "cores": 1, "kind": "port",
+                               "sample": f"oracle/train_oracle.py (numpy restatement): one Adam update of {ns} parameters, one loss_fn of {B * K} rows"}
     return out
 
 

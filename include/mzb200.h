@@ -326,6 +326,35 @@ int rb_gather(const rb_ring *ring, int n, const int64_t *idx, int64_t *past_acti
               float *states, float *rewards, float *visit_counts, float *values, float *value_buffer,
               float *reward_sums, int32_t *status, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step, first slice: the loss and the optimizer update.  The
+ * backward passes of the three networks are not part of this library yet.
+ *
+ * mz_loss replaces loss_fn (train_torch.py:33-66) + ScalarTransforms.supports_representation
+ * (utils.py:30-64) + what loss.backward() (train_torch.py:515) produces for the three logit tensors.
+ *   rows = batch * K samples (the .view(-1, n) of :49-63); supports float32[n_supports] =
+ *   ScalarTransforms.supports (utils.py:19); pred_reward / pred_value float32[rows][n_supports] raw logits,
+ *   pred_policy float32[rows][n_actions] raw logits; observed_reward / value_target float32[rows] scalars;
+ *   visit_counts float32[rows][n_actions] (un-normalised, :58).
+ *   losses float32[4] = {(1/K)(reward + value + policy), reward_loss, value_loss, policy_loss}, each a
+ *   kl_div(..., reduction="batchmean") = sum / rows.
+ *   d_reward / d_value / d_policy (same shapes as the logits, any may be NULL) = d losses[0] / d logits.
+ *   scratch: mz_loss_scratch_bytes(rows) bytes, 8-byte aligned, ZEROED ONCE by the caller (the kernel
+ *   leaves it ready for the next call); reduction order is fixed, results are deterministic.
+ *
+ * mz_adam replaces MuZeroAgent.optimizer.step() (networks.py:268: torch.optim.Adam(lr, weight_decay=1e-4),
+ * betas (0.9, 0.999), eps 1e-8) for ONE flat float32 buffer of n parameters (16-byte aligned): L2 weight
+ * decay added to the gradient, bias-corrected moments, same operation order as torch's single-tensor path.
+ * step = number of updates including this one (torch's state["step"] after the increment).
+ */
+size_t mz_loss_scratch_bytes(int rows);
+int mz_loss(int rows, int K, int n_supports, int n_actions, const float *supports, const float *pred_reward, const float *pred_value,
+            const float *pred_policy, const float *observed_reward, const float *value_target, const float *visit_counts,
+            float *losses, float *d_reward, float *d_value, float *d_policy, void *scratch, void *stream);
+int mz_adam(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, double lr, double beta1, double beta2,
+            double eps, double weight_decay, int step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,11 @@ def _declare(L: C.CDLL) -> None:
         "rb_append": [vp, i32, i32] + [vp] * 6 + [i32, vp, vp, i32, i32, vp, vp, vp],
         "rb_gather": [vp, i32] + [vp] * 11,
     })
+    L.mz_loss_scratch_bytes.argtypes, L.mz_loss_scratch_bytes.restype = [i32], C.c_size_t
+    sig.update({
+        "mz_loss": [i32, i32, i32, i32] + [vp] * 13,
+        "mz_adam": [C.c_longlong, vp, vp, vp, vp] + [C.c_double] * 5 + [i32, vp],
+    })
     for name, args in sig.items():
         f = getattr(L, name)
         f.argtypes, f.restype = args, i32

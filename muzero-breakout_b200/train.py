@@ -1,0 +1,134 @@
+"""Loss and optimizer ends of the reference's training step on the device (first slice),
+backed by csrc/train.cu through the C ABI (mz_loss / mz_adam, include/mzb200.h).
+
+    reference                                                      here
+    loss_fn(observed_reward, predicted_reward, ...,                same call, same return tuple; ONE launch computes the three
+            target_transformation, K)  train_torch.py:33-66        batch-mean KL divergences, the total and its gradient w.r.t. the
+                                                                   three logit tensors; `loss.backward()` (train_torch.py:515) hands
+                                                                   those stored gradients to autograd
+    ScalarTransforms.supports_representation  utils.py:30-64       fused into the same launch (pass the bound method, the
+                                                                   ScalarTransforms object or the supports tensor)
+    MuZeroAgent.optimizer = torch.optim.Adam(self.parameters(),    Adam(module_or_params, lr, weight_decay): parameters and gradients
+        lr, weight_decay=1e-4)  networks.py:268;                   re-pointed into two flat fp32 buffers, `step()` = ONE launch
+        optimizer.zero_grad() / optimizer.step()  :497,516         (28 B per parameter, HBM-bound), `zero_grad()` = one memset
+
+The backward passes of the three networks still run in PyTorch.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _supports_of(target_transformation) -> torch.Tensor:
+    if isinstance(target_transformation, torch.Tensor):
+        return target_transformation
+    owner = getattr(target_transformation, "__self__", target_transformation)   # bound supports_representation -> ScalarTransforms
+    sup = getattr(owner, "supports", None)
+    if sup is None:
+        raise TypeError("target_transformation must be ScalarTransforms.supports_representation, a ScalarTransforms or the supports tensor")
+    return sup
+
+
+class _Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_reward, pred_value, pred_policy, obs_reward, value_target, visits, supports, K):
+        _lib.require_cuda()
+        dev = pred_reward.device
+        if dev.type != "cuda":
+            raise RuntimeError("loss_fn needs CUDA tensors (there is no CPU fallback)")
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        pr, pv, pp = f(pred_reward), f(pred_value), f(pred_policy)
+        n_sup, n_act = pr.shape[-1], pp.shape[-1]
+        rows = pr.numel() // n_sup
+        o, v, c, s = f(obs_reward), f(value_target), f(visits), f(supports)
+        if not (pv.shape == pr.shape and pp.numel() == rows * n_act and o.numel() == rows and v.numel() == rows
+                and c.numel() == rows * n_act and s.numel() == n_sup):
+            raise ValueError("loss_fn: inconsistent shapes")
+        L = _lib.lib()
+        scratch = torch.zeros((L.mz_loss_scratch_bytes(rows) + 7) // 8, dtype=torch.int64, device=dev)
+        losses = torch.empty(4, dtype=torch.float32, device=dev)
+        d_r, d_v, d_p = torch.empty_like(pr), torch.empty_like(pv), torch.empty_like(pp)
+        with torch.cuda.device(dev):
+            _lib.check(L.mz_loss(rows, int(K), n_sup, n_act, _p(s), _p(pr), _p(pv), _p(pp), _p(o), _p(v), _p(c), _p(losses),
+                                 _p(d_r), _p(d_v), _p(d_p), _p(scratch), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(d_r, d_v, d_p)
+        parts = tuple(losses[i] for i in (1, 2, 3))
+        ctx.mark_non_differentiable(*parts)
+        return (losses[0],) + parts
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        d_r, d_v, d_p = ctx.saved_tensors
+        return g * d_r, g * d_v, g * d_p, None, None, None, None, None
+
+
+def loss_fn(observed_reward, predicted_reward, bootstrapped_reward, predicted_value, visit_counts, predicted_policy,
+            target_transformation, K):
+    """Drop-in for train_torch.py:33-66.  Returns (loss, reward_loss, value_loss, policy_loss) as 0-dim CUDA tensors;
+    `loss` carries the autograd edge to the three prediction tensors."""
+    return _Loss.apply(predicted_reward, predicted_value, predicted_policy, observed_reward, bootstrapped_reward, visit_counts,
+                       _supports_of(target_transformation), K)
+
+
+class Adam:
+    """torch.optim.Adam as networks.py:268 builds it (betas (0.9, 0.999), eps 1e-8, L2 weight decay added to the gradient), over
+    flat buffers: every parameter's `.data` and `.grad` become views into `self.flat_param` / `self.flat_grad`, so autograd
+    accumulates straight into the flat gradient and `step()` is one mz_adam launch."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4):
+        _lib.require_cuda()
+        params = list(params.parameters()) if isinstance(params, torch.nn.Module) else list(params)
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("Adam: no parameters")
+        dev = params[0].device
+        if any(p.device != dev or p.dtype != torch.float32 for p in params) or dev.type != "cuda":
+            raise RuntimeError("Adam: parameters must be float32 CUDA tensors on one device (there is no CPU fallback)")
+        self.params, self.lr, self.betas, self.eps, self.weight_decay = params, float(lr), tuple(betas), float(eps), float(weight_decay)
+        self.step_count = 0
+        offs, n = [], 0
+        for p in params:                      # 16-byte aligned segments; the padding holds zeros and stays zero
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                seg = self.flat_param[o:o + p.numel()].view(p.shape)
+                seg.copy_(p)
+                gseg = self.flat_grad[o:o + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    gseg.copy_(p.grad)
+                p.data = seg
+                p.grad = gseg
+        self._offsets = offs
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Zeros the flat gradient (the views stay attached: `set_to_none` is accepted and ignored)."""
+        self.flat_grad.zero_()
+
+    def step(self):
+        self.step_count += 1
+        dev = self.flat_param.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mz_adam(self.flat_param.numel(), _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg),
+                                          _p(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                          self.step_count, torch.cuda.current_stream(dev).cuda_stream))
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr, "betas": self.betas,
+                "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])

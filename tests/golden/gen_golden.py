@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by RUNNING THE UNMODIFIED REFERENCE (/root/reference).
 
 Build container only (the reference is not on the GPU box):
-    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|replay|all]
+    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|replay|train|all]
 
 Outputs (np.savez_compressed, all small):
     env_config1.npz  BASELINE.json configs[0]: B=24, torch.manual_seed(42), 10 000 steps, episode
@@ -13,6 +13,9 @@ Outputs (np.savez_compressed, all small):
                      network golden (rep-net output, per-simulation dynamics/prediction outputs)
     replay.npz       replay_buffer.py ObservationTrajectory + ReplayBuffer fed the way train_torch.py:204-208,
                      223-225,313-332 feeds them (synthetic trajectories of 3..261 moves, FIFO eviction at 150 samples)
+    train.npz        train_torch.py loss_fn (:33-66) with utils.py ScalarTransforms.supports_representation under autograd
+                     (losses + gradients w.r.t. the three logit tensors), and 5 steps of the optimizer networks.py:268 builds
+                     (torch.optim.Adam(lr=config.yaml:28, weight_decay=1e-4)) on a 4099-element parameter
 """
 from __future__ import annotations
 
@@ -310,6 +313,48 @@ def gen_replay(cap=150, K=5, hist=32, discount=0.985, n_sum=24):
           ("past_actions", "future_actions", "states", "rewards", "visit_counts", "values")})
 
 
+def gen_train(B=64, K=5, n_params=4099, steps=5):
+    """loss_fn + backward, and Adam, from the reference / torch themselves."""
+    import train_torch as ref_train                      # the reference (import has no side effects beyond set_seed(42))
+    from utils import ScalarTransforms
+
+    tr = ScalarTransforms(CFG["model"])
+    g = torch.Generator().manual_seed(5)
+    out = {"supports": tr.supports.numpy().copy(), "K": np.array(K)}
+    for case, scale in (("a", 1.0), ("b", 4.0)):
+        pr = (torch.randn(B, K, 11, generator=g) * scale).requires_grad_()
+        pv = (torch.randn(B, K, 11, generator=g) * scale).requires_grad_()
+        pp = (torch.randn(B, K, 3, generator=g) * scale).requires_grad_()
+        # rewards as Breakout gives them (0, +1, -1, +5, +6), value targets over the range the supports cover, a few exactly on a support
+        obs_r = torch.tensor([0.0, 1.0, -1.0, 5.0, 6.0])[torch.randint(0, 5, (B, K), generator=g)]
+        val = (torch.rand(B, K, generator=g) - 0.5) * (60.0 if case == "b" else 8.0)
+        val[0, :3] = torch.tensor([0.0, 3.0, -3.0])
+        vis = torch.multinomial(torch.rand(B * K, 3, generator=g) ** 2 + 1e-3, 50, replacement=True, generator=g)
+        vis = torch.stack([(vis == a).sum(1) for a in range(3)], 1).reshape(B, K, 3).to(torch.float32)
+        vis[1, 0] = torch.tensor([50.0, 0.0, 0.0])
+        loss, rl, vl, pl = ref_train.loss_fn(observed_reward=obs_r, predicted_reward=pr, bootstrapped_reward=val, predicted_value=pv,
+                                             visit_counts=vis, predicted_policy=pp, target_transformation=tr.supports_representation, K=K)
+        loss.backward()
+        out.update({f"{case}_pred_reward": pr.detach().numpy(), f"{case}_pred_value": pv.detach().numpy(), f"{case}_pred_policy": pp.detach().numpy(),
+                    f"{case}_obs_reward": obs_r.numpy(), f"{case}_value_target": val.numpy(), f"{case}_visits": vis.numpy(),
+                    f"{case}_losses": np.array([loss.item(), rl.item(), vl.item(), pl.item()], np.float32),
+                    f"{case}_target_reward": tr.supports_representation(obs_r).numpy(), f"{case}_target_value": tr.supports_representation(val).numpy(),
+                    f"{case}_d_reward": pr.grad.numpy(), f"{case}_d_value": pv.grad.numpy(), f"{case}_d_policy": pp.grad.numpy()})
+        print("train loss case", case, [float(x) for x in out[f"{case}_losses"]])
+    p = torch.nn.Parameter(torch.randn(n_params, generator=g))
+    opt = torch.optim.Adam([p], lr=CFG["model"]["learning_rate"], weight_decay=0.0001)     # networks.py:268
+    out["adam_p0"] = p.detach().numpy().copy()
+    out["adam_lr"] = np.array(CFG["model"]["learning_rate"])
+    for s in range(steps):
+        p.grad = torch.randn(n_params, generator=g) * (0.1 if s % 2 else 0.003)
+        out[f"adam_g{s}"] = p.grad.numpy().copy()
+        opt.step()
+        st = opt.state[p]
+        out[f"adam_p{s + 1}"], out[f"adam_m{s + 1}"], out[f"adam_v{s + 1}"] = p.detach().numpy().copy(), st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+    print("train: adam steps", steps, "params", n_params)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.chdir("/tmp")
@@ -319,3 +364,4 @@ if __name__ == "__main__":
     if what in ("mcts", "all"): gen_mcts_fake()
     if what in ("net", "all"): gen_mcts_real()
     if what in ("replay", "all"): gen_replay()
+    if what in ("train", "all"): gen_train()

@@ -117,6 +117,27 @@ def test_replay_buffer_mirrors_reference_signature():
             rb.get_batched_states(torch.tensor([0]))
 
 
+def test_training_ends_mirror_reference_signature():
+    """loss_fn keeps train_torch.py:33-42's parameter names; mz_loss / mz_adam argument checks run without a GPU."""
+    from muzero_breakout_b200 import train
+    assert list(inspect.signature(train.loss_fn).parameters) == ["observed_reward", "predicted_reward", "bootstrapped_reward", "predicted_value",
+                                                                 "visit_counts", "predicted_policy", "target_transformation", "K"]
+    L = mzb.lib()
+    assert L.mz_loss_scratch_bytes(2560) == 20 * 3 * 8 + 16 and L.mz_loss_scratch_bytes(0) == 0
+    assert L.mz_loss(0, 5, 11, 3, *([None] * 13)) != 0 and b"rows" in L.mzb_last_error()
+    assert L.mz_loss(10, 5, 40, 3, *([None] * 13)) != 0 and b"n_supports" in L.mzb_last_error()
+    assert L.mz_loss(10, 5, 11, 3, *([None] * 13)) != 0 and b"null" in L.mzb_last_error()
+    assert L.mz_adam(16, None, None, None, None, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0 and b"null" in L.mzb_last_error()
+    assert L.mz_adam(16, 64, 64, 64, 64, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None) != 0 and b"step" in L.mzb_last_error()
+    assert L.mz_adam(16, 68, 64, 64, 64, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0 and b"aligned" in L.mzb_last_error()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            train.loss_fn(torch.zeros(2, 5), torch.zeros(2, 5, 11), torch.zeros(2, 5), torch.zeros(2, 5, 11), torch.ones(2, 5, 3),
+                          torch.zeros(2, 5, 3), torch.linspace(-5, 5, 11), 5)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            train.Adam([torch.nn.Parameter(torch.zeros(4))])
+
+
 def test_mcts_class_mirrors_reference_signature():
     from muzero_breakout_b200.src.mcts import MCTSSearchVec
     cfg = {"num_simulations": 50, "actions": [0, 1, 2], "latent_resolution": [4, 5],

@@ -1,0 +1,151 @@
+"""GPU parity tests of the training step's loss and optimizer ends (muzero-breakout_b200/train.py -> mz_loss / mz_adam,
+csrc/train.cu) against the reference's golden vectors (tests/golden/train.npz: loss_fn of train_torch.py:33-66 under autograd,
+torch.optim.Adam of networks.py:268) and the numpy oracle (oracle/train_oracle.py).  Floating point: the north star's fp32
+tolerance 1e-5 relative for the losses and gradients; Adam moments bit-exact, parameters within 1 ulp."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_oracle as T
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "train.npz"))
+K = int(G["K"])
+RTOL = 1e-5
+
+
+def _cuda(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_() if grad else t
+
+
+def _run_loss(pr, pv, pp, obs, val, vis, supports, K):
+    from muzero_breakout_b200.train import loss_fn
+    tpr, tpv, tpp = _cuda(pr, True), _cuda(pv, True), _cuda(pp, True)
+    out = loss_fn(observed_reward=_cuda(obs), predicted_reward=tpr, bootstrapped_reward=_cuda(val), predicted_value=tpv,
+                  visit_counts=_cuda(vis), predicted_policy=tpp, target_transformation=_cuda(supports), K=K)
+    out[0].backward()
+    return np.array([float(x.detach()) for x in out], np.float32), tpr.grad.cpu().numpy(), tpv.grad.cpu().numpy(), tpp.grad.cpu().numpy()
+
+
+def _close(got, want, name):
+    assert got.shape == want.shape, name
+    assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (name, float(np.abs(got - want).max()), float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_loss_fn_matches_reference_goldens(case):
+    g = lambda k: G[f"{case}_{k}"]
+    losses, d_r, d_v, d_p = _run_loss(g("pred_reward"), g("pred_value"), g("pred_policy"), g("obs_reward"), g("value_target"), g("visits"),
+                                      G["supports"], K)
+    np.testing.assert_allclose(losses, g("losses"), rtol=RTOL, atol=0)
+    _close(d_r, g("d_reward"), "d_reward"); _close(d_v, g("d_value"), "d_value"); _close(d_p, g("d_policy"), "d_policy")
+
+
+def test_loss_fn_minibatch_size_vs_oracle_and_deterministic():
+    """config.yaml's minibatch (512 x K=5) plus a ragged row count; a (B, K, n) grad_output scaling; two calls bit-identical."""
+    rng = np.random.default_rng(3)
+    for B in (512, 77):
+        pr, pv = (rng.standard_normal((B, K, 11)).astype(np.float32) * 2 for _ in range(2))
+        pp = rng.standard_normal((B, K, 3)).astype(np.float32) * 2
+        obs = rng.choice(np.array([0, 1, -1, 5, 6], np.float32), size=(B, K))
+        val = ((rng.random((B, K)) - 0.5) * 40).astype(np.float32)
+        vis = rng.multinomial(50, [0.2, 0.5, 0.3], size=(B, K)).astype(np.float32)
+        got = _run_loss(pr, pv, pp, obs, val, vis, G["supports"], K)
+        want_l = np.array(T.loss_fn(obs, pr, val, pv, vis, pp, G["supports"], K), np.float32)
+        np.testing.assert_allclose(got[0], want_l, rtol=RTOL, atol=0)
+        for a, b, name in zip(got[1:], T.loss_grads(obs, pr, val, pv, vis, pp, G["supports"], K), ("d_reward", "d_value", "d_policy")):
+            _close(a, b, name)
+        again = _run_loss(pr, pv, pp, obs, val, vis, G["supports"], K)
+        assert all(np.array_equal(x.view(np.uint32), y.view(np.uint32)) for x, y in zip(got, again))
+
+
+def test_loss_fn_accepts_the_reference_call_forms_and_rejects_cpu():
+    from muzero_breakout_b200.train import loss_fn
+
+    class Transforms:                                    # stands in for utils.ScalarTransforms (has .supports and the bound method)
+        supports = _cuda(G["supports"])
+
+        def supports_representation(self, x):
+            raise AssertionError("the fused kernel computes the targets itself")
+
+    g = lambda k: _cuda(G[f"a_{k}"])
+    tr = Transforms()
+    a = loss_fn(g("obs_reward"), g("pred_reward"), g("value_target"), g("pred_value"), g("visits"), g("pred_policy"), tr.supports_representation, K)
+    b = loss_fn(g("obs_reward"), g("pred_reward"), g("value_target"), g("pred_value"), g("visits"), g("pred_policy"), tr, K)
+    assert all(float(x) == float(y) for x, y in zip(a, b))
+    with pytest.raises(RuntimeError):
+        loss_fn(*(torch.from_numpy(G[f"a_{k}"]) for k in ("obs_reward", "pred_reward", "value_target", "pred_value", "visits", "pred_policy")),
+                torch.from_numpy(G["supports"]), K)
+
+
+def _ulp(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+def test_adam_matches_torch_goldens():
+    from muzero_breakout_b200 import _lib
+    L = _lib.lib()
+    p, m, v = _cuda(G["adam_p0"]), torch.zeros(4099, device="cuda"), torch.zeros(4099, device="cuda")
+    for s in range(5):
+        grad = _cuda(G[f"adam_g{s}"])
+        _lib.check(L.mz_adam(4099, p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), float(G["adam_lr"]), 0.9, 0.999, 1e-8, 1e-4, s + 1,
+                             torch.cuda.current_stream().cuda_stream))
+        assert np.array_equal(m.cpu().numpy(), G[f"adam_m{s + 1}"]) and np.array_equal(v.cpu().numpy(), G[f"adam_v{s + 1}"]), f"moments, step {s + 1}"
+        u = _ulp(p.cpu().numpy(), G[f"adam_p{s + 1}"])
+        assert u.max() <= 1 and (u != 0).mean() < 1e-2, f"parameters, step {s + 1}: max {u.max()} ulp"
+        p.copy_(_cuda(G[f"adam_p{s + 1}"]))
+
+
+def test_adam_class_on_a_module_vs_torch_optimizer():
+    """The flat-buffer optimizer on a small module with ragged parameter sizes, 6 steps of real backward passes, against
+    torch.optim.Adam on a CPU copy (weight decay 1e-4 as networks.py:268)."""
+    from muzero_breakout_b200.train import Adam
+    torch.manual_seed(1)
+    make = lambda: torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3, padding=1), torch.nn.BatchNorm2d(7), torch.nn.ReLU(), torch.nn.Flatten(),
+                                       torch.nn.Linear(7 * 4 * 5, 11))
+    ref = make()
+    net = make().cuda()
+    net.load_state_dict(ref.state_dict())
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=2e-4, weight_decay=1e-4)
+    opt = Adam(net, lr=2e-4, weight_decay=1e-4)
+    assert all(p.data_ptr() >= opt.flat_param.data_ptr() for p in net.parameters())
+    x = torch.randn(6, 16, 3, 4, 5)
+    for s in range(6):
+        opt_ref.zero_grad(); opt.zero_grad()
+        ref(x[s]).square().mean().backward()
+        net(x[s].cuda()).square().mean().backward()
+        opt_ref.step(); opt.step()
+    for (n, a), b in zip(net.named_parameters(), ref.parameters()):
+        assert float((a.detach().cpu() - b.detach()).abs().max()) <= 2e-5 * float(b.detach().abs().max()), n
+
+
+def test_adam_full_parameter_count_vs_oracle():
+    """42 205 081 parameters (rep + dyn + pred), two updates: moments bit-exact, parameters within 1 ulp."""
+    from muzero_breakout_b200 import _lib
+    L = _lib.lib()
+    n = 42_205_081
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(n, dtype=np.float32) * 0.05
+    p, m, v = _cuda(p0), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    op, om, ov = p0, np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for s in range(2):
+        g = rng.standard_normal(n, dtype=np.float32) * 1e-3
+        grad = _cuda(g)
+        _lib.check(L.mz_adam(n, p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, s + 1,
+                             torch.cuda.current_stream().cuda_stream))
+        op, om, ov = T.adam_step(op, g, om, ov, s + 1)
+        assert np.array_equal(m.cpu().numpy(), om) and np.array_equal(v.cpu().numpy(), ov)
+        assert _ulp(p.cpu().numpy(), op).max() == 0, "same operation order as the oracle: bit-exact"
+
+
+def test_train_abi_argument_errors():
+    from muzero_breakout_b200 import _lib
+    L = _lib.lib()
+    assert L.mz_loss(0, 5, 11, 3, *([None] * 13)) != 0 and b"rows" in L.mzb_last_error()
+    assert L.mz_adam(16, None, None, None, None, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0
+    t = torch.zeros(32, device="cuda")
+    assert L.mz_adam(16, t.data_ptr() + 4, t.data_ptr(), t.data_ptr(), t.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0
+    assert L.mz_adam(16, t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None) != 0
