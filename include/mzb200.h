@@ -326,6 +326,11 @@ int rb_gather(const rb_ring *ring, int n, const int64_t *idx, int64_t *past_acti
               float *states, float *rewards, float *visit_counts, float *values, float *value_buffer,
               float *reward_sums, int32_t *status, void *stream);
 
+/* The representation-network input of a training minibatch, straight from the rings: out float[n][2*hist][320] =
+ * torch.cat((get_batched_states(idx).view(n, hist, 16, 20), _encode_actions(get_batched_past_actions(idx))), dim=1)
+ * (train_torch.py:392,500; _encode_actions :279-293 = past_action / n_actions as constant planes). */
+int rb_gather_input(const rb_ring *ring, int n, const int64_t *idx, int n_actions, float *out, int32_t *status, void *stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * Training step, first slice: the loss and the optimizer update.  The

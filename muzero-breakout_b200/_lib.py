@@ -97,6 +97,7 @@ def _declare(L: C.CDLL) -> None:
     sig.update({
         "rb_append": [vp, i32, i32] + [vp] * 6 + [i32, vp, vp, i32, i32, vp, vp, vp],
         "rb_gather": [vp, i32] + [vp] * 11,
+        "rb_gather_input": [vp, i32, vp, i32, vp, vp, vp],
     })
     L.mz_loss_scratch_bytes.argtypes, L.mz_loss_scratch_bytes.restype = [i32], C.c_size_t
     sig.update({

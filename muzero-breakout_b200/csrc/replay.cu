@@ -199,6 +199,39 @@ rb_gather_kernel(rb_ring r, int n, const long long *__restrict__ idx, long long 
     if (reward_sums && t == 0) reward_sums[i] = ok ? r.reward_sum[phys] : 0.0f;
 }
 
+// Representation-network input of a training minibatch: cat(states.view(n, hist, 16, 20), _encode_actions(past_actions)) along the plane axis
+// (train_torch.py:392,500 with :279-293): planes 0..hist-1 = the frame window, planes hist..2*hist-1 = past_action / n_actions as constant planes.
+__global__ void __launch_bounds__(256)
+rb_gather_input_kernel(rb_ring r, int n, const long long *__restrict__ idx, float n_actions, float *__restrict__ out, int32_t *__restrict__ status)
+{
+    const int i = blockIdx.x;
+    const unsigned long long total = r.state[1], cap = (unsigned long long)r.cap_samples;
+    const long long length = (long long)(total < cap ? total : cap);
+    long long li = idx[i];
+    if (li < 0) li += length;
+    const int hist = r.hist;
+    const bool ok = li >= 0 && li < length;
+    if (!ok && threadIdx.x == 0) atomicOr(status, MZB_RB_ERR_BAD_INDEX);
+    const size_t phys = (size_t)((total - (unsigned long long)length + (unsigned long long)(ok ? li : 0)) % cap);
+    const unsigned long long meta = ok ? r.meta[phys] : 0ull;
+    const unsigned long long ent = meta & 0xffffffffull, CE = (unsigned long long)r.cap_entries;
+    const int s = (int)((meta >> 32) & 0xffff);
+    auto slot_of = [&](int e) { return (size_t)((ent + (unsigned long long)e) % CE); };
+    float4 *dst = reinterpret_cast<float4 *>(out + (size_t)i * 2 * hist * FRAME);
+    for (int w = threadIdx.x; w < 2 * hist * FRAME_V4; w += blockDim.x) {
+        const int j = w / FRAME_V4, q = w - j * FRAME_V4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && j < hist) {
+            v = reinterpret_cast<const float4 *>(r.frame + slot_of(max(0, s + j - (hist - 2))) * FRAME)[q];   // as rb_gather's states
+        } else if (ok) {
+            const int li2 = s + (j - hist);                                                                    // as rb_gather's past_actions
+            const float a = __fdiv_rn((float)r.action[slot_of(li2 >= hist ? li2 - (hist - 1) : 0)], n_actions);
+            v = make_float4(a, a, a, a);
+        }
+        __stcs(dst + w, v);                                                                                    // written once, read by the rep net
+    }
+}
+
 int check_ring(const rb_ring *r)
 {
     MZB_CHECK_ARG(r, "ring is NULL");
@@ -259,6 +292,16 @@ int rb_gather(const rb_ring *ring, int n, const int64_t *idx, int64_t *past_acti
     rb_gather_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(*ring, n, (const long long *)idx, (long long *)past_actions,
                                                                      (long long *)future_actions, states, rewards, visit_counts, values,
                                                                      value_buffer, reward_sums, status);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int rb_gather_input(const rb_ring *ring, int n, const int64_t *idx, int n_actions, float *out, int32_t *status, void *stream)
+{
+    if (check_ring(ring)) return -1;
+    MZB_CHECK_ARG(n >= 0 && n_actions > 0 && status && (n == 0 || (idx && out)), "bad argument");
+    if (n == 0) return 0;
+    rb_gather_input_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(*ring, n, (const long long *)idx, (float)n_actions, out, status);
     MZB_LAUNCH_CHECK();
     return 0;
 }

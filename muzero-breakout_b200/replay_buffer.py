@@ -242,6 +242,20 @@ class ReplayBuffer:
         o = self._gather(batch_idxs, ("past_actions", "states", "visit_counts", "future_actions", "rewards", "values"))
         return o["past_actions"], o["states"], o["visit_counts"], o["future_actions"], o["rewards"], o["values"]
 
+    def repnet_input(self, batch_idxs, n_actions=3):
+        """`torch.cat((input_states, input_actions_encoded), dim=1)` of train_torch.py:500 for the samples `batch_idxs`, (n, 2*seq_len, 16, 20),
+        from ONE launch (rb_gather_input): the frame window + `_encode_actions` (:279-293) of the past actions, no intermediate tensors."""
+        self._alloc()
+        dev, h = self._dev, self.hist_seq_len
+        idx = torch.as_tensor(batch_idxs).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        n = int(idx.numel())
+        out = torch.empty((n, 2 * h, 16, 20), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().rb_gather_input(C.byref(self._ring), n, _p(idx), int(n_actions), _p(out), _p(self._status), self._stream()))
+        if self.output_device == "cpu":
+            out = out.cpu()
+            self._raise_on_status()
+        return out
+
     def get_reward_sums(self):
         """replay_buffer.py:212-216: the reward sums of the newest num_rewards_to_sum samples, as Python floats."""
         n = min(self.length, self.num_rewards_to_sum)

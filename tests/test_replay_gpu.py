@@ -53,6 +53,13 @@ def test_save_observation_trajectory_matches_reference_goldens(golden_dir):
             mb = rb.minibatch(perm)                                             # one launch, train_torch.py:455-484 order
             for got, f in zip(mb, ("past_actions", "states", "visit_counts", "future_actions", "rewards", "values")):
                 assert np.array_equal(got.cpu().numpy(), g[tag + f][perm.numpy()]), f
+            # rep-net input of the training step from one launch: cat(states, _encode_actions(past_actions)) of train_torch.py:392,500
+            # with :291-293 (actions / n_actions broadcast over the 16 x 20 plane), from the reference's own getter outputs
+            st, pa = torch.from_numpy(g[tag + "states"][perm.numpy()]), torch.from_numpy(g[tag + "past_actions"][perm.numpy()])
+            planes = torch.ones((len(perm), p["hist"], 16, 20)) * (pa / 3)[:, :, None, None].expand(-1, -1, 16, 20)
+            want_in = torch.cat((st.view(len(perm), -1, 16, 20), planes), dim=1)
+            got_in = rb.repnet_input(perm, n_actions=3)
+            assert got_in.is_cuda and got_in.shape == want_in.shape and torch.equal(got_in.cpu(), want_in)
             assert rb.get_reward_sums() == list(g[tag + "reward_sums"])
             assert rb.reward_sums == list(g[tag + "reward_sums_all"])
             assert np.array_equal(torch.stack(rb.value_buffer).numpy(), g[tag + "value_buffer"])
