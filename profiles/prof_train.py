@@ -1,0 +1,62 @@
+"""The training step's two ends on their own (csrc/train.cu, rb_gather_input): a few launches each, for the launch list / ncu capture.
+    python profiles/prof_train.py
+    ncu --set full --clock-control none --import-source on -k regex:'adam_kernel|loss_kernel|rb_gather_input' -c 6 -o gpurun_out/r1_train python profiles/prof_train.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from muzero_breakout_b200 import _lib
+from muzero_breakout_b200.replay_buffer import ReplayBuffer
+from muzero_breakout_b200.train import loss_fn
+
+L = _lib.lib()
+dev = torch.device("cuda:0")
+n = 42_205_081
+p, g = torch.randn(n, device=dev) * 0.05, torch.randn(n, device=dev) * 1e-3
+m, v = torch.zeros_like(p), torch.zeros_like(p)
+st = torch.cuda.current_stream().cuda_stream
+B, K = 512, 5
+pr, pv, pp = torch.randn(B, K, 11, device=dev), torch.randn(B, K, 11, device=dev), torch.randn(B, K, 3, device=dev)
+obs, val = torch.randint(-1, 2, (B, K), device=dev).float(), (torch.rand(B, K, device=dev) - 0.5) * 20
+vis, sup = torch.randint(1, 30, (B, K, 3), device=dev).float(), torch.linspace(-5, 5, 11, device=dev)
+T, E = 64, 1024
+rec = dict(action=torch.randint(0, 3, (T, E), device=dev), reward=torch.zeros(T, E, device=dev), value=torch.rand(T, E, device=dev),
+           visits=torch.randint(0, 51, (T, E, 3), device=dev), frames=torch.rand(T, E, 1, 16, 20, device=dev),
+           recorded=torch.ones(T, E, dtype=torch.bool, device=dev), initial_gray=torch.rand(E, 1, 16, 20, device=dev))
+rb = ReplayBuffer(32, K, 60000, 0.985, 512, device=dev, max_moves=261)
+rb.save_episode(rec)
+idx = torch.randperm(rb.length, device=dev)[:B]
+
+
+def timed(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3
+
+
+step = [0]
+
+
+def adam():
+    step[0] += 1
+    _lib.check(L.mz_adam(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, step[0], st))
+
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+us = timed(adam, reps)
+print(f"mz_adam, {n} parameters: {us:.1f} us = {n * 28 / us / 1e3:.0f} GB/s (28 B per parameter)")
+us = timed(lambda: loss_fn(obs, pr, val, pv, vis, pp, sup, K), reps)
+print(f"loss_fn, {B * K} rows: {us:.1f} us")
+us = timed(lambda: rb.repnet_input(idx), reps)
+print(f"repnet_input, {B} samples: {us:.1f} us = {B * 120 * 1024 / us / 1e3:.0f} GB/s (40 KB read + 80 KB written per sample)")
+us = timed(lambda: torch.cat((rb.get_batched_states(idx).view(B, -1, 16, 20),
+                              torch.ones((B, 32, 16, 20), device=dev) * (rb.get_batched_past_actions(idx) / 3)[:, :, None, None].expand(-1, -1, 16, 20)), dim=1), reps)
+print(f"  the same from two gathers + _encode_actions + cat in torch: {us:.1f} us")
