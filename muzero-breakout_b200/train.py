@@ -12,7 +12,11 @@ backed by csrc/train.cu through the C ABI (mz_loss / mz_adam, include/mzb200.h).
         lr, weight_decay=1e-4)  networks.py:268;                   re-pointed into two flat fp32 buffers, `step()` = ONE launch
         optimizer.zero_grad() / optimizer.step()  :497,516         (28 B per parameter, HBM-bound), `zero_grad()` = one memset
 
-The backward passes of the three networks still run in PyTorch.  There is no CPU fallback.
+    conv backward w.r.t. its input (autograd of nn.Conv2d,         ConvDgrad(weight): the data gradient of a stride-1 "same" convolution IS a
+        networks.py:11,24-25, inside loss.backward())              convolution of dY with the transposed, tap-flipped weights, so it runs on the
+                                                                   acting path's tcgen05 kernel (csrc/conv_tc.cu) with re-packed weights
+
+The rest of the backward pass (weight gradients, training-mode BatchNorm) still runs in PyTorch.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -132,3 +136,34 @@ class Adam:
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+
+
+class ConvDgrad:
+    """dL/dx of `y = conv2d(x, weight, padding=k//2)` (stride 1; the only convolution form in networks.py) on the tensor cores:
+    dx = conv2d(dy, weight.transpose(0, 1).flip(2, 3), padding=k//2), evaluated by the acting path's tcgen05 implicit-GEMM kernel with
+    bf16 operands and fp32 accumulation.  Channels-last tensors: dy (n, H, W, cout) bf16 in, dx (n, H, W, cin) fp32 out."""
+
+    def __init__(self, weight: torch.Tensor, device="cuda"):
+        _lib.require_cuda()
+        cout, cin, k, _ = weight.shape
+        if k not in (1, 3) or cout % 64 or cin not in (128, 256):
+            raise ValueError("ConvDgrad: built for the 1x1 / 3x3 convolutions of networks.py with cout % 64 == 0 and cin in (128, 256) (one UMMA N)")
+        wt = weight.detach().to(torch.float32).transpose(0, 1).flip(2, 3)                  # (cin, cout, k, k): the dgrad filter
+        wp = wt.permute(0, 2, 3, 1).reshape(cin, k * k, cout // 64, 64).permute(1, 2, 0, 3)    # tile-contiguous [tap][cout/64][cin][64], as networks.py _conv
+        self.w = wp.contiguous().to(device=device, dtype=torch.bfloat16)
+        self.cin, self.cout, self.k = cin, cout, k
+        self.scale = torch.ones(cin, dtype=torch.float32, device=device)
+        self.shift = torch.zeros(cin, dtype=torch.float32, device=device)
+
+    def __call__(self, dy: torch.Tensor) -> torch.Tensor:
+        from .src.networks import ACT, BF16, OP_CONV, Program
+        n, H, W, c = dy.shape
+        if c != self.cout or dy.dtype != torch.bfloat16 or not dy.is_cuda or not dy.is_contiguous():
+            raise ValueError("ConvDgrad: dy must be a contiguous CUDA bf16 tensor (n, H, W, cout)")
+        dx16 = torch.empty((n, H, W, self.cin), dtype=torch.bfloat16, device=dy.device)
+        dx = torch.empty((n, H, W, self.cin), dtype=torch.float32, device=dy.device)
+        prog = Program(n)
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=self.cout, cout=self.cin, ksize=self.k, act=ACT["none"], use_tc=1, w_layout=1,
+                 src=dy, dst=dx16, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift)
+        prog.run()
+        return dx

@@ -149,3 +149,21 @@ def test_train_abi_argument_errors():
     t = torch.zeros(32, device="cuda")
     assert L.mz_adam(16, t.data_ptr() + 4, t.data_ptr(), t.data_ptr(), t.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0
     assert L.mz_adam(16, t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 2e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None) != 0
+
+
+@pytest.mark.parametrize("case", [(512, 4, 5, 256, 256, 3), (77, 4, 5, 256, 128, 3), (33, 4, 5, 256, 256, 1), (6, 8, 10, 256, 256, 3), (4, 16, 20, 128, 256, 3), (2048, 4, 5, 256, 256, 3)],
+                         ids=lambda c: "n%d_%dx%d_c%d-%d_k%d" % c)
+def test_conv_dgrad_on_tensor_cores_vs_autograd(case):
+    """The input gradient of the networks' convolutions (autograd of nn.Conv2d, networks.py:11,24-25) through the tcgen05 kernel with re-packed
+    weights, against torch autograd in fp32 on the same bf16-rounded operands (the tolerance of the forward convolution test)."""
+    from muzero_breakout_b200.train import ConvDgrad
+    n, H, W, cin, cout, k = case
+    g = torch.Generator().manual_seed(n + cin + cout + k)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16()
+    dy = torch.randn(n, cout, H, W, generator=g).bfloat16()
+    x = torch.zeros(n, cin, H, W, requires_grad=True)
+    torch.nn.functional.conv2d(x, w.float(), padding=k // 2).backward(dy.float())
+    got = ConvDgrad(w)(dy.permute(0, 2, 3, 1).contiguous().cuda()).permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all()
+    err = float((got - x.grad).abs().max() / x.grad.abs().max())
+    assert err <= 2e-4, f"dgrad rel err {err:.2e}"
