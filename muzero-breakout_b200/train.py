@@ -126,6 +126,9 @@ class Adam:
             _lib.check(_lib.lib().mz_adam(self.flat_param.numel(), _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg),
                                           _p(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                           self.step_count, torch.cuda.current_stream(dev).cuda_stream))
+        # the kernel writes through raw pointers: bump the parameters' version counters like an in-place torch op would, so that
+        # anything keyed on them (MCTSSearchVec's re-pack check, autograd's saved-tensor checks) sees the update
+        torch.autograd.graph.increment_version(self.params)
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr, "betas": self.betas,

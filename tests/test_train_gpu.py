@@ -117,7 +117,9 @@ def test_adam_class_on_a_module_vs_torch_optimizer():
         opt_ref.zero_grad(); opt.zero_grad()
         ref(x[s]).square().mean().backward()
         net(x[s].cuda()).square().mean().backward()
+        v0 = [p._version for p in net.parameters()]
         opt_ref.step(); opt.step()
+        assert all(p._version > v for p, v in zip(net.parameters(), v0)), "step() must bump the version counters (MCTSSearchVec re-pack check)"
     for (n, a), b in zip(net.named_parameters(), ref.parameters()):
         assert float((a.detach().cpu() - b.detach()).abs().max()) <= 2e-5 * float(b.detach().abs().max()), n
 
