@@ -360,6 +360,17 @@ int mz_loss(int rows, int K, int n_supports, int n_actions, const float *support
 int mz_adam(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, double lr, double beta1, double beta2,
             double eps, double weight_decay, int step, void *stream);
 
+/* Weight gradient of a stride-1 "same" 3x3 / 1x1 convolution with 256 input and 256 output channels (the residual trunks,
+ * networks.py:24-25; autograd of nn.Conv2d inside loss.backward(), train_torch.py:515) on the tensor cores (csrc/wgrad.cu):
+ *   dw float32[256][256][ksize][ksize] (PyTorch's weight layout) = sum_{n,y,x} dy[n][y][x][co] * x[n][y+ky-pad][x+kx-pad][ci].
+ * Both operands are given TRANSPOSED to channel-major [256][H*W][ns] (ns = mz_wgrad_padded_samples(n), padding samples zero),
+ * 16-bit (dtype MZ_BF16 / MZ_F16): mz_wgrad_transpose makes that layout from a channels-last [n][H*W][C] tensor.
+ * partial: mz_wgrad_partial_bytes(ksize, n) bytes of scratch (per-tap, per-K-split fp32 partial sums, reduced in a fixed order). */
+int mz_wgrad_padded_samples(int n);
+size_t mz_wgrad_partial_bytes(int ksize, int n);
+int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream);
+int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

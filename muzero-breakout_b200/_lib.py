@@ -103,7 +103,11 @@ def _declare(L: C.CDLL) -> None:
     sig.update({
         "mz_loss": [i32, i32, i32, i32] + [vp] * 13,
         "mz_adam": [C.c_longlong, vp, vp, vp, vp] + [C.c_double] * 5 + [i32, vp],
+        "mz_wgrad_transpose": [i32, i32, i32, vp, vp, vp],
+        "mz_conv_wgrad": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     })
+    L.mz_wgrad_padded_samples.argtypes, L.mz_wgrad_padded_samples.restype = [i32], i32
+    L.mz_wgrad_partial_bytes.argtypes, L.mz_wgrad_partial_bytes.restype = [i32, i32], C.c_size_t
     for name, args in sig.items():
         f = getattr(L, name)
         f.argtypes, f.restype = args, i32

@@ -1,0 +1,279 @@
+// Weight gradient of the 3x3 / 1x1 256 -> 256 convolutions (autograd of nn.Conv2d, src/networks.py:11,24-25, inside
+// loss.backward() train_torch.py:515) on the B200 tensor cores:  dW[co][ci][ky][kx] = sum over (sample n, pixel (y,x)) of
+// dY[n][y][x][co] * X[n][y+ky-1][x+kx-1][ci].
+//
+// As a GEMM per tap: M = co (256 = one CTA pair, tcgen05 cta_group::2), N = ci (256, one UMMA N), K = samples x pixels.  In the
+// channels-last activation layout K is the OUTER index of both operands, so they are first transposed to channel-major,
+// pixel, sample ([C][P][ns], ns = samples padded to 64 with zeros; wgrad_transpose_kernel, 2 x 5 MB per layer at 512 samples):
+// then both operands are K-major exactly like the forward convolution's (same TMA boxes, SWIZZLE_128B, same UMMA descriptors),
+// the tap is a constant column offset (p' - p) * ns between the two operands, and the zero-padding pixels of a tap are simply
+// not in its K range (no masking, no zero work -- the forward kernel's per-pixel tap skipping, seen from the other side).
+//
+// Tiles: (tap, K-split) -- 9 taps x up to 8 splits of the sample chunks = 72 CTA pairs on the 148 SMs; every pair accumulates
+// its 256 x 256 fp32 partial in TMEM and writes it to `partial[tap][split]`; wgrad_reduce_kernel sums the splits in a fixed order
+// (deterministic) into PyTorch's weight layout (cout, cin, k, k).
+// Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (pair leader), warps 2-9 epilogue.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int WG_C = 256;                       // cin = cout
+constexpr int WG_MAX_SPLITS = 8;
+constexpr size_t WG_SMEM = (size_t)STAGES * STAGE_BYTES + 256;
+
+struct WgradParams {
+    int ns, H, W, taps, chunks, splits, ntiles, f16;
+    float *partial;                             // [taps][splits][256][256]
+};
+
+// k-steps of tile (tap, split): pixels whose shifted partner is inside the image x the split's 64-sample chunks
+struct WgTile {
+    int dy, dx, c0, c1;
+};
+__device__ __forceinline__ WgTile wg_decode(const WgradParams &p, int tile)
+{
+    WgTile t;
+    const int tap = tile / p.splits, sp = tile - tap * p.splits;
+    t.dy = p.taps == 1 ? 0 : tap / 3 - 1;
+    t.dx = p.taps == 1 ? 0 : tap % 3 - 1;
+    t.c0 = (int)((long long)sp * p.chunks / p.splits);
+    t.c1 = (int)((long long)(sp + 1) * p.chunks / p.splits);
+    return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const int P = p.H * p.W;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane per CTA) =====================
+        if (lane == 0) {
+            const uint32_t lead_full = map_to_cta(bar_full, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+                const WgTile t = wg_decode(p, tile);
+                for (int pix = 0; pix < P; ++pix) {
+                    const int y = pix / p.W, x = pix - y * p.W;
+                    if (y + t.dy < 0 || y + t.dy >= p.H || x + t.dx < 0 || x + t.dx >= p.W) continue;
+                    const int pix2 = pix + t.dy * p.W + t.dx;
+                    for (int c = t.c0; c < t.c1; ++c) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * STAGE_BYTES);      // bytes of both CTAs
+                        else mbar_arrive_cluster(lead_full + 8 * stage);
+                        tma_load_2d(sa, &map_dy, lead_full + 8 * stage, pix * p.ns + c * BLOCK_K, rank * 128);    // my 128 co rows
+                        tma_load_2d(sb, &map_x, lead_full + 8 * stage, pix2 * p.ns + c * BLOCK_K, rank * 128);    // my half of the ci rows
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (pair leader only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = instr_desc(WG_C, p.f16 != 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * WG_C);
+                const WgTile t = wg_decode(p, tile);
+                int npix = 0;
+                for (int pix = 0; pix < P; ++pix) {
+                    const int y = pix / p.W, x = pix - y * p.W;
+                    npix += (y + t.dy >= 0 && y + t.dy < p.H && x + t.dx >= 0 && x + t.dx < p.W) ? 1 : 0;
+                }
+                const int ksteps = npix * (t.c1 - t.c0);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ks | k) ? 1u : 0u);
+                    umma_commit_pair(bar_empty + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(bar_tfull + 8 * buf);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9): TMEM -> fp32 partial =====================
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int co = rank * 128 + quarter * 32 + lane;                 // TMEM lane = output row
+        const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
+        int it = 0;
+        for (int tile = cluster_id; tile < p.ntiles; tile += nclusters, ++it) {
+            const int buf = it & 1;
+            const WgTile t = wg_decode(p, tile);
+            int npix = 0;
+            for (int pix = 0; pix < P; ++pix) {
+                const int y = pix / p.W, x = pix - y * p.W;
+                npix += (y + t.dy >= 0 && y + t.dy < p.H && x + t.dx >= 0 && x + t.dx < p.W) ? 1 : 0;
+            }
+            const bool empty = npix * (t.c1 - t.c0) == 0;                // no k-step: nothing was accumulated, the partial is zero
+            float *dst = p.partial + ((size_t)tile * WG_C + co) * WG_C + half * 128;
+            uint32_t acc[2][32];
+            mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * WG_C + half * 128);
+            tmem_ld32_async(taddr, acc[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_wait(acc[c & 1]);
+                if (c + 1 < 4) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
+                float4 *fp = reinterpret_cast<float4 *>(dst + c * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    fp[q] = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                  : make_float4(__uint_as_float(acc[c & 1][q * 4]), __uint_as_float(acc[c & 1][q * 4 + 1]),
+                                                __uint_as_float(acc[c & 1][q * 4 + 2]), __uint_as_float(acc[c & 1][q * 4 + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// [n][P][C] (channels-last, 16-bit) -> [C][P][ns], samples n..ns-1 zero.  grid (ns/32, C/32, P), block (32, 8)
+__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst)
+{
+    __shared__ uint16_t tile[32][33];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, pix = blockIdx.z;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int s = n0 + r;
+        tile[r][threadIdx.x] = s < n ? src[((size_t)s * P + pix) * C + c0 + threadIdx.x] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) dst[((size_t)(c0 + r) * P + pix) * ns + n0 + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, const float *__restrict__ partial, float *__restrict__ dw)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;            // co * 256 + ci
+    if (i >= WG_C * WG_C) return;
+    for (int tap = 0; tap < taps; ++tap) {
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc += partial[((size_t)(tap * splits + s)) * WG_C * WG_C + i];
+        dw[(size_t)i * taps + tap] = acc;
+    }
+}
+
+int wg_splits(int ns) { const int chunks = ns / BLOCK_K; return chunks < WG_MAX_SPLITS ? chunks : WG_MAX_SPLITS; }
+
+}  // namespace
+
+extern "C" {
+
+int mz_wgrad_padded_samples(int n) { return n <= 0 ? 0 : (n + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
+
+size_t mz_wgrad_partial_bytes(int ksize, int n)
+{
+    if ((ksize != 1 && ksize != 3) || n <= 0) return 0;
+    return (size_t)ksize * ksize * wg_splits(mz_wgrad_padded_samples(n)) * WG_C * WG_C * sizeof(float);
+}
+
+int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream)
+{
+    MZB_CHECK_ARG(n > 0 && P > 0 && C > 0 && C % 32 == 0 && src && dst, "bad argument");
+    const int ns = mz_wgrad_padded_samples(n);
+    MZB_CHECK_ARG(P <= 65535 && C / 32 <= 65535, "image or channel count too large");
+    wgrad_transpose_kernel<<<dim3(ns / 32, C / 32, P), dim3(32, 8), 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream)
+{
+    MZB_CHECK_ARG(n > 0 && H > 0 && W > 0 && (ksize == 1 || ksize == 3) && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
+    MZB_CHECK_ARG(dy_t && x_t && partial && dw, "null pointer");
+    MZB_CHECK_ARG((((uintptr_t)dy_t | (uintptr_t)x_t | (uintptr_t)partial) & 15) == 0, "buffers must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { mzb::set_error("mz_conv_wgrad: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+    WgradParams p{};
+    p.ns = mz_wgrad_padded_samples(n);
+    p.H = H; p.W = W; p.taps = ksize * ksize;
+    p.chunks = p.ns / BLOCK_K;
+    p.splits = wg_splits(p.ns);
+    p.ntiles = p.taps * p.splits;
+    p.f16 = dtype == MZ_F16;
+    p.partial = partial;
+    const long long K = (long long)H * W * p.ns;
+    MZB_CHECK_ARG(K < (1ll << 31), "samples x pixels too large for one launch");
+    CUtensorMap maps[2];
+    const void *ptrs[2] = {dy_t, x_t};
+    for (int i = 0; i < 2; ++i) {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)WG_C};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {BLOCK_K, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&maps[i], p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptrs[i]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mzb::set_error("mz_conv_wgrad: cuTensorMapEncodeTiled failed: %d", (int)r); return -2; }
+    }
+    static bool attr_set[64] = {};
+    if (mzb::first_use_on_device(attr_set))
+        MZB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    const int clusters = p.ntiles < mzb::kNumSMs / 2 ? p.ntiles : mzb::kNumSMs / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = WG_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MZB_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel, maps[0], maps[1], p));
+    MZB_LAUNCH_CHECK();
+    wgrad_reduce_kernel<<<WG_C * WG_C / 256, 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

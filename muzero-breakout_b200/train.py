@@ -170,3 +170,24 @@ class ConvDgrad:
                  src=dy, dst=dx16, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift)
         prog.run()
         return dx
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int) -> torch.Tensor:
+    """dL/dweight of `y = conv2d(x, weight, padding=ksize//2)` for the 256 -> 256 trunk convolutions, (256, 256, k, k) float32, on the
+    tensor cores (mz_conv_wgrad, csrc/wgrad.cu).  Channels-last 16-bit tensors: dy (n, H, W, 256), x (n, H, W, 256)."""
+    _lib.require_cuda()
+    n, H, W, c = x.shape
+    if dy.shape != x.shape or c != 256 or x.dtype != dy.dtype or x.dtype not in (torch.bfloat16, torch.float16) or not (x.is_cuda and dy.is_cuda):
+        raise ValueError("conv_wgrad: dy and x must be CUDA bf16 / fp16 tensors of the same shape (n, H, W, 256)")
+    L, dev = _lib.lib(), x.device
+    ns = L.mz_wgrad_padded_samples(n)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    dy_t = torch.empty((256, H * W, ns), dtype=x.dtype, device=dev)
+    x_t = torch.empty_like(dy_t)
+    partial = torch.empty(L.mz_wgrad_partial_bytes(ksize, n) // 4, dtype=torch.float32, device=dev)
+    dw = torch.empty((256, 256, ksize, ksize), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(dy.contiguous()), _p(dy_t), st))
+        _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(x.contiguous()), _p(x_t), st))
+        _lib.check(L.mz_conv_wgrad(n, H, W, ksize, 2 if x.dtype == torch.float16 else 1, _p(dy_t), _p(x_t), _p(partial), _p(dw), st))
+    return dw

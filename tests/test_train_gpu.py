@@ -169,3 +169,22 @@ def test_conv_dgrad_on_tensor_cores_vs_autograd(case):
     assert torch.isfinite(got).all()
     err = float((got - x.grad).abs().max() / x.grad.abs().max())
     assert err <= 2e-4, f"dgrad rel err {err:.2e}"
+
+
+@pytest.mark.parametrize("case", [(512, 4, 5, 3), (77, 4, 5, 3), (1, 4, 5, 3), (300, 4, 5, 1), (40, 8, 10, 3), (2560, 4, 5, 3)], ids=lambda c: "n%d_%dx%d_k%d" % c)
+def test_conv_wgrad_on_tensor_cores_vs_autograd(case):
+    """The weight gradient of the trunks' 256 -> 256 convolutions (tcgen05, K = samples x pixels, csrc/wgrad.cu) against torch autograd in
+    fp32 on the same bf16-rounded operands; deterministic (fixed-order split reduction)."""
+    from muzero_breakout_b200.train import conv_wgrad
+    n, H, W, k = case
+    g = torch.Generator().manual_seed(n + H + k)
+    x = torch.randn(n, 256, H, W, generator=g).bfloat16()
+    dy = torch.randn(n, 256, H, W, generator=g).bfloat16()
+    w = torch.zeros(256, 256, k, k, requires_grad=True)
+    torch.nn.functional.conv2d(x.float(), w, padding=k // 2).backward(dy.float())
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
+    got = conv_wgrad(cl(dy), cl(x), k)
+    assert torch.isfinite(got).all()
+    err = float((got.cpu() - w.grad).abs().max() / w.grad.abs().max())
+    assert err <= 2e-4, f"wgrad rel err {err:.2e}"
+    assert torch.equal(got, conv_wgrad(cl(dy), cl(x), k))
