@@ -524,8 +524,26 @@ def bench_train_ends(dev, rank, world, cpu=True):
     vis = torch.randint(1, 30, (B, K, 3), device=dev, generator=g).float()
     sup = torch.linspace(-5, 5, 11, device=dev)
     loss_ms = timed(lambda: loss_fn(obs, pr, val, pv, vis, pp, sup, K), 50)
+    # weight gradient of one trunk convolution over the 5 x 512 (dY, X) pairs of a training step (the K unroll steps share their weights)
+    nb = B * K
+    xa, dya = torch.randn(nb, 4, 5, 256, device=dev, generator=g).bfloat16(), torch.randn(nb, 4, 5, 256, device=dev, generator=g).bfloat16()
+    ns = L.mz_wgrad_padded_samples(nb)
+    dy_t, x_t = torch.empty(256, 20, ns, dtype=torch.bfloat16, device=dev), torch.empty(256, 20, ns, dtype=torch.bfloat16, device=dev)
+    partial = torch.empty(L.mz_wgrad_partial_bytes(3, nb) // 4, dtype=torch.float32, device=dev)
+    dw = torch.empty(256, 256, 3, 3, device=dev)
+
+    def wgrad():
+        _lib.check(L.mz_wgrad_transpose(nb, 20, 256, dya.data_ptr(), dy_t.data_ptr(), stream))
+        _lib.check(L.mz_wgrad_transpose(nb, 20, 256, xa.data_ptr(), x_t.data_ptr(), stream))
+        _lib.check(L.mz_conv_wgrad(nb, 4, 5, 3, 1, dy_t.data_ptr(), x_t.data_ptr(), partial.data_ptr(), dw.data_ptr(), stream))
+
+    wg_ms = timed(wgrad, 20)
+    wg_flop = 130 * nb * 256 * 256 * 2
     peaks = measured_peaks()
-    out = {"adam": {"ms": adam_ms, "parameters": n, "GBps": n * 28 / adam_ms / 1e6, "frac_of_hbm_peak": n * 28 / adam_ms / 1e6 / peaks["hbm"],
+    out = {"wgrad": {"ms": wg_ms, "samples": nb, "TFLOPs": wg_flop / wg_ms / 1e9, "frac_of_tensor_peak": wg_flop / wg_ms / 1e9 / peaks["bf16"],
+                     "what": "3x3 256->256 weight gradient on tcgen05: 2 transposes + mz_conv_wgrad (9 taps x 8 K-splits of CTA pairs) + fixed-order split reduction; "
+                             "in-bounds-tap FLOPs; peak = burst cuBLAS bf16 (a kernel timed alone)"},
+           "adam": {"ms": adam_ms, "parameters": n, "GBps": n * 28 / adam_ms / 1e6, "frac_of_hbm_peak": n * 28 / adam_ms / 1e6 / peaks["hbm"],
                     "bytes_per_parameter": 28, "what": "mz_adam: one launch over the flat fp32 parameter / gradient / moment buffers (1.18 GB of traffic, larger than L2)"},
            "loss": {"ms": loss_ms, "rows": B * K, "what": "train.loss_fn: one mz_loss launch (3 KL divergences + total + gradients w.r.t. the logits) + output allocations"}}
     if cpu and rank == 0 and world == 1:

@@ -178,17 +178,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
     }
 }
 
-// [n][P][C] (channels-last, 16-bit) -> [C][P][ns], samples n..ns-1 zero.  grid (ns/32, C/32, P), block (32, 8)
+// [n][P][C] (channels-last, 16-bit) -> [C][P][ns], samples n..ns-1 zero.  One CTA = 64 samples x 64 channels of one pixel: 32-byte
+// loads along the channels, 32-byte stores along the samples, through a padded shared-memory tile.  grid (ns/64, C/64, P), 256 threads
 __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst)
 {
-    __shared__ uint16_t tile[32][33];
-    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, pix = blockIdx.z;
-    for (int r = threadIdx.y; r < 32; r += 8) {
+    __shared__ uint16_t tile[64][64 + 2];                    // row pitch 132 bytes = 33 words: column reads hit 32 different banks
+    const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, pix = blockIdx.z;
+    const int r = threadIdx.x >> 2, q = (threadIdx.x & 3) * 16;
+    {
         const int s = n0 + r;
-        tile[r][threadIdx.x] = s < n ? src[((size_t)s * P + pix) * C + c0 + threadIdx.x] : (uint16_t)0;
+        uint4 v[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (s < n) {
+            const uint4 *g = reinterpret_cast<const uint4 *>(src + ((size_t)s * P + pix) * C + c0 + q);
+            v[0] = __ldg(g); v[1] = __ldg(g + 1);
+        }
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(&tile[r][q]);   // (r * 66 + q) * 2 bytes: 4-byte aligned (q even)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t32[i] = w[i];
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) dst[((size_t)(c0 + r) * P + pix) * ns + n0 + threadIdx.x] = tile[threadIdx.x][r];
+    {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (uint32_t)tile[q + 2 * i][r] | ((uint32_t)tile[q + 2 * i + 1][r] << 16);   // channel c0 + r, samples n0 + q ..
+        uint4 *g = reinterpret_cast<uint4 *>(dst + ((size_t)(c0 + r) * P + pix) * ns + n0 + q);
+        g[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        g[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
 }
 
 // dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order
@@ -219,10 +236,11 @@ size_t mz_wgrad_partial_bytes(int ksize, int n)
 
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream)
 {
-    MZB_CHECK_ARG(n > 0 && P > 0 && C > 0 && C % 32 == 0 && src && dst, "bad argument");
+    MZB_CHECK_ARG(n > 0 && P > 0 && C > 0 && C % 64 == 0 && src && dst, "bad argument");
+    MZB_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "buffers must be 16-byte aligned");
     const int ns = mz_wgrad_padded_samples(n);
-    MZB_CHECK_ARG(P <= 65535 && C / 32 <= 65535, "image or channel count too large");
-    wgrad_transpose_kernel<<<dim3(ns / 32, C / 32, P), dim3(32, 8), 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst);
+    MZB_CHECK_ARG(P <= 65535 && C / 64 <= 65535, "image or channel count too large");
+    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst);
     MZB_LAUNCH_CHECK();
     return 0;
 }

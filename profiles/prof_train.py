@@ -60,3 +60,42 @@ print(f"repnet_input, {B} samples: {us:.1f} us = {B * 120 * 1024 / us / 1e3:.0f}
 us = timed(lambda: torch.cat((rb.get_batched_states(idx).view(B, -1, 16, 20),
                               torch.ones((B, 32, 16, 20), device=dev) * (rb.get_batched_past_actions(idx) / 3)[:, :, None, None].expand(-1, -1, 16, 20)), dim=1), reps)
 print(f"  the same from two gathers + _encode_actions + cat in torch: {us:.1f} us")
+
+# weight / data gradients of one trunk convolution at the training minibatch (512 samples, 4x5 latent, 3x3 256 -> 256)
+from muzero_breakout_b200.train import ConvDgrad, conv_wgrad
+nb = 512
+xa = torch.randn(nb, 4, 5, 256, device=dev).bfloat16()
+dya = torch.randn(nb, 4, 5, 256, device=dev).bfloat16()
+ns = L.mz_wgrad_padded_samples(nb)
+dy_t, x_t = torch.empty(256, 20, ns, dtype=torch.bfloat16, device=dev), torch.empty(256, 20, ns, dtype=torch.bfloat16, device=dev)
+partial = torch.empty(L.mz_wgrad_partial_bytes(3, nb) // 4, dtype=torch.float32, device=dev)
+dw = torch.empty(256, 256, 3, 3, device=dev)
+flop = 130 * nb * 256 * 256 * 2          # in-bounds (pixel, tap) pairs only, as for the forward convolution
+us = timed(lambda: (_lib.check(L.mz_wgrad_transpose(nb, 20, 256, dya.data_ptr(), dy_t.data_ptr(), st)),
+                    _lib.check(L.mz_wgrad_transpose(nb, 20, 256, xa.data_ptr(), x_t.data_ptr(), st))), reps)
+print(f"wgrad transposes (2 x {nb * 20 * 256 * 2 / 1e6:.1f} MB): {us:.1f} us")
+us = timed(lambda: _lib.check(L.mz_conv_wgrad(nb, 4, 5, 3, 1, dy_t.data_ptr(), x_t.data_ptr(), partial.data_ptr(), dw.data_ptr(), st)), reps)
+print(f"mz_conv_wgrad, {nb} samples 3x3 256->256: {us:.1f} us = {flop / us / 1e6:.0f} TFLOP/s of in-bounds-tap work (kernel + split reduction)")
+wdg = ConvDgrad(torch.randn(256, 256, 3, 3) / 48)
+us = timed(lambda: wdg(dya), reps)
+print(f"ConvDgrad, {nb} samples: {us:.1f} us = {flop / us / 1e6:.0f} TFLOP/s (forward kernel, incl. Program build + 2 output allocations)")
+w32 = torch.randn(256, 256, 3, 3, device=dev)
+xn, dyn = xa.permute(0, 3, 1, 2).float().contiguous(), dya.permute(0, 3, 1, 2).float().contiguous()
+us = timed(lambda: torch.nn.grad.conv2d_weight(xn, w32.shape, dyn, padding=1), reps)
+print(f"  torch (cuDNN fp32/TF32) conv2d_weight on the same shapes: {us:.1f} us")
+xb, dyb = xa.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), dya.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+us = timed(lambda: torch.nn.grad.conv2d_weight(xb, w32.shape, dyb, padding=1), reps)
+print(f"  torch (cuDNN bf16, channels_last) conv2d_weight: {us:.1f} us")
+
+# the K unroll steps share their weights: one wgrad launch per layer over all 5 x 512 (dY, X) pairs of a training step
+nb5 = 2560
+xa5, dya5 = torch.randn(nb5, 4, 5, 256, device=dev).bfloat16(), torch.randn(nb5, 4, 5, 256, device=dev).bfloat16()
+dy_t5, x_t5 = torch.empty(256, 20, nb5, dtype=torch.bfloat16, device=dev), torch.empty(256, 20, nb5, dtype=torch.bfloat16, device=dev)
+partial5 = torch.empty(L.mz_wgrad_partial_bytes(3, nb5) // 4, dtype=torch.float32, device=dev)
+us_t = timed(lambda: (_lib.check(L.mz_wgrad_transpose(nb5, 20, 256, dya5.data_ptr(), dy_t5.data_ptr(), st)),
+                      _lib.check(L.mz_wgrad_transpose(nb5, 20, 256, xa5.data_ptr(), x_t5.data_ptr(), st))), reps)
+us = timed(lambda: _lib.check(L.mz_conv_wgrad(nb5, 4, 5, 3, 1, dy_t5.data_ptr(), x_t5.data_ptr(), partial5.data_ptr(), dw.data_ptr(), st)), reps)
+print(f"mz_conv_wgrad, {nb5} samples: {us:.1f} us = {flop * 5 / us / 1e6:.0f} TFLOP/s (+ transposes {us_t:.1f} us)")
+xb5, dyb5 = xa5.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), dya5.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+us = timed(lambda: torch.nn.grad.conv2d_weight(xb5, w32.shape, dyb5, padding=1), reps)
+print(f"  torch (cuDNN bf16, channels_last) conv2d_weight, {nb5} samples: {us:.1f} us")
