@@ -371,6 +371,24 @@ size_t mz_wgrad_partial_bytes(int ksize, int n);
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream);
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
 
+/* Training-mode nn.BatchNorm2d of a ConvBlock / ResidualBlock (networks.py:12,16-17,26-35 under train_mode(), train_torch.py:372)
+ * on channels-last rows: z float32[M][C] = the convolution output incl. its bias, M = samples * H * W.
+ *   forward:  batch mean / biased variance per channel -> save_mean, save_invstd = 1/sqrt(var + eps) (float32[C]);
+ *             y = act(gamma * (z - mean) * invstd + beta (+ res)), written 16-bit (y, dtype MZ_BF16 / MZ_F16) and/or float32 (y_f32);
+ *             running_mean / running_var (may be NULL) updated in place with torch's rule (momentum, unbiased variance).
+ *   backward: g = dy * act'(pre-activation) (dy float32[M][C]); dbeta = sum g, dgamma = sum g * xhat,
+ *             dz = gamma * invstd * (g - dbeta/M - xhat * dgamma/M) as float32 (dz) and/or 16-bit (dz16, the operand of the
+ *             convolution gradients); dres (may be NULL) = g, the gradient of the residual input.
+ * res: the residual added before the activation (16-bit, NULL for a ConvBlock).  act: MZ_ACT_NONE / RELU / LEAKY_RELU.
+ * scratch: mz_bn_scratch_bytes(M, C) bytes (fp64 per-CTA partial sums, added in a fixed order: deterministic). */
+size_t mz_bn_scratch_bytes(int M, int C);
+int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const float *beta, const void *res, int dtype, int act, double eps,
+                    double momentum, float *running_mean, float *running_var, float *save_mean, float *save_invstd, void *y, float *y_f32,
+                    void *scratch, void *stream);
+int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int act,
+                    const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres, void *scratch,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

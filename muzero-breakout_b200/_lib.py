@@ -106,6 +106,11 @@ def _declare(L: C.CDLL) -> None:
         "mz_wgrad_transpose": [i32, i32, i32, vp, vp, vp],
         "mz_conv_wgrad": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     })
+    sig.update({
+        "mz_bn_train_fwd": [i32, i32, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double] + [vp] * 8,
+        "mz_bn_train_bwd": [i32, i32, vp, vp, vp, vp, vp, i32, i32] + [vp] * 9,
+    })
+    L.mz_bn_scratch_bytes.argtypes, L.mz_bn_scratch_bytes.restype = [i32, i32], C.c_size_t
     L.mz_wgrad_padded_samples.argtypes, L.mz_wgrad_padded_samples.restype = [i32], i32
     L.mz_wgrad_partial_bytes.argtypes, L.mz_wgrad_partial_bytes.restype = [i32, i32], C.c_size_t
     for name, args in sig.items():

@@ -191,3 +191,41 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int) -> torch.Tensor:
         _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(x.contiguous()), _p(x_t), st))
         _lib.check(L.mz_conv_wgrad(n, H, W, ksize, 2 if x.dtype == torch.float16 else 1, _p(dy_t), _p(x_t), _p(partial), _p(dw), st))
     return dw
+
+
+_ACT = {"none": 0, "relu": 1, "leaky_relu": 2}
+
+
+def _dt(t):
+    return 2 if t == torch.float16 else 1
+
+
+def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.1, running_mean=None, running_var=None, out_dtype=torch.bfloat16):
+    """Training-mode BatchNorm2d (+ residual) + activation of a ConvBlock / ResidualBlock (networks.py:16-17,31-35) on channels-last rows.
+    z: float32 (..., C) convolution output incl. bias.  Returns (y 16-bit, y float32, save_mean, save_invstd); running stats updated in place."""
+    _lib.require_cuda()
+    L, dev, C_ = _lib.lib(), z.device, z.shape[-1]
+    M = z.numel() // C_
+    z = z.contiguous()
+    y, y32 = torch.empty(z.shape, dtype=out_dtype, device=dev), torch.empty_like(z)
+    mean, invstd = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
+    scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mz_bn_train_fwd(M, C_, _p(z), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], eps, momentum, _p(running_mean), _p(running_var),
+                                     _p(mean), _p(invstd), _p(y), _p(y32), _p(scratch), torch.cuda.current_stream(dev).cuda_stream))
+    return y, y32, mean, invstd
+
+
+def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16):
+    """Backward of bn_train_forward.  dy: float32 gradient of the block output.  Returns (dz float32, dz 16-bit, dgamma, dbeta, dres float32)."""
+    _lib.require_cuda()
+    L, dev, C_ = _lib.lib(), z.device, z.shape[-1]
+    M = z.numel() // C_
+    z, dy = z.contiguous(), dy.contiguous()
+    dz, dz16, dres = torch.empty_like(z), torch.empty(z.shape, dtype=out_dtype, device=dev), torch.empty_like(z)
+    dgamma, dbeta = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
+    scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mz_bn_train_bwd(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta),
+                                     _p(dz), _p(dz16), _p(dres), _p(scratch), torch.cuda.current_stream(dev).cuda_stream))
+    return dz, dz16, dgamma, dbeta, dres

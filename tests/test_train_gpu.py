@@ -188,3 +188,50 @@ def test_conv_wgrad_on_tensor_cores_vs_autograd(case):
     err = float((got.cpu() - w.grad).abs().max() / w.grad.abs().max())
     assert err <= 2e-4, f"wgrad rel err {err:.2e}"
     assert torch.equal(got, conv_wgrad(cl(dy), cl(x), k))
+
+
+@pytest.mark.parametrize("case", [(512, 4, 5, 256, True, "relu"), (77, 4, 5, 256, False, "relu"), (3, 16, 20, 128, True, "none"), (64, 4, 5, 64, False, "leaky_relu"),
+                                  (2560, 4, 5, 256, True, "relu")], ids=lambda c: "n%d_%dx%d_c%d_res%d_%s" % c)
+def test_bn_train_forward_backward_vs_torch(case):
+    """Training-mode BatchNorm2d (+ residual) + activation, forward (output, saved statistics, running statistics) and backward (d input, d gamma,
+    d beta, d residual) against torch's nn.BatchNorm2d in train mode on the CPU in fp32: the north star's fp32 tolerance, 1e-5 of each tensor's range."""
+    from muzero_breakout_b200.train import bn_train_backward, bn_train_forward
+    n, H, W, C, use_res, act = case
+    g = torch.Generator().manual_seed(n + C)
+    z = (torch.randn(n, C, H, W, generator=g) * 1.5 + torch.randn(1, C, 1, 1, generator=g)).requires_grad_()
+    res16 = torch.randn(n, C, H, W, generator=g).bfloat16() if use_res else None
+    res = res16.float().requires_grad_() if use_res else None
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5); bn.bias.copy_(torch.randn(C, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1); bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    bn.train()
+    pre = bn(z) + (res if use_res else 0)
+    want = {"relu": torch.relu, "none": lambda t: t, "leaky_relu": torch.nn.functional.leaky_relu}[act](pre)
+    dy = torch.randn(n, C, H, W, generator=g)
+    want.backward(dy)
+
+    cl = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    back = lambda t: t.float().cpu().permute(0, 3, 1, 2)
+    rm, rv = rm0.cuda(), rv0.cuda()
+    gam, bet = bn.weight.detach().cuda(), bn.bias.detach().cuda()
+    y16, y32, mean, invstd = bn_train_forward(cl(z), gam, bet, res=cl(res16) if use_res else None, act=act, running_mean=rm, running_var=rv)
+    dz, dz16, dgamma, dbeta, dres = bn_train_backward(cl(z), cl(dy), gam, bet, mean, invstd, res=cl(res16) if use_res else None, act=act)
+    def tol(a, b, t, name, keep=None):
+        d = (a - b).abs()
+        if keep is not None:
+            d = d * keep
+        assert float(d.max()) <= t * float(b.abs().max()), f"{name}: {float(d.max() / b.abs().max()):.2e}"
+
+    # an activation mask may legitimately flip where the pre-activation is within rounding of zero: those elements are left out
+    keep = (pre.detach().abs() > 1e-4).float()
+    tol(back(y32), want.detach(), 1e-5, "y")
+    tol(back(y16), want.detach(), 5e-3, "y (bf16)")
+    tol(rm.cpu(), bn.running_mean, 1e-5, "running_mean"); tol(rv.cpu(), bn.running_var, 1e-5, "running_var")
+    tol(back(dz), z.grad, 2e-5, "dz", keep)
+    tol(back(dz16), z.grad, 5e-3, "dz (bf16)", keep)
+    tol(dgamma.cpu(), bn.weight.grad, 2e-5, "dgamma"); tol(dbeta.cpu(), bn.bias.grad, 2e-5, "dbeta")
+    if use_res:
+        tol(back(dres), res.grad, 1e-5, "dres", keep)
+    assert keep.mean() > 0.999
