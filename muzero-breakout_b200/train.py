@@ -229,3 +229,61 @@ def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", ou
         _lib.check(L.mz_bn_train_bwd(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta),
                                      _p(dz), _p(dz16), _p(dres), _p(scratch), torch.cuda.current_stream(dev).cuda_stream))
     return dz, dz16, dgamma, dbeta, dres
+
+
+class ResidualBlockTrain:
+    """One training step through a ResidualBlock (networks.py:19-35: relu(bn2(conv2(relu(bn1(conv1 x)))) + x), 256 channels, train mode) made of
+    this library's kernels only: tcgen05 convolutions (forward: conv_tc.cu; data gradient: the same kernel on the transposed, flipped weights;
+    weight gradient: wgrad.cu) and the training-mode BatchNorm kernels (bn.cu).  Channels-last bf16 activations, fp32 statistics and gradients.
+    The convolution biases get no gradient here: a BatchNorm follows each convolution and subtracts the batch mean, so d loss / d bias is zero
+    (torch returns rounding noise for it)."""
+
+    def __init__(self, conv1_w, conv1_b, bn1_w, bn1_b, conv2_w, conv2_b, bn2_w, bn2_b, device="cuda", eps=1e-5, momentum=0.1):
+        _lib.require_cuda()
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.w = [conv1_w.detach(), conv2_w.detach()]
+        self.wt = [self._pack(w, device) for w in self.w]                  # forward: tile-contiguous [tap][cin/64][cout][64] bf16
+        self.dgrad = [ConvDgrad(w, device) for w in self.w]
+        self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
+        self.running_mean = [torch.zeros(256, device=device) for _ in range(2)]
+        self.running_var = [torch.ones(256, device=device) for _ in range(2)]
+        self.ones = torch.ones(256, device=device)
+        self.eps, self.momentum = eps, momentum
+        self._saved = None
+
+    @staticmethod
+    def _pack(w, device):
+        cout, cin, k, _ = w.shape
+        return w.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k, cin // 64, 64).permute(1, 2, 0, 3).contiguous().to(device=device, dtype=torch.bfloat16)
+
+    def _conv(self, x16, i):
+        from .src.networks import ACT, BF16, OP_CONV, Program
+        n, H, W, _ = x16.shape
+        z16 = torch.empty_like(x16)
+        z = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
+        prog = Program(n)
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=256, cout=256, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst=z16, dst_f32=z,
+                 w=self.wt[i], scale=self.ones, shift=self.b[i])
+        prog.run()
+        return z
+
+    def forward(self, x16: torch.Tensor):
+        """x16: (n, H, W, 256) bf16 channels-last.  Returns (y bf16, y float32)."""
+        z1 = self._conv(x16, 0)
+        h16, _, m1, s1 = bn_train_forward(z1, self.gamma[0], self.beta[0], None, "relu", self.eps, self.momentum, self.running_mean[0], self.running_var[0])
+        z2 = self._conv(h16, 1)
+        y16, y32, m2, s2 = bn_train_forward(z2, self.gamma[1], self.beta[1], x16, "relu", self.eps, self.momentum, self.running_mean[1], self.running_var[1])
+        self._saved = (x16, z1, h16, z2, m1, s1, m2, s2)
+        return y16, y32
+
+    def backward(self, dy: torch.Tensor):
+        """dy: float32 gradient of the block output.  Returns (dx float32, {parameter name: gradient})."""
+        x16, z1, h16, z2, m1, s1, m2, s2 = self._saved
+        dz2, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu")
+        dw2 = conv_wgrad(dz2_16, h16, 3)
+        dh = self.dgrad[1](dz2_16)
+        dz1, dz1_16, dg1, db1, _ = bn_train_backward(z1, dh, self.gamma[0], self.beta[0], m1, s1, None, "relu")
+        dw1 = conv_wgrad(dz1_16, x16, 3)
+        dx = self.dgrad[0](dz1_16)
+        dx += dres                                      # the skip connection's gradient
+        return dx, {"conv1.weight": dw1, "bn1.weight": dg1, "bn1.bias": db1, "conv2.weight": dw2, "bn2.weight": dg2, "bn2.bias": db2}

@@ -99,3 +99,34 @@ print(f"mz_conv_wgrad, {nb5} samples: {us:.1f} us = {flop * 5 / us / 1e6:.0f} TF
 xb5, dyb5 = xa5.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last), dya5.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
 us = timed(lambda: torch.nn.grad.conv2d_weight(xb5, w32.shape, dyb5, padding=1), reps)
 print(f"  torch (cuDNN bf16, channels_last) conv2d_weight, {nb5} samples: {us:.1f} us")
+
+# one ResidualBlock training step (forward + backward, 512 samples) through this library's kernels vs torch / cuDNN on the same GPU
+from muzero_breakout_b200.train import ResidualBlockTrain
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.networks import _Res          # profiling script only: the torch restatement of networks.py:19-35 as the cuDNN comparison
+blk = _Res(256, "relu").cuda().train()
+sd = {k: v.detach() for k, v in blk.state_dict().items()}
+ours = ResidualBlockTrain(sd["conv1.weight"], sd["conv1.bias"], sd["bn1.weight"], sd["bn1.bias"], sd["conv2.weight"], sd["conv2.bias"], sd["bn2.weight"], sd["bn2.bias"])
+x16 = torch.rand(nb, 4, 5, 256, device=dev).bfloat16()
+dyf = torch.randn(nb, 4, 5, 256, device=dev)
+us = timed(lambda: (ours.forward(x16), ours.backward(dyf)), reps)
+print(f"ResidualBlockTrain forward + backward, {nb} samples: {us:.1f} us (22 launches + allocations, no buffer reuse yet)")
+xt = x16.permute(0, 3, 1, 2).float().contiguous().requires_grad_()
+dyt = dyf.permute(0, 3, 1, 2).contiguous()
+def torch_step():
+    for p_ in blk.parameters(): p_.grad = None
+    xt.grad = None
+    blk(xt).backward(dyt)
+us = timed(torch_step, reps)
+print(f"  torch (cuDNN fp32/TF32) forward + backward of the same block: {us:.1f} us")
+blk16 = _Res(256, "relu").cuda().train().to(memory_format=torch.channels_last)
+xt16 = x16.permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last).requires_grad_()
+dyt16 = dyt.contiguous(memory_format=torch.channels_last)
+def torch_step16():
+    for p_ in blk16.parameters(): p_.grad = None
+    xt16.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o = blk16(xt16)
+    o.backward(dyt16.to(o.dtype))
+us = timed(torch_step16, reps)
+print(f"  torch autocast bf16, channels_last: {us:.1f} us")
