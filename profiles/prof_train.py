@@ -130,3 +130,17 @@ def torch_step16():
     o.backward(dyt16.to(o.dtype))
 us = timed(torch_step16, reps)
 print(f"  torch autocast bf16, channels_last: {us:.1f} us")
+
+# the same step captured once as a CUDA graph (static shapes; every launch is stream-ordered, no host sync inside)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        ours.forward(x16); ours.backward(dyf)
+torch.cuda.current_stream().wait_stream(side)
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    ours.forward(x16)
+    g_dx, g_grads = ours.backward(dyf)
+us = timed(graph.replay, reps)
+print(f"ResidualBlockTrain forward + backward as a CUDA graph replay: {us:.1f} us")
