@@ -208,16 +208,20 @@ __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int
     }
 }
 
-// dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order
+// dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order.  One thread per (tap, co, ci):
+// its <= 8 loads are independent and coalesced over ci; grid (256 * 256 / 256, taps)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, const float *__restrict__ partial, float *__restrict__ dw)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;            // co * 256 + ci
-    if (i >= WG_C * WG_C) return;
-    for (int tap = 0; tap < taps; ++tap) {
-        float acc = 0.0f;
-        for (int s = 0; s < splits; ++s) acc += partial[((size_t)(tap * splits + s)) * WG_C * WG_C + i];
-        dw[(size_t)i * taps + tap] = acc;
-    }
+    const int tap = blockIdx.y;
+    const float *src = partial + (size_t)tap * splits * WG_C * WG_C + i;
+    float v[WG_MAX_SPLITS];
+#pragma unroll
+    for (int s = 0; s < WG_MAX_SPLITS; ++s) v[s] = s < splits ? __ldcs(src + (size_t)s * WG_C * WG_C) : 0.0f;
+    float acc = 0.0f;
+#pragma unroll
+    for (int s = 0; s < WG_MAX_SPLITS; ++s) acc += v[s];     // index order; the padding terms are exact zeros
+    dw[(size_t)i * taps + tap] = acc;
 }
 
 int wg_splits(int ns) { const int chunks = ns / BLOCK_K; return chunks < WG_MAX_SPLITS ? chunks : WG_MAX_SPLITS; }
@@ -289,7 +293,7 @@ int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, c
     cfg.numAttrs = 1;
     MZB_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel, maps[0], maps[1], p));
     MZB_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<WG_C * WG_C / 256, 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw);
+    wgrad_reduce_kernel<<<dim3(WG_C * WG_C / 256, p.taps), 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw);
     MZB_LAUNCH_CHECK();
     return 0;
 }
