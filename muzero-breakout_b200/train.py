@@ -151,12 +151,17 @@ class ConvDgrad:
         cout, cin, k, _ = weight.shape
         if k not in (1, 3) or cout % 64 or cin not in (128, 256):
             raise ValueError("ConvDgrad: built for the 1x1 / 3x3 convolutions of networks.py with cout % 64 == 0 and cin in (128, 256) (one UMMA N)")
-        wt = weight.detach().to(torch.float32).transpose(0, 1).flip(2, 3)                  # (cin, cout, k, k): the dgrad filter
+        wt = self.dgrad_filter(weight)
         wp = wt.permute(0, 2, 3, 1).reshape(cin, k * k, cout // 64, 64).permute(1, 2, 0, 3)    # tile-contiguous [tap][cout/64][cin][64], as networks.py _conv
         self.w = wp.contiguous().to(device=device, dtype=torch.bfloat16)
         self.cin, self.cout, self.k = cin, cout, k
         self.scale = torch.ones(cin, dtype=torch.float32, device=device)
         self.shift = torch.zeros(cin, dtype=torch.float32, device=device)
+
+    @staticmethod
+    def dgrad_filter(weight: torch.Tensor) -> torch.Tensor:
+        """(cout, cin, k, k) forward filter -> (cin, cout, k, k) filter whose "same" convolution with dy is dx: channels swapped, taps flipped."""
+        return weight.detach().to(torch.float32).transpose(0, 1).flip(2, 3)
 
     def __call__(self, dy: torch.Tensor) -> torch.Tensor:
         from .src.networks import ACT, BF16, OP_CONV, Program

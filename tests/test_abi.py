@@ -130,7 +130,28 @@ def test_training_ends_mirror_reference_signature():
     assert L.mz_adam(16, None, None, None, None, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0 and b"null" in L.mzb_last_error()
     assert L.mz_adam(16, 64, 64, 64, 64, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 0, None) != 0 and b"step" in L.mzb_last_error()
     assert L.mz_adam(16, 68, 64, 64, 64, 2e-4, 0.9, 0.999, 1e-8, 1e-4, 1, None) != 0 and b"aligned" in L.mzb_last_error()
+    # convolution gradients / training-mode BatchNorm: host-side size queries and argument checks
+    assert [L.mz_wgrad_padded_samples(n) for n in (0, 1, 64, 65, 512)] == [0, 64, 64, 128, 512]
+    assert L.mz_wgrad_partial_bytes(3, 512) == 9 * 8 * 256 * 256 * 4 and L.mz_wgrad_partial_bytes(1, 100) == 2 * 256 * 256 * 4
+    assert L.mz_wgrad_partial_bytes(2, 512) == 0
+    assert L.mz_conv_wgrad(512, 4, 5, 2, 1, 64, 64, 64, 64, None) != 0 and b"bad argument" in L.mzb_last_error()
+    assert L.mz_conv_wgrad(512, 4, 5, 3, 0, 64, 64, 64, 64, None) != 0          # fp32 operands are not built
+    assert L.mz_conv_wgrad(512, 4, 5, 3, 1, None, 64, 64, 64, None) != 0 and b"null" in L.mzb_last_error()
+    assert L.mz_wgrad_transpose(512, 20, 100, 64, 64, None) != 0                 # channels not a multiple of 64
+    assert L.mz_bn_scratch_bytes(10240, 256) == 80 * 2 * 256 * 8 and L.mz_bn_scratch_bytes(10240, 6) == 0
+    assert L.mz_bn_train_fwd(0, 256, *([None] * 4), 1, 1, 1e-5, 0.1, *([None] * 8)) != 0 and b"M must be positive" in L.mzb_last_error()
+    assert L.mz_bn_train_fwd(64, 256, 64, 64, 64, None, 1, 3, 1e-5, 0.1, None, None, 64, 64, 64, None, 64, None) != 0 and b"activation" in L.mzb_last_error()
+    assert L.mz_bn_train_bwd(64, 256, 64, 64, 64, 64, None, 0, 1, *([64] * 4), 64, None, None, 64, None) != 0 and b"16-bit" in L.mzb_last_error()
+    # the data gradient's weight pack: dx = conv2d(dy, w.transpose(0, 1).flip(2, 3)) (train.ConvDgrad), checked against autograd on the CPU
+    w, dy = torch.randn(8, 4, 3, 3), torch.randn(2, 8, 4, 5)
+    x = torch.zeros(2, 4, 4, 5, requires_grad=True)
+    torch.nn.functional.conv2d(x, w, padding=1).backward(dy)
+    assert torch.allclose(torch.nn.functional.conv2d(dy, train.ConvDgrad.dgrad_filter(w), padding=1), x.grad, atol=1e-5)
     if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            train.ConvDgrad(torch.zeros(256, 256, 3, 3))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            train.conv_wgrad(torch.zeros(2, 4, 5, 256), torch.zeros(2, 4, 5, 256), 3)
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             train.loss_fn(torch.zeros(2, 5), torch.zeros(2, 5, 11), torch.zeros(2, 5), torch.zeros(2, 5, 11), torch.ones(2, 5, 3),
                           torch.zeros(2, 5, 3), torch.linspace(-5, 5, 11), 5)
