@@ -292,3 +292,54 @@ class ResidualBlockTrain:
         dx = self.dgrad[0](dz1_16)
         dx += dres                                      # the skip connection's gradient
         return dx, {"conv1.weight": dw1, "bn1.weight": dg1, "bn1.bias": db1, "conv2.weight": dw2, "bn2.weight": dg2, "bn2.bias": db2}
+
+
+class TrunkTrain:
+    """A run of train-mode ResidualBlocks (the 14-block trunks of the dynamics / prediction networks, networks.py:124-131,190-197) as one training
+    step: forward keeps every block's saved tensors, backward walks the blocks in reverse.  `graph=True` captures forward + backward once as a
+    CUDA graph (static shapes, fixed input / output-gradient buffers) and replays it."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        self._graph = None
+
+    @classmethod
+    def from_state_dict(cls, sd: dict, prefixes, device="cuda"):
+        """prefixes: state_dict key prefixes of the ResidualBlocks, e.g. ["pred_net.res_blocks.0.", ...] (keys conv1/bn1/conv2/bn2 .weight/.bias)."""
+        return cls(ResidualBlockTrain(*[sd[p + k] for k in ("conv1.weight", "conv1.bias", "bn1.weight", "bn1.bias", "conv2.weight", "conv2.bias",
+                                                             "bn2.weight", "bn2.bias")], device=device) for p in prefixes)
+
+    def forward(self, x16):
+        y32 = None
+        for b in self.blocks:
+            x16, y32 = b.forward(x16)
+        return x16, y32
+
+    def backward(self, dy):
+        grads = []
+        for b in reversed(self.blocks):
+            dy, g = b.backward(dy)
+            grads.append(g)
+        return dy, grads[::-1]
+
+    def step(self, x16, dy, graph: bool = False):
+        """forward(x16) then backward(dy).  Returns (y bf16, y float32, dx float32, [per-block gradient dicts])."""
+        if not graph:
+            y16, y32 = self.forward(x16)
+            return (y16, y32) + self.backward(dy)
+        if self._graph is None or self._in[0].shape != x16.shape:
+            self._in = (torch.empty_like(x16), torch.empty_like(dy))
+            self._in[0].copy_(x16); self._in[1].copy_(dy)
+            side = torch.cuda.Stream(device=x16.device)
+            side.wait_stream(torch.cuda.current_stream(x16.device))
+            with torch.cuda.stream(side):                                  # warm-up outside the capture (first-use attribute calls, allocator)
+                for _ in range(2):
+                    self.forward(self._in[0]); self.backward(self._in[1])
+            torch.cuda.current_stream(x16.device).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                y16, y32 = self.forward(self._in[0])
+                self._out = (y16, y32) + self.backward(self._in[1])
+        self._in[0].copy_(x16); self._in[1].copy_(dy)
+        self._graph.replay()
+        return self._out

@@ -144,3 +144,26 @@ with torch.cuda.graph(graph):
     g_dx, g_grads = ours.backward(dyf)
 us = timed(graph.replay, reps)
 print(f"ResidualBlockTrain forward + backward as a CUDA graph replay: {us:.1f} us")
+
+# a 14-block trunk (dynamics / prediction network body) as one training step, CUDA-graph replay vs torch
+from muzero_breakout_b200.train import TrunkTrain
+trunk_t = torch.nn.Sequential(*[_Res(256, "relu") for _ in range(14)]).cuda().train()
+sd14 = {k: v.detach() for k, v in trunk_t.state_dict().items()}
+trunk = TrunkTrain.from_state_dict(sd14, [f"{i}." for i in range(14)])
+us = timed(lambda: trunk.step(x16, dyf, graph=True), max(reps // 2, 2))
+print(f"TrunkTrain 14 ResidualBlocks forward + backward, {nb} samples, CUDA-graph replay: {us / 1e3:.2f} ms")
+def torch_trunk():
+    for p_ in trunk_t.parameters(): p_.grad = None
+    xt.grad = None
+    trunk_t(xt).backward(dyt)
+us = timed(torch_trunk, max(reps // 2, 2))
+print(f"  torch (cuDNN fp32/TF32): {us / 1e3:.2f} ms")
+trunk_t16 = trunk_t.to(memory_format=torch.channels_last)
+def torch_trunk16():
+    for p_ in trunk_t16.parameters(): p_.grad = None
+    xt16.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o = trunk_t16(xt16)
+    o.backward(dyt16.to(o.dtype))
+us = timed(torch_trunk16, max(reps // 2, 2))
+print(f"  torch autocast bf16, channels_last: {us / 1e3:.2f} ms")

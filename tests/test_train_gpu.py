@@ -277,3 +277,43 @@ def test_residual_block_training_step_vs_torch(n):
         assert rel(ours.running_mean[i].cpu(), bn.running_mean) <= 2e-2 and rel(ours.running_var[i].cpu(), bn.running_var) <= 2e-2
     # the convolution biases feed a BatchNorm: their gradient is zero up to rounding, which is why the block does not compute it
     assert float(blk.conv1.bias.grad.abs().max()) <= 1e-3 * float(blk.bn1.bias.grad.abs().max())
+
+
+def test_trunk_training_step_chain_and_graph_replay():
+    """Three chained ResidualBlocks, forward + backward, eager vs CUDA-graph replay bit-identical, and against the torch restatement (mask-stable
+    BatchNorm parameters as above; the bf16 rounding points accumulate over the blocks)."""
+    from muzero_breakout_b200.train import TrunkTrain
+    from oracle.networks import _Res
+    torch.manual_seed(5)
+    blocks = torch.nn.Sequential(*[_Res(256, "relu") for _ in range(3)])
+    with torch.no_grad():
+        for blk in blocks:
+            for m in (blk.conv1, blk.conv2):
+                m.weight.copy_(m.weight.bfloat16().float())
+            for m in (blk.bn1, blk.bn2):
+                m.weight.copy_(torch.rand(256) * 0.4 + 0.3); m.bias.copy_(torch.where(torch.arange(256) % 2 == 0, 3.0, -3.0))
+    blocks.train()
+    n = 130
+    x = torch.rand(n, 256, 4, 5).bfloat16().float().requires_grad_()
+    y = blocks(x)
+    dy = torch.randn(n, 256, 4, 5)
+    y.backward(dy)
+    sd = {k: v.detach() for k, v in blocks.state_dict().items()}
+    trunk = TrunkTrain.from_state_dict(sd, [f"{i}." for i in range(3)])
+    cl = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().cuda()
+    x16, dyc = cl(x).bfloat16(), cl(dy)
+    y16, y32, dx, grads = trunk.step(x16, dyc)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    back = lambda t: t.float().cpu().permute(0, 3, 1, 2)
+    errs = {"y": rel(back(y32), y.detach()), "dx": rel(back(dx), x.grad)}
+    for i, g in enumerate(grads):
+        for k, gk in g.items():
+            mod, par = k.split(".")
+            errs[f"{i}.{k}"] = rel(gk.cpu(), getattr(getattr(blocks[i], mod), par).grad)
+    print(errs)
+    assert max(errs.values()) <= 3e-2, errs
+    trunk2 = TrunkTrain.from_state_dict(sd, [f"{i}." for i in range(3)])
+    for _ in range(2):                                             # capture, then a second replay
+        gy16, gy32, gdx, ggrads = trunk2.step(x16, dyc, graph=True)
+    assert torch.equal(gy16, y16) and torch.equal(gdx, dx)
+    assert all(torch.equal(a[k], b[k]) for a, b in zip(ggrads, grads) for k in a)
