@@ -556,7 +556,7 @@ def bench_train_ends(dev, rank, world, cpu=True):
     peaks = measured_peaks()
     out = {"trunk_step": {"ms": trunk_ms, "samples": B, "blocks": 14,
                           "what": "train.TrunkTrain: forward + backward of 14 train-mode ResidualBlocks (tcgen05 conv / dgrad / wgrad + BatchNorm kernels), "
-                                  "one CUDA-graph replay incl. the two input copies; torch + cuDNN on the same GPU: 8.0 ms TF32 / 6.7 ms autocast bf16 "
+                                  "one CUDA-graph replay incl. the two input copies; torch + cuDNN on the same GPU: 8.0 ms TF32 / 6.6 ms autocast bf16 "
                                   "(profiles/r1_train_ends_timing.txt)"},
            "wgrad": {"ms": wg_ms, "samples": nb, "TFLOPs": wg_flop / wg_ms / 1e9, "frac_of_tensor_peak": wg_flop / wg_ms / 1e9 / peaks["bf16"],
                      "what": "3x3 256->256 weight gradient on tcgen05: 2 transposes + mz_conv_wgrad (9 taps x 8 K-splits of CTA pairs) + fixed-order split reduction; "

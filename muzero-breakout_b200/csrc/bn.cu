@@ -2,7 +2,7 @@
 // train_torch.py:372) on channels-last [M = samples x pixels][C] tensors: batch statistics, normalise (+ residual) + activation,
 // running-statistics update, and the backward pass (ReLU mask, d gamma, d beta, d input, d residual).  All HBM-bound:
 //   forward   read z (4 B) twice + write y (2 B [+ 4 B])            backward   read dy, z (+ y) twice + write dz (4 B [+ 2 B])
-// Reductions over the M rows go through per-CTA fp64 partial sums that one CTA adds in index order: deterministic, and the
+// Reductions over the M rows go through per-CTA fp64 partial sums that one warp per channel adds in a fixed order: deterministic, and the
 // sum / sum-of-squares variance does not lose digits to cancellation.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -12,7 +12,7 @@
 namespace {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_ROWS = 128;         // rows per CTA of the reduction kernels
+constexpr int BN_ROWS = 32;          // rows per CTA of the reduction kernels (320 CTAs at a 512-sample minibatch of 4x5 latents)
 
 __device__ __forceinline__ float from16(uint16_t u, bool f16)
 {
@@ -105,34 +105,46 @@ bn_reduce_kernel(int M, int C, int mode, const float *__restrict__ z, const floa
     }
 }
 
-// forward finalize: one CTA; mean, biased variance -> invstd; running statistics (unbiased variance, torch's momentum rule)
+// sum of the per-CTA partials of channel c (both quantities) by one warp: lanes stride over the CTAs, then a shuffle tree -- a fixed order,
+// and the loads of a warp are all in flight at once (a serial loop over the partials took 20-35 us per call, profiles/r1_block_step_launches.csv)
+__device__ __forceinline__ void bn_warp_sums(int C, int nblocks, const double *__restrict__ partial, int c, int lane, double &s, double &q)
+{
+    s = 0.0; q = 0.0;
+    for (int b = lane; b < nblocks; b += 32) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); q += __shfl_down_sync(0xffffffffu, q, o); }
+}
+
+// forward finalize (one warp per channel): mean, biased variance -> invstd; running statistics (unbiased variance, torch's momentum rule)
 __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_finalize_kernel(int M, int C, int nblocks, const double *__restrict__ partial, double eps, double momentum, float *__restrict__ running_mean,
                        float *__restrict__ running_var, float *__restrict__ save_mean, float *__restrict__ save_invstd)
 {
-    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-        double s = 0.0, q = 0.0;
-        for (int b = 0; b < nblocks; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
-        const double mean = s / M;
-        double var = q / M - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        save_mean[c] = (float)mean;
-        save_invstd[c] = (float)(1.0 / sqrt(var + eps));
-        if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
-        if (running_var) running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * (M > 1 ? var * M / (M - 1) : var));
-    }
+    const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;                                   // warp-uniform
+    double s, q;
+    bn_warp_sums(C, nblocks, partial, c, lane, s, q);
+    if (lane != 0) return;
+    const double mean = s / M;
+    double var = q / M - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var + eps));
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+    if (running_var) running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * (M > 1 ? var * M / (M - 1) : var));
 }
 
-// backward finalize: d beta = sum g, d gamma = sum g * xhat
+// backward finalize (one warp per channel): d beta = sum g, d gamma = sum g * xhat
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ dgamma, float *__restrict__ dbeta)
 {
-    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-        double s = 0.0, q = 0.0;
-        for (int b = 0; b < nblocks; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
-        dbeta[c] = (float)s;
-        dgamma[c] = (float)q;
-    }
+    const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s, q;
+    bn_warp_sums(C, nblocks, partial, c, lane, s, q);
+    if (lane != 0) return;
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)q;
 }
 
 // y = act(gamma * (z - mean) * invstd + beta (+ res))
@@ -202,7 +214,7 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
     bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 0, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch);
     MZB_LAUNCH_CHECK();
-    bn_fwd_finalize_kernel<<<1, BN_THREADS, 0, st>>>(M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd);
+    bn_fwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd);
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
     bn_fwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
@@ -225,7 +237,7 @@ int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *
     bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
                                                    (double *)scratch);
     MZB_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<1, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, dgamma, dbeta);
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
     bn_bwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
