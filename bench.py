@@ -626,7 +626,8 @@ def main():
     ap.add_argument("--env-steps", type=int, default=200)
     ap.add_argument("--trees", type=int, default=4096, help="mcts workload: roots per GPU (BASELINE.json configs[2])")
     ap.add_argument("--sims", type=int, default=50)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "f16", "f32"])
+    ap.add_argument("--precision", default="f16", choices=["bf16", "f16", "f32"],
+                    help="f16 (default): fp16 tensor-core operands, fp32 accumulation, fp16 + e4m3 residual stream -- the 16-bit mode that meets the north star's 1e-3")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -150,14 +150,22 @@ int mz_tree_step(const mz_tree_args *args, void *stream);
  *
  *   MZ_OP_CONV      dst = act((conv_k(src) [+ act_bias[act_idx]]) * scale + shift [+ res])
  *                   conv_k: k x k, stride 1, zero padding k/2 (nn.Conv2d of networks.py:12,26,28,47,65);
- *                   scale/shift = conv bias + eval-mode BatchNorm folded per channel (:16-17,31-35);
+ *                   scale/shift = conv bias + eval-mode BatchNorm folded per channel (:16-17,31-35); scale == NULL
+ *                   means 1 (the BatchNorm scale is already folded into w: what the 16-bit packers do);
+ *                   16-bit residual stream (res_lo / dst_lo, optional): the value added is res + res_lo / LO_SCALE and
+ *                   the rounding error of the 16-bit dst is kept as dst_lo = e4m3((x - dst) * LO_SCALE), LO_SCALE = 2048
+ *                   (fp16) / 256 (bf16) -- the stream of a ResidualBlock chain (:31-35) then carries 15 / 12
+ *                   significant bits instead of 11 / 8 while the tensor-core operands stay 16-bit.  A correction
+ *                   plane is mz_conv_lo_bytes() bytes in a layout private to the convolution kernels (it is only
+ *                   ever exchanged between convolutions of the same shape and batch);
  *                   act_bias = contribution of the three spatially-constant one-hot action planes of
  *                   the dynamics input (:295), a [3][H*W][cout] table, selected per sample by act_idx
  *   MZ_OP_POOL2     2x2 average pool, stride 2 (:43,82,92)
  *   MZ_OP_SCALE     MuZeroAgent._scale_state (:314-328): per sample (x - min) / (max - min + 1e-8) over
  *                   all H*W*C elements of the fp32 src; written to dst and, if dst2 != NULL, also to
  *                   dst2 + (i * dst2_stride + dst2_slot[i]) * (H*W*C*elsize)   (the tree's latent store)
- *   MZ_OP_HEAD      Flatten(C,H,W) -> Linear (:147-149,207-209,221-223) on a channels-last src, then
+ *   MZ_OP_HEAD      Flatten(C,H,W) -> Linear (:147-149,207-209,221-223) on a channels-last src (cin channels read out of
+ *                   pixel rows of cout channels; cout = 0 means cin: a dense tensor), then
  *                   head_mode 0: raw logits; 1: inverted_softmax_expectation (utils.py:74-81) -> out[n];
  *                   2: softmax probabilities -> out[n][nout] (mcts.py:100,199)
  *   MZ_OP_NCHW_IN   float32 NCHW src -> channels-last dst (+ optional dst2 as for MZ_OP_SCALE)
@@ -184,7 +192,7 @@ typedef struct mz_op {
     const void *res;         /* conv: residual (same shape as dst) or NULL */
     float *dst_f32;          /* conv / pool: optional extra float32 copy of dst (input of MZ_OP_SCALE) */
     const void *w;           /* conv: [cout][ksize*ksize*cin], tap-major then channel; head: float32 [nout][H*W*cin] in (y,x,c) order */
-    const float *scale;      /* [cout] */
+    const float *scale;      /* [cout], or NULL = 1 */
     const float *shift;      /* [cout]; head: bias [nout] */
     const float *act_bias;   /* conv: [3][H*W][cout] or NULL */
     const int32_t *act_idx;  /* conv: [n] */
@@ -193,9 +201,15 @@ typedef struct mz_op {
     int64_t dst2_stride;     /* slots per sample in dst2 */
     float *out;              /* head: see head_mode */
     float *out_logits;       /* head: optional raw logits [n][nout] */
+    const void *res_lo;      /* conv, 16-bit: correction plane of res or NULL (= 0) */
+    void *dst_lo;            /* conv, 16-bit: correction plane of dst or NULL (not kept) */
+    const float *res_f32;    /* conv, 16-bit: the residual as float32 [n][H][W][cout] INSTEAD of res / res_lo (a stream that enters
+                                the network as float32, e.g. the latent argument of MuZeroAgent.evaluate_state), or NULL */
 } mz_op;
 
 int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream);
+/* bytes of a correction plane (res_lo / dst_lo) of an [nsamples][H][W][cout] convolution output */
+size_t mz_conv_lo_bytes(int nsamples, int H, int W, int cout, int ksize);
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -218,24 +232,31 @@ int mz_sample_actions(int B, const int64_t *visits, double temperature, uint64_t
 
 
 /* ------------------------------------------------------------------------------------------------
- * Fused residual trunk: a run of consecutive MZ_OP_CONV records that are all bf16 / use_tc / w_layout 1 /
- * 3x3 / 256 -> 256 on the 4x5 latent and touch at most three activation buffers is executed by ONE persistent
- * launch (csrc/conv_stack.cu); layers are ordered per 128-sample group through device counters instead of
- * kernel boundaries.
+ * Fused residual trunk: a run of consecutive MZ_OP_CONV records that are all 16-bit / use_tc / w_layout 1 /
+ * scale == NULL / 256 -> 256 on the 4x5 latent (3x3; 1x1 only as trailing records whose outputs nothing in the run
+ * reads: the head ConvBlocks, networks.py:138-146,200-218) and touch at most MZ_STACK_MAX_BUFS activation buffers is
+ * executed by ONE persistent launch (csrc/conv_stack.cu); layers are ordered per 128-sample group through device
+ * counters instead of kernel boundaries.
  *   mz_stack_layer_bytes()  size of one device-resident layer descriptor
  *   mz_stack_build          fills a HOST blob (64-byte aligned, n_ops * mz_stack_layer_bytes() bytes) from the op
- *                           records; bufs[n_bufs] (<= 3) are the activation buffers the ops' src/dst/res point to.
+ *                           records; bufs[n_bufs] are the activation buffers the ops' src/dst/res point to.
  *                           The caller copies the blob to device memory once.
- *   mz_stack_run            runs the trunk on samples [sample0, sample0 + nsamples) of the buffers: blob_dev = the
- *                           uploaded blob, bufs = the same buffers in the same order (base pointers), act_idx as in mz_op
- *                           (base pointer), done = int32 [n_layers * ceil(nsamples/128) * 20] scratch (zeroed here, on
- *                           the stream).  Large batches are run as several launches over sample slices whose two live
- *                           activation buffers fit the 126 MB L2 (hosts: 4096 samples = 84 MB).
+ *   mz_stack_scratch_bytes  size of the dependency-counter scratch of a launch over nsamples samples
+ *   mz_stack_run            runs the trunk on samples [sample0, sample0 + nsamples) of the buffers (sample0 a multiple of
+ *                           256): blob_dev = the uploaded blob, bufs = the same buffers in the same order (base
+ *                           pointers), act_idx as in mz_op (base pointer), scratch = mz_stack_scratch_bytes(n_layers,
+ *                           nsamples) bytes, 16-byte aligned, ZEROED ONCE by the caller and then owned by the launches
+ *                           of this (trunk, nsamples): they keep a launch epoch in it, so a CUDA-graph replay needs no
+ *                           reset.  slice_samples (a multiple of 256, or 0): the launch walks the samples slice by slice,
+ *                           all layers of a slice before the next one, so that the live activations of a slice (hosts:
+ *                           2048 samples = 52 MB) stay in the L2 while the pipelines never drain between slices.
  */
+#define MZ_STACK_MAX_BUFS 5
 size_t mz_stack_layer_bytes(void);
+size_t mz_stack_scratch_bytes(int n_layers, int nsamples);
 int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes, const void *const *bufs, int n_bufs);
-int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, void *const *bufs, int n_bufs, const int32_t *act_idx,
-                 int32_t *done, int dtype, void *stream);
+int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, int slice_samples, void *const *bufs, int n_bufs,
+                 const int32_t *act_idx, void *scratch, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Latency-mode residual trunk (csrc/conv_lat.cu): the same run of stackable convolutions as mz_stack_*, for SMALL

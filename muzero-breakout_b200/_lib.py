@@ -77,6 +77,8 @@ def _declare(L: C.CDLL) -> None:
     L.mz_tree_nodes.argtypes, L.mz_tree_nodes.restype = [i32], i32
     L.mz_stack_layer_bytes.argtypes, L.mz_stack_layer_bytes.restype = [], C.c_size_t
     L.mz_lat_layer_bytes.argtypes, L.mz_lat_layer_bytes.restype = [], C.c_size_t
+    L.mz_stack_scratch_bytes.argtypes, L.mz_stack_scratch_bytes.restype = [i32, i32], C.c_size_t
+    L.mz_conv_lo_bytes.argtypes, L.mz_conv_lo_bytes.restype = [i32, i32, i32, i32, i32], C.c_size_t
     L.mz_lat_max_samples.argtypes, L.mz_lat_max_samples.restype = [], i32
     L.mz_lat_max_layers.argtypes, L.mz_lat_max_layers.restype = [], i32
     L.mz_lat_scratch_bytes.argtypes, L.mz_lat_scratch_bytes.restype = [i32], C.c_size_t
@@ -87,7 +89,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_run": [vp, i32, i32, vp],
         "mz_rep_input": [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp],
         "mz_stack_build": [vp, i32, vp, C.c_size_t, vp, i32],
-        "mz_stack_run": [vp, i32, i32, i32, vp, i32, vp, vp, i32, vp],
+        "mz_stack_run": [vp, i32, i32, i32, i32, vp, i32, vp, vp, i32, vp],
         "mz_lat_build": [vp, i32, vp, C.c_size_t],
         "mz_lat_run": [vp, i32, i32, i32, vp, vp, i32, vp],
         "mz_sample_actions": [i32, vp, C.c_double, u64, C.c_uint32, vp, vp, vp, vp],

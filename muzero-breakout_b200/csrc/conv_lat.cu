@@ -53,14 +53,17 @@ constexpr int MAX_LAYERS = 32;           // descriptors are staged in shared mem
 static_assert(KSTEPS % WARPS == 0 && STEPS_PER_WARP == 18 && WARPS * 32 == CH, "K split: two k16 steps of each of the 9 taps per warp");
 
 struct LatOperands {                     // 64 bytes; staged in shared memory
-    const float *scale, *shift;          // [256]
+    const float *shift;                  // [256] (the BatchNorm scale is folded into the weights: mz_op.scale == NULL)
+    uint8_t *lo;                         // e4m3 correction plane of the residual stream, [row][channel] bytes, or NULL (flags: bits 1-2)
     const float *act_bias;               // [3][20][256] or NULL
     float *dst_f32;                      // optional fp32 copy of the output or NULL
     const void *src;                     // activations [n][20][256], 16-bit
     void *dst;
     const void *res;                     // or NULL
     int act;
-    short k1;                            // 1x1 convolution (centre tap only, 4 weight units): the reward / value heads' ConvBlocks (networks.py:138-146, 212-218)
+    short k1;                            // bit 0: 1x1 convolution (centre tap only, 4 weight units): the reward / value heads' ConvBlocks (networks.py:138-146, 212-218);
+                                         // bit 1: the residual's correction is read from lo; bit 2: the output's correction is written to lo;
+                                         // bit 3: res points at a float32 residual
     short cout;                          // 256, or 128 for the two halves of a split last layer (policy + value head convolutions)
 };
 struct alignas(64) LatLayer {            // device-resident descriptor of one convolution of the trunk
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             int ns = tile % NSLICES, rec = layer;
             if (p.split_last && layer == p.nlayers - 1 && ns >= NSLICES / 2) { rec = layer + 1; ns -= NSLICES / 2; }
             const uint32_t bar = bar_w + 8 * (seq & 1), dst0 = sW_u + (uint32_t)(seq & 1) * W_BYTES;
-            if (sOps[rec].k1) {                                    // one box of 4 units (the map's box is (64, 16, 4))
+            if (sOps[rec].k1 & 1) {                                // one box of 4 units (the map's box is (64, 16, 4))
                 mbar_expect_tx(bar, 4 * NS * 128);
                 tma_load_units(dst0, &p.layers[rec].map_w, bar, 0, ns * NS, 0);
             } else {
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         LTRACE(1);
         // epilogue operands that do not depend on the math: fetched now, used after the reduction
         const int co = ns * NS + e_c;
-        const float2 sc = __ldg(reinterpret_cast<const float2 *>(L->scale + co)), sf = __ldg(reinterpret_cast<const float2 *>(L->shift + co));
+        const float2 sf = __ldg(reinterpret_cast<const float2 *>(L->shift + co));
         float2 ab[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -338,7 +341,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             if (r < nrows) {
                 const int s = s0 + r / HW, pix = r % HW;
                 if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * cout + co));
-                if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * cout + co)), F16);
+                if (L->k1 & 8) rs[h] = __ldcg(reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(L->res) + ((size_t)s0 * HW + r) * cout + co));
+                else if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * cout + co)), F16);
+                if (L->k1 & 2) {                                  // 16-bit residual stream + e4m3 correction (tc_common.cuh: split2 / lo2)
+                    const float2 l = lo2(__ldcg(reinterpret_cast<const uint16_t *>(L->lo + ((size_t)s0 * HW + r) * cout + co)), F16);
+                    rs[h].x += l.x; rs[h].y += l.y;
+                }
             }
         }
         if (layer == 0) {
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 mma16816<F16>(acc[mt][1], a[mt], b[2], b[3]);
             }
         };
-        if (L->k1) {                                                // centre tap only: this warp's two k16 steps
+        if (L->k1 & 1) {                                            // centre tap only: this warp's two k16 steps
             load_frags(8, 0, af[0], bf[0]);
             load_frags(9, 0, af[1], bf[1]);
             mma_step(af[0], bf[0]);
@@ -466,12 +474,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
         for (int h = 0; h < 2; ++h) {
             const int r = e_r0 + h * 8;
             if (r < nrows) {
-                float x0 = (v[h * 2] + ab[h].x) * sc.x + sf.x + rs[h].x;
-                float x1 = (v[h * 2 + 1] + ab[h].y) * sc.y + sf.y + rs[h].y;
+                float x0 = (v[h * 2] + ab[h].x) + sf.x + rs[h].x;
+                float x1 = (v[h * 2 + 1] + ab[h].y) + sf.y + rs[h].y;
                 x0 = activate(x0, L->act);
                 x1 = activate(x1, L->act);
                 const size_t o = ((size_t)s0 * HW + r) * cout + co;
-                const uint32_t packed = pack2(x0, x1, F16);
+                uint32_t packed;
+                if (L->k1 & 4) {
+                    uint16_t l;
+                    packed = split2(x0, x1, F16, l);
+                    *reinterpret_cast<uint16_t *>(L->lo + o) = l;
+                } else packed = pack2(x0, x1, F16);
                 if (layer + 1 < p.nlayers) {                      // the next layer's items poll this word
                     uint2 *w = p.ll + ((size_t)(layer & 1) * p.rtiles + rt) * (ROWS * CH / 2) + (size_t)r * (CH / 2) + (co >> 1);
                     const unsigned long long word = (unsigned long long)packed | ((unsigned long long)(flag_base + (uint32_t)layer + 1u) << 32);
@@ -589,7 +602,9 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
         MZB_CHECK_ARG(o.op == MZ_OP_CONV && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.dtype == ops[0].dtype && o.w_layout == 1 && (o.ksize == 3 || o.ksize == 1) && o.cin == CH &&
                           o.cout == (half ? CH / 2 : CH) && o.H == LAT_H && o.W == LAT_W,
                       "op is not a 3x3 / 1x1 256->256 16-bit convolution on the 4x5 latent with tile-contiguous weights (or one of two final 256->128 ones)");
-        MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
+        MZB_CHECK_ARG(o.src && o.dst && o.w && o.shift && o.src != o.dst, "missing operand, or a convolution in place on its own input");
+        MZB_CHECK_ARG(!o.scale, "the latency-mode trunk takes weights with the BatchNorm scale folded in (scale == NULL)");
+        MZB_CHECK_ARG((!o.res_lo || o.res) && (!o.res_lo || !o.dst_lo || o.res_lo == o.dst_lo), "correction planes: res_lo needs res; a layer that reads and writes one uses the same plane (in-place stream)");
         MZB_CHECK_ARG(!o.act_bias || o.act_idx, "act_bias without act_idx");
         // every layer reads the previous layer's output (the layer counters order exactly that); the two halves of a split last layer
         // both read the output of the layer before them and write different buffers
@@ -597,7 +612,10 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
         MZB_CHECK_ARG(i == 0 || o.src == ops[prev].dst, "the layers must form a chain: each one reads the previous one's output");
         MZB_CHECK_ARG(o.dst != ops[0].src, "no layer may overwrite the trunk's input (its rows are loaded by every CTA at its own pace)");
         MZB_CHECK_ARG(!half || (!o.res && !o.act_bias && ops[n_ops - 1].dst != ops[n_ops - 2].dst), "split last layer: no residual / action bias, two destinations");
-        L[i].o = LatOperands{o.scale, o.shift, o.act_bias, o.dst_f32, o.src, o.dst, o.res, o.act, (short)(o.ksize == 1), (short)o.cout};
+        uint8_t *lo = reinterpret_cast<uint8_t *>(o.dst_lo ? o.dst_lo : const_cast<void *>(o.res_lo));
+        MZB_CHECK_ARG(!o.res_f32 || !o.res, "res_f32 replaces res / res_lo");
+        L[i].o = LatOperands{o.shift, lo, o.act_bias, o.dst_f32, o.src, o.dst, o.res_f32 ? (const void *)o.res_f32 : o.res, o.act,
+                             (short)((o.ksize == 1 ? 1 : 0) | (o.res_lo ? 2 : 0) | (o.dst_lo ? 4 : 0) | (o.res_f32 ? 8 : 0)), (short)o.cout};
         cuuint64_t dims[3] = {64, (cuuint64_t)o.cout, (cuuint64_t)(o.ksize == 1 ? CH / 64 : W_UNITS)};
         cuuint64_t strides[2] = {128, (cuuint64_t)o.cout * 128};
         cuuint32_t box[3] = {64, NS, (cuuint32_t)(o.ksize == 1 ? CH / 64 : W_BOX)};
@@ -643,9 +661,31 @@ int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const i
         MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));
     }
     const int ntiles = p.rtiles * NSLICES;
-    const int grid = ntiles < mzb::kNumSMs ? ntiles : mzb::kNumSMs;     // all CTAs co-resident (see the header comment)
-    if (p.f16) conv_lat_kernel<true><<<grid, THREADS, LAT_SMEM, st>>>(p);
-    else conv_lat_kernel<false><<<grid, THREADS, LAT_SMEM, st>>>(p);
+    // all CTAs must be co-resident (items wait on other CTAs' outputs): the grid never exceeds what this device / context can
+    // hold at once (one CTA per SM by shared memory; fewer SMs than a full B200 under MIG / MPS limits), and the launch is
+    // cooperative so that it starts only when the whole grid fits beside whatever else is running
+    static int resident[64] = {};
+    int d = 0;
+    MZB_CUDA(cudaGetDevice(&d));
+    if (d < 0 || d >= 64 || resident[d] == 0) {
+        int per_sm = 0, sms = 0;
+        MZB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_lat_kernel<true>, THREADS, LAT_SMEM));
+        MZB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
+        if (per_sm * sms < 1) { mzb::set_error("mz_lat_run: the latency-mode trunk does not fit on this device"); return -2; }
+        if (d >= 0 && d < 64) resident[d] = per_sm * sms;
+    }
+    const int cap = resident[d] < mzb::kNumSMs ? resident[d] : mzb::kNumSMs;
+    const int grid = ntiles < cap ? ntiles : cap;
+    static int coop = -1;
+    if (coop < 0) { const char *e = getenv("MZB_LAT_COOP"); coop = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = LAT_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = coop ? 1 : 0;
+    if (p.f16) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_lat_kernel<true>, p));
+    else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_lat_kernel<false>, p));
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -50,6 +50,9 @@ struct ConvParams {
     float *dst_f32;
     const float *scale, *shift, *act_bias;
     const int *act_idx;
+    const uint8_t *res_lo;   // e4m3 correction planes of the residual / the output (tc_common.cuh: split2 / lo2), tile-private layout
+    uint8_t *dst_lo;
+    const float *res_f32;    // fp32 residual instead of res / res_lo
 };
 
 // profiling trace (debug & 8): per-tile timestamps of cluster 0's leader CTA, read back with mz_conv_trace()
@@ -110,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();                  // the driver honours __align__(1024) on the dynamic segment; fail loudly if not
 
-    for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale ? p.scale[i] : 1.0f; s_shift[i] = p.shift[i]; }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -221,6 +224,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long m = valid ? ((long long)s * p.H + y) * p.W + x : -1;   // global output row, -1 = nothing to write
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
             const bool has_res = p.res != nullptr;
+            // correction planes: [CTA tile][epilogue warp][2 * nchunks][32 lanes] x 16 bytes (same as conv_stack.cu in pixel mode)
+            const size_t lo_tile = p.mode == 1 ? (size_t)(t.s0 / BLOCK_M) * (p.H * p.W) + (size_t)(t.y0 * p.W + t.x0) : (size_t)2 * tile + rank;
+            const size_t lo_off = (lo_tile * NUM_EPI_WARPS + (warp - 2)) * (2 * nchunks * 512) + (size_t)lane * 16;
+            uint4 lo_in[2 * nchunks];
+            if (p.res_lo && valid) {
+#pragma unroll
+                for (int i = 0; i < 2 * nchunks; ++i) lo_in[i] = __ldcg(reinterpret_cast<const uint4 *>(p.res_lo + lo_off + i * 512));
+            }
             if (warp == 2 && lane == 0) TRACE(3, it);
             if (has_res) {                                               // coalesced residual prefetch into the staging tile:
                 // cp.async (global -> shared, 16 bytes each, no register staging) so that all 16 requests of a lane are
@@ -283,17 +294,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                     v[q * 8 + e * 2 + 1] += f.y;
                                 }
                             }
+                            if (p.res_lo) {
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const uint4 l4 = lo_in[(2 * c + i) < 2 * nchunks ? 2 * c + i : 0];
+                                    const uint32_t w[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float2 f = lo2((uint16_t)(w[e >> 1] >> ((e & 1) * 16)), p.f16);
+                                        v[i * 16 + e * 2] += f.x;
+                                        v[i * 16 + e * 2 + 1] += f.y;
+                                    }
+                                }
+                            }
+                        }
+                        if (p.res_f32) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 t4 = __ldcg(reinterpret_cast<const float4 *>(p.res_f32 + m * N + c0) + q);
+                                v[q * 4] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
+                            }
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = kRelu ? fmaxf(v[j], 0.0f) : activate(v[j], p.act);
+                        uint32_t hi[16];
+                        if (p.dst_lo) {
+                            uint32_t lw[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 u4;
-                            uint32_t *h = reinterpret_cast<uint32_t *>(&u4);
+                            for (int e = 0; e < 16; e += 2) {
+                                uint16_t l0, l1;
+                                hi[e] = split2(v[e * 2], v[e * 2 + 1], p.f16, l0);
+                                hi[e + 1] = split2(v[e * 2 + 2], v[e * 2 + 3], p.f16, l1);
+                                lw[e >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                            }
+                            __stcg(reinterpret_cast<uint4 *>(p.dst_lo + lo_off + (2 * c) * 512), make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                            __stcg(reinterpret_cast<uint4 *>(p.dst_lo + lo_off + (2 * c + 1) * 512), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                        } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) h[e] = pack2(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1], p.f16);
-                            *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = u4;
+                            for (int e = 0; e < 16; ++e) hi[e] = pack2(v[e * 2], v[e * 2 + 1], p.f16);
                         }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
                         if (p.dst_f32) {
                             float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
 #pragma unroll
@@ -337,11 +379,49 @@ extern "C" int mz_conv_trace(unsigned long long *host_out)   // profiling aid: c
     return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(unsigned long long) * 8 * 64) == cudaSuccess ? 0 : -2;
 }
 
+namespace {
+
+// the two tilings of conv_tc_launch and which one a shape gets (predicted cost = waves x taps per tile)
+struct Tiling { int mode, S, hb, tile_rows, ytiles, groups, ntiles; };
+Tiling choose_tiling(int n, int H, int W, int ksize)
+{
+    // spatial tiling: S samples x hb rows x W columns with S*hb*W <= 128, hb | H, as many rows as possible
+    int best = 0, s_hb = 1, s_S = 1;
+    for (int hb = 1; hb <= H; ++hb) {
+        if (H % hb || hb * W > BLOCK_M) continue;
+        int S = BLOCK_M / (hb * W);
+        if (S > 256) S = 256;
+        const int rows = S * hb * W;
+        if (rows > best || (rows == best && hb > s_hb)) { best = rows; s_hb = hb; s_S = S; }
+    }
+    const long long sp_pairs = best > 0 ? (((n + s_S - 1) / s_S + 1) / 2) : 0;                       // sample-group pairs
+    const long long sp_tiles = sp_pairs * (best > 0 ? H / s_hb : 0);
+    // pixel tiling: 128 samples x one pixel; predicted cost = waves x average in-bounds taps
+    const long long px_groups = ((n + BLOCK_M - 1) / BLOCK_M + 1) / 2, px_tiles = px_groups * H * W;   // pairs of 128-sample groups
+    double px_taps = 1.0;
+    if (ksize == 3) px_taps = (double)(3 * H - 2) * (3 * W - 2) / (H * W);
+    auto waves = [](long long tiles) { return (double)((tiles + mzb::kNumSMs / 2 - 1) / (mzb::kNumSMs / 2)); };
+    const double cost_px = waves(px_tiles) * px_taps, cost_sp = best > 0 ? waves(sp_tiles) * (ksize * ksize) : 1e30;
+    if (cost_px <= cost_sp) return Tiling{1, BLOCK_M, 1, BLOCK_M, 1, (int)px_groups, (int)px_tiles};
+    return Tiling{0, s_S, s_hb, best, H / s_hb, 1, (int)sp_tiles};
+}
+
+}  // namespace
+
+// a correction plane covers whole CTA tiles (128 rows x cout bytes each, two per pair-tile); the CUDA-core and latency-mode
+// kernels use the first n*H*W*cout bytes of it as a plain [row][channel] array
+extern "C" size_t mz_conv_lo_bytes(int nsamples, int H, int W, int cout, int ksize)
+{
+    if (nsamples <= 0 || H <= 0 || W <= 0 || cout <= 0 || W > 256) return 0;
+    const Tiling t3 = choose_tiling(nsamples, H, W, ksize == 1 ? 1 : 3);
+    return (size_t)t3.ntiles * 2 * BLOCK_M * cout;
+}
+
 namespace mzb {
 
 int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
 {
-    MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift, "conv_tc: null pointer");
+    MZB_CHECK_ARG(o.src && o.dst && o.w && o.shift, "conv_tc: null pointer");
     MZB_CHECK_ARG((o.ksize == 1 || o.ksize == 3) && o.cin % BLOCK_K == 0 && (o.cout == 128 || o.cout == 256), "conv_tc: unsupported shape");
     MZB_CHECK_ARG(!o.act_bias || o.act_idx, "conv_tc: act_bias needs act_idx");
     EncodeTiledFn enc = encode_fn();
@@ -349,31 +429,15 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
 
     ConvParams p{};
     p.n = n; p.H = o.H; p.W = o.W; p.cin = o.cin; p.cout = o.cout; p.taps = o.ksize * o.ksize; p.pad = o.ksize / 2; p.act = o.act;
-    // spatial tiling: S samples x hb rows x W columns with S*hb*W <= 128, hb | H, as many rows as possible
-    int best = 0, s_hb = 1, s_S = 1;
-    for (int hb = 1; hb <= o.H; ++hb) {
-        if (o.H % hb || hb * o.W > BLOCK_M) continue;
-        int S = BLOCK_M / (hb * o.W);
-        if (S > 256) S = 256;
-        const int rows = S * hb * o.W;
-        if (rows > best || (rows == best && hb > s_hb)) { best = rows; s_hb = hb; s_S = S; }
-    }
     MZB_CHECK_ARG(o.W <= 256, "conv_tc: image too wide");
-    const long long sp_pairs = best > 0 ? (((n + s_S - 1) / s_S + 1) / 2) : 0;                       // sample-group pairs
-    const long long sp_tiles = sp_pairs * (best > 0 ? o.H / s_hb : 0);
-    // pixel tiling: 128 samples x one pixel; predicted cost = waves x average in-bounds taps
-    const long long px_groups = ((n + BLOCK_M - 1) / BLOCK_M + 1) / 2, px_tiles = px_groups * o.H * o.W;   // pairs of 128-sample groups
-    double px_taps = 1.0;
-    if (o.ksize == 3) px_taps = (double)(3 * o.H - 2) * (3 * o.W - 2) / (o.H * o.W);
-    auto waves = [](long long tiles) { return (double)((tiles + kNumSMs / 2 - 1) / (kNumSMs / 2)); };
-    const double cost_px = waves(px_tiles) * px_taps, cost_sp = best > 0 ? waves(sp_tiles) * p.taps : 1e30;
-    if (cost_px <= cost_sp) {
-        p.mode = 1; p.S = BLOCK_M; p.hb = 1; p.tile_rows = BLOCK_M; p.ytiles = 1; p.groups = (int)px_groups; p.ntiles = (int)px_tiles;
-    } else {
-        p.mode = 0; p.S = s_S; p.hb = s_hb; p.tile_rows = best; p.ytiles = o.H / s_hb; p.groups = 1; p.ntiles = (int)sp_tiles;
-    }
+    const Tiling tl = choose_tiling(n, o.H, o.W, o.ksize);
+    p.mode = tl.mode; p.S = tl.S; p.hb = tl.hb; p.tile_rows = tl.tile_rows; p.ytiles = tl.ytiles; p.groups = tl.groups; p.ntiles = tl.ntiles;
     p.dst = (__nv_bfloat16 *)o.dst; p.res = (const __nv_bfloat16 *)o.res; p.dst_f32 = o.dst_f32;
     p.scale = o.scale; p.shift = o.shift; p.act_bias = o.act_bias; p.act_idx = o.act_idx;
+    p.res_lo = reinterpret_cast<const uint8_t *>(o.res_lo); p.dst_lo = reinterpret_cast<uint8_t *>(o.dst_lo);
+    MZB_CHECK_ARG(!o.res_lo || o.res, "conv_tc: res_lo without res");
+    MZB_CHECK_ARG(!o.res_f32 || !o.res, "conv_tc: res_f32 replaces res / res_lo");
+    p.res_f32 = o.res_f32;
     p.w_tiled = o.w_layout == 1;
     p.f16 = o.dtype == MZ_F16;
     const CUtensorMapDataType tm_type = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;

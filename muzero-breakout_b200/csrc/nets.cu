@@ -8,6 +8,7 @@
 // utils.py ScalarTransforms.inverted_softmax_expectation :74-81 of the reference.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -25,6 +26,17 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// 16-bit residual stream + e4m3 correction (see tc_common.cuh: split2 / lo2): LO_SCALE = 2048 (fp16) / 256 (bf16)
+template <typename T> __device__ __forceinline__ float lo_scale_of() { return 1.0f; }
+template <> __device__ __forceinline__ float lo_scale_of<__half>() { return 2048.0f; }
+template <> __device__ __forceinline__ float lo_scale_of<__nv_bfloat16>() { return 256.0f; }
+__device__ __forceinline__ float lo_decode(uint8_t b)
+{
+    const __half_raw r = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3);
+    return __half2float(*reinterpret_cast<const __half *>(&r));
+}
+__device__ __forceinline__ uint8_t lo_encode(float d) { return (uint8_t)__nv_cvt_float_to_fp8(d, __NV_SATFINITE, __NV_E4M3); }
 
 __device__ __forceinline__ float activate(float v, int act)
 {
@@ -46,7 +58,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(int M, int H, int W, int cin, int cout, int ksize, int act, const T *__restrict__ src, T *__restrict__ dst,
                  const T *__restrict__ res, float *__restrict__ dst_f32, const T *__restrict__ w, const float *__restrict__ scale,
-                 const float *__restrict__ shift, const float *__restrict__ act_bias, const int *__restrict__ act_idx)
+                 const float *__restrict__ shift, const float *__restrict__ act_bias, const int *__restrict__ act_idx,
+                 const uint8_t *__restrict__ res_lo, uint8_t *__restrict__ dst_lo, const float *__restrict__ res_f32)
 {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
@@ -106,10 +119,14 @@ conv_simt_kernel(int M, int H, int W, int cin, int cout, int ksize, int act, con
             const int n = n0 + tx * 4 + j;
             float v = acc[i][j];
             if (ab) v += ab[n];
-            v = v * scale[n] + shift[n];
+            v = v * (scale ? scale[n] : 1.0f) + shift[n];
             if (res) v += to_f(res[(size_t)m * cout + n]);
+            if (res_lo) v += lo_decode(res_lo[(size_t)m * cout + n]) * (1.0f / lo_scale_of<T>());
+            if (res_f32) v += res_f32[(size_t)m * cout + n];
             v = activate(v, act);
-            dst[(size_t)m * cout + n] = from_f<T>(v);
+            const T hi = from_f<T>(v);
+            dst[(size_t)m * cout + n] = hi;
+            if (dst_lo) dst_lo[(size_t)m * cout + n] = lo_encode((v - to_f(hi)) * lo_scale_of<T>());
             if (dst_f32) dst_f32[(size_t)m * cout + n] = v;
         }
     }
@@ -249,9 +266,12 @@ __device__ __forceinline__ void load8(const __half *p, float (&f)[8])
 
 template <typename T, int NOUT>
 __global__ void __launch_bounds__(HEAD_THREADS, 4)
-head_kernel(int n, int feat, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
+head_kernel(int n, int feat, int cin, int cstride, int mode, const T *__restrict__ src, const float *__restrict__ w, const float *__restrict__ bias,
             float *__restrict__ out, float *__restrict__ out_logits)
 {
+    // src rows are pixels of cstride channels of which this head reads cin (cstride == cin: a dense [n][feat] tensor; the policy and value
+    // heads read the two halves of one 256-channel buffer that a single trunk layer wrote)
+    const int pixels = feat / cin;
     __shared__ float s_part[HEAD_THREADS / 32][HEAD_SAMPLES][NOUT];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int s0 = blockIdx.x * HEAD_SAMPLES;
@@ -265,7 +285,7 @@ head_kernel(int n, int feat, int mode, const T *__restrict__ src, const float *_
         float xv[HEAD_SAMPLES][8];
 #pragma unroll
         for (int s = 0; s < HEAD_SAMPLES; ++s) {
-            if (s < ns) load8(src + (size_t)(s0 + s) * feat + e, xv[s]);
+            if (s < ns) load8(src + ((size_t)(s0 + s) * pixels + e / cin) * cstride + e % cin, xv[s]);
             else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) xv[s][q] = 0.0f;
@@ -329,7 +349,9 @@ int launch_head(const mz_op &o, int n, cudaStream_t st)
     const int feat = o.H * o.W * o.cin;
     if (feat % 8) { mzb::set_error("head: feature count %d is not a multiple of 8", feat); return -1; }
     const int grid = (n + HEAD_SAMPLES - 1) / HEAD_SAMPLES;
-#define MZB_HEAD(NO) head_kernel<T, NO><<<grid, HEAD_THREADS, 0, st>>>(n, feat, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits)
+    const int cstride = o.cout > 0 ? o.cout : o.cin;
+    if (o.cin % 8 || cstride % 8 || cstride < o.cin) { mzb::set_error("head: channels %d / row stride %d", o.cin, cstride); return -1; }
+#define MZB_HEAD(NO) head_kernel<T, NO><<<grid, HEAD_THREADS, 0, st>>>(n, feat, o.cin, cstride, o.head_mode, (const T *)o.src, (const float *)o.w, o.shift, o.out, o.out_logits)
     switch (o.nout) {
         case 3: MZB_HEAD(3); break;
         case 11: MZB_HEAD(11); break;
@@ -373,13 +395,15 @@ int run_op(const mz_op &o, int n, cudaStream_t st)
 {
     switch (o.op) {
         case MZ_OP_CONV: {
-            MZB_CHECK_ARG(o.src && o.dst && o.w && o.scale && o.shift, "conv: null pointer");
+            MZB_CHECK_ARG(o.src && o.dst && o.w && o.shift, "conv: null pointer");
+            MZB_CHECK_ARG((!o.res_lo || o.res) && (sizeof(T) == 2 || (!o.res_lo && !o.dst_lo)), "conv: correction planes belong to a 16-bit residual stream");
             MZB_CHECK_ARG((o.ksize == 1 || o.ksize == 3) && o.cin % TK == 0 && o.cout % TN == 0, "conv: unsupported shape");
             MZB_CHECK_ARG(!o.act_bias || o.act_idx, "conv: act_bias needs act_idx");
             const int M = n * o.H * o.W;
             dim3 grid((M + TM - 1) / TM, o.cout / TN);
             conv_simt_kernel<T><<<grid, 256, 0, st>>>(M, o.H, o.W, o.cin, o.cout, o.ksize, o.act, (const T *)o.src, (T *)o.dst,
-                                                     (const T *)o.res, o.dst_f32, (const T *)o.w, o.scale, o.shift, o.act_bias, o.act_idx);
+                                                     (const T *)o.res, o.dst_f32, (const T *)o.w, o.scale, o.shift, o.act_bias, o.act_idx,
+                                                     (const uint8_t *)o.res_lo, (uint8_t *)o.dst_lo, o.res_f32);
             break;
         }
         case MZ_OP_POOL2: {

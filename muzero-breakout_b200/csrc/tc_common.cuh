@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -68,6 +69,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// Plain (cta_group-less) TMA tile load into THIS CTA's shared memory, bytes signalled on this CTA's mbarrier `bar`
+// (a shared::cta address is a valid shared::cluster address of the executing CTA): the epilogue's residual tiles
+__device__ __forceinline__ void tma_load_4d_cta(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// TMA tile store shared -> global (bulk async-group completion); rows / pixels outside the tensor are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have READ their shared-memory source (the staging tile may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed: their global writes are performed
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (the TMA store that reads them)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank)
 {
@@ -155,6 +180,33 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool f16)
     if (f16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t *>(&h); }
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// ---------------------------------------------------------------- residual stream: 16-bit value + 8-bit correction
+// The residual stream x_k of a ResidualBlock chain (networks.py:31-35: x_{k+1} = act(bn2(conv2(..)) + x_k)) is the one
+// place where 16-bit STORAGE compounds: every block would add a fresh rounding of the whole stream (14 blocks per trunk).
+// The stream is therefore kept as hi = 16-bit round(x) (the tensor-core operand of the next convolution) plus
+// lo = e4m3((x - hi) * LO_SCALE) in a second, 1-byte plane that only the convolution epilogues read and write:
+// x ~ hi + lo / LO_SCALE carries 15 (fp16) / 12 (bf16) significant bits.  |x - hi| <= ulp(hi)/2, so the scaled difference is at most
+// |hi| and e4m3 (max 448, saturating) holds it for |x| < 448; x - hi and the scaling are exact in fp32.
+// Measured against the fp32 reference (profiles/emulate_precision.py): fp16 trunks 1.3-1.7e-3 -> 4.4-6.1e-4 of range.
+__device__ __forceinline__ float lo_scale(bool f16) { return f16 ? 2048.0f : 256.0f; }
+// two fp32 results -> packed 16-bit pair (returned) and their two e4m3 corrections (low byte = first value)
+__device__ __forceinline__ uint32_t split2(float a, float b, bool f16, uint16_t &lo)
+{
+    const uint32_t h = pack2(a, b, f16);
+    const float2 back = unpack2(h, f16);
+    const float sc = lo_scale(f16);
+    lo = __nv_cvt_float2_to_fp8x2(make_float2((a - back.x) * sc, (b - back.y) * sc), __NV_SATFINITE, __NV_E4M3);
+    return h;
+}
+// the two corrections of a packed e4m3 pair as floats, already divided by LO_SCALE
+__device__ __forceinline__ float2 lo2(uint16_t lo, bool f16)
+{
+    const __half2_raw r = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)lo, __NV_E4M3);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r));
+    const float inv = f16 ? (1.0f / 2048.0f) : (1.0f / 256.0f);
+    return make_float2(f.x * inv, f.y * inv);
 }
 
 __device__ __forceinline__ float activate(float v, int act)

@@ -8,7 +8,7 @@ Same constructor and call signature, so train_torch.py:90-92 can load it by name
     public mutable attributes .noise_weight (train_torch.py:135) and .mu_zero (:449,451)
 
 What runs: the root prediction, then num_simulations x { dynamics + prediction networks on one leaf
-per tree (tcgen05 bf16, or fp32 CUDA cores with precision="f32") -> fused backup + next selection
+per tree (tcgen05 fp16 / bf16, or fp32 CUDA cores with precision="f32") -> fused backup + next selection
 (csrc/tree.cu) }, all enqueued on one CUDA stream with no host synchronisation inside the search and,
 by default, replayed as one CUDA graph.  Trees are flat per-root arrays in HBM; latents of expanded
 nodes live in a preallocated [B][num_simulations+2] store.
@@ -19,7 +19,7 @@ visit (:121,:163-175), one tie-break draw per pUCT call (:297), root value = sum
 Randomness: Dirichlet(0.25) root noise (:114) is sampled per call on the device (or passed in with
 noise=...); the tie-break draw is the counter-based stream u32(seed, tree, call counter) % count.
 
-Extra, optional: cfg["search"] keys "precision" ("bf16" default / "f32"), "seed", "use_graph",
+Extra, optional: cfg["search"] keys "precision" ("f16" default: within 1e-3 of the fp32 networks / "bf16" / "f32"), "seed", "use_graph",
 "output_device" ("cpu" default / "cuda"); search(..., noise=, seed=) for reproducible runs.
 There is no CPU fallback.
 """
@@ -167,7 +167,7 @@ class MCTSSearchVec:
         if list(self.actions) != [0, 1, 2]:
             raise ValueError("the tree kernels are built for actions [0, 1, 2] (config.yaml:6)")
         s = cfg["search"]
-        self.precision = s.get("precision", "bf16")
+        self.precision = s.get("precision", "f16")
         self.seed = int(s.get("seed", 0))
         self.use_graph = bool(s.get("use_graph", True))
         self.output_device = s.get("output_device", "cpu")

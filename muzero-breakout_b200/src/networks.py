@@ -9,12 +9,15 @@ evaluate the representation / dynamics / prediction networks.
         .prediction(hidden)                    <-> MuZeroAgent.evaluate_state            :300-312
         .inverted_softmax_expectation(logits)  <-> ScalarTransforms (utils.py:74-81)
 
-precision "bf16": bf16 weights and activations, tcgen05 tensor-core convolutions (csrc/conv_tc.cu, conv_stack.cu),
-fp32 accumulation and epilogues; "f16": the same path and speed with fp16 storage (11-bit mantissa: ~8x closer to
-the fp32 reference, range 65504); "f32": fp32 everything on CUDA cores (the 1e-5 parity path).
-Eval-mode BatchNorm and the conv bias are folded into a per-channel fp32 (scale, shift) applied in the
-convolution epilogue; the three one-hot action planes of the dynamics input become a per-action bias
-table (they are spatially constant, so their convolution is a [3][20][256] lookup).
+precision "f16" (the default of the search): fp16 weights and activations, tcgen05 tensor-core convolutions
+(csrc/conv_tc.cu, conv_stack.cu), fp32 accumulation and epilogues, the residual stream of every ResidualBlock chain
+carried as fp16 + an e4m3 correction plane (15 significant bits; csrc/tc_common.cuh) -- within 1e-3 of the fp32
+reference (BASELINE.json north_star; profiles/emulate_precision.py); "bf16": the same path and speed with bf16 storage
+(8-bit mantissa: 3-6e-3 of the reference); "f32": fp32 everything on CUDA cores (the 1e-5 parity path).
+Eval-mode BatchNorm and the conv bias are folded: on the 16-bit paths the BatchNorm scale goes into the weights before
+they are rounded and the epilogue adds a per-channel fp32 shift; the fp32 path keeps (scale, shift) in the epilogue.
+The three one-hot action planes of the dynamics input become a per-action bias table (they are spatially constant,
+so their convolution is a [3][20][256] lookup).
 There is no CPU path: everything here needs a CUDA device.
 """
 from __future__ import annotations
@@ -30,7 +33,11 @@ from .. import _lib
 OP_CONV, OP_POOL2, OP_SCALE, OP_HEAD, OP_NCHW_IN, OP_NHWC_OUT = range(6)
 F32, BF16, F16 = 0, 1, 2
 FUSE_MAX_SAMPLES = int(os.environ.get("MZB_FUSE_MAX_SAMPLES", "1000000"))
-STACK_CHUNK = int(os.environ.get("MZB_STACK_CHUNK", "4096"))     # samples per trunk launch: two live activation buffers of 4096 samples = 84 MB stay in the 126 MB L2
+# samples per slice of a trunk launch (all layers of a slice before the next slice, inside the one launch).  Measured on B200 at 4096 roots
+# (profiles/README.md, round 2): one slice of 4096 3.82 ms per simulation step, two of 2048 4.06, four of 1024 5.16 -- fewer sample groups in
+# flight leave the CTA pairs waiting on each other's layers, which costs more than the DRAM write-back of the 105 MB working set
+STACK_SLICE = int(os.environ.get("MZB_STACK_SLICE", "4096"))
+LO_STREAM = os.environ.get("MZB_NO_LO", "0") != "1"              # 16-bit residual streams carry an e4m3 correction plane
 ACT = {"none": 0, "relu": 1, "leaky_relu": 2, "silu": 3, "gelu": 4}   # utils.py:99-108
 
 
@@ -42,7 +49,7 @@ class MzOp(C.Structure):
                 ("src", C.c_void_p), ("dst", C.c_void_p), ("res", C.c_void_p), ("dst_f32", C.c_void_p), ("w", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("act_bias", C.c_void_p), ("act_idx", C.c_void_p),
                 ("dst2", C.c_void_p), ("dst2_slot", C.c_void_p), ("dst2_stride", C.c_int64),
-                ("out", C.c_void_p), ("out_logits", C.c_void_p)]
+                ("out", C.c_void_p), ("out_logits", C.c_void_p), ("res_lo", C.c_void_p), ("dst_lo", C.c_void_p), ("res_f32", C.c_void_p)]
 
 
 def _p(t):
@@ -50,9 +57,9 @@ def _p(t):
 
 
 def _stackable(o) -> bool:
-    """3x3 256->256 tensor-core convolution on the 4x5 latent with tile-contiguous weights (csrc/conv_stack.cu)."""
-    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize == 3 and o.cin == 256
-            and o.cout == 256 and o.H == 4 and o.W == 5)
+    """3x3 / 1x1 256->256 tensor-core convolution on the 4x5 latent with tile-contiguous, scale-folded weights (csrc/conv_stack.cu)."""
+    return (o.op == OP_CONV and o.dtype in (BF16, F16) and o.use_tc == 1 and o.w_layout == 1 and o.ksize in (1, 3) and o.cin == 256
+            and o.cout == 256 and o.H == 4 and o.W == 5 and not o.scale)
 
 
 def lat_max_samples() -> int:
@@ -100,7 +107,7 @@ class _Stack:
             for ptr in (o.src, o.dst, o.res):
                 if ptr and ptr not in bufs:
                     bufs.append(ptr)
-        self.ok = len(bufs) <= 3
+        self.ok = len(bufs) <= 5                         # MZ_STACK_MAX_BUFS
         if not self.ok:
             return
         lb = L.mz_stack_layer_bytes()
@@ -111,20 +118,19 @@ class _Stack:
         _lib.check(L.mz_stack_build(arr, self.nlayers, host, self.nlayers * lb, self.bufs, self.nbufs))
         blob = torch.frombuffer((C.c_uint8 * (self.nlayers * lb)).from_address(host), dtype=torch.uint8).clone()
         self.blob = blob.to(device)
-        # sample slices: equal chunks of whole 256-sample group pairs, at most ~STACK_CHUNK samples each
-        nchunks = 1 if n <= STACK_CHUNK * 5 // 4 else (n + STACK_CHUNK - 1) // STACK_CHUNK
-        per = ((n + nchunks - 1) // nchunks + 255) // 256 * 256
-        self.chunks = [(s0, min(per, n - s0)) for s0 in range(0, n, per)]
-        self.done = torch.zeros(self.nlayers * ((per + 127) // 128) * 20, dtype=torch.int32, device=device)
+        # one launch; inside it the samples are walked in slices of ~STACK_SLICE (whole 256-sample pair tiles, equal sizes)
+        nsl = 1 if n <= STACK_SLICE * 5 // 4 else (n + STACK_SLICE - 1) // STACK_SLICE
+        self.slice = 0 if nsl == 1 else ((n + nsl - 1) // nsl + 255) // 256 * 256
+        self.chunks = [(0, n)]
+        self.done = torch.zeros((L.mz_stack_scratch_bytes(self.nlayers, n) + 3) // 4, dtype=torch.int32, device=device)   # zeroed once; the launches keep their epoch in it
 
     def run(self, st):
         L = _lib.lib()
         if self.lat:
             _lib.check(L.mz_lat_run(self.blob.data_ptr(), self.nlayers, self.flags, self.n, self.act_idx, self.done.data_ptr(), self.dtype, st))
             return
-        for s0, cnt in self.chunks:
-            _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, s0, cnt, self.bufs, self.nbufs, self.act_idx,
-                                      self.done.data_ptr(), self.dtype, st))
+        _lib.check(L.mz_stack_run(self.blob.data_ptr(), self.nlayers, 0, self.n, self.slice, self.bufs, self.nbufs, self.act_idx,
+                                  self.done.data_ptr(), self.dtype, st))
 
 
 class Program:
@@ -321,6 +327,8 @@ class PackedNetworks:
         self.dt = {"bf16": BF16, "f16": F16, "f32": F32}[precision]
         half = precision in ("bf16", "f16")
         self.use_tc = half if use_tc is None else bool(use_tc and half)
+        self.fold_scale = half
+        self.lo_stream = half and LO_STREAM
         self.fuse_stacks = self.use_tc and os.environ.get("MZB_NO_STACK", "0") != "1"   # whole trunks in one persistent launch
         self.lat_max = None        # None: trunks of batches <= lat_max_samples() run in latency mode; 0: always the tcgen05 trunk
         self.num_supports = int(cfg.get("num_supports", 11))
@@ -344,6 +352,9 @@ class PackedNetworks:
             shift = (b - sd[bn_key + ".running_mean"]) * a + sd[bn_key + ".bias"]
         else:
             a, shift = torch.ones(cout, dtype=torch.float64), b
+        if self.fold_scale:                                # 16-bit paths: the scale goes into the weights before they are rounded
+            w = w * a.view(-1, 1, 1, 1)
+            a = None
         act_bias = None
         if cin_used is not None and cin_used < cin:        # dynamics conv_block: channels >= cin_used are the action planes
             H, W = self.latent_hw
@@ -354,11 +365,27 @@ class PackedNetworks:
             act_bias = self._dev(torch.stack(planes), torch.float32)                                          # [3][HW][cout]
             w = w[:, :cin_used]
         wp = w.permute(0, 2, 3, 1).reshape(cout, -1)       # [cout][(ky*k+kx)*cin + c]
-        cv = _Conv(self._dev(wp, self.dtype), self._dev(a, torch.float32), self._dev(shift, torch.float32), k, act, act_bias)
+        cv = _Conv(self._dev(wp, self.dtype), None if a is None else self._dev(a, torch.float32), self._dev(shift, torch.float32), k, act, act_bias)
         if self.use_tc and cv.cin % 64 == 0:               # tile-contiguous copy for the TMA loads: [tap][cin/64][cout][64]
             cv.w = self._dev(wp.reshape(cout, k * k, cv.cin // 64, 64).permute(1, 2, 0, 3), self.dtype)
             cv.w_layout = 1
         return cv
+
+    def _pv_conv(self, sd, act):
+        """Policy (3x3 256->128) and value (1x1 256->128) head ConvBlocks (networks.py:200-218) as ONE 3x3 256->256 convolution: output
+        channels 0-127 = the policy ConvBlock, 128-255 = the value ConvBlock with its 1x1 weights in the centre tap (the other eight
+        taps are exact zeros, so the sums are the 1x1 convolution's).  The tensor-core trunk runs it as its last layer."""
+        pk, vk = "pred_net.policy_head.0", "pred_net.value_head.0"
+        wp_, wv_ = sd[pk + ".conv.weight"], sd[vk + ".conv.weight"]
+        if not (self.use_tc and wp_.shape[2] == 3 and wv_.shape[2] == 1 and wp_.shape[1] == wv_.shape[1] == self.latent_ch
+                and wp_.shape[0] + wv_.shape[0] == self.latent_ch):
+            return None
+        wv3 = torch.zeros(wv_.shape[0], wv_.shape[1], 3, 3, dtype=wv_.dtype)
+        wv3[:, :, 1, 1] = wv_[:, :, 0, 0]
+        both = {"c.weight": torch.cat([wp_, wv3]), "c.bias": torch.cat([sd[pk + ".conv.bias"], sd[vk + ".conv.bias"]])}
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            both["b." + k] = torch.cat([sd[pk + ".bn." + k], sd[vk + ".bn." + k]])
+        return self._conv(both, "c", "b", act)
 
     def _res(self, sd, prefix, act):
         return (self._conv(sd, prefix + ".conv1", prefix + ".bn1", act), self._conv(sd, prefix + ".conv2", prefix + ".bn2", act))
@@ -401,6 +428,7 @@ class PackedNetworks:
         self.value_conv = self._conv(sd, "pred_net.value_head.0.conv", "pred_net.value_head.0.bn", a)
         self.value_lin = self._linear(sd, "pred_net.value_head.2", self.value_conv.cout, hw)
         self.num_actions = self.policy_lin.nout
+        self.pv_conv = self._pv_conv(sd, a)
         self._consolidate()
 
     def holders(self):
@@ -421,6 +449,8 @@ class PackedNetworks:
         for c, lin in ((self.reward_conv, self.reward_lin), (self.policy_conv, self.policy_lin), (self.value_conv, self.value_lin)):
             conv(c)
             out.extend([(lin, "w"), (lin, "b")])
+        if self.pv_conv is not None:
+            conv(self.pv_conv)
         return out
 
     def _consolidate(self):
@@ -449,22 +479,32 @@ class PackedNetworks:
     def buf(self, n, hw, c, dtype=None):
         return torch.empty((n, hw, c), dtype=dtype or self.dtype, device=self.device)
 
-    def _add_conv(self, prog, cv: _Conv, H, W, src, dst, res=None, dst_f32=None, act_idx=None):
+    def _add_conv(self, prog, cv: _Conv, H, W, src, dst, res=None, dst_f32=None, act_idx=None, res_lo=None, dst_lo=None, res_f32=None):
         prog.add(op=OP_CONV, dtype=self.dt, H=H, W=W, cin=cv.cin, cout=cv.cout, ksize=cv.ksize, act=cv.act,
                  use_tc=int(self.use_tc), w_layout=cv.w_layout, src=src, dst=dst, res=res, dst_f32=dst_f32, w=cv.w, scale=cv.scale, shift=cv.shift,
-                 act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx)
+                 act_bias=cv.act_bias if act_idx is not None else None, act_idx=act_idx, res_lo=res_lo, dst_lo=dst_lo, res_f32=res_f32)
 
-    def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None, mid=None):
+    def lo_plane(self, n, H, W, c):
+        """Correction plane of a 16-bit residual stream [n][H*W][c] (csrc/tc_common.cuh: split2 / lo2), or None on the fp32 path."""
+        if not self.lo_stream:
+            return None
+        nbytes = int(_lib.lib().mz_conv_lo_bytes(n, H, W, c, 3))
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+
+    def _add_res_blocks(self, prog, blocks, H, W, bufs, cur, last_f32=None, mid=None, lo=None, lo_valid=False, keep_lo=False):
         """bufs: same-shaped activation buffers; cur: index of the one holding the input.  Each block writes its
         output IN PLACE over its input: conv2's epilogue reads the residual element and then writes the result to
         the same address from the same thread, and no tile reads the block input during conv2 (its operand is the
-        mid buffer).  Two live buffers per network keep 4096 samples' activations (2 x 42 MB bf16) inside the L2.
+        mid buffer).  lo: the stream's correction plane (lo_valid: it holds the correction of the input); the last block
+        keeps it only if keep_lo (something after it continues the stream).
         Returns the index holding the output (= cur)."""
         mid = (cur + 1) % len(bufs) if mid is None else mid
         for i, (c1, c2) in enumerate(blocks):
+            last = i == len(blocks) - 1
             self._add_conv(prog, c1, H, W, bufs[cur], bufs[mid])
-            self._add_conv(prog, c2, H, W, bufs[mid], bufs[cur], res=bufs[cur],
-                           dst_f32=last_f32 if i == len(blocks) - 1 else None)
+            self._add_conv(prog, c2, H, W, bufs[mid], bufs[cur], res=bufs[cur], dst_f32=last_f32 if last else None,
+                           res_lo=lo if lo_valid else None, dst_lo=lo if (lo is not None and (keep_lo or not last)) else None)
+            lo_valid = lo is not None
         return cur
 
     def _add_head(self, prog, conv, lin, H, W, src, mid, mode, out, out_logits=None):
@@ -473,27 +513,48 @@ class PackedNetworks:
         prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=nout, head_mode=mode, src=mid, w=w, shift=b,
                  out=out, out_logits=out_logits)
 
-    def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2):
-        """14 residual blocks + policy head + value head (networks.py:225-241) on `src` [n][20][256]."""
+    def _lat(self, n) -> bool:
+        """does a batch of n samples run its trunks in latency mode (csrc/conv_lat.cu)?"""
+        return self.use_tc and self.fuse_stacks and n <= (lat_max_samples() if self.lat_max is None else self.lat_max)
+
+    def prediction_program(self, n, src, bufs, mid, pi, value, policy_logits=None, value_logits=None, value_mode=1, pi_mode=2, src_f32=None):
+        """14 residual blocks + policy head + value head (networks.py:225-241) on `src` [n][20][256].  src_f32: the same latents as
+        float32 [n][20][256] when the caller has them in full precision (the first block's residual is then exact; the search's
+        latents come from the 16-bit store and are exact as they are)."""
         H, W = self.latent_hw
         prog = Program(n, self.fuse_stacks, self.lat_max)
+        lo = self.lo_plane(n, H, W, self.latent_ch)
+        if lo is not None:
+            prog.keep.append(lo)
         c1, c2 = self.pred_res[0]                                   # first block reads src directly (src, bufs[0], bufs[1]: three buffers)
         self._add_conv(prog, c1, H, W, src, bufs[0])
-        self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=src)
-        cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 1, mid=0)
+        f32_res = src_f32 if (src_f32 is not None and self.dt != F32) else None
+        self._add_conv(prog, c2, H, W, bufs[0], bufs[1], res=None if f32_res is not None else src, res_f32=f32_res,
+                       dst_lo=lo if len(self.pred_res) > 1 else None)   # src from the 16-bit latent store is exact: no correction plane
+        cur = self._add_res_blocks(prog, self.pred_res[1:], H, W, bufs, 1, mid=0, lo=lo, lo_valid=lo is not None)
+        pc, vc = self.policy_conv, self.value_conv
+        if self.pv_conv is not None and not self._lat(n) and mid.shape[-1] == self.pv_conv.cout:
+            # tensor-core trunk: both head ConvBlocks as ONE more 3x3 256->256 layer of the trunk launch (the value head's 1x1 weights sit in
+            # the centre tap of output channels 128-255); the two Linear heads read the halves of its 256-channel rows
+            self._add_conv(prog, self.pv_conv, H, W, bufs[cur], mid)
+            mid_v = mid.view(-1)[pc.cout:]
+            for lin, conv, src_, mode, out, logits in ((self.policy_lin, pc, mid, pi_mode, pi, policy_logits), (self.value_lin, vc, mid_v, value_mode, value, value_logits)):
+                prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, cout=self.pv_conv.cout, nout=lin.nout, head_mode=mode, src=src_, w=lin.w, shift=lin.b,
+                         out=out, out_logits=logits)
+            return prog
         # both head ConvBlocks first (they read the same trunk output and write the two halves of `mid`), then the two Linear heads:
         # in latency mode the pair rides as the last, split layer of the trunk launch
-        half = n * H * W * self.policy_conv.cout
-        mid_p = mid.view(-1)[:half].view(n, H * W, self.policy_conv.cout)
-        if self.policy_conv.cout + self.value_conv.cout <= mid.shape[-1]:
-            mid_v = mid.view(-1)[half:half + n * H * W * self.value_conv.cout].view(n, H * W, self.value_conv.cout)
+        half = n * H * W * pc.cout
+        mid_p = mid.view(-1)[:half].view(n, H * W, pc.cout)
+        if pc.cout + vc.cout <= mid.shape[-1]:
+            mid_v = mid.view(-1)[half:half + n * H * W * vc.cout].view(n, H * W, vc.cout)
         else:                                                      # head ConvBlocks wider than half the latent: a buffer of its own
-            mid_v = self.buf(n, H * W, self.value_conv.cout)
+            mid_v = self.buf(n, H * W, vc.cout)
             prog.keep.append(mid_v)
-        self._add_conv(prog, self.policy_conv, H, W, bufs[cur], mid_p)
-        self._add_conv(prog, self.value_conv, H, W, bufs[cur], mid_v)
-        for lin, conv, src_, mode, out, logits in ((self.policy_lin, self.policy_conv, mid_p, pi_mode, pi, policy_logits),
-                                                   (self.value_lin, self.value_conv, mid_v, value_mode, value, value_logits)):
+        self._add_conv(prog, pc, H, W, bufs[cur], mid_p)
+        self._add_conv(prog, vc, H, W, bufs[cur], mid_v)
+        for lin, conv, src_, mode, out, logits in ((self.policy_lin, pc, mid_p, pi_mode, pi, policy_logits),
+                                                   (self.value_lin, vc, mid_v, value_mode, value, value_logits)):
             prog.add(op=OP_HEAD, dtype=self.dt, H=H, W=W, cin=conv.cout, nout=lin.nout, head_mode=mode, src=src_, w=lin.w, shift=lin.b,
                      out=out, out_logits=logits)
         return prog
@@ -504,8 +565,11 @@ class PackedNetworks:
         282-298).  src [n][20][256] parent latents, act_idx int32 [n]; scaled latent -> dst (and dst2)."""
         H, W = self.latent_hw
         prog = Program(n, self.fuse_stacks, self.lat_max)
-        self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx)
-        cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32)
+        lo = self.lo_plane(n, H, W, self.latent_ch)
+        if lo is not None:
+            prog.keep.append(lo)
+        self._add_conv(prog, self.dyn_first, H, W, src, bufs[0], act_idx=act_idx, dst_lo=lo if self.dyn_res else None)
+        cur = self._add_res_blocks(prog, self.dyn_res, H, W, bufs, 0, last_f32=f32, lo=lo, lo_valid=lo is not None)
         self._add_head(prog, self.reward_conv, self.reward_lin, H, W, bufs[cur], mid, reward_mode, reward, reward_logits)
         prog.add(op=OP_SCALE, dtype=self.dt, H=H, W=W, cin=self.latent_ch, src=f32, dst=dst, dst2=dst2, dst2_slot=dst2_slot,
                  dst2_stride=dst2_stride)
@@ -527,16 +591,26 @@ class PackedNetworks:
         src, cur = xin, None
         n_pool = sum(1 for kind, _ in self.rep if kind == "pool")
         pools = 0
-        for kind, item in self.rep:
+        # the residual stream's correction plane (one buffer: it follows the stream; a plane is only ever exchanged between two
+        # convolutions of the same shape, and a pool / plain convolution reads the 16-bit stream alone)
+        lo = self.lo_plane(n, H, W, cmax)
+        if lo is not None:
+            prog.keep.append(lo)
+        lo_valid = False
+        for idx, (kind, item) in enumerate(self.rep):
+            nxt_kind = self.rep[idx + 1][0] if idx + 1 < len(self.rep) else None
             if kind == "conv":
                 nxt = 0 if cur is None else (cur + 1) % 3
-                self._add_conv(prog, item, H, W, src, bufs[nxt])
+                self._add_conv(prog, item, H, W, src, bufs[nxt], dst_lo=lo if nxt_kind == "res" else None)
+                lo_valid = lo is not None and nxt_kind == "res"
                 cur, src = nxt, bufs[nxt]
                 ch = item.cout
             elif kind == "res":
-                cur = self._add_res_blocks(prog, [item], H, W, bufs, cur)
+                cur = self._add_res_blocks(prog, [item], H, W, bufs, cur, lo=lo, lo_valid=lo_valid, keep_lo=nxt_kind == "res")
+                lo_valid = lo is not None and nxt_kind == "res"
                 src = bufs[cur]
             else:
+                lo_valid = False
                 pools += 1
                 nxt = (cur + 1) % 3
                 prog.add(op=OP_POOL2, dtype=self.dt, H=H, W=W, cin=ch, src=src, dst=bufs[nxt],
@@ -575,7 +649,10 @@ class PackedNetworks:
         mid = self.buf(n, H * W, self.latent_ch)
         pol = torch.empty((n, self.num_actions), dtype=torch.float32, device=self.device)
         val = torch.empty((n, self.num_supports), dtype=torch.float32, device=self.device)
-        prog.extend(self.prediction_program(n, x, bufs, mid, None, None, pol, val, value_mode=0, pi_mode=0))
+        x32 = h.permute(0, 2, 3, 1).reshape(n, H * W, self.latent_ch).contiguous() if self.dt != F32 else None   # exact residual of the first block
+        if x32 is not None:
+            prog.keep.append(x32)
+        prog.extend(self.prediction_program(n, x, bufs, mid, None, None, pol, val, value_mode=0, pi_mode=0, src_f32=x32))
         prog.run()
         return pol, val
 

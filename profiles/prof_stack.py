@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from muzero_breakout_b200 import _lib
 from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG, PackedNetworks, random_state_dict
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
-nets = PackedNetworks(random_state_dict(seed=0, bn_jitter=0.2), DEFAULT_MODEL_CFG, precision="bf16")
+nets = PackedNetworks(random_state_dict(seed=0, bn_jitter=0.2), DEFAULT_MODEL_CFG, precision=os.environ.get("MZB_PREC", "f16"))
 h = torch.rand(n, 256, 4, 5)
 for _ in range(3): nets.prediction(h)
 torch.cuda.synchronize()

@@ -69,8 +69,8 @@ def test_one_layer_vs_torch(case):
     td, dt = (torch.bfloat16, BF16) if prec == "bf16" else (torch.float16, F16)
     g = torch.Generator().manual_seed(n * 7 + use_res + 2 * use_ab)
     x = torch.randn(n, 256, 4, 5, generator=g).to(td)
-    w = (torch.randn(256, 256, k, k, generator=g) / (16.0 * k)).to(td)
-    scale = torch.rand(256, generator=g) + 0.5
+    scale = torch.rand(256, generator=g) + 0.5              # the BatchNorm scale is folded into the 16-bit weights (mz_op.scale == NULL)
+    w = (torch.randn(256, 256, k, k, generator=g) / (16.0 * k) * scale.view(-1, 1, 1, 1)).to(td)
     shift = torch.randn(256, generator=g) * 0.1
     res = torch.randn(n, 256, 4, 5, generator=g).to(td) if use_res else None
     ab = torch.randn(3, 20, 256, generator=g) * 0.2 if use_ab else None
@@ -78,19 +78,19 @@ def test_one_layer_vs_torch(case):
     want = F.conv2d(x.float(), w.float(), padding=k // 2)
     if use_ab:
         want = want + ab[idx.long()].view(n, 4, 5, 256).permute(0, 3, 1, 2)
-    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    want = want + shift.view(1, -1, 1, 1)
     if use_res:
         want = want + res.float()
     want = {"relu": torch.relu, "none": lambda t: t, "silu": F.silu}[act](want)
 
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
-    keep = dict(src=nhwc(x), res=nhwc(res) if use_res else None, scale=scale.cuda(), shift=shift.cuda(), ab=ab.cuda() if use_ab else None,
+    keep = dict(src=nhwc(x), res=nhwc(res) if use_res else None, shift=shift.cuda(), ab=ab.cuda() if use_ab else None,
                 idx=idx.cuda(), w=w.permute(0, 2, 3, 1).reshape(256, k * k, 4, 64).permute(1, 2, 0, 3).contiguous().cuda(),
                 dst=torch.full((n, 4, 5, 256), float("nan"), dtype=td, device="cuda"),
                 dst32=torch.full((n, 4, 5, 256), float("nan"), dtype=torch.float32, device="cuda"))
     op = MzOp()
     for k, v in dict(op=OP_CONV, dtype=dt, H=4, W=5, cin=256, cout=256, ksize=k, act=ACT[act], use_tc=1, w_layout=1, src=keep["src"], dst=keep["dst"],
-                     res=keep["res"], dst_f32=keep["dst32"], w=keep["w"], scale=keep["scale"], shift=keep["shift"], act_bias=keep["ab"],
+                     res=keep["res"], dst_f32=keep["dst32"], w=keep["w"], scale=None, shift=keep["shift"], act_bias=keep["ab"],
                      act_idx=keep["idx"] if use_ab else None).items():
         setattr(op, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
     done = _run_layers([op], n, dt)
@@ -134,8 +134,9 @@ def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
         n1 = _lib.launch_count()
         b = tc.dynamics(h, _planes(acts)) + tc.prediction(h)
         # latency form: layout in, ONE launch for the dynamics network (trunk + reward ConvBlock + reward head + _scale_state), layout out;
-        # layout in, ONE launch for the prediction network (trunk + policy / value ConvBlocks + both heads)
-        assert n1 - n0 == 5 and _lib.launch_count() - n1 == 12, (n1 - n0, _lib.launch_count() - n1)
+        # layout in, ONE launch for the prediction network (trunk + policy / value ConvBlocks + both heads); tcgen05 form: layout in, trunk +
+            # reward ConvBlock, reward head, _scale_state, layout out; layout in, trunk + both head ConvBlocks, two heads = 9 launches
+        assert n1 - n0 == 5 and _lib.launch_count() - n1 == 9, (n1 - n0, _lib.launch_count() - n1)
         for x, y, o, what in zip(a, b, (oh, orew, opol, oval), ("latent", "reward", "policy", "value")):
             assert torch.isfinite(x).all()
             assert rel(x, y) <= 2e-2, f"n={n} {what}: latency trunk vs tcgen05 trunk {rel(x, y):.2e}"
@@ -143,7 +144,8 @@ def test_networks_latency_trunk_vs_tcgen05_trunk(agent, n):
 
 
 def test_f16_latency_trunk_vs_reference(golden_dir):
-    """precision="f16" at the golden batch (5 roots): latency trunk against the reference's fp32 outputs, 2.5e-3."""
+    """precision="f16" (the search's default) at the golden batch (5 roots): latency trunk against the reference's fp32 outputs,
+    within the north star's 1e-3 (max |err| / max |ref| per tensor)."""
     from muzero_breakout_b200.src.networks import PackedNetworks
     torch.manual_seed(0)
     a = OracleAgent()
@@ -157,4 +159,4 @@ def test_f16_latency_trunk_vs_reference(golden_dir):
     errs = dict(h2=rel(h2, rec["dyn_h"]), rew=rel(rew, rec["dyn_reward_logits"]), pol=rel(pol, rec["root_policy_logits"]), val=rel(val, rec["root_value_logits"]))
     print("f16 latency trunk vs fp32 reference (rel to range):", {k: f"{v:.2e}" for k, v in errs.items()})
     for k, e in errs.items():
-        assert e <= 2.5e-3, f"{k}: {e:.2e}"
+        assert e <= 1e-3, f"{k}: {e:.2e}"

@@ -2,11 +2,13 @@
 
 Tolerances (max abs error / max abs reference value, i.e. relative to the tensor's range):
   fp32 path  vs outputs of the reference networks (golden)          1e-5   (BASELINE.json north_star)
-  tcgen05 bf16 conv vs fp32 torch conv on the same bf16 operands     2e-4 on the fp32 side output
+  fp16 tensor-core pipeline (the search's default: fp16 operands, fp32 accumulation, fp16 + e4m3 residual stream)
+      vs the reference networks (golden + the fp32 oracle at 300 samples)        1e-3   (BASELINE.json north_star)
+      -- for the fused trunk (conv_stack.cu), one launch per layer (conv_tc.cu) and the latency trunk (conv_lat.cu)
+  tcgen05 conv vs fp32 torch conv on the same 16-bit operands        2e-4 on the fp32 side output
   bf16 pipeline vs the same pipeline on CUDA cores (same bf16 rounding points)   2e-2 (a few bf16 ulps)
-  bf16 pipeline vs the fp32 reference networks (golden)              reported, bounded at 3e-2 (bf16 has an
-      8-bit mantissa and activations are rounded 29x per network: 1e-3 relative of the fp32 reference is not
-      reachable with bf16 storage; see DESIGN.md "precision")
+  bf16 pipeline vs the fp32 reference networks (golden)              reported, bounded at 1e-2 (bf16 has an 8-bit
+      mantissa: the convolution operands alone cost 3-6e-3; see DESIGN.md "precision")
 """
 import os
 
@@ -153,7 +155,7 @@ def test_bf16_pipeline_tensor_cores_vs_cuda_cores_and_reference(agent, rec):
     for k, e in same.items():      # same rounding points; a flipped bf16 rounding (ulp 3.9e-3 of the value) propagates
         assert e <= 2e-2, f"{k}: tensor-core vs CUDA-core bf16 pipelines differ by {e:.2e}"
     for k, e in errs.items():
-        assert e <= 3e-2, f"{k}: bf16 pipeline deviates {e:.2e} from the fp32 reference"
+        assert e <= 1e-2, f"{k}: bf16 pipeline deviates {e:.2e} from the fp32 reference"
 
 
 @pytest.mark.parametrize("n", [5, 130, 3000, 9473])
@@ -178,17 +180,84 @@ def test_fused_trunk_launch_equals_layer_by_layer(agent, n):
             assert torch.equal(x, y), f"n={n} rep={rep} {what}: fused and per-layer launches differ (max {float((x - y).abs().max()):.3e})"
 
 
-def test_f16_pipeline_vs_reference(agent, rec):
-    """precision="f16": same tensor-core kernels with fp16 storage.  Measured here against the fp32 reference outputs;
-    bound 2.5e-3 relative to range (emulation of the rounding points on the CPU predicts ~1.2e-3)."""
-    from muzero_breakout_b200.src.networks import PackedNetworks
-    nets = PackedNetworks(agent, agent.cfg, precision="f16")
+def _f16_errs(nets, rec):
     h = torch.from_numpy(rec["hidden"])
     h2, rew = nets.dynamics(h, _planes(rec["dyn_actions"]))
     pol, val = nets.prediction(h)
+    pol2, val2 = nets.prediction(torch.from_numpy(rec["dyn_h"]))
     hid = nets.representation(torch.from_numpy(rec["rep_in"]))
-    errs = dict(h2=rel(h2, rec["dyn_h"]), rew=rel(rew, rec["dyn_reward_logits"]), pol=rel(pol, rec["root_policy_logits"]),
-                val=rel(val, rec["root_value_logits"]), hid=rel(hid, rec["hidden"]))
-    print("f16 tensor-core pipeline vs fp32 reference (rel to range):", {k: f"{v:.2e}" for k, v in errs.items()})
+    return dict(h2=rel(h2, rec["dyn_h"]), rew=rel(rew, rec["dyn_reward_logits"]), pol=rel(pol, rec["root_policy_logits"]),
+                val=rel(val, rec["root_value_logits"]), pol2=rel(pol2, rec["pred_policy_logits"]), val2=rel(val2, rec["pred_value_logits"]),
+                hid=rel(hid, rec["hidden"]))
+
+
+@pytest.mark.parametrize("path", ["fused_trunk", "per_layer", "latency_trunk"])
+def test_f16_pipeline_vs_reference(agent, rec, path):
+    """precision="f16", the mode the search and bench.py default to: fp16 operands on the tensor cores, fp32 accumulation, residual
+    stream as fp16 + e4m3 correction.  Against the reference's own fp32 outputs (golden): within the north star's 1e-3 on every
+    output, for each of the three kernels that can run the trunks."""
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    nets = PackedNetworks(agent, agent.cfg, precision="f16")
+    if path == "fused_trunk":
+        nets.lat_max = 0                       # 5 samples would otherwise take the latency trunk
+    elif path == "per_layer":
+        nets.fuse_stacks = False
+    errs = _f16_errs(nets, rec)
+    print(f"f16 {path} vs fp32 reference (rel to range):", {k: f"{v:.2e}" for k, v in errs.items()})
     for k, e in errs.items():
-        assert e <= 2.5e-3, f"{k}: f16 pipeline deviates {e:.2e} from the fp32 reference"
+        assert e <= 1e-3, f"{path} {k}: f16 pipeline deviates {e:.2e} from the fp32 reference"
+
+
+def test_f16_fused_trunk_vs_oracle_300(agent):
+    """the same bound on a batch that spans several 128-sample groups and an odd group count (300 = 3 groups), against the fp32
+    torch restatement of the reference networks evaluated here."""
+    from muzero_breakout_b200.src.networks import PackedNetworks
+    nets = PackedNetworks(agent, agent.cfg, precision="f16")
+    n = 300
+    g = torch.Generator().manual_seed(5)
+    h = torch.rand(n, 256, 4, 5, generator=g)
+    acts = torch.randint(0, 3, (n,), generator=g)
+    with torch.no_grad():
+        oh, orew = agent.hidden_state_transition(h, _planes(acts))
+        opol, oval = agent.evaluate_state(h)
+    for rep in range(2):                       # twice: the second launch runs at the next epoch of the dependency counters
+        h2, rew = nets.dynamics(h, _planes(acts))
+        pol, val = nets.prediction(h)
+        errs = dict(h2=rel(h2, oh), rew=rel(rew, orew), pol=rel(pol, opol), val=rel(val, oval))
+        print("f16 fused trunk, 300 samples, vs fp32 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+        for k, e in errs.items():
+            assert e <= 1e-3, f"rep {rep} {k}: {e:.2e}"
+
+
+def test_residual_stream_correction_plane():
+    """mz_op.res_lo / dst_lo: a convolution that keeps the e4m3 correction of its 16-bit output, followed by one that adds
+    (output + correction) as its residual, against the same two convolutions with an exact fp32 residual.  bf16 makes the
+    difference visible: without the plane the residual carries 2^-9 relative error, with it 2^-13."""
+    from muzero_breakout_b200 import _lib
+    from muzero_breakout_b200.src.networks import ACT, BF16, OP_CONV, Program
+    for (n, H, W, c, use_tc) in ((200, 4, 5, 256, 1), (3, 16, 20, 128, 1), (9, 4, 5, 256, 0)):
+        g = torch.Generator().manual_seed(n)
+        x1 = torch.randn(n, c, H, W, generator=g).bfloat16()
+        x2 = torch.randn(n, c, H, W, generator=g).bfloat16()
+        w1 = (4 * torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).bfloat16()
+        w2 = (0.05 * torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).bfloat16()
+        shift = torch.randn(c, generator=g) * 0.1
+        y1 = F.conv2d(x1.float(), w1.float(), padding=1) + shift.view(1, -1, 1, 1)                   # stream value, exact
+        want = F.conv2d(x2.float(), w2.float(), padding=1) + shift.view(1, -1, 1, 1) + y1
+        nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
+        tile = lambda w: (w.permute(0, 2, 3, 1).reshape(c, 9, c // 64, 64).permute(1, 2, 0, 3) if use_tc else w.permute(0, 2, 3, 1).reshape(c, -1)).contiguous().cuda()
+        s16 = torch.full((n, H, W, c), float("nan"), dtype=torch.bfloat16, device="cuda")
+        out16 = torch.full_like(s16, float("nan"))
+        out32 = torch.full((n, H, W, c), float("nan"), dtype=torch.float32, device="cuda")
+        lo = torch.zeros(int(_lib.lib().mz_conv_lo_bytes(n, H, W, c, 3)), dtype=torch.uint8, device="cuda")
+        errs = {}
+        for with_lo in (True, False):
+            prog = Program(n)
+            common = dict(op=OP_CONV, dtype=BF16, H=H, W=W, cin=c, cout=c, ksize=3, act=ACT["none"], use_tc=use_tc, w_layout=use_tc, scale=None, shift=shift.cuda())
+            prog.add(src=nhwc(x1), dst=s16, w=tile(w1), dst_lo=lo if with_lo else None, **common)
+            prog.add(src=nhwc(x2), dst=out16, res=s16, res_lo=lo if with_lo else None, dst_f32=out32, w=tile(w2), **common)
+            prog.run()
+            torch.cuda.synchronize()
+            errs[with_lo] = rel(out32.permute(0, 3, 1, 2).cpu(), want)
+        print(f"n={n} {H}x{W} c={c} use_tc={use_tc}: residual with correction plane {errs[True]:.2e}, without {errs[False]:.2e}")
+        assert errs[True] <= 1.5e-4 and errs[False] > 3 * errs[True], errs
