@@ -63,6 +63,7 @@ struct StackParams {
     int trace;                           // profiling (env MZB_STACK_TRACE): cluster 0's leader records timestamps
     int debug;                           // timing experiments only (env MZB_STACK_DEBUG; results are garbage): 1 = weight tiles loaded for a tile's
                                          // first k-step only, 2 = activation tiles likewise, 4 = the epilogue skips the TMA store wait
+    int nap;                             // ns the scout sleeps between two polls of the counters
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
     int rot;                             // tile -> CTA-pair assignment is rotated by rot pairs per layer (evens out the 4/6/9-tap tile costs)
     int n, groups;                       // samples, 128-sample groups
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // the whole warp walks the loops (converged); one elected lane issues (see elect_one)
+        {
             const uint32_t lead_full = map_to_cta(bar_full, 0);
             int stage = 0, seq = 0;
             uint32_t phase = 0;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     const int pix = tile / V.spairs, g = V.g0 + 2 * (tile - pix * V.spairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0) & ltaps;
-                    if (tile == first) STRACE(0, layer);
+                    if (tile == first && lane == 0) STRACE(0, layer);
                     ++seq;
                     if (layer > 0) {
                         // the scout warp has seen the previous layer's output of this sample group complete at the in-bounds
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    if (tile == first) STRACE(1, layer);
+                    if (tile == first && lane == 0) STRACE(1, layer);
                     bool first_ks = true;
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((taps >> tap) & 1u)) continue;
@@ -204,10 +206,12 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                             const uint32_t sa = smem_base + A_OFF + stage * A_SLOT, sb = smem_base + B_OFF + stage * B_SLOT;
                             const bool do_a = first_ks || !(p.debug & 2), do_b = first_ks || !(p.debug & 1);
                             first_ks = false;
-                            if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * ((do_a ? A_SLOT : 0) + (do_b ? B_SLOT : 0)));
-                            else mbar_arrive_cluster(lead_full + 8 * stage);
-                            if (do_a) tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
-                            if (do_b) tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (wrow + kc) * N + rank * (N / 2));
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * ((do_a ? A_SLOT : 0) + (do_b ? B_SLOT : 0)));
+                                else mbar_arrive_cluster(lead_full + 8 * stage);
+                                if (do_a) tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
+                                if (do_b) tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (wrow + kc) * N + rank * (N / 2));
+                            }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -216,7 +220,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
-        if (lane == 0 && rank == 0) {
+        // the whole warp walks the loops (converged: the barrier waits are warp-wide); one elected lane issues the MMAs and commits
+        if (rank == 0) {
             const uint32_t idesc = instr_desc(N, p.f16 != 0);
             int stage = 0, it = 0;
             uint32_t phase = 0;
@@ -228,29 +233,32 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 for (int tile = first; tile < V.ntiles; tile += nclusters, ++it) {
                     const int buf = it & 1;
                     const int pix = tile / V.spairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
-                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4] = gtime_ns();
+                    const bool tr4 = p.trace == 4 && blockIdx.x == 0 && it < 96 && lane == 0;
+                    if (tr4) g_stack_trace[it * 4] = gtime_ns();
                     mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 1] = gtime_ns();
+                    if (tr4) g_stack_trace[it * 4 + 1] = gtime_ns();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
                     const int ksteps = __popc(tap_mask(y0, x0) & ltaps) * kchunks;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        if (ks == 0 && tile == first) STRACE(2, layer);
-                        if (p.trace == 4 && ks == 0 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 2] = gtime_ns();
+                        if (ks == 0 && tile == first && lane == 0) STRACE(2, layer);
+                        if (tr4 && ks == 0) g_stack_trace[it * 4 + 2] = gtime_ns();
                         const uint32_t sa = smem_base + A_OFF + stage * A_SLOT, sb = smem_base + B_OFF + stage * B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                                           (ks | k) ? 1u : 0u);
-                        umma_commit_pair(bar_empty + 8 * stage);
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16_pair(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                               (ks | k) ? 1u : 0u);
+                            umma_commit_pair(bar_empty + 8 * stage);
+                        }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit_pair(bar_tfull + 8 * buf);
-                    if (tile == first) STRACE(3, layer);
-                    if (p.trace == 4 && blockIdx.x == 0 && it < 96) g_stack_trace[it * 4 + 3] = (gtime_ns() - g_stack_trace[it * 4 + 2]) | ((unsigned long long)ksteps << 40);   // issue time | k-steps
+                    if (elect_one()) umma_commit_pair(bar_tfull + 8 * buf);
+                    if (tile == first && lane == 0) STRACE(3, layer);
+                    if (tr4) g_stack_trace[it * 4 + 3] = (gtime_ns() - g_stack_trace[it * 4 + 2]) | ((unsigned long long)ksteps << 40);   // issue time | k-steps
                 }
             }
         }
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         if (++spins > (1u << 28)) __trap();
                     }
                 }
-                if (res >= 0 && live && lane == 0) {
+                if (res >= 0 && live && elect_one()) {
                     asm volatile("fence.proxy.async;" ::: "memory");
                     mbar_expect_tx(bar_res, EPI_WARP);
                     tma_load_4d_cta(stg, &p.map_epi[res], bar_res, col0, x0, y0, s0w);
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 tc_fence_before();
                 fence_async_smem();                                          // my st.shared -> visible to the TMA store
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {
                     mbar_arrive_cluster(lead_tempty + 8 * buf);              // accumulator drained: the pair's next-but-one tile may reuse it
                     if (live) {
                         tma_store_4d(&p.map_epi[dst], stg, col0, x0, y0, s0w);
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         }
                         if (ready) break;
                         if (++spins > (1u << 26)) __trap();
-                        __nanosleep(32);
+                        __nanosleep(p.nap);
                     }
                     asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire: pairs with the epilogues' red.release
                 }
@@ -579,6 +587,10 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     if (!enc) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled not available from the driver"); return -2; }
     cudaStream_t st = (cudaStream_t)stream;
     StackParams p{};
+    static int promo_a = -1;
+    if (promo_a < 0) { const char *e = getenv("MZB_STACK_L2PROMO"); promo_a = e ? atoi(e) : 3; }
+    const CUtensorMapL2promotion l2p = promo_a == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_a == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_a == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     for (int b = 0; b < MAX_BUFS; ++b) {
         void *ptr = (__nv_bfloat16 *)bufs[b < n_bufs ? b : 0] + (size_t)sample0 * HW * CH;    // this launch's slice of the samples
         cuuint64_t dims[4] = {CH, LAT_W, LAT_H, (cuuint64_t)nsamples};
@@ -587,11 +599,11 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
         const CUtensorMapDataType tm = dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
         cuuint32_t box[4] = {BLOCK_K, 1, 1, BLOCK_M};
         CUresult r = enc(&p.map_act[b], tm, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint32_t box_e[4] = {BLOCK_K, 1, 1, 32};
         if (r == CUDA_SUCCESS)
             r = enc(&p.map_epi[b], tm, 4, ptr, dims, strides, box_e, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_run: cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return -2; }
     }
     p.f16 = dtype == MZ_F16;
@@ -602,6 +614,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     p.act_idx = act_idx ? act_idx + sample0 : nullptr;
     p.elem_off = (long long)sample0 * HW * CH;
     { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_STACK_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
+    { static int nap = -1; if (nap < 0) { const char *e = getenv("MZB_STACK_NAP"); nap = e ? atoi(e) : 32; } p.nap = nap; }
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("MZB_STACK_DEBUG"); dbg = e ? atoi(e) : 0; } p.debug = dbg; }
     { static int fine = -1; if (fine < 0) { const char *e = getenv("MZB_STACK_FINE"); fine = e ? atoi(e) : 1; } p.fine = fine; }
     { static int rot = -1; if (rot < 0) { const char *e = getenv("MZB_STACK_ROT"); rot = e ? atoi(e) : 13; } p.rot = rot; }

@@ -37,10 +37,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// One lane of a CONVERGED warp (all 32 lanes must call it).  Unlike `lane == 0`, the elect.sync predicate tells ptxas that exactly one
+// lane runs the guarded code, so instructions of the uniform datapath (UTCHMMA, UTMALDG / UTMASTG, UTCBAR) are issued straight-line
+// with their operands in uniform registers; behind a divergent `lane == 0` branch every one of them is wrapped in an
+// ELECT / BRA.U.ANY "waterfall" loop with R2UR moves (seen in the SASS of the round-1 kernels' MMA issue loop).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n.reg .b32 rx;\n.reg .pred px;\n"
+        "elect.sync rx|px, %2;\n"
+        "@px mov.s32 %1, 1;\n"
+        "mov.s32 %0, rx;\n}"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
     // bounded spin: a protocol bug traps (launch error reported to the host) instead of hanging the GPU
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         asm volatile(
             "{\n.reg .pred p;\n"
