@@ -21,6 +21,14 @@ import sys
 import threading
 import time
 
+REFERENCE_ARM = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:]) and any(a.startswith("--impl") for a in sys.argv[1:])
+if REFERENCE_ARM:
+    # the reference arm times the reference's CPU path on the host cores: its hard-coded "cuda" device strings are redirected to
+    # "cpu" (baseline/ref.py) only when no GPU is visible, so hide the GPUs before torch is imported
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):       # torchrun sets OMP_NUM_THREADS=1: the arm uses every host core
+        os.environ.pop(_k, None)
+
 import numpy as np
 import torch
 
@@ -251,14 +259,14 @@ FLOP_CONV_VALID = 496_962_560 + 486_932_480      # conv layers only (no Linear h
 FLOP_CONV_DENSE = 687_093_760 + 673_710_080
 
 
-def _time_prog(prog, reps=50):
+def _time_fn(fn, reps=50):
     """mean duration over `reps` back-to-back runs: long enough (~0.2 s) that the clocks settle under the power cap,
     like inside a search and like the sustained cuBLAS figure the roofline divides by"""
-    prog.run(); torch.cuda.synchronize()
+    fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        prog.run()
+        fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
@@ -277,14 +285,41 @@ def bench_mcts(args, rank, local, world):
     g = torch.Generator(device=dev).manual_seed(5 + rank)
     hiddens = [torch.rand((B, 256, 4, 5), generator=g, device=dev) for _ in range(2)]    # root latents are in [0,1] (_scale_state)
     mask = torch.ones((B, 3), device=dev)
+    # N > 1 (BASELINE.json configs[3]): the algorithm's two exchange steps run INSIDE the timed loop -- the packed target weights are
+    # broadcast from rank 0 every 15th search (train_torch.py:361-367 refreshes the target network every 15 iterations) and every search's
+    # per-env trajectory record (gray frame, action, reward, visit counts, value: train_torch.py:204-208) is all-gathered
+    coll = None
+    if world > 1:
+        from muzero_breakout_b200 import parallel
+        coll = {"bc_ms": [], "ag_ms": [], "bytes_bc": 0}
+        rec = torch.zeros((B, parallel.RECORD_FLOATS), device=dev)
+
+    def one_search(i, timed):
+        if coll is not None and i % 15 == 0:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record(); coll["bytes_bc"] = parallel.broadcast_weights(nets, src=0); ev[1].record()
+            if timed:
+                coll["bc_ms"].append(ev)
+        value, visits = m.search(hiddens[i & 1], mask, 0)
+        if coll is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            rec[:, 322:325] = visits; rec[:, 325] = value                 # this move's record (the frame / action / reward columns come from the env step)
+            gathered = parallel.all_gather_trajectory(rec, equal_shards=True)
+            ev[1].record()
+            assert gathered.shape[0] == world * B
+            if timed:
+                coll["ag_ms"].append(ev)
+        return value, visits
+
     for i in range(W):
-        m.search(hiddens[i & 1], mask, 0)
+        one_search(i, False)
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(K):
-            value, visits = m.search(hiddens[i & 1], mask, 0)
+            value, visits = one_search(i, True)
         e1.record()
         barrier_sync(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
@@ -292,23 +327,40 @@ def bench_mcts(args, rank, local, world):
     plan = next(iter(m._plans.values()))
     launches = K * plan.kernels_per_search
 
-    # dominant kernel: the tcgen05 convolution (58 launches per simulation step); timed alone over one
-    # simulation step's conv ops with CUDA events on the launching stream
-    conv_prog = Program(B, plan.sim_prog.fuse)
-    conv_prog.ops = [o for o in plan.sim_prog.ops if o.op == OP_CONV]
-    conv_prog.keep = plan.sim_prog.keep
-    conv_ms = _time_prog(conv_prog)
-    step_ms = _time_prog(plan.sim_prog)
-    n_conv = len(conv_prog.ops)
-    # the dominant kernel alone: the residual-trunk launches (conv_stack_kernel) of one simulation step
-    from muzero_breakout_b200.src.networks import _stackable
-    trunk_prog = Program(B, plan.sim_prog.fuse)
-    trunk_prog.ops = [o for o in conv_prog.ops if _stackable(o)]
-    trunk_prog.keep = plan.sim_prog.keep
-    if not trunk_prog.ops:                                  # fp32 parity path: no tensor-core trunk, report all convolutions
-        trunk_prog = conv_prog
-    trunk_ms = _time_prog(trunk_prog)
-    n_trunk, trunk_launches = len(trunk_prog.ops), trunk_prog.n_kernels
+    # dominant kernel: the persistent tcgen05 trunk launches (conv_stack_kernel) of one simulation step, timed alone with CUDA events
+    # on the launching stream, back to back for ~0.2 s (clocks settle under the power cap like inside a search)
+    prog = plan.sim_prog
+    if prog._segs is None:
+        prog._build()
+    pv_w = nets.pv_conv.w.data_ptr() if nets.pv_conv is not None else None
+
+    def conv_flop(o):
+        """in-bounds-tap FLOPs per sample of one convolution record on the 4x5 latent"""
+        if pv_w is not None and o.w == pv_w:          # policy 3x3 256->128 + value 1x1 256->128 packed as one 3x3 256->256 layer: count the two ConvBlocks
+            return (130 + 20) * 256 * 128 * 2
+        return (130 if o.ksize == 3 else 20) * o.cin * o.cout * 2
+
+    stacks, trunk_flop, n_trunk, i_op = [], 0, 0, 0
+    for kind, item, cnt in prog._segs:
+        if kind == "stack":
+            stacks.append(item)
+            for o in prog.ops[i_op:i_op + cnt]:
+                if o.op == OP_CONV:
+                    trunk_flop += conv_flop(o); n_trunk += 1
+        i_op += cnt
+    st = torch.cuda.current_stream(dev).cuda_stream
+    if stacks:
+        trunk_ms = _time_fn(lambda: [s_.run(st) for s_ in stacks])
+        trunk_launches = len(stacks)
+        kernel_name = "conv_stack_kernel (tcgen05 residual trunk + head ConvBlocks)" if not stacks[0].lat else "conv_lat_kernel (latency-mode trunk)"
+    else:                                                   # fp32 parity path: no tensor-core trunk, report all convolutions
+        conv_prog = Program(B, False)
+        conv_prog.ops = [o for o in prog.ops if o.op == OP_CONV]
+        conv_prog.keep = prog.keep
+        trunk_ms = _time_fn(conv_prog.run)
+        trunk_flop, n_trunk, trunk_launches = sum(conv_flop(o) for o in conv_prog.ops), len(conv_prog.ops), conv_prog.n_kernels
+        kernel_name = "conv_simt_kernel (fp32 CUDA cores)"
+    step_ms = _time_fn(prog.run)
 
     # e2e: the reference-facing call with a HOST latent tensor in and HOST results out
     cfg2 = dict(cfg); cfg2["search"] = dict(cfg["search"], output_device="cpu")
@@ -326,46 +378,35 @@ def bench_mcts(args, rank, local, world):
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
 
     collectives = None
-    if world > 1:
-        # the only exchange steps of the algorithm, timed separately (device events, max over ranks)
-        import torch.distributed as dist
-        from muzero_breakout_b200 import parallel
-        def timed(fn, reps=5):
-            fn(); barrier_sync(world)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record(); barrier_sync(world)
-            return max_over_ranks(a.elapsed_time(b) / reps, world)
-        nbytes = parallel.broadcast_weights(nets, src=0)
-        bc_ms = timed(lambda: parallel.broadcast_weights(nets, src=0))
-        rec = torch.rand((B, parallel.RECORD_FLOATS), device=dev)
-        ag_ms = timed(lambda: parallel.all_gather_trajectory(rec))
-        collectives = {"weights_broadcast_ms": bc_ms, "weights_bytes": nbytes, "weights_broadcast_GBps": nbytes / bc_ms / 1e6,
-                       "trajectory_allgather_ms": ag_ms, "trajectory_bytes_per_rank": rec.numel() * 4,
-                       "trajectory_allgather_GBps_per_rank_in": rec.numel() * 4 * (world - 1) / ag_ms / 1e6, "backend": "nccl"}
+    if coll is not None:
+        # the exchange steps as they ran inside the timed loop above (device events per call, mean over calls, max over ranks)
+        torch.cuda.synchronize()
+        bc_ms = max_over_ranks(float(np.mean([a_.elapsed_time(b_) for a_, b_ in coll["bc_ms"]])) if coll["bc_ms"] else 0.0, world)
+        ag_ms = max_over_ranks(float(np.mean([a_.elapsed_time(b_) for a_, b_ in coll["ag_ms"]])), world)
+        rec_bytes = B * parallel.RECORD_FLOATS * 4
+        collectives = {"in_timed_loop": True, "backend": "nccl", "weights_broadcasts": len(coll["bc_ms"]), "weights_broadcast_ms": bc_ms,
+                       "weights_bytes": coll["bytes_bc"], "weights_broadcast_GBps": coll["bytes_bc"] / bc_ms / 1e6 if bc_ms else None,
+                       "trajectory_allgathers": len(coll["ag_ms"]), "trajectory_allgather_ms": ag_ms, "trajectory_bytes_per_rank": rec_bytes,
+                       "trajectory_allgather_GBps_per_rank_in": rec_bytes * (world - 1) / ag_ms / 1e6,
+                       "share_of_step": (bc_ms * len(coll["bc_ms"]) + ag_ms * len(coll["ag_ms"])) / ms}
 
     peaks = measured_peaks()
     sims = world * B * S * K
-    achieved = FLOP_TRUNK_LAYER_VALID * n_trunk * B / (trunk_ms * 1e-3) / 1e12
+    achieved = trunk_flop * B / (trunk_ms * 1e-3) / 1e12
+    tol_met = args.precision in ("f16", "f32")
     out = {
         "metric": "latent_mcts_simulations_per_s", "value": sims / (ms * 1e-3), "unit": "simulations/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "tolerance_met": tol_met,
         "config": {"workload": f"mcts: MCTSSearchVec.search, {B} roots x {S} simulations per GPU, random-init MuZero networks (config.yaml sizes), {args.precision}",
-                   "trees_per_gpu": B, "num_simulations": S, "step": "one search() call = root prediction + S x (dynamics + prediction + backup/select)",
+                   "trees_per_gpu": B, "num_simulations": S, "step": "one search() call = root prediction + S x (dynamics + prediction + backup/select)"
+                   + (" + the trajectory all-gather; target-weight broadcast every 15th search" if world > 1 else ""),
                    "l2": f"latent store {B * (S + 2) * 10240 * (4 if args.precision == 'f32' else 2) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
-                   "cuda_graph": bool(m.use_graph)},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": TRUNK_TRAFFIC_PER_SAMPLE_LAYER * n_trunk * B / trunk_launches,
-                     "traffic_source": "profiles/r1_conv_stack_scout_full.txt (ncu --set full, the 28-layer trunk launch at 4096 samples, scaled by layers x samples per launch)", "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
-                     "kernel": f"conv_stack_kernel (tcgen05 residual trunk): {n_trunk} 3x3 256->256 conv layers of one simulation step in {trunk_launches} launches", "flop_convention": "valid taps only (BASELINE.md section 3)",
-                     "flop_per_launch": FLOP_TRUNK_LAYER_VALID * n_trunk * B / trunk_launches, "kernel_ms": trunk_ms / trunk_launches,
-                     "all_convs": {"layers": n_conv, "launches": conv_prog.n_kernels, "ms_per_sim_step": conv_ms, "achieved": FLOP_CONV_VALID * B / (conv_ms * 1e-3) / 1e12,
-                                   "flop_per_leaf": FLOP_CONV_VALID},
-                     "conv_ms_per_sim_step": conv_ms, "all_kernels_ms_per_sim_step": step_ms,
-                     "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12},
+                   "cuda_graph": bool(m.use_graph),
+                   "arithmetic": {"f16": "fp16 tensor-core operands, fp32 accumulation and epilogues, residual stream as fp16 + e4m3 correction", "bf16": "bf16 operands, fp32 accumulation",
+                                  "f32": "fp32 CUDA cores"}[args.precision],
+                   "tolerance": "network outputs within 1e-3 (f16) / 1e-5 (f32) of the fp32 reference, range-relative: tests/test_networks_gpu.py" if tol_met
+                   else "bf16 storage: 3-6e-3 of the fp32 reference (misses the north star's 1e-3; use --precision f16)"},
         "e2e": {"value": world * B * S * Ke / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": B * (5120 * 4 + 12), "d2h_bytes_per_step": B * (4 + 24),
                 "steps": Ke, "api": "MCTSSearchVec.search(hidden_state, action_mask, training_iteration) with host tensors in and out"},
         "gpu_launches": int(launches),
@@ -373,6 +414,19 @@ def bench_mcts(args, rank, local, world):
     }
     if collectives:
         out["collectives"] = collectives
+    out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                       "frac": achieved / peaks["bf16_sustained"], "traffic": TRUNK_TRAFFIC_PER_SAMPLE_LAYER * n_trunk * B / trunk_launches,
+                       "traffic_source": "profiles/r1_conv_stack_scout_full.txt (ncu --set full, 28-layer trunk launch at 4096 samples, scaled by layers x samples per launch)",
+                       "peak_source": peaks["src"] + " (sustained cuBLAS bf16, same power cap)",
+                       "kernel": f"{kernel_name}: {n_trunk} conv layers of one simulation step in {trunk_launches} launches", "flop_convention": "valid taps only (BASELINE.md section 3)",
+                       "flop_per_launch": trunk_flop * B / trunk_launches, "kernel_ms": trunk_ms / trunk_launches,
+                       "all_kernels_ms_per_sim_step": step_ms,
+                       "search_achieved_valid_tap": (FLOP_LEAF_VALID * S + FLOP_ROOT_PRED_VALID) * B * K / (ms * 1e-3) / 1e12}
+    if rank == 0 and world == 1 and not args.no_aux:
+        try:                                  # the reference as it is on the same GPU (torch + cuDNN): never let it take the headline line down
+            out["gpu_reference"] = gpu_reference(args, sd, dev, B, step_ms)
+        except Exception as e:                # noqa: BLE001
+            out["gpu_reference"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_acting:
         out["acting"] = bench_acting(args, m, dev, rank, world)
     if not args.no_aux:
@@ -578,30 +632,188 @@ def bench_train_ends(dev, rank, world, cpu=True):
     return out
 
 
-def cpu_mcts(args, sd=None, trees=24, budget_s=25.0):
-    """CPU port of the reference search (oracle/: C tree bookkeeping + fp32 torch networks on all host threads),
-    bounded sample: `trees` roots x args.sims simulations."""
-    import oracle
-    from oracle.networks import OracleAgent
+def _reference():
+    """(ref shim, src.mcts, src.networks, utils, environment.parallel_breakout) of the UNMODIFIED reference checkout (baseline/_ref: copied
+    from /root/reference by __graft_entry__.build(), git-ignored, ships to the GPU box), or None when it is not there."""
+    from baseline import ref
+    if ref.ref_dir() is None:
+        return None
+    ref.install()
+    import importlib
+    return (ref,) + tuple(importlib.import_module(n) for n in ("src.mcts", "src.networks", "utils", "environment.parallel_breakout"))
+
+
+def _use_all_cores():
+    cores = os.cpu_count() or 1
+    before = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    return cores, before
+
+
+def cpu_mcts(args, sd=None, trees=24, budget_s=25.0, max_calls=20, warmup=0):
+    """The reference search on the host cores, bounded sample: `trees` roots x args.sims simulations per call (config.yaml's own n_parallel).
+    kind "reference": the unmodified src/mcts.py MCTSSearchVec + src/networks.py MuZeroAgent (fp32, eval mode, no_grad) from baseline/_ref on
+    every host thread; kind "port" (no checkout on this box): oracle/mcts_oracle.c tree + the fp32 torch restatement of the networks."""
     from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG, random_state_dict
     sd = sd or random_state_dict(DEFAULT_MODEL_CFG, seed=0, bn_jitter=0.2)
-    agent = OracleAgent()
-    agent.load_state_dict(sd, strict=False)
-    agent.eval_mode()
+    cores, before = _use_all_cores()
     g = torch.Generator().manual_seed(1)
     hidden = torch.rand(trees, 256, 4, 5, generator=g)
-    noise = torch.distributions.Dirichlet(torch.full((3,), 0.25)).sample((trees,))
+    R = _reference()
+    if R is not None:
+        ref, rmcts, rnets, rutils, _ = R
+        cfg = ref.load_cfg()
+        cfg["num_simulations"] = args.sims
+        agent = rnets.MuZeroAgent(cfg["model"])
+        agent.load_state_dict(sd, strict=False)
+        agent.eval()
+        search_obj = rmcts.MCTSSearchVec(cfg, agent, rutils.ScalarTransforms(cfg["model"]))
+        mask = torch.ones(trees, 3)
+
+        def call(i):
+            with torch.no_grad():
+                v, n = search_obj.search(hidden, mask, 0)
+            assert int(n.sum()) == trees * args.sims
+        kind, what = "reference", "unmodified reference src/mcts.py MCTSSearchVec.search + src/networks.py MuZeroAgent (baseline/_ref, fp32 CPU, eval, no_grad)"
+    else:
+        import oracle
+        from oracle.networks import OracleAgent
+        agent = OracleAgent()
+        agent.load_state_dict(sd, strict=False)
+        agent.eval_mode()
+        noise = torch.distributions.Dirichlet(torch.full((3,), 0.25)).sample((trees,))
+
+        def call(i):
+            oracle.search(agent, hidden, noise, seed=i, num_simulations=args.sims)
+        kind, what = "port", "oracle/mcts_oracle.c tree + fp32 torch networks (oracle/networks.py); no reference checkout on this box"
+    for i in range(warmup):
+        call(i)
     n, t0 = 0, time.perf_counter()
     while True:
-        oracle.search(agent, hidden, noise, seed=n, num_simulations=args.sims)
+        call(n)
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 20:
+        if el > budget_s or n >= max_calls:
             break
-    cores = torch.get_num_threads()
-    return {"value": trees * args.sims * n / el, "unit": "simulations/s", "cores": cores, "kind": "port",
-            "sample": f"{n} search() calls of {trees} roots x {args.sims} simulations: oracle/mcts_oracle.c tree + fp32 torch networks "
-                      f"(oracle/networks.py) on {cores} threads of {os.cpu_count()} cpus, {el:.1f} s"}, el / n * 1e3
+    return {"value": trees * args.sims * n / el, "unit": "simulations/s", "cores": cores, "kind": kind, "torch_threads": torch.get_num_threads(),
+            "torch_threads_before_set": before, "calls": n,
+            "sample": f"{n} search() calls of {trees} roots x {args.sims} simulations: {what} on {cores} threads, {el:.1f} s"}, el / n * 1e3
+
+
+def cpu_env_reference(args, envs, budget_s=15.0, max_steps=200):
+    """The unmodified reference environment (environment/parallel_breakout.py BreakoutEnvironment.step, torch ops on the host) at `envs`
+    environments, random actions; None when there is no checkout on this box."""
+    R = _reference()
+    if R is None:
+        return None
+    ref, _, _, _, renv = R
+    cores, before = _use_all_cores()
+    cfg = ref.load_cfg()["environment"]
+    cfg = dict(cfg, n_parallel=envs)
+    env = renv.BreakoutEnvironment(cfg)
+    torch.manual_seed(0)
+    state, _ = env.reset()
+    done = torch.zeros(envs, dtype=torch.bool)
+    g = torch.Generator().manual_seed(1)
+    acts = torch.randint(0, 3, (16, envs), generator=g)
+    state, _, done, _ = env.step(state, acts[0], done)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        state, _, done, _ = env.step(state, acts[n % 16], done)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= max_steps:
+            break
+    return {"value": envs * n / el, "unit": "env-steps/s", "cores": cores, "kind": "reference", "torch_threads": torch.get_num_threads(),
+            "sample": f"{n} steps of {envs} envs: unmodified reference environment/parallel_breakout.py BreakoutEnvironment.step (baseline/_ref, torch CPU ops) "
+                      f"on {cores} threads, {el:.1f} s"}, el / n * 1e3
+
+
+def gpu_reference(args, sd, dev, samples, our_step_ms):
+    """The reference AS IT IS on the same GPU (SURVEY.md section 8d's bar for the network kernels): its own nn.Modules under torch + cuDNN,
+    (a) one simulation step's networks (hidden_state_transition + evaluate_state) on `samples` leaves, fp32 (TF32 off / on) and autocast bf16
+    with channels_last, (b) the reference-as-written search (cuda networks + Python dict trees, src/mcts.py:24-71) at config.yaml's 24 roots."""
+    R = _reference()
+    if R is None:
+        return {"unavailable": "no reference checkout on this box (baseline/_ref is copied by __graft_entry__.build() in the build container)"}
+    ref, rmcts, rnets, rutils, _ = R
+    cfg = ref.load_cfg()
+    cfg["num_simulations"] = args.sims
+    agent = rnets.MuZeroAgent(cfg["model"])           # hard-coded "cuda" = the current device
+    agent.load_state_dict(sd, strict=False)
+    agent.eval()
+    g = torch.Generator(device=dev).manual_seed(3)
+    h = torch.rand((samples, 256, 4, 5), device=dev, generator=g)
+    a = torch.zeros((samples, 3, 4, 5), device=dev)
+    a[torch.arange(samples, device=dev), torch.randint(0, 3, (samples,), device=dev, generator=g)] = 1.0
+
+    def sim_step():
+        with torch.no_grad():
+            hs, r = agent.hidden_state_transition(h, a)
+            p, v = agent.evaluate_state(hs)
+        return p
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {"samples": samples, "what": "unmodified reference MuZeroAgent.hidden_state_transition + evaluate_state (one simulation step's networks) under "
+                                        "torch + cuDNN on this GPU, eval mode, no_grad; ms per simulation step", "ours_ms": our_step_ms}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        out["fp32_ms"] = timed(sim_step)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+        out["tf32_ms"] = timed(sim_step)
+        agent_cl = agent.to(memory_format=torch.channels_last)
+        h_cl, a_cl = h.contiguous(memory_format=torch.channels_last), a.contiguous(memory_format=torch.channels_last)
+
+        def sim_step_bf16():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                hs, r = agent_cl.hidden_state_transition(h_cl, a_cl)
+                p, v = agent_cl.evaluate_state(hs)
+            return p
+        out["autocast_bf16_channels_last_ms"] = timed(sim_step_bf16)
+        out["speedup_vs_best_reference_mode"] = min(out["fp32_ms"], out["tf32_ms"], out["autocast_bf16_channels_last_ms"]) / our_step_ms
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    # the reference search as written, on the GPU: 24 roots (config.yaml n_parallel)
+    search_obj = rmcts.MCTSSearchVec(cfg, agent, rutils.ScalarTransforms(dict(cfg["model"], device=str(dev))))
+    h24, mask = h[:24].contiguous(), torch.ones(24, 3, device=dev)
+    with torch.no_grad():
+        search_obj.search(h24, mask, 0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            v, cnt = search_obj.search(h24, mask, 0)
+        torch.cuda.synchronize()
+        el = (time.perf_counter() - t0) / n
+    out["search_24_roots"] = {"ms_per_search": el * 1e3, "value": 24 * args.sims / el, "unit": "simulations/s",
+                              "what": "unmodified reference MCTSSearchVec.search (cuda networks + Python dict trees, src/mcts.py:24-71), 24 roots x 50 simulations"}
+    return out
+
+
+def cpu_baseline_subprocess(primary, args):
+    """`bench.py --impl reference` as a child process (it hides the GPUs before importing torch): ~25 s of CPU work for the MCTS sample,
+    ~10 s for the env one."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "both" if (primary == "mcts" and args.workload == "both") else primary,
+           "--sims", str(args.sims), "--trees", str(args.trees), "--envs", str(args.envs), "--steps", "50" if primary == "env" else "4",
+           "--ref-budget", "25"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(lines[-1])
+    except Exception as e:                     # noqa: BLE001
+        return {"cpu_baseline": {"error": f"{type(e).__name__}: {e}"}}
 
 
 def main():
@@ -624,39 +836,54 @@ def main():
                     help="both: MCTS line with the env results nested under 'env' (default)")
     ap.add_argument("--envs", type=int, default=65536, help="env workload: environments per GPU")
     ap.add_argument("--env-steps", type=int, default=200)
-    ap.add_argument("--trees", type=int, default=4096, help="mcts workload: roots per GPU (BASELINE.json configs[2])")
+    ap.add_argument("--trees", type=int, default=None, help="mcts workload: roots per GPU (default 4096 = BASELINE.json configs[2] on one GPU; "
+                    "8192 under torchrun = configs[3]'s 65 536 roots over 8 GPUs)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--precision", default="f16", choices=["bf16", "f16", "f32"],
                     help="f16 (default): fp16 tensor-core operands, fp32 accumulation, fp16 + e4m3 residual stream -- the 16-bit mode that meets the north star's 1e-3")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--reset-every", type=int, default=32, help="env workload: start new games every this many steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: wall-clock bound of the timed CPU loop, seconds")
     ap.add_argument("--no-acting", action="store_true", help="skip the whole-move (rep net + search + env) aux measurement")
     ap.add_argument("--no-aux", action="store_true", help="skip the config.yaml-default (24 envs / roots) aux measurements")
     args = ap.parse_args()
+    if args.trees is None:
+        args.trees = 4096 if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) == 1 else 8192
     args.warmup = max(args.warmup, 3)
     primary = "env" if args.workload == "env" else "mcts"
     if args.steps is None:
         args.steps = 200 if primary == "env" else 5
 
     if args.impl == "reference":
+        # the reference's own CPU implementation of the path on this box's host cores (rank 0 only; the other ranks exit 0 without work)
         if int(os.environ.get("RANK", "0")) != 0:
             return
+        budget = args.ref_budget                              # the whole arm ends within a few minutes whatever --steps says
         if primary == "env":
-            base, ms = cpu_env(args, budget_s=20.0)
-            metric, unit, wl = "breakout_env_steps_per_s", "env-steps/s", "env: BreakoutEnvironment.step, reference-format outputs (fp32 (B,3,16,20) frames + reward + done + valid)"
+            envs = min(args.envs, 65536)
+            res = cpu_env_reference(args, envs, budget_s=budget, max_steps=args.steps)
+            if res is None:
+                res = cpu_env(args, budget_s=20.0)
+            base, ms = res
+            metric, unit = "breakout_env_steps_per_s", "env-steps/s"
+            wl = f"env: BreakoutEnvironment.step, reference-format outputs (fp32 (B,3,16,20) frames + reward + done + valid), {envs} envs, host cores"
+            cfgd = {"workload": wl, "envs_per_gpu": envs}
         else:
-            base, ms = cpu_mcts(args, budget_s=60.0)
+            trees = 24
+            base, ms = cpu_mcts(args, budget_s=budget, max_calls=args.steps, warmup=1)
             metric, unit = "latent_mcts_simulations_per_s", "simulations/s"
-            wl = f"mcts: MCTSSearchVec.search, {args.trees} roots x {args.sims} simulations per GPU, random-init MuZero networks (config.yaml sizes), fp32 CPU"
+            wl = (f"mcts: MCTSSearchVec.search, {trees} roots x {args.sims} simulations per step (bounded sample: config.yaml's own n_parallel; the B200 arm runs "
+                  f"{args.trees} roots per GPU), random-init MuZero networks (config.yaml sizes), fp32 on the host cores")
+            cfgd = {"workload": wl, "trees_per_gpu": trees, "num_simulations": args.sims, "b200_arm_trees_per_gpu": args.trees}
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit,
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "n_gpus": args.gpus, "steps": base.get("calls", args.steps), "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl}, "cpu_baseline": base,
+                "config": cfgd, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         if args.workload == "both":
-            env_base, _ = cpu_env(args, budget_s=15.0)
-            line["env"] = {"metric": "breakout_env_steps_per_s", "value": env_base["value"], "unit": "env-steps/s", "cpu_baseline": env_base}
+            res = cpu_env_reference(args, 65536, budget_s=30.0, max_steps=50) or cpu_env(args, budget_s=15.0)
+            line["env"] = {"metric": "breakout_env_steps_per_s", "value": res[0]["value"], "unit": "env-steps/s", "cpu_baseline": res[0]}
         emit(line)
         return
 
@@ -673,12 +900,14 @@ def main():
         out = bench_env(args, rank, local, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            # cpu_baseline = the reference arm itself (same code, GPUs hidden, every host core), run as a child process on a bounded sample
+            cb = cpu_baseline_subprocess(primary, args)
             if primary == "mcts":
-                out["cpu_baseline"], _ = cpu_mcts(args, sd)
-                if "env" in out:
-                    out["env"]["cpu_baseline"], _ = cpu_env(args)
+                out["cpu_baseline"] = cb.get("cpu_baseline", cb)
+                if "env" in out and "env" in cb:
+                    out["env"]["cpu_baseline"] = cb["env"]["cpu_baseline"]
             else:
-                out["cpu_baseline"], _ = cpu_env(args)
+                out["cpu_baseline"] = cb.get("cpu_baseline", cb)
         emit(out)
     if world > 1:
         import torch.distributed as dist

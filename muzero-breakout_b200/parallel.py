@@ -80,10 +80,15 @@ def unpack_record(rec: torch.Tensor):
     return g, rec[:, 320].long(), rec[:, 321], rec[:, 322:325].long(), rec[:, 325]
 
 
-def all_gather_trajectory(local: torch.Tensor, group=None) -> torch.Tensor:
+def all_gather_trajectory(local: torch.Tensor, group=None, equal_shards: bool = False) -> torch.Tensor:
     """(B_local, F) from every rank -> (sum B_local, F), rank-major = global env index order for
-    shard_range shards.  Ranks may hold different B_local."""
+    shard_range shards.  Ranks may hold different B_local; equal_shards=True asserts they do not and skips the size
+    exchange (one collective and no host synchronisation per call: the per-move form of an acting loop)."""
     world = dist.get_world_size(group)
+    if equal_shards:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     sizes = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
     sizes = [int(s.item()) for s in sizes]

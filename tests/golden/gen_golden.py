@@ -1,7 +1,7 @@
 """Generate the committed golden vectors by RUNNING THE UNMODIFIED REFERENCE (/root/reference).
 
 Build container only (the reference is not on the GPU box):
-    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|replay|train|all]
+    cd /root/repo && python tests/golden/gen_golden.py [env|fuzz|play|mcts|net|replay|train|acting|all]
 
 Outputs (np.savez_compressed, all small):
     env_config1.npz  BASELINE.json configs[0]: B=24, torch.manual_seed(42), 10 000 steps, episode
@@ -16,6 +16,10 @@ Outputs (np.savez_compressed, all small):
     train.npz        train_torch.py loss_fn (:33-66) with utils.py ScalarTransforms.supports_representation under autograd
                      (losses + gradients w.r.t. the three logit tensors), and 5 steps of the optimizer networks.py:268 builds
                      (torch.optim.Adam(lr=config.yaml:28, weight_decay=1e-4)) on a 4099-element parameter
+    acting.npz       one episode of the reference's own RLSystem._run_episode (train_torch.py:171-233) on the reference environment with
+                     injected search outputs and an injected uniform stream for the Categorical draw: rep-net inputs of every move
+                     (_pad_initial_state :313-332, _prepare_mcts_input :259-277, _encode_actions :279-293), sampling probabilities
+                     (:192-193), actions, and the ObservationTrajectory lists the loop appended (:204-208)
 """
 from __future__ import annotations
 
@@ -355,6 +359,96 @@ def gen_train(B=64, K=5, n_params=4099, steps=5):
     print("train: adam steps", steps, "params", n_params)
 
 
+def gen_acting(B=4, seed=3, env_seed=21, temperature=0.5, sims=50):
+    """The reference's own acting loop with everything that is not the acting glue injected."""
+    import types
+
+    import train_torch as ref_train
+    from refshim import rng_u32
+
+    M64 = (1 << 64) - 1
+    ep_seed = (seed * 0x9E3779B97F4A7C15 + 0 * 0xC2B2AE3D27D4EB4F + 7) & M64       # acting.Actor's stream key for episode 0 of Actor(seed=seed)
+    g = torch.Generator().manual_seed(99)
+    rec = dict(rep_inputs=[], probs=[], u=[], visits=[], value=[])
+    state_ = dict(move=0, env=0)
+
+    class InjectedCategorical:                      # train_torch.py:196-197: Categorical(probs[i]).sample(), one per env in env order
+        def __init__(self, probs):
+            self.p = probs
+
+        def sample(self):
+            i, mv = state_["env"], state_["move"] - 1
+            state_["env"] += 1
+            u = np.float32((rng_u32(ep_seed, i, mv) >> 8) / 16777216.0)
+            p = self.p.numpy()
+            rec["probs"].append(p.copy()); rec["u"].append(u)
+            a = 0 if u < p[0] else (1 if u < np.float32(p[0] + p[1]) else 2)
+            if p[a] == 0:
+                a = 2 if p[2] > 0 else (1 if p[1] > 0 else 0)
+            return torch.tensor(a)
+
+    class TorchProxy:                               # the module-global `torch` of train_torch with distributions.Categorical replaced
+        distributions = types.SimpleNamespace(Categorical=InjectedCategorical)
+
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+    R = ref_train.RLSystem
+    sysm = object.__new__(R)
+    sysm.n_parallel, sysm.state_history_length, sysm.actions, sysm.n_actions = B, 32, [0, 1, 2], 3
+    sysm.real_resolution, sysm.K, sysm.temperature, sysm.training_iteration = (16, 20), 5, temperature, 0
+    sysm.action_stats, sysm.acting_step = torch.tensor([]), 0
+    sysm.environment = BreakoutEnvironment(dict(CFG["environment"], n_parallel=B))
+    saved = []
+    sysm.replay_buffer = types.SimpleNamespace(save_observation_trajectory=saved.append, get_reward_sums=lambda: [0.0])
+    sysm.filewriter = types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+
+    def sample_action(self, state, mask):           # _sample_action (:236-257) with the networks + search replaced by preset outputs
+        ins = torch.stack([self._prepare_mcts_input(state[i], self.observation_trajectories[i], self.real_resolution) for i in range(B)])
+        rec["rep_inputs"].append(ins.numpy().copy())
+        c = torch.sort(torch.randint(0, sims + 1, (B, 2), generator=g), dim=1)[0]
+        visits = torch.stack([c[:, 0], c[:, 1] - c[:, 0], sims - c[:, 1]], 1).to(torch.int64)
+        value = (torch.rand(B, generator=g) * 6 - 1).float()
+        rec["visits"].append(visits.numpy().copy()); rec["value"].append(value.numpy().copy())
+        state_["move"] += 1; state_["env"] = 0
+        return value, visits
+
+    sysm._sample_action = types.MethodType(sample_action, sysm)
+    torch.manual_seed(env_seed)
+    initial_state, _ = sysm.environment.reset()
+    init_np, dx0 = initial_state.numpy().copy(), sysm.environment.ball_dx.numpy().astype(np.int8).copy()
+    sysm._pad_initial_state(sysm.convert_to_grayscale(initial_state))
+    real_torch = ref_train.torch
+    ref_train.torch = TorchProxy()
+    try:
+        sysm._run_episode(initial_state)
+    finally:
+        ref_train.torch = real_torch
+    T = state_["move"]
+    trajs = sysm.observation_trajectories
+    out = dict(meta=np.array([B, T, seed, env_seed, sims], np.int64), temperature=np.array(temperature), ep_seed=np.array(ep_seed, np.uint64),
+               initial_state=init_np, initial_dx=dx0, rep_inputs=np.stack(rec["rep_inputs"]),
+               probs=np.stack(rec["probs"]).reshape(T, B, 3), u=np.array(rec["u"], np.float32).reshape(T, B),
+               visits=np.stack(rec["visits"]), value=np.stack(rec["value"]), lengths=np.array([t.length for t in trajs], np.int64),
+               saved=np.array([any(t is s_ for s_ in saved) for t in trajs]))
+    for i, t in enumerate(trajs):
+        out[f"t{i}_actions"] = np.array([int(a) for a in t.actions], np.int64)
+        out[f"t{i}_states"] = torch.stack(t.states).numpy()
+        out[f"t{i}_rewards"] = np.array([float(r) for r in t.rewards], np.float32)
+        out[f"t{i}_visits"] = torch.stack([v.float() for v in t.visit_counts]).numpy()
+        out[f"t{i}_values"] = np.array([float(v) for v in t.values], np.float32)
+    # the sampling expression alone (train_torch.py:192-193) on many visit-count rows and three temperatures
+    c = torch.sort(torch.randint(0, sims + 1, (3000, 2), generator=g), dim=1)[0]
+    vis = torch.stack([c[:, 0], c[:, 1] - c[:, 0], sims - c[:, 1]], 1).to(torch.int64)
+    out["s_visits"] = vis.numpy()
+    for k, temp in enumerate((1.0, 0.5, 0.25)):
+        w = vis ** (1 / temp)
+        out[f"s_probs{k}"] = (w / w.sum(dim=1, keepdim=True)).numpy()
+    out["s_temps"] = np.array([1.0, 0.5, 0.25])
+    np.savez_compressed(os.path.join(HERE, "acting.npz"), **out)
+    print("acting: moves", T, "lengths", out["lengths"].tolist(), "saved", out["saved"].tolist(), "bytes", os.path.getsize(os.path.join(HERE, "acting.npz")))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.chdir("/tmp")
@@ -365,3 +459,4 @@ if __name__ == "__main__":
     if what in ("net", "all"): gen_mcts_real()
     if what in ("replay", "all"): gen_replay()
     if what in ("train", "all"): gen_train()
+    if what in ("acting", "all"): gen_acting()

@@ -37,6 +37,29 @@ def test_library_is_sm100a_native():
     assert "sm_100a" in out
 
 
+def test_sass_census_shows_blackwell_tensor_core_and_tma_instructions():
+    """profiles/sass_census.py (cuobjdump -sass of the built library): the trunk kernels issue tcgen05 pair MMAs (UTCHMMA.2CTA), TMA
+    tensor loads (UTMALDG) and -- the fused trunk's epilogue -- TMA tensor stores (UTMASTG); accumulators come back through LDTM."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import sass_census
+    per = sass_census.census(mzb.build())                    # keyed by the mangled kernel names
+    def find(sub):
+        hits = [v for k, v in per.items() if sub in k]
+        assert hits, f"no kernel named *{sub}* in the library"
+        return hits
+    for c in find("conv_stack_kernel"):
+        assert c["UTCHMMA"] >= 4 and c["UTMALDG"] >= 4 and c["UTMASTG"] >= 2 and c["LDTM"] >= 1 and c["full:UTCHMMA.2CTA"] >= 4
+    for name in ("conv_tc_kernel", "wgrad_kernel"):
+        for c in find(name):
+            assert c["UTCHMMA"] >= 4 and c["UTMALDG"] >= 2 and c["LDTM"] >= 1
+    for c in find("conv_lat_kernel"):
+        assert c["HMMA"] >= 100 and c["UTMALDG"] >= 1          # the latency-mode trunk: warp MMAs fed by TMA weight slices
+
+
 def test_env_class_mirrors_reference_signature():
     from muzero_breakout_b200.environment.parallel_breakout import BreakoutEnvironment, MuZeroEnvironment
     env = BreakoutEnvironment(ENV_CFG)

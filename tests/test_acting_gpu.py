@@ -1,4 +1,5 @@
-"""GPU tests of the on-device acting loop (muzero-breakout_b200/acting.py, csrc/acting.cu) against a
+"""GPU tests of the on-device acting loop (muzero-breakout_b200/acting.py, csrc/acting.cu) against the reference's own acting loop
+(tests/golden/acting.npz: RLSystem._run_episode with injected search outputs and uniforms), and against a
 restatement of the reference's history / recording semantics (train_torch.py:171-233, 259-332) and the CPU
 environment oracle."""
 import numpy as np
@@ -108,3 +109,72 @@ def test_bf16_episode_runs_and_is_consistent():
     assert torch.all(out["visits"].sum(-1) == sims)
     out2 = actor.run_episode()                                   # a second episode reuses the buffers
     assert out2["action"].shape[1] == B
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# pinned against the reference's own acting loop: tests/golden/acting.npz = one episode of RLSystem._run_episode (train_torch.py:171-233)
+# on the reference environment with injected search outputs and an injected uniform stream (tests/golden/gen_golden.py acting)
+class _PresetSearch:
+    """stands in for MCTSSearchVec in Actor: the golden's per-move (value, visit counts) instead of a search"""
+
+    def __init__(self, real, value, visits):
+        self.real, self.value, self.visits, self.t = real, value, visits, 0
+
+    def packed_networks(self):
+        return self.real.packed_networks()
+
+    def search(self, hidden, mask, it):
+        t = self.t
+        self.t += 1
+        return torch.from_numpy(self.value[t]).cuda(), torch.from_numpy(self.visits[t]).cuda()
+
+
+def test_actor_episode_matches_reference_run_episode(golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "acting.npz"))
+    B, T, seed, env_seed, sims = (int(x) for x in g["meta"])
+    actor, _ = make(B, sims, "f32", temperature=float(g["temperature"]), seed=seed, max_moves=261)
+    actor.mcts = _PresetSearch(actor.mcts, g["value"], g["visits"])
+    actor.keep_rep_inputs = []
+    torch.manual_seed(env_seed)                                  # the reference's reset() draws (parallel_breakout.py:116-136)
+    out = actor.run_episode()
+    assert np.array_equal(out["initial_state"].cpu().numpy(), g["initial_state"])
+    assert out["action"].shape[0] == T, "the episode ends when every game is done (train_torch.py:184)"
+    act, recd = out["action"].cpu().numpy(), out["recorded"].cpu().numpy()
+    rew, frames = out["reward"].cpu().numpy(), out["frames"].cpu().numpy()
+    vis, val = out["visits"].cpu().numpy(), out["value"].cpu().numpy()
+    lengths = g["lengths"]
+    for t in range(T):
+        live = t < lengths                                         # env b is recorded for its first lengths[b] moves
+        assert np.array_equal(recd[t], live)
+        got = actor.keep_rep_inputs[t].cpu().numpy()
+        # bit-exact rep-net input for every game still running (a finished game's trajectory stops growing in the reference, :205)
+        assert np.array_equal(got[live], g["rep_inputs"][t][live]), f"move {t}: rep-net input differs from _prepare_mcts_input"
+    for b in range(B):
+        n = int(lengths[b])
+        assert np.array_equal(act[:n, b], g[f"t{b}_actions"][32:]), "actions = CDF pick of the injected uniforms on the reference's probabilities"
+        assert np.array_equal(frames[:n, b], g[f"t{b}_states"][31:])
+        assert np.array_equal(rew[:n, b], g[f"t{b}_rewards"][32:])
+        assert np.array_equal(vis[:n, b].astype(np.float32), g[f"t{b}_visits"][32:])
+        assert np.array_equal(val[:n, b], g[f"t{b}_values"][32:])
+    assert np.array_equal(out["initial_gray"].cpu().numpy()[:, 0], np.stack([g[f"t{b}_states"][0, 0] for b in range(B)]))
+
+
+def test_sample_actions_matches_reference_probabilities(golden_dir):
+    import os
+    from muzero_breakout_b200 import _lib
+    from oracle import acting_oracle as A
+    g = np.load(os.path.join(golden_dir, "acting.npz"))
+    visits = torch.from_numpy(g["s_visits"]).cuda()
+    B, seed, step = visits.shape[0], 1234, 9
+    for k, temp in enumerate(g["s_temps"]):
+        action = torch.empty(B, dtype=torch.int64, device="cuda")
+        probs = torch.empty((B, 3), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().mz_sample_actions(B, visits.data_ptr(), float(temp), seed, step, action.data_ptr(), None, probs.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+        want = g[f"s_probs{k}"]                                    # visit_counts ** (1/T) / sum, evaluated by the reference's torch expression
+        assert np.allclose(probs.cpu().numpy(), want, atol=2e-6, rtol=0)
+        u = np.array([(rng_u32(seed, b, step) >> 8) / 16777216.0 for b in range(B)], np.float32)
+        pick = np.array([A.pick(u[b], want[b]) for b in range(B)])
+        near = (np.abs(u - want[:, 0]) < 1e-5) | (np.abs(u - want[:, 0] - want[:, 1]) < 1e-5)       # powf last-bit differences at a CDF boundary
+        assert np.array_equal(action.cpu().numpy()[~near], pick[~near]) and near.mean() < 0.01

@@ -49,6 +49,8 @@ def _worker(rank, world, port, q):
             rec = parallel.pack_record(gray, idx % 3, idx.float() * 0.5, torch.stack([idx, idx + 1, 50 - 2 * idx - 1], 1), idx.float() / 7)
             allrec = parallel.all_gather_trajectory(rec)
             assert allrec.shape == (total, parallel.RECORD_FLOATS)
+            if total % world == 0:           # the per-move form of an acting loop: no size exchange
+                assert torch.equal(parallel.all_gather_trajectory(rec, equal_shards=True), allrec)
             g2, a2, r2, n2, v2 = parallel.unpack_record(allrec)
             full = torch.arange(total)
             assert torch.equal(a2, full % 3) and torch.equal(r2, full.float() * 0.5) and torch.equal(n2[:, 0], full)
