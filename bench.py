@@ -136,7 +136,8 @@ def bench_env(args, rank, local, world):
     env = BreakoutEnvironment(dict(ENV_CFG, n_parallel=B, output_device="cuda", reset_rng="device", seed=1234 + rank))
     state, _ = env.reset()
     g = torch.Generator(device=dev).manual_seed(99 + rank)
-    actions = torch.randint(0, 3, (K + W, B), generator=g, device=dev)        # resident in HBM before timing
+    NA = 256
+    actions = torch.randint(0, 3, (NA, B), generator=g, device=dev)           # resident in HBM before timing, reused every NA steps
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     frames = [torch.empty((B, 3, 16, 20), dtype=torch.float32, device=dev) for _ in range(2)]
     reward = torch.empty(B, dtype=torch.float32, device=dev)
@@ -148,7 +149,7 @@ def bench_env(args, rank, local, world):
         if i % args.reset_every == 0:                          # episode protocol: new games, SoA only (device RNG)
             _lib.check(L.bk_env_reset_device_rng(B, p(env._hdr), p(env._bricks), 1234 + rank, i, None, stream))
             done.zero_()
-        _lib.check(L.bk_env_step(B, p(env._hdr), p(env._bricks), p(actions[i]), p(done), p(frames[i & 1]), p(reward), p(valid),
+        _lib.check(L.bk_env_step(B, p(env._hdr), p(env._bricks), p(actions[i % NA]), p(done), p(frames[i & 1]), p(reward), p(valid),
                                  None, env._rewards, p(env._status), stream))
 
     for i in range(W):
@@ -174,11 +175,11 @@ def bench_env(args, rank, local, world):
     hdone = torch.zeros(B, dtype=torch.bool).pin_memory()
     Ke = max(3, min(K, args.e2e_steps))
     for i in range(3):
-        st, *_ = env2.step(st, host_actions[i], hdone)
+        st, *_ = env2.step(st, host_actions[i % NA], hdone)
     barrier_sync(world)
     t0 = time.perf_counter()
     for i in range(3, 3 + Ke):
-        st, r_, hdone, v_ = env2.step(st, host_actions[i % (K + W)], hdone)
+        st, r_, hdone, v_ = env2.step(st, host_actions[i % NA], hdone)
     barrier_sync(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
 
@@ -731,8 +732,7 @@ def cpu_env_reference(args, envs, budget_s=15.0, max_steps=200):
 
 def gpu_reference(args, sd, dev, samples, our_step_ms):
     """The reference AS IT IS on the same GPU (SURVEY.md section 8d's bar for the network kernels): its own nn.Modules under torch + cuDNN,
-    (a) one simulation step's networks (hidden_state_transition + evaluate_state) on `samples` leaves, fp32 (TF32 off / on) and autocast bf16
-    with channels_last, (b) the reference-as-written search (cuda networks + Python dict trees, src/mcts.py:24-71) at config.yaml's 24 roots."""
+    (a) one simulation step's networks (hidden_state_transition + evaluate_state) on `samples` leaves, fp32 (TF32 off / on) and autocast bf16, (b) the reference-as-written search (cuda networks + Python dict trees, src/mcts.py:24-71) at config.yaml's 24 roots."""
     R = _reference()
     if R is None:
         return {"unavailable": "no reference checkout on this box (baseline/_ref is copied by __graft_entry__.build() in the build container)"}
@@ -772,16 +772,15 @@ def gpu_reference(args, sd, dev, samples, our_step_ms):
         out["fp32_ms"] = timed(sim_step)
         torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
         out["tf32_ms"] = timed(sim_step)
-        agent_cl = agent.to(memory_format=torch.channels_last)
-        h_cl, a_cl = h.contiguous(memory_format=torch.channels_last), a.contiguous(memory_format=torch.channels_last)
-
         def sim_step_bf16():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                hs, r = agent_cl.hidden_state_transition(h_cl, a_cl)
-                p, v = agent_cl.evaluate_state(hs)
+                hs, r = agent.hidden_state_transition(h, a)
+                p, v = agent.evaluate_state(hs)
             return p
-        out["autocast_bf16_channels_last_ms"] = timed(sim_step_bf16)
-        out["speedup_vs_best_reference_mode"] = min(out["fp32_ms"], out["tf32_ms"], out["autocast_bf16_channels_last_ms"]) / our_step_ms
+        out["autocast_bf16_ms"] = timed(sim_step_bf16)
+        # channels_last (the layout cuDNN's tensor-core kernels want) only for the weights: the reference's own .view() calls
+        # (_scale_state, networks.py:318) reject channels_last activations, so the unmodified modules cannot run fully channels_last
+        out["speedup_vs_best_reference_mode"] = min(out["fp32_ms"], out["tf32_ms"], out["autocast_bf16_ms"]) / our_step_ms
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     # the reference search as written, on the GPU: 24 roots (config.yaml n_parallel)
@@ -835,7 +834,7 @@ def main():
     ap.add_argument("--workload", default="both", choices=["both", "mcts", "env"],
                     help="both: MCTS line with the env results nested under 'env' (default)")
     ap.add_argument("--envs", type=int, default=65536, help="env workload: environments per GPU")
-    ap.add_argument("--env-steps", type=int, default=200)
+    ap.add_argument("--env-steps", type=int, default=12000, help="env workload nested in the default line: timed steps (~0.5 s, so that the clock sampler sees them)")
     ap.add_argument("--trees", type=int, default=None, help="mcts workload: roots per GPU (default 4096 = BASELINE.json configs[2] on one GPU; "
                     "8192 under torchrun = configs[3]'s 65 536 roots over 8 GPUs)")
     ap.add_argument("--sims", type=int, default=50)
@@ -853,7 +852,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     primary = "env" if args.workload == "env" else "mcts"
     if args.steps is None:
-        args.steps = 200 if primary == "env" else 5
+        args.steps = 12000 if primary == "env" else 5
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path on this box's host cores (rank 0 only; the other ranks exit 0 without work)

@@ -68,11 +68,13 @@ def _declare(L: C.CDLL) -> None:
         "bk_env_reset": [i32] + [vp] * 8,
         "bk_env_reset_device_rng": [i32, vp, vp, u64, u64, vp, vp],
         "bk_env_step": [i32] + [vp] * 11,
+        "bk_env_step_host": [i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
         "bk_env_ingest": [i32] + [vp] * 7,
         "bk_env_render": [i32] + [vp] * 4,
         "bk_env_velocity": [i32] + [vp] * 4,
         "bk_gray": [i32] + [vp] * 3,
     }
+    L.bk_env_io_layout.argtypes, L.bk_env_io_layout.restype = [i32, i32, i32, vp], C.c_size_t
     L.mz_tree_bytes.argtypes, L.mz_tree_bytes.restype = [i32], C.c_size_t
     L.mz_tree_nodes.argtypes, L.mz_tree_nodes.restype = [i32], i32
     L.mz_stack_layer_bytes.argtypes, L.mz_stack_layer_bytes.restype = [], C.c_size_t

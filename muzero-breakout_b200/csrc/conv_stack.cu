@@ -38,6 +38,7 @@ constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
 
 struct alignas(64) StackLayer {          // device-resident descriptor of one convolution of the trunk
     CUtensorMap map_b;                   // tile-contiguous weights [taps][4][256][64], box = 128 rows (half of N = 256)
+    CUtensorMap map_b64;                 // same tensor, box = 64 rows (half of N = 128: the output-channel-split items of small batches)
     const float *shift;                  // [256]
     const float *act_bias;               // [3][20][256] or NULL
     float *dst_f32;                      // optional fp32 copy of the output or NULL
@@ -49,7 +50,7 @@ struct alignas(64) StackLayer {          // device-resident descriptor of one co
     uint32_t taps;                       // taps of the kernel: 0x1FF (3x3) or 0x010 (1x1: the centre)
     int k1;                              // 1x1: the weight tensor holds the one tap at index 0
 };
-static_assert(sizeof(StackLayer) == 256, "layout");
+static_assert(sizeof(StackLayer) == 384, "layout");
 
 struct StackParams {
     CUtensorMap map_act[MAX_BUFS];       // activation buffers as (channel, x, y, sample) TMA tensors, box = 64 ch x 128 samples (A operand)
@@ -67,6 +68,7 @@ struct StackParams {
     int fine;                            // 1: wait for the 3x3 neighbour pixel tiles only; 0: for all 20 pixel tiles of the group
     int rot;                             // tile -> CTA-pair assignment is rotated by rot pairs per layer (evens out the 4/6/9-tap tile costs)
     int n, groups;                       // samples, 128-sample groups
+    int nsplit;                          // items per (pixel, group pair) tile: 1, or 2 output-channel halves (NT = 128)
     int nslices, slice_groups;           // the samples are walked as nslices slices of slice_groups groups (all layers of a slice before the
                                          // next slice, inside the one launch: the live activations of a slice stay in the L2)
     long long elem_off;                  // element offset of this launch's first sample in [n][20][256] side tensors (dst_f32, correction planes)
@@ -114,13 +116,25 @@ __device__ __forceinline__ VLayer vlayer(const StackParams &p, int vl)
     v.g0 = sl * p.slice_groups;
     v.sgroups = min(p.slice_groups, p.groups - v.g0);
     v.spairs = (v.sgroups + 1) >> 1;
-    v.ntiles = HW * v.spairs;
+    v.ntiles = HW * v.spairs * p.nsplit;          // items: (pixel, group pair) tiles x output-channel splits
     return v;
 }
 
+// kF16: the 16-bit element type is a compile-time constant (fp16 / bf16) -- as a run-time flag the epilogue's conversions were
+// compiled as both variants + a select per element
+// NT: output channels per work item.  256 = a whole pixel tile (large batches).  128 = the tile is split into two output-channel
+// halves that run on different CTA pairs (batches of ~100 ... ~1500 samples, where a layer has fewer pixel tiles than the chip has CTA
+// pairs and the 9-tap tiles are the critical path of every layer: the halves take half the tensor time each and need no reduction;
+// the price is that both halves load the tile's activations, which the L2 absorbs at these sizes).
+template <bool kF16, int NT>
 __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __grid_constant__ StackParams p)
 {
     constexpr int N = CH;
+    constexpr int NSPLIT = CH / NT;                 // items per pixel tile
+    constexpr int WCOLS = NT / 2;                   // columns per epilogue warp
+    constexpr int NCHUNK = WCOLS / 32;              // 32-column TMEM chunks per epilogue warp
+    constexpr int NSUB = WCOLS / 64;                // 64-channel staging sub-tiles (TMA boxes) per epilogue warp
+    constexpr int B_BYTES = (NT / 2) * BLOCK_K * 2; // this CTA's half of an item's weight tile per k-chunk
     extern __shared__ __align__(1024) uint8_t smem[];
     float *s_shift = reinterpret_cast<float *>(smem + SS_OFF);       // the current layer's 256 shifts
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BAR_OFF);
@@ -176,11 +190,12 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const int src = L->src, k1 = L->k1;
                 const uint32_t ltaps = L->taps;
                 const int first = first_tile(vl);
-                for (int tile = first; tile < V.ntiles; tile += nclusters) {
+                for (int item = first; item < V.ntiles; item += nclusters) {
+                    const int tile = item / NSPLIT, nh = item - tile * NSPLIT;
                     const int pix = tile / V.spairs, g = V.g0 + 2 * (tile - pix * V.spairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0) & ltaps;
-                    if (tile == first && lane == 0) STRACE(0, layer);
+                    if (item == first && lane == 0) STRACE(0, layer);
                     ++seq;
                     if (layer > 0) {
                         // the scout warp has seen the previous layer's output of this sample group complete at the in-bounds
@@ -194,7 +209,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    if (tile == first && lane == 0) STRACE(1, layer);
+                    if (item == first && lane == 0) STRACE(1, layer);
                     bool first_ks = true;
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((taps >> tap) & 1u)) continue;
@@ -207,10 +222,13 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                             const bool do_a = first_ks || !(p.debug & 2), do_b = first_ks || !(p.debug & 1);
                             first_ks = false;
                             if (elect_one()) {
-                                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * ((do_a ? A_SLOT : 0) + (do_b ? B_SLOT : 0)));
+                                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * ((do_a ? A_SLOT : 0) + (do_b ? B_BYTES : 0)));
                                 else mbar_arrive_cluster(lead_full + 8 * stage);
                                 if (do_a) tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
-                                if (do_b) tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (wrow + kc) * N + rank * (N / 2));
+                                if (do_b) {
+                                    if (NT == CH) tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (wrow + kc) * N + rank * (N / 2));
+                                    else tma_load_2d(sb, &L->map_b64, lead_full + 8 * stage, 0, (wrow + kc) * N + nh * NT + rank * (NT / 2));
+                                }
                             }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
         // ===================== MMA issuer (pair leader only) =====================
         // the whole warp walks the loops (converged: the barrier waits are warp-wide); one elected lane issues the MMAs and commits
         if (rank == 0) {
-            const uint32_t idesc = instr_desc(N, p.f16 != 0);
+            const uint32_t idesc = instr_desc(NT, kF16);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int vl = 0; vl < nvl; ++vl) {
@@ -230,8 +248,9 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const int layer = V.layer;
                 const uint32_t ltaps = p.layers[layer].taps;
                 const int first = first_tile(vl);
-                for (int tile = first; tile < V.ntiles; tile += nclusters, ++it) {
+                for (int item = first; item < V.ntiles; item += nclusters, ++it) {
                     const int buf = it & 1;
+                    const int tile = item / NSPLIT;
                     const int pix = tile / V.spairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const bool tr4 = p.trace == 4 && blockIdx.x == 0 && it < 96 && lane == 0;
                     if (tr4) g_stack_trace[it * 4] = gtime_ns();
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        if (ks == 0 && tile == first && lane == 0) STRACE(2, layer);
+                        if (ks == 0 && item == first && lane == 0) STRACE(2, layer);
                         if (tr4 && ks == 0) g_stack_trace[it * 4 + 2] = gtime_ns();
                         const uint32_t sa = smem_base + A_OFF + stage * A_SLOT, sb = smem_base + B_OFF + stage * B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
@@ -257,7 +276,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                     if (elect_one()) umma_commit_pair(bar_tfull + 8 * buf);
-                    if (tile == first && lane == 0) STRACE(3, layer);
+                    if (item == first && lane == 0) STRACE(3, layer);
                     if (tr4) g_stack_trace[it * 4 + 3] = (gtime_ns() - g_stack_trace[it * 4 + 2]) | ((unsigned long long)ksteps << 40);   // issue time | k-steps
                 }
             }
@@ -265,13 +284,12 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
     } else if (warp < 2 + NUM_EPI_WARPS) {
         // ===================== epilogue (warps 2..9) =====================
         const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
-        const int col0 = half * (N / 2);                                     // this warp's 128 output channels
         const int etid = threadIdx.x - 64;                                   // 0..255 among the epilogue threads
         const uint32_t stg = smem_base + EPI_OFF + ew * EPI_WARP;            // two SWIZZLE_128B tiles [32 rows][64 channels]
         const uint32_t srow = stg + lane * 128;
         const uint32_t bar_res = bar_res0 + 8 * ew;
         const uint32_t lead_tempty = map_to_cta(bar_tempty, 0);
-        const bool f16 = p.f16 != 0;
+        constexpr bool f16 = kF16;
         uint32_t res_phase = 0;
         int it = 0;
         for (int vl = 0; vl < nvl; ++vl) {
@@ -291,8 +309,10 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
             const float *res_f32 = L->res_f32 ? L->res_f32 + p.elem_off : nullptr;
             const int act = L->act;
             const int first = first_tile(vl);
-            for (int tile = first; tile < V.ntiles; tile += nclusters, ++it) {
+            for (int item = first; item < V.ntiles; item += nclusters, ++it) {
                 const int buf = it & 1;
+                const int tile = item / NSPLIT, nh = item - tile * NSPLIT;
+                const int col0 = nh * NT + half * WCOLS;                     // this warp's WCOLS output channels
                 const int pix = tile / V.spairs, gl = 2 * (tile - pix * V.spairs) + rank, g = V.g0 + gl;
                 const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                 const int s0w = g * BLOCK_M + quarter * 32;                  // first sample of this warp's 32 rows
@@ -301,8 +321,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const bool valid = live && s < p.n;
                 const long long m = (long long)s * HW + pix;                 // global output row
                 const float *ab = (valid && act_bias) ? act_bias + ((size_t)p.act_idx[s] * HW + pix) * N : nullptr;
-                // correction planes, tile-private layout: [group][pixel][epilogue warp][8][32 lanes] x 16 bytes
-                const size_t lo_off = (((size_t)g * HW + pix) * NUM_EPI_WARPS + ew) * (8 * 32 * 16) + (size_t)lane * 16;
+                // correction planes, item-private layout: [group][pixel][split][epilogue warp][2 * NCHUNK][32 lanes] x 16 bytes
+                const size_t lo_off = ((((size_t)g * HW + pix) * NSPLIT + nh) * NUM_EPI_WARPS + ew) * (2 * NCHUNK * 32 * 16) + (size_t)lane * 16;
                 if (layer > 0) {
                     // This tile's inputs -- the residual and its correction, written by an earlier layer's epilogue of the same
                     // (group, pixel), possibly on another SM -- are ordered before the previous layer's counters the scout has
@@ -317,29 +337,29 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 }
                 if (res >= 0 && live && elect_one()) {
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    mbar_expect_tx(bar_res, EPI_WARP);
-                    tma_load_4d_cta(stg, &p.map_epi[res], bar_res, col0, x0, y0, s0w);
-                    tma_load_4d_cta(stg + 4096, &p.map_epi[res], bar_res, col0 + 64, x0, y0, s0w);
+                    mbar_expect_tx(bar_res, NSUB * 4096);
+#pragma unroll
+                    for (int sub = 0; sub < NSUB; ++sub) tma_load_4d_cta(stg + sub * 4096, &p.map_epi[res], bar_res, col0 + 64 * sub, x0, y0, s0w);
                 }
-                uint4 lo_in[8];
+                uint4 lo_in[2 * NCHUNK];
                 if (res_lo && valid) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) lo_in[i] = __ldcg(reinterpret_cast<const uint4 *>(res_lo + lo_off + i * 512));
+                    for (int i = 0; i < 2 * NCHUNK; ++i) lo_in[i] = __ldcg(reinterpret_cast<const uint4 *>(res_lo + lo_off + i * 512));
                 }
                 uint32_t acc[2][32];
                 mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
                 tc_fence_after();
-                if (warp == 2 && lane == 0 && tile == first) STRACE(4, layer);
+                if (warp == 2 && lane == 0 && item == first) STRACE(4, layer);
                 if (res >= 0 && live) {
                     mbar_wait(bar_res, res_phase);
                     res_phase ^= 1;
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + col0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * N + half * WCOLS);
                 tmem_ld32_async(taddr, acc[0]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < NCHUNK; ++c) {
                     tmem_wait(acc[c & 1]);
-                    if (c + 1 < 4) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
+                    if (c + 1 < NCHUNK) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
                     if (valid) {
                         const int c0 = col0 + c * 32;
                         float v[32];
@@ -433,8 +453,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 if (elect_one()) {
                     mbar_arrive_cluster(lead_tempty + 8 * buf);              // accumulator drained: the pair's next-but-one tile may reuse it
                     if (live) {
-                        tma_store_4d(&p.map_epi[dst], stg, col0, x0, y0, s0w);
-                        tma_store_4d(&p.map_epi[dst], stg + 4096, col0 + 64, x0, y0, s0w);
+#pragma unroll
+                        for (int sub = 0; sub < NSUB; ++sub) tma_store_4d(&p.map_epi[dst], stg + sub * 4096, col0 + 64 * sub, x0, y0, s0w);
                         tma_store_commit();
                         tma_store_wait();                                    // global writes performed (and the staging tile is free again)
                         asm volatile("fence.proxy.async;" ::: "memory");
@@ -444,7 +464,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     }
                 }
                 __syncwarp();                                                // nobody overwrites the staging tile before the store has read it
-                if (warp == 2 && lane == 0 && tile == first) STRACE(5, layer);
+                if (warp == 2 && lane == 0 && item == first) STRACE(5, layer);
             }
         }
     } else if (lane == 0) {
@@ -453,14 +473,15 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
         // done[L][g][q] of the in-bounds neighbour pixels q (one L2 round trip for all of them), acquires, and publishes the
         // running count of cleared tiles in shared memory.  The producer's own wait is then a shared-memory read, so the
         // flag round trip + fence (~2 us) no longer sits between the last load of one tile and the first of the next.
-        const int target = (epoch + 1) * NUM_EPI_WARPS;
+        const int target = (epoch + 1) * NUM_EPI_WARPS * NSPLIT;      // every item's 8 epilogue warps arrive once per launch
         int seq = 0;
         for (int vl = 0; vl < nvl; ++vl) {
             const VLayer V = vlayer(p, vl);
             const int layer = V.layer;
             const uint32_t ltaps = p.layers[layer].taps;
             const int first = first_tile(vl);
-            for (int tile = first; tile < V.ntiles; tile += nclusters) {
+            for (int item = first; item < V.ntiles; item += nclusters) {
+                const int tile = item / NSPLIT;
                 const int pix = tile / V.spairs, gl = 2 * (tile - pix * V.spairs) + rank, g = V.g0 + gl;
                 const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                 ++seq;
@@ -565,6 +586,10 @@ int mz_stack_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_byt
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&l.map_b, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cuuint32_t box64[2] = {BLOCK_K, CH / 4};
+        if (r == CUDA_SUCCESS)
+            r = enc(&l.map_b64, o.dtype == MZ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(o.w), dims, strides, box64, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_stack_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
     // every layer but the first must read what an earlier layer of the run (or the caller) wrote; the counters only order
@@ -622,10 +647,18 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.slice_groups = slice_samples > 0 && slice_samples < nsamples ? slice_samples / BLOCK_M : p.groups;
     p.nslices = (p.groups + p.slice_groups - 1) / p.slice_groups;
-    const int max_tiles = HW * ((p.slice_groups + 1) / 2);          // pair-tiles of a (full) slice per layer
+    // output-channel-split items (two CTA pairs per pixel tile) while a layer has fewer pixel tiles than ~2 per CTA pair: a pure function
+    // of the batch size (the scratch counters of a (trunk, nsamples) always see the same split); MZB_STACK_NSPLIT_MAX overrides the limit
+    static int nsplit_max = -1;
+    if (nsplit_max < 0) { const char *e = getenv("MZB_STACK_NSPLIT_MAX"); nsplit_max = e ? atoi(e) : 768; }
+    p.nsplit = nsamples <= nsplit_max ? 2 : 1;
+    const int max_tiles = HW * ((p.slice_groups + 1) / 2) * p.nsplit;          // items of a (full) slice per layer
     static bool attr_set[64] = {};
     if (mzb::first_use_on_device(attr_set)) {
-        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(conv_stack_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STACK_SMEM));
         // every CTA pair must be resident at once (pairs wait on each other's counters): one CTA per SM by shared memory, so the
         // grid may not exceed what this device / context can co-schedule
     }
@@ -651,7 +684,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
         int d = 0;
         cudaGetDevice(&d);
         if (d < 0 || d >= 64 || cached[d] == 0) {
-            MZB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, conv_stack_kernel, &cfg));
+            MZB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, conv_stack_kernel<true, 256>, &cfg));
             if (d >= 0 && d < 64) cached[d] = max_clusters;
         } else max_clusters = cached[d];
     }
@@ -660,7 +693,13 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     if (clusters > max_clusters) clusters = max_clusters;       // fewer SMs than a full B200 (MIG / MPS limits): still all co-resident
     cfg.gridDim = dim3(2 * clusters);
     cfg.numAttrs = coop ? 2 : 1;
-    MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel, p));
+    if (p.nsplit == 2) {
+        if (p.f16) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<true, 128>, p));
+        else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<false, 128>, p));
+    } else {
+        if (p.f16) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<true, 256>, p));
+        else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_stack_kernel<false, 256>, p));
+    }
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -396,6 +396,42 @@ int bk_env_step(int B, uint64_t *hdr, uint32_t *bricks, const int64_t *action, u
     return 0;
 }
 
+size_t bk_env_io_layout(int B, int want_state, int want_gray, size_t *off8)
+{
+    // [frames | gray | reward | valid | done | action | status]: everything 16-byte aligned; [done | action | status] is what the host sends
+    auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t o = 0, off[8];
+    off[0] = o; o += want_state ? up((size_t)B * 3840) : 0;
+    off[1] = o; o += want_gray ? up((size_t)B * 1280) : 0;
+    off[2] = o; o += up((size_t)B * 4);
+    off[3] = o; o += up((size_t)B * 12);
+    off[4] = o; o += up((size_t)B);
+    off[5] = o; o += up((size_t)B * 8);
+    off[6] = o; o += 16;
+    off[7] = o;
+    if (off8) for (int i = 0; i < 8; ++i) off8[i] = off[i];
+    return o;
+}
+
+int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, const void *host_in, void *host_out, int want_state,
+                     int want_gray, const float *rewards4, void *stream)
+{
+    MZB_CHECK_ARG(B > 0 && hdr && bricks && io_dev && host_in && host_out && rewards4, "bad argument");
+    size_t off[8];
+    bk_env_io_layout(B, want_state, want_gray, off);
+    uint8_t *io = reinterpret_cast<uint8_t *>(io_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    MZB_CUDA(cudaMemcpyAsync(io + off[4], host_in, off[7] - off[4], cudaMemcpyHostToDevice, st));        // done | action | status = 0
+    int rc = bk_env_step(B, hdr, bricks, reinterpret_cast<const int64_t *>(io + off[5]), io + off[4],
+                         want_state ? reinterpret_cast<float *>(io + off[0]) : nullptr, reinterpret_cast<float *>(io + off[2]),
+                         reinterpret_cast<float *>(io + off[3]), want_gray ? reinterpret_cast<float *>(io + off[1]) : nullptr, rewards4,
+                         reinterpret_cast<int32_t *>(io + off[6]), stream);
+    if (rc) return rc;
+    MZB_CUDA(cudaMemcpyAsync(host_out, io, off[7], cudaMemcpyDeviceToHost, st));
+    MZB_CUDA(cudaStreamSynchronize(st));
+    return *reinterpret_cast<const int32_t *>(reinterpret_cast<const uint8_t *>(host_out) + off[6]) & 0x7fffffff;
+}
+
 int bk_env_ingest(int B, const float *state, const int64_t *ball_dx, const float *ball_dy, uint64_t *hdr,
                   uint32_t *bricks, int32_t *status, void *stream)
 {

@@ -71,6 +71,17 @@ def _to_host(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _status_message(bits: int) -> str:
+    msgs = []
+    if bits & 1:
+        msgs.append("ball left the grid (the reference raises IndexError, parallel_breakout.py:243)")
+    if bits & 2:
+        msgs.append("ingested state is not a valid Breakout frame (0/1 planes, one ball pixel, 6-cell paddle on row 15)")
+    if bits & 4:
+        msgs.append("action outside {0,1,2}")
+    return "; ".join(msgs)
+
+
 class BreakoutEnvironment(MuZeroEnvironment):
     def __init__(self, cfg: dict, width: int = 10, height: int = 15, paddle_width: int = 6, brick_rows: int = 3,
                  device: str = "cuda"):
@@ -97,6 +108,7 @@ class BreakoutEnvironment(MuZeroEnvironment):
         self._hdr = self._bricks = self._status = None
         self._last_state = None                                 # tensor handed out last (identity check)
         self._last_version = -1
+        self._host_io = {}                                      # (B, want_state, want_gray) -> packed staging buffers of the host-tensor step
         self._rewards = (ctypes.c_float * 4)(self.paddle_hit_reward, self.brick_hit_reward,
                                              self.game_lost_reward, self.game_won_reward)
 
@@ -144,6 +156,8 @@ class BreakoutEnvironment(MuZeroEnvironment):
         dev = self._cuda
         if state is not None and not self._is_ours(state):
             self._ingest(state)
+        if self.device == "cpu" and not action.is_cuda and not done_mask.is_cuda:
+            return self._step_host(B, action, done_mask, want_gray, want_state)
         act = action if (action.is_cuda and action.dtype == torch.int64 and action.is_contiguous()) else \
             action.to(dev, torch.int64, non_blocking=True).contiguous()
         if act.numel() != B or done_mask.numel() != B:
@@ -170,6 +184,46 @@ class BreakoutEnvironment(MuZeroEnvironment):
             return out_state, reward, done_mask, valid, gray
         return out_state, reward, done_mask, valid
 
+    def _step_host(self, B, action, done_mask, want_gray, want_state):
+        """The reference's call (host tensors in and out) as ONE library call: one pinned staging buffer up (done | action | status = 0),
+        the step kernel, one packed buffer down (frames | gray | reward | valid | done | action | status), one synchronisation -- instead
+        of two uploads, five downloads and a status read.  The outputs are views of a freshly allocated pinned block (torch's caching
+        host allocator), so tensors a caller keeps from earlier steps are never overwritten."""
+        if action.numel() != B or done_mask.numel() != B:
+            raise ValueError(f"action/done_mask must have {B} elements")
+        key = (B, bool(want_state), bool(want_gray))
+        lay = self._host_io.get(key)
+        if lay is None:
+            off = (ctypes.c_size_t * 8)()
+            total = int(_lib.lib().bk_env_io_layout(B, int(want_state), int(want_gray), off))
+            off = [int(o) for o in off]
+            hin = torch.zeros(total - off[4], dtype=torch.uint8).pin_memory()
+            lay = dict(off=off, total=total, io=torch.empty(total, dtype=torch.uint8, device=self._cuda), hin=hin,
+                       hin_done=hin[:B], hin_act=hin[off[5] - off[4]:off[5] - off[4] + 8 * B].view(torch.int64))
+            self._host_io[key] = lay
+        off = lay["off"]
+        lay["hin_done"].copy_(done_mask.reshape(B))
+        lay["hin_act"].copy_(action.reshape(B))
+        hout = torch.empty(lay["total"], dtype=torch.uint8, pin_memory=True)
+        rc = _lib.lib().bk_env_step_host(B, _ptr(self._hdr), _ptr(self._bricks), _ptr(lay["io"]), _ptr(lay["hin"]), _ptr(hout), int(want_state),
+                                         int(want_gray), self._rewards, self._stream())
+        if rc < 0:
+            _lib.check(rc)
+        if rc > 0:
+            raise IndexError(_status_message(rc))
+        out_state = None
+        if want_state:
+            out_state = hout[off[0]:off[0] + B * 3840].view(torch.float32).view(B, 3, 16, 20)
+            self._last_state, self._last_version = out_state, out_state._version
+        else:
+            self._last_state = None
+        reward = hout[off[2]:off[2] + 4 * B].view(torch.float32)
+        valid = hout[off[3]:off[3] + 12 * B].view(torch.float32).view(B, 3)
+        done_mask.copy_(hout[off[4]:off[4] + B].view(torch.bool).view(done_mask.shape))      # in place: callers alias it (train_torch.py:179)
+        if want_gray:
+            return out_state, reward, done_mask, valid, hout[off[1]:off[1] + B * 1280].view(torch.float32).view(B, 1, 16, 20)
+        return out_state, reward, done_mask, valid
+
     # ------------------------------------------------------------------ extras
     @property
     def ball_dx(self) -> torch.Tensor:
@@ -194,14 +248,7 @@ class BreakoutEnvironment(MuZeroEnvironment):
         bits = int(self._status.item())
         if bits:
             self._status.zero_()
-            msgs = []
-            if bits & 1:
-                msgs.append("ball left the grid (the reference raises IndexError, parallel_breakout.py:243)")
-            if bits & 2:
-                msgs.append("ingested state is not a valid Breakout frame (0/1 planes, one ball pixel, 6-cell paddle on row 15)")
-            if bits & 4:
-                msgs.append("action outside {0,1,2}")
-            raise IndexError("; ".join(msgs))
+            raise IndexError(_status_message(bits))
 
     def gray(self, state: torch.Tensor) -> torch.Tensor:
         """convert_to_grayscale (train_torch.py:334-358) on the device."""
