@@ -385,11 +385,24 @@ def bench_mcts(args, rank, local, world):
         bc_ms = max_over_ranks(float(np.mean([a_.elapsed_time(b_) for a_, b_ in coll["bc_ms"]])) if coll["bc_ms"] else 0.0, world)
         ag_ms = max_over_ranks(float(np.mean([a_.elapsed_time(b_) for a_, b_ in coll["ag_ms"]])), world)
         rec_bytes = B * parallel.RECORD_FLOATS * 4
-        collectives = {"in_timed_loop": True, "backend": "nccl", "weights_broadcasts": len(coll["bc_ms"]), "weights_broadcast_ms": bc_ms,
-                       "weights_bytes": coll["bytes_bc"], "weights_broadcast_GBps": coll["bytes_bc"] / bc_ms / 1e6 if bc_ms else None,
-                       "trajectory_allgathers": len(coll["ag_ms"]), "trajectory_allgather_ms": ag_ms, "trajectory_bytes_per_rank": rec_bytes,
-                       "trajectory_allgather_GBps_per_rank_in": rec_bytes * (world - 1) / ag_ms / 1e6,
-                       "share_of_step": (bc_ms * len(coll["bc_ms"]) + ag_ms * len(coll["ag_ms"])) / ms}
+        # the same two collectives back to back right after a barrier (no rank skew in the number): what the links deliver
+        def alone(fn, reps=5):
+            fn(); barrier_sync(world)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(reps):
+                fn()
+            b_.record(); barrier_sync(world)
+            return max_over_ranks(a_.elapsed_time(b_) / reps, world)
+        bc_alone = alone(lambda: parallel.broadcast_weights(nets, src=0))
+        ag_alone = alone(lambda: parallel.all_gather_trajectory(rec, equal_shards=True))
+        collectives = {"in_timed_loop": True, "backend": "nccl", "weights_broadcasts": len(coll["bc_ms"]), "weights_bytes": coll["bytes_bc"],
+                       "weights_broadcast_ms_in_loop": bc_ms, "weights_broadcast_ms_alone": bc_alone, "weights_broadcast_GBps": coll["bytes_bc"] / bc_alone / 1e6,
+                       "trajectory_allgathers": len(coll["ag_ms"]), "trajectory_bytes_per_rank": rec_bytes,
+                       "trajectory_allgather_ms_in_loop": ag_ms, "trajectory_allgather_ms_alone": ag_alone,
+                       "trajectory_allgather_GBps_per_rank_in": rec_bytes * (world - 1) / ag_alone / 1e6,
+                       "share_of_step": (bc_ms * len(coll["bc_ms"]) + ag_ms * len(coll["ag_ms"])) / ms,
+                       "note": "in_loop = per call inside the timed searches, waiting for the slowest rank's search included; alone = back to back after a barrier"}
 
     peaks = measured_peaks()
     sims = world * B * S * K

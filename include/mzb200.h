@@ -78,12 +78,14 @@ int bk_env_step(int B, uint64_t *hdr, uint32_t *bricks, const int64_t *action, u
  * ONE host->device copy, the step kernel, ONE device->host copy, one stream synchronisation.
  *   bk_env_io_layout  byte offsets of {frames, gray, reward, valid, done, action, status, total} in the packed buffer (16-byte aligned
  *                     regions; frames / gray have size 0 when not wanted); returns the total size.
- *   bk_env_step_host  io_dev: device buffer of `total` bytes; host_in: pinned, the [done | action | status = 0] part of the layout
- *                     (total - offset[done] bytes); host_out: pinned, `total` bytes, receives the whole packed buffer.  Returns the
- *                     status bits of this step (MZB_ENV_ERR_*, >= 0) or a negative error code. */
+ *   bk_env_step_host  io_dev: device buffer of `total` bytes; host_in: pinned staging block of total - offset[done] bytes (the
+ *                     [done | action | status] part of the layout; filled by the call); host_out: pinned, `total` bytes, receives
+ *                     the whole packed buffer; action_host int64[B] / done_host uint8[B]: the caller's host arrays (done_host is
+ *                     read AND written, like the reference's in-place done_mask).  Returns the status bits of this step
+ *                     (MZB_ENV_ERR_*, >= 0) or a negative error code. */
 size_t bk_env_io_layout(int B, int want_state, int want_gray, size_t *off8);
-int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, const void *host_in, void *host_out, int want_state,
-                     int want_gray, const float *rewards4, void *stream);
+int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, void *host_in, void *host_out, const int64_t *action_host,
+                     uint8_t *done_host, int want_state, int want_gray, const float *rewards4, void *stream);
 
 /* dense frame -> SoA (used when the caller hands step() a state tensor this library did not
  * produce).  ball_dx int64[B] / ball_dy float32[B] may be NULL (= keep the velocities in hdr). */

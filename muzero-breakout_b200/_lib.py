@@ -68,7 +68,7 @@ def _declare(L: C.CDLL) -> None:
         "bk_env_reset": [i32] + [vp] * 8,
         "bk_env_reset_device_rng": [i32, vp, vp, u64, u64, vp, vp],
         "bk_env_step": [i32] + [vp] * 11,
-        "bk_env_step_host": [i32, vp, vp, vp, vp, vp, i32, i32, vp, vp],
+        "bk_env_step_host": [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp],
         "bk_env_ingest": [i32] + [vp] * 7,
         "bk_env_render": [i32] + [vp] * 4,
         "bk_env_velocity": [i32] + [vp] * 4,

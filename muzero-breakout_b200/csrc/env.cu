@@ -6,6 +6,8 @@
 //   reset :107-139, get_valid_actions :141-155, step :158-254, and the caller-side
 //   convert_to_grayscale train_torch.py:334-358.  See include/mzb200.h for the C ABI and DESIGN.md
 //   for the layout and the roofline (HBM-bound: 3840 B frame write per env-step dominates).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -413,15 +415,19 @@ size_t bk_env_io_layout(int B, int want_state, int want_gray, size_t *off8)
     return o;
 }
 
-int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, const void *host_in, void *host_out, int want_state,
-                     int want_gray, const float *rewards4, void *stream)
+int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, void *host_in, void *host_out, const int64_t *action_host,
+                     uint8_t *done_host, int want_state, int want_gray, const float *rewards4, void *stream)
 {
-    MZB_CHECK_ARG(B > 0 && hdr && bricks && io_dev && host_in && host_out && rewards4, "bad argument");
+    MZB_CHECK_ARG(B > 0 && hdr && bricks && io_dev && host_in && host_out && action_host && done_host && rewards4, "bad argument");
     size_t off[8];
     bk_env_io_layout(B, want_state, want_gray, off);
-    uint8_t *io = reinterpret_cast<uint8_t *>(io_dev);
+    uint8_t *io = reinterpret_cast<uint8_t *>(io_dev), *hin = reinterpret_cast<uint8_t *>(host_in);
+    const uint8_t *hout = reinterpret_cast<const uint8_t *>(host_out);
     cudaStream_t st = (cudaStream_t)stream;
-    MZB_CUDA(cudaMemcpyAsync(io + off[4], host_in, off[7] - off[4], cudaMemcpyHostToDevice, st));        // done | action | status = 0
+    memcpy(hin, done_host, (size_t)B);                                           // the caller's tensors -> the pinned staging block
+    memcpy(hin + (off[5] - off[4]), action_host, (size_t)B * 8);
+    memset(hin + (off[6] - off[4]), 0, 16);
+    MZB_CUDA(cudaMemcpyAsync(io + off[4], hin, off[7] - off[4], cudaMemcpyHostToDevice, st));           // done | action | status = 0
     int rc = bk_env_step(B, hdr, bricks, reinterpret_cast<const int64_t *>(io + off[5]), io + off[4],
                          want_state ? reinterpret_cast<float *>(io + off[0]) : nullptr, reinterpret_cast<float *>(io + off[2]),
                          reinterpret_cast<float *>(io + off[3]), want_gray ? reinterpret_cast<float *>(io + off[1]) : nullptr, rewards4,
@@ -429,7 +435,8 @@ int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, const
     if (rc) return rc;
     MZB_CUDA(cudaMemcpyAsync(host_out, io, off[7], cudaMemcpyDeviceToHost, st));
     MZB_CUDA(cudaStreamSynchronize(st));
-    return *reinterpret_cast<const int32_t *>(reinterpret_cast<const uint8_t *>(host_out) + off[6]) & 0x7fffffff;
+    memcpy(done_host, hout + off[4], (size_t)B);                                 // done_mask is updated in place (parallel_breakout.py:204,247)
+    return *reinterpret_cast<const int32_t *>(hout + off[6]) & 0x7fffffff;
 }
 
 int bk_env_ingest(int B, const float *state, const int64_t *ball_dx, const float *ball_dy, uint64_t *hdr,

@@ -113,6 +113,7 @@ __device__ __forceinline__ int puct_select(const Params &p, const TreeView &t, i
     const unsigned cand = __ballot_sync(0xffffffffu, lane < NA && score == best);   // :294-296
     const unsigned u32 = mzb::mz_rng_u32(p.seed, (uint32_t)tree, (uint32_t)ctr);    // :297, one draw per call
     ctr += 1;
+    if (cand == 0u) return 0;                                         // every score NaN (non-finite network output): nothing compares equal; action 0
     int pick = (int)(u32 % (unsigned)__popc(cand));
     return __fns(cand, 0, pick + 1);                                  // pick-th set bit, ascending action order
 }
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) tree_kernel(Params p)
             for (int i = lane; i < meta_rows; i += 32) meta[i] = g[p.lay.meta_off() + i];
             __syncwarp();
             const int4 m = meta[0];
-            nslots = m.x; ctr = m.y; len = m.z; parent = m.w & 0xFFFF; action = (m.w >> 16) & 0x3; leaf = (m.w >> 18);
+            nslots = m.x; ctr = m.y; len = m.z; parent = m.w & 0xFFFF; action = (m.w >> 16) & 0x3; leaf = (int)((unsigned)m.w >> 18);
             backup(p, t, path, tree, lane, parent, action, leaf, len);
             __syncwarp();
             if (p.sim + 1 < p.S) {
@@ -322,7 +323,7 @@ int mz_puct_tables(int num_simulations, double c1, double c2, float *s_tab_host,
 
 static int fill(Params &p, const mz_tree_args *a)
 {
-    MZB_CHECK_ARG(a && a->B > 0 && a->num_simulations > 0 && a->num_simulations < 16000, "bad B / num_simulations");
+    MZB_CHECK_ARG(a && a->B > 0 && a->num_simulations > 0 && a->num_simulations <= 8190, "bad B / num_simulations (at most 8190: node slots are 13-bit fields of the selection record)");
     MZB_CHECK_ARG(a->trees && a->s_tab && a->k_tab && a->value && a->pi, "null pointer");
     MZB_CHECK_ARG(a->leaf_parent && a->leaf_action && a->leaf_slot, "null selection outputs");
     MZB_CHECK_ARG((a->latent_bytes % 16) == 0, "latent_bytes must be a multiple of 16");

@@ -197,31 +197,33 @@ class BreakoutEnvironment(MuZeroEnvironment):
             off = (ctypes.c_size_t * 8)()
             total = int(_lib.lib().bk_env_io_layout(B, int(want_state), int(want_gray), off))
             off = [int(o) for o in off]
-            hin = torch.zeros(total - off[4], dtype=torch.uint8).pin_memory()
-            lay = dict(off=off, total=total, io=torch.empty(total, dtype=torch.uint8, device=self._cuda), hin=hin,
-                       hin_done=hin[:B], hin_act=hin[off[5] - off[4]:off[5] - off[4] + 8 * B].view(torch.int64))
+            assert all(o % 4 == 0 for o in off)
+            lay = dict(off=[o // 4 for o in off], words=total // 4, io=torch.empty(total, dtype=torch.uint8, device=self._cuda),
+                       hin=torch.zeros(total - off[4], dtype=torch.uint8).pin_memory())
             self._host_io[key] = lay
-        off = lay["off"]
-        lay["hin_done"].copy_(done_mask.reshape(B))
-        lay["hin_act"].copy_(action.reshape(B))
-        hout = torch.empty(lay["total"], dtype=torch.uint8, pin_memory=True)
-        rc = _lib.lib().bk_env_step_host(B, _ptr(self._hdr), _ptr(self._bricks), _ptr(lay["io"]), _ptr(lay["hin"]), _ptr(hout), int(want_state),
-                                         int(want_gray), self._rewards, self._stream())
-        if rc < 0:
-            _lib.check(rc)
-        if rc > 0:
+        act = action if (action.dtype == torch.int64 and action.is_contiguous()) else action.to(torch.int64).contiguous()
+        in_place = done_mask.dtype in (torch.bool, torch.uint8) and done_mask.is_contiguous()
+        dm = done_mask if in_place else done_mask.to(torch.bool).contiguous()
+        off = lay["off"]                                                     # in 4-byte words
+        hout = torch.empty(lay["words"], dtype=torch.float32, pin_memory=True)
+        rc = _lib.lib().bk_env_step_host(B, self._hdr.data_ptr(), self._bricks.data_ptr(), lay["io"].data_ptr(), lay["hin"].data_ptr(), hout.data_ptr(),
+                                         act.data_ptr(), dm.data_ptr(), int(want_state), int(want_gray), self._rewards, self._stream())
+        if rc:
+            if rc < 0:
+                _lib.check(rc)
             raise IndexError(_status_message(rc))
+        if not in_place:
+            done_mask.copy_(dm)                                              # in place: callers alias it (train_torch.py:179)
         out_state = None
         if want_state:
-            out_state = hout[off[0]:off[0] + B * 3840].view(torch.float32).view(B, 3, 16, 20)
+            out_state = hout[off[0]:off[0] + B * 960].view(B, 3, 16, 20)
             self._last_state, self._last_version = out_state, out_state._version
         else:
             self._last_state = None
-        reward = hout[off[2]:off[2] + 4 * B].view(torch.float32)
-        valid = hout[off[3]:off[3] + 12 * B].view(torch.float32).view(B, 3)
-        done_mask.copy_(hout[off[4]:off[4] + B].view(torch.bool).view(done_mask.shape))      # in place: callers alias it (train_torch.py:179)
+        reward = hout[off[2]:off[2] + B]
+        valid = hout[off[3]:off[3] + 3 * B].view(B, 3)
         if want_gray:
-            return out_state, reward, done_mask, valid, hout[off[1]:off[1] + B * 1280].view(torch.float32).view(B, 1, 16, 20)
+            return out_state, reward, done_mask, valid, hout[off[1]:off[1] + B * 320].view(B, 1, 16, 20)
         return out_state, reward, done_mask, valid
 
     # ------------------------------------------------------------------ extras

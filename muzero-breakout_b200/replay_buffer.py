@@ -89,6 +89,8 @@ class ReplayBuffer:
         self._ring = None
         self._host_counts = [0, 0]       # mirror of the device ring state (entries written, samples appended)
         self._counts_valid = True
+        self._pending = {}               # the reference's list attributes assigned by a checkpoint load (train_torch.py:659-668)
+        self._min_entries = 0
 
     # ---------------------------------------------------------------- device state
     def _alloc(self):
@@ -99,7 +101,7 @@ class ReplayBuffer:
         dev = torch.device(self._device if self._device is not None else f"cuda:{torch.cuda.current_device()}")
         self._dev = dev
         cap, K = self.max_length, self.K
-        ce = int(L.rb_entries_for(cap, K, self.max_moves))
+        ce = max(int(L.rb_entries_for(cap, K, self.max_moves)), int(self._min_entries))
         if ce <= 0 or ce >= 2 ** 31:
             raise ValueError(f"bad replay geometry: max_length={cap} K={K} max_moves={self.max_moves}")
         f32, i32 = torch.float32, torch.int32
@@ -136,6 +138,19 @@ class ReplayBuffer:
     def length(self) -> int:
         self._sync_counts()
         return min(self._host_counts[1], self.max_length)
+
+    @length.setter
+    def length(self, n):
+        """train_torch.py:666 assigns it after the lists while loading a checkpoint: accepted when it agrees with them (the ring state is the
+        authority); `rb.length = 0` alone empties the buffer."""
+        n = int(n)
+        lists = [v for k, v in self._pending.items() if k != "reward_sums"]
+        if lists and any(len(v) != n for v in lists):
+            raise ValueError(f"length = {n} disagrees with the assigned buffers ({[len(v) for v in lists]} samples)")
+        if not self._pending and n != self.length:
+            if n != 0:
+                raise ValueError("length can only be assigned together with the sample lists (checkpoint load) or set to 0")
+            self.empty_buffer()
 
     def __len__(self):
         return self.length
@@ -203,7 +218,9 @@ class ReplayBuffer:
     def _gather(self, batch_idxs, want):
         self._alloc()
         L, dev, K, h = _lib.lib(), self._dev, self.K, self.hist_seq_len
-        idx = torch.as_tensor(batch_idxs).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        idx = torch.as_tensor(batch_idxs)
+        self._check_indices(idx)
+        idx = idx.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         n = int(idx.numel())
         shapes = dict(past_actions=((n, h), torch.int64), future_actions=((n, K), torch.int64),
                       states=((n, h, 1, 16, 20), torch.float32), rewards=((n, K), torch.float32),
@@ -217,6 +234,17 @@ class ReplayBuffer:
             out = {k: v.cpu() for k, v in out.items()}
             self._raise_on_status()
         return out
+
+    def _check_indices(self, idx):
+        """The reference raises IndexError on an out-of-range sample index (list indexing, replay_buffer.py:174).  Host indices are checked
+        here whenever the sample count is known without a device read (always, unless the last append was a device-side save_episode);
+        device-resident indices are checked by the kernel, whose status word is read by the next host-facing call (.length,
+        get_reward_sums, any output_device="cpu" getter) -- deferred, like every asynchronous CUDA error."""
+        if not idx.is_cuda and idx.numel() and self._counts_valid:
+            n = min(self._host_counts[1], self.max_length)
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < -n or hi >= n:
+                raise IndexError(f"sample index out of range for a replay buffer of {n} samples")
 
     def get_batched_past_actions(self, batch_idxs):
         return self._gather(batch_idxs, ("past_actions",))["past_actions"]
@@ -247,7 +275,9 @@ class ReplayBuffer:
         from ONE launch (rb_gather_input): the frame window + `_encode_actions` (:279-293) of the past actions, no intermediate tensors."""
         self._alloc()
         dev, h = self._dev, self.hist_seq_len
-        idx = torch.as_tensor(batch_idxs).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        idx = torch.as_tensor(batch_idxs)
+        self._check_indices(idx)
+        idx = idx.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         n = int(idx.numel())
         out = torch.empty((n, 2 * h, 16, 20), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().rb_gather_input(C.byref(self._ring), n, _p(idx), int(n_actions), _p(out), _p(self._status), self._stream()))
@@ -278,18 +308,106 @@ class ReplayBuffer:
             return []
         return list(self._gather(torch.arange(n), (field,))[field].cpu().unbind(0))
 
-    past_actions_buffer = property(lambda self: self._materialise("past_actions"))
-    future_actions_buffer = property(lambda self: self._materialise("future_actions"))
-    state_buffer = property(lambda self: self._materialise("states"))
-    reward_buffer = property(lambda self: self._materialise("rewards"))
-    visit_counts_buffer = property(lambda self: self._materialise("visit_counts"))
-    value_buffer = property(lambda self: self._materialise("value_buffer"))
-    bootstrapped_values = property(lambda self: self._materialise("values"))
+    # Assigning them (the reference's _load_weights, train_torch.py:659-668, assigns all eight one after the other) restores the buffer:
+    # the assignments are collected and, once the set is complete, _restore() rebuilds the device rings from the per-sample lists.
+    _LIST_FIELDS = {"past_actions_buffer": "past_actions", "future_actions_buffer": "future_actions", "state_buffer": "states",
+                    "reward_buffer": "rewards", "visit_counts_buffer": "visit_counts", "value_buffer": "value_buffer",
+                    "bootstrapped_values": "values"}
+
+    def _list_property(attr, field):              # noqa: N805 (class-body helper)
+        def get(self):
+            return self._materialise(field)
+
+        def set_(self, value):
+            self._pending[attr] = list(value)
+            self._restore_if_complete()
+        return property(get, set_)
+
+    for _attr, _field in _LIST_FIELDS.items():
+        locals()[_attr] = _list_property(_attr, _field)
+    del _attr, _field, _list_property
 
     @property
     def reward_sums(self):
         n = self.length
         return [] if n == 0 else self._gather(torch.arange(n), ("reward_sums",))["reward_sums"].cpu().tolist()
+
+    @reward_sums.setter
+    def reward_sums(self, value):
+        self._pending["reward_sums"] = [float(v) for v in value]
+        self._restore_if_complete()
+
+    def _restore_if_complete(self):
+        need = set(self._LIST_FIELDS) | {"reward_sums"}
+        if need <= set(self._pending):
+            pend, self._pending = self._pending, {}
+            self._restore(pend)
+
+    def _restore(self, pend):
+        """Rebuild the rings from the reference's per-sample lists (sample j: 32 past actions, 32-frame window, K future actions / rewards /
+        visit counts / values / value targets, reward sum; oldest first).  Consecutive samples that are each other's shift by one move
+        (samples s, s+1 of one trajectory, the way save_observation_trajectory appends them, replay_buffer.py:106-152) are merged into one
+        stored trajectory whose first sample starts at padded-list index 32 (beyond the padding rows, which the lists no longer identify);
+        a sample that continues nothing starts a trajectory of its own.  Every get_batched_* output is then exactly the assigned row."""
+        n = len(pend["past_actions_buffer"])
+        if any(len(v) != n for v in pend.values()):
+            raise ValueError("the assigned replay-buffer lists have different lengths")
+        if n > self.max_length:
+            raise ValueError(f"{n} samples assigned to a buffer of max_length {self.max_length}")
+        self.empty_buffer()
+        if n == 0:
+            return
+        h, K, FR = self.hist_seq_len, self.K, self.FRAME
+        st = lambda key, dt, shape: torch.stack([torch.as_tensor(x) for x in pend[key]]).to(dt).reshape((n,) + shape).cpu()
+        past, fut = st("past_actions_buffer", torch.int64, (h,)), st("future_actions_buffer", torch.int64, (K,))
+        frames = st("state_buffer", torch.float32, (h, FR))
+        rew, vis = st("reward_buffer", torch.float32, (K,)), st("visit_counts_buffer", torch.float32, (K, 3))
+        val, tgt = st("value_buffer", torch.float32, (K,)), st("bootstrapped_values", torch.float32, (K,))
+        rsum = torch.tensor(pend["reward_sums"], dtype=torch.float32)
+        # sample j continues sample j-1 iff every window is its shift by one move
+        cont = torch.zeros(n, dtype=torch.bool)
+        if n > 1:
+            c = (past[1:, :-1] == past[:-1, 1:]).all(1) & (past[1:, -1] == fut[:-1, 0]) & (fut[1:, :-1] == fut[:-1, 1:]).all(1)
+            c &= (frames[1:, :-1] == frames[:-1, 1:]).flatten(1).all(1) & (rew[1:, :-1] == rew[:-1, 1:]).all(1)
+            c &= (val[1:, :-1] == val[:-1, 1:]).all(1) & (vis[1:, :-1] == vis[:-1, 1:]).flatten(1).all(1) & (rsum[1:] == rsum[:-1])
+            cont[1:] = c
+        first = torch.nonzero(~cont).flatten()                           # first sample of every run
+        run_of = torch.cumsum((~cont).long(), 0) - 1                      # run index of every sample
+        d = torch.arange(n) - first[run_of]                               # position in its run
+        run_len = torch.diff(torch.cat([first, torch.tensor([n])]))
+        if int(run_len.max()) + h + K > self.max_moves:
+            raise ValueError("a restored trajectory exceeds max_moves")
+        ent_cnt = h + K + run_len                                         # entries 0 .. 31 + K + m of a run of m samples
+        ent_base = torch.cumsum(ent_cnt, 0) - ent_cnt
+        total_e = int(ent_cnt.sum())
+        self._min_entries = total_e + int(_lib.lib().rb_entries_for(self.max_length, K, self.max_moves))
+        if self._ring is not None and (self._ring.cap_entries < self._min_entries or self._ring.cap_samples != self.max_length):
+            self._ring = None                                             # needs a larger entry ring than the acting loop's / max_length was reassigned (:667)
+        self._alloc()
+        t, dev = self._t, self._dev
+        e_frame = torch.zeros((total_e, FR)); e_act = torch.zeros(total_e, dtype=torch.int32)
+        e_rew = torch.zeros(total_e); e_val = torch.zeros(total_e); e_vis = torch.zeros((total_e, 3))
+        fb, ar = ent_base[:, None], torch.arange
+        # first sample of a run (start 32): frames -> entries 2..33, past actions -> entries 1..32, futures -> entries 33..32+K
+        e_frame[(fb + 2 + ar(h)[None, :]).flatten()] = frames[first].reshape(-1, FR)
+        e_frame[ent_base] = frames[first, 0]; e_frame[ent_base + 1] = frames[first, 0]
+        e_act[(fb + 1 + ar(h)[None, :]).flatten()] = past[first].flatten().int()
+        fut_idx = (fb + h + 1 + ar(K)[None, :]).flatten()
+        e_act[fut_idx] = fut[first].flatten().int(); e_rew[fut_idx] = rew[first].flatten(); e_val[fut_idx] = val[first].flatten()
+        e_vis[fut_idx] = vis[first].reshape(-1, 3)
+        # every later sample of a run adds one move: its newest frame -> entry 33 + d, its last future row -> entry 32 + K + d
+        later = torch.nonzero(cont).flatten()
+        if later.numel():
+            eb = ent_base[run_of[later]]
+            e_frame[eb + h + 1 + d[later]] = frames[later, -1]
+            li = eb + h + K + d[later]
+            e_act[li] = fut[later, -1].int(); e_rew[li] = rew[later, -1]; e_val[li] = val[later, -1]; e_vis[li] = vis[later, -1]
+        meta = ent_base[run_of] | ((h + d) << 32) | ((ent_cnt[run_of] - 1) << 48)
+        for key, src in (("frame", e_frame), ("action", e_act), ("reward", e_rew), ("value", e_val), ("visits", e_vis)):
+            t[key][:total_e].copy_(src.to(dev))
+        t["meta"][:n].copy_(meta.to(dev)); t["target"][:n].copy_(tgt.to(dev)); t["reward_sum"][:n].copy_(rsum.to(dev))
+        t["state"].copy_(torch.tensor([total_e, n], dtype=torch.int64))
+        self._host_counts, self._counts_valid = [total_e, n], True
 
     def state_dict(self):
         self._alloc()

@@ -333,8 +333,8 @@ class PackedNetworks:
         self.lat_max = None        # None: trunks of batches <= lat_max_samples() run in latency mode; 0: always the tcgen05 trunk
         self.num_supports = int(cfg.get("num_supports", 11))
         self.supports_min, self.supports_max = cfg.get("supports_min", -5), cfg.get("supports_max", 5)
-        if (self.supports_min, self.supports_max, self.num_supports) != (-5, 5, 11) and self.supports_max - self.supports_min != self.num_supports - 1:
-            raise ValueError("the fused head kernel assumes unit-spaced supports centred on 0 (config.yaml:30-32)")
+        if self.supports_min != -self.supports_max or self.supports_max - self.supports_min != self.num_supports - 1:
+            raise ValueError("the fused head kernel assumes unit-spaced supports centred on 0, e.g. linspace(-5, 5, 11) (config.yaml:30-32)")
         acts = {k: ACT[cfg.get(k, {}).get("activation", "relu")] for k in ("representation_network", "dynamics_network", "prediction_network")}
         sd = {k: v.detach().to("cpu", torch.float64) for k, v in sd.items() if v.dtype.is_floating_point}
         self._pack(sd, acts)

@@ -131,14 +131,49 @@ class Adam:
         torch.autograd.graph.increment_version(self.params)
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr, "betas": self.betas,
-                "eps": self.eps, "weight_decay": self.weight_decay}
+        """torch.optim.Adam's own layout ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}), so the checkpoint the
+        reference writes (train_torch.py:624 `optimizer.state_dict()`) and reads (:652) is interchangeable with torch's optimizer."""
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self.params, self._offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+        """Accepts torch.optim.Adam's state_dict (one param group; every parameter's step must agree: the kernel keeps one step counter)
+        and this class's earlier flat layout ("step", "exp_avg", "exp_avg_sq", ...)."""
+        if "param_groups" not in sd:                       # flat layout of earlier versions
+            self.step_count = int(sd["step"])
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
+            return
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("Adam.load_state_dict: expected one parameter group over the same parameters")
+        g = groups[0]
+        if g.get("amsgrad") or g.get("maximize"):
+            raise ValueError("Adam.load_state_dict: amsgrad / maximize are not built")
+        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        steps = set()
+        for idx, (p, o) in zip(g["params"], zip(self.params, self._offsets)):
+            st = sd["state"].get(idx)
+            if st is None:
+                steps.add(0)
+                continue
+            steps.add(int(float(st["step"])))
+            n = p.numel()
+            self.exp_avg[o:o + n].view(p.shape).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + n].view(p.shape).copy_(st["exp_avg_sq"])
+        if len(steps) > 1:
+            raise ValueError(f"Adam.load_state_dict: parameters have different step counts {sorted(steps)}; the flat update keeps one")
+        self.step_count = steps.pop() if steps else 0
 
 
 class ConvDgrad:

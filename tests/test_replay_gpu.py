@@ -67,7 +67,9 @@ def test_save_observation_trajectory_matches_reference_goldens(golden_dir):
     # Python list indexing: negative indices count from the newest sample; out of range raises like the reference
     last = rb.get_batched_rewards(torch.tensor([-1, 0]))
     assert np.array_equal(last.cpu().numpy(), g["s1_rewards"][[-1, 0]])
-    rb.get_batched_rewards(torch.tensor([rb.length]))
+    with pytest.raises(IndexError):                              # host indices: checked before the launch
+        rb.get_batched_rewards(torch.tensor([rb.length]))
+    rb.get_batched_rewards(torch.tensor([rb.length]).cuda())     # device indices: the kernel flags it, the next host-facing call raises
     with pytest.raises(IndexError):
         rb.get_reward_sums()
     rb.empty_buffer()
@@ -203,3 +205,43 @@ def test_acting_episode_into_replay_buffer():
         got = rb._gather(torch.from_numpy(idx), (f,))[f].cpu().numpy()
         assert np.array_equal(got, orc.batch(f, idx).astype(got.dtype)), f
     assert rb.get_reward_sums() == orc.reward_sums()
+
+
+def test_checkpoint_restore_through_the_reference_list_attributes(golden_dir):
+    """train_torch.py:627-636 pickles the reference ReplayBuffer's per-sample lists and :659-668 assigns them back one after the other:
+    the same sequence of assignments on a fresh drop-in buffer must reproduce every get_batched_* output (incl. after FIFO eviction),
+    and the restored buffer keeps working (further trajectories append and evict as before)."""
+    from muzero_breakout_b200.replay_buffer import ReplayBuffer
+    g, p, trajs = load_replay_golden(golden_dir)
+    src = ReplayBuffer(p["hist"], p["K"], p["cap"], p["discount"], p["n_sum"])
+    for tr in trajs[:-2]:                                        # past the capacity: the oldest samples are already evicted
+        src.save_observation_trajectory(_ref_trajectory(tr))
+    n = src.length
+    assert n == p["cap"]
+    ckpt = {k: getattr(src, k) for k in ("past_actions_buffer", "future_actions_buffer", "state_buffer", "reward_buffer", "visit_counts_buffer",
+                                         "value_buffer", "reward_sums", "length", "max_length", "bootstrapped_values")}
+    assert isinstance(ckpt["state_buffer"], list) and tuple(ckpt["state_buffer"][0].shape) == (p["hist"], 1, 16, 20)
+    dst = ReplayBuffer(p["hist"], p["K"], p["cap"], p["discount"], p["n_sum"])
+    for k in ("past_actions_buffer", "future_actions_buffer", "state_buffer", "reward_buffer", "visit_counts_buffer", "value_buffer",
+              "reward_sums", "length", "max_length", "bootstrapped_values"):           # the order of train_torch.py:659-668
+        setattr(dst, k, ckpt[k])
+    assert dst.length == n
+    idx = torch.arange(n)
+    for f, getter in GETTERS.items():
+        assert torch.equal(getattr(dst, getter)(idx), getattr(src, getter)(idx)), f
+    assert dst.get_reward_sums() == src.get_reward_sums() and dst.reward_sums == src.reward_sums
+    assert all(torch.equal(a, b) for a, b in zip(dst.value_buffer, src.value_buffer))
+    for tr in trajs[-2:]:                                        # both keep going identically
+        src.save_observation_trajectory(_ref_trajectory(tr)); dst.save_observation_trajectory(_ref_trajectory(tr))
+    assert dst.length == src.length == p["cap"]
+    for f, getter in GETTERS.items():
+        assert torch.equal(getattr(dst, getter)(idx), getattr(src, getter)(idx)), f
+    # samples in an arbitrary order (nothing continues anything: one stored trajectory per sample, a larger entry ring)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5))[:40]
+    shuf = ReplayBuffer(p["hist"], p["K"], p["cap"], p["discount"], p["n_sum"])
+    for k in ("past_actions_buffer", "future_actions_buffer", "state_buffer", "reward_buffer", "visit_counts_buffer", "value_buffer", "bootstrapped_values"):
+        setattr(shuf, k, [getattr(src, k)[i] for i in perm.tolist()])
+    shuf.reward_sums = [src.reward_sums[i] for i in perm.tolist()]
+    shuf.length = 40
+    for f, getter in GETTERS.items():
+        assert torch.equal(getattr(shuf, getter)(torch.arange(40)), getattr(src, getter)(perm)), f

@@ -122,6 +122,22 @@ def test_adam_class_on_a_module_vs_torch_optimizer():
         assert all(p._version > v for p, v in zip(net.parameters(), v0)), "step() must bump the version counters (MCTSSearchVec re-pack check)"
     for (n, a), b in zip(net.named_parameters(), ref.parameters()):
         assert float((a.detach().cpu() - b.detach()).abs().max()) <= 2e-5 * float(b.detach().abs().max()), n
+    # checkpoint interchange (train_torch.py:624,652): torch.optim.Adam's state_dict layout both ways
+    sd, sd_ref = opt.state_dict(), opt_ref.state_dict()
+    assert sd.keys() == sd_ref.keys() and sd["param_groups"][0]["params"] == sd_ref["param_groups"][0]["params"]
+    for i, st in sd_ref["state"].items():
+        assert float(sd["state"][i]["step"]) == float(st["step"]) == 6 and sd["state"][i]["exp_avg"].shape == st["exp_avg"].shape
+        assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), st["exp_avg"], rtol=1e-2, atol=1e-8)      # GPU (TF32 conv) vs CPU gradients
+    fresh_ref = torch.optim.Adam(make().parameters(), lr=1.0)
+    fresh_ref.load_state_dict({"state": {i: {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in st.items()} for i, st in sd["state"].items()},
+                               "param_groups": sd["param_groups"]})        # torch accepts what we emit
+    assert fresh_ref.param_groups[0]["lr"] == 2e-4
+    net2 = make().cuda()
+    opt2 = Adam(net2, lr=1.0, weight_decay=0.0)
+    opt2.load_state_dict(sd_ref)                                            # and we accept what torch emits
+    assert opt2.step_count == 6 and opt2.lr == 2e-4 and opt2.weight_decay == 1e-4
+    for i, (p_, o) in enumerate(zip(opt2.params, opt2._offsets)):
+        assert torch.equal(opt2.exp_avg_sq[o:o + p_.numel()].view(p_.shape).cpu(), sd_ref["state"][i]["exp_avg_sq"])
 
 
 def test_adam_full_parameter_count_vs_oracle():
