@@ -44,6 +44,7 @@ constexpr int NSLICES = CH / NS;         // 16
 constexpr int KSTEPS = 9 * CH / 16;      // 144 k16 steps per item
 constexpr int WARPS = 8, THREADS = WARPS * 32;
 constexpr int STEPS_PER_WARP = KSTEPS / WARPS;   // 18
+constexpr int KEEP_WAVES = 4;            // items per CTA and layer whose residual stream stays in registers (4 waves = mz_lat_max_samples())
 constexpr int A_PITCH = CH * 2 + 16;     // 528 B: consecutive rows start 16 bytes apart modulo 128 -> conflict-free ldmatrix without an XOR
 constexpr int A_BYTES = 64 * A_PITCH;    // 33 KB: [64 rows][528 B]
 constexpr int W_UNITS = 9 * (CH / 64);   // 36 (tap, 64-channel chunk) units of [16 rows][128 B]
@@ -103,6 +104,7 @@ struct LatParams {
     int split_last;                      // the last layer is two 128-channel convolutions of the same input (records nlayers-1 and nlayers): slices 0-7 / 8-15
     int trace;                           // profiling (env MZB_LAT_TRACE=1): CTA 0's thread 0 records phase timestamps per layer
     int w_early;                         // 1 (default): the next item's weights are requested before this item's math, 0: right after it
+    int reg_stream;                      // 1 (default): launches with one item per CTA and layer keep the residual stream in registers (env MZB_LAT_REGSTREAM)
 };
 
 __device__ unsigned long long g_lat_trace[8 * 64];
@@ -250,6 +252,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     const int ntiles = p.rtiles * NSLICES;
     const int tpc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA per layer (>= 1)
     const int total = p.nlayers * tpc;
+    // one item per layer: the residual stream stays in this thread's registers between the layers that produce and consume it
+    const bool reg_stream = tpc <= KEEP_WAVES && p.reg_stream;
+    float2 kept_all[KEEP_WAVES][2];
+#pragma unroll
+    for (int w = 0; w < KEEP_WAVES; ++w) kept_all[w][0] = kept_all[w][1] = make_float2(0.f, 0.f);
     if (sW_u & 1023u) __trap();
 
     for (int i = tid; i < (p.nlayers + p.split_last) * 4; i += THREADS)
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
     if (total > 0) weights_async(0);
 
     for (int seq = 0; seq < total; ++seq) {
-        const int layer = seq / tpc, tile = (int)blockIdx.x + (seq - layer * tpc) * (int)gridDim.x;
+        const int layer = seq / tpc, wave = seq - layer * tpc, tile = (int)blockIdx.x + wave * (int)gridDim.x;
         const int rt = tile / NSLICES;
         int ns = tile - rt * NSLICES, rec = layer;                // ns: 16-channel slice of this item's convolution
         if (p.split_last && layer == p.nlayers - 1 && ns >= NSLICES / 2) { rec = layer + 1; ns -= NSLICES / 2; }
@@ -341,9 +348,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             if (r < nrows) {
                 const int s = s0 + r / HW, pix = r % HW;
                 if (L->act_bias) ab[h] = __ldg(reinterpret_cast<const float2 *>(L->act_bias + ((size_t)p.act_idx[s] * HW + pix) * cout + co));
-                if (L->k1 & 8) rs[h] = __ldcg(reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(L->res) + ((size_t)s0 * HW + r) * cout + co));
+                if (reg_stream && (L->k1 & 32)) {                // this thread's own fp32 output of two layers ago (same item = same wave)
+#pragma unroll
+                    for (int w = 0; w < KEEP_WAVES; ++w) if (w == wave) rs[h] = kept_all[w][h];
+                }
+                else if (L->k1 & 8) rs[h] = __ldcg(reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(L->res) + ((size_t)s0 * HW + r) * cout + co));
                 else if (L->res) rs[h] = unpack2(__ldcg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint16_t *>(L->res) + ((size_t)s0 * HW + r) * cout + co)), F16);
-                if (L->k1 & 2) {                                  // 16-bit residual stream + e4m3 correction (tc_common.cuh: split2 / lo2)
+                if ((L->k1 & 2) && !(reg_stream && (L->k1 & 32))) {   // 16-bit residual stream + e4m3 correction (tc_common.cuh: split2 / lo2)
                     const float2 l = lo2(__ldcg(reinterpret_cast<const uint16_t *>(L->lo + ((size_t)s0 * HW + r) * cout + co)), F16);
                     rs[h].x += l.x; rs[h].y += l.y;
                 }
@@ -480,7 +491,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
                 x1 = activate(x1, L->act);
                 const size_t o = ((size_t)s0 * HW + r) * cout + co;
                 uint32_t packed;
-                if (L->k1 & 4) {
+                if (reg_stream && (L->k1 & 16)) {
+#pragma unroll
+                    for (int w = 0; w < KEEP_WAVES; ++w) if (w == wave) kept_all[w][h] = make_float2(x0, x1);
+                }
+                if ((L->k1 & 4) && !(reg_stream && (L->k1 & 16))) {
                     uint16_t l;
                     packed = split2(x0, x1, F16, l);
                     *reinterpret_cast<uint16_t *>(L->lo + o) = l;
@@ -624,6 +639,17 @@ int mz_lat_build(const mz_op *ops, int n_ops, void *blob_host, size_t blob_bytes
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_lat_build: cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return -2; }
     }
+    // Residual stream in registers: a layer whose residual is the output of the layer two before it (conv2 of a ResidualBlock adding the
+    // previous block's output) finds that output -- in fp32, before any 16-bit rounding -- in the registers of the very thread that
+    // computed it, because the item -> CTA -> thread mapping is the same in every 256 -> 256 layer.  Bit 4: keep the outputs; bit 5: the
+    // residual is the kept value (no 16-bit residual load, no correction plane traffic).  Used by launches with one item per CTA and layer.
+    for (int i = 2; i < n_ops; ++i) {
+        const bool half = split && i >= n_ops - 2;
+        if (!half && ops[i].res && !ops[i].res_f32 && ops[i].res == ops[i - 2].dst && ops[i].cout == CH && ops[i - 2].cout == CH) {
+            L[i].o.k1 = (short)(L[i].o.k1 | 32);
+            L[i - 2].o.k1 = (short)(L[i - 2].o.k1 | 16);
+        }
+    }
     return (split ? 1 : 0) | (ntails << 1);       // flags for mz_lat_run: bit 0 = the last two convolution records are the halves of a split layer, bits 1-2 = tail ops
 }
 
@@ -655,6 +681,7 @@ int mz_lat_run(const void *blob_dev, int n_ops, int flags, int nsamples, const i
     p.act_idx = act_idx;
     { static int tr = -1; if (tr < 0) { const char *e = getenv("MZB_LAT_TRACE"); tr = e ? atoi(e) : 0; } p.trace = tr; }
     { static int we = -1; if (we < 0) { const char *e = getenv("MZB_LAT_W_EARLY"); we = e ? atoi(e) : 1; } p.w_early = we; }
+    { static int rg = -1; if (rg < 0) { const char *e = getenv("MZB_LAT_REGSTREAM"); rg = e ? atoi(e) : 1; } p.reg_stream = rg; }
     static bool attr_set[64] = {};
     if (mzb::first_use_on_device(attr_set)) {
         MZB_CUDA(cudaFuncSetAttribute(conv_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM));

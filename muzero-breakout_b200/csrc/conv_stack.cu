@@ -34,6 +34,8 @@
 namespace {
 
 constexpr int MAX_BUFS = MZ_STACK_MAX_BUFS;
+#define MZ_STACK_MAX_PAIRS 74
+#define MZ_STACK_MAX_LPT_ITEMS 448
 constexpr int HW = 20, LAT_W = 5, LAT_H = 4, CH = 256;
 
 struct alignas(64) StackLayer {          // device-resident descriptor of one convolution of the trunk
@@ -72,6 +74,11 @@ struct StackParams {
     int nslices, slice_groups;           // the samples are walked as nslices slices of slice_groups groups (all layers of a slice before the
                                          // next slice, inside the one launch: the live activations of a slice stay in the L2)
     long long elem_off;                  // element offset of this launch's first sample in [n][20][256] side tensors (dst_f32, correction planes)
+    // static balanced schedule (single-slice launches): the items of a layer cost 4, 6 or 9 tap-units; lpt_items[lpt_off[c] .. lpt_off[c + 1])
+    // are the items CTA pair c runs in every layer (longest-processing-time-first assignment, ascending item order within a pair)
+    int use_lpt;
+    uint16_t lpt_off[MZ_STACK_MAX_PAIRS + 2];
+    uint16_t lpt_items[MZ_STACK_MAX_LPT_ITEMS];
 };
 
 __device__ unsigned long long g_stack_trace[6 * 64];
@@ -152,6 +159,14 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
     if (smem_base & 1023u) __trap();
     // first tile of this CTA pair in `layer`; the pair then strides by nclusters.  All warp roles walk the same list.
     auto first_tile = [&](int vl) { return (cluster_id + vl * p.rot) % nclusters; };
+    // this pair's items of virtual layer vl: count and k-th item (rotated round-robin, or the static balanced schedule)
+    const int lpt0 = p.use_lpt ? p.lpt_off[cluster_id] : 0, lptn = p.use_lpt ? p.lpt_off[cluster_id + 1] - lpt0 : 0;
+    auto item_count = [&](int vl, int ntiles) {
+        if (p.use_lpt) return lptn;
+        const int f = first_tile(vl);
+        return f < ntiles ? (ntiles - f + nclusters - 1) / nclusters : 0;
+    };
+    auto item_at = [&](int vl, int k) { return p.use_lpt ? (int)p.lpt_items[lpt0 + k] : first_tile(vl) + k * nclusters; };
     const int nvl = p.nslices * p.nlayers;
 
     if (threadIdx.x == 0) *s_ready = 0;
@@ -189,13 +204,15 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const StackLayer *L = p.layers + layer;
                 const int src = L->src, k1 = L->k1;
                 const uint32_t ltaps = L->taps;
-                const int first = first_tile(vl);
-                for (int item = first; item < V.ntiles; item += nclusters) {
+                const int nit = item_count(vl, V.ntiles);
+                for (int ik = 0; ik < nit; ++ik) {
+                    const int item = item_at(vl, ik);
+                    const bool item0 = ik == 0;
                     const int tile = item / NSPLIT, nh = item - tile * NSPLIT;
                     const int pix = tile / V.spairs, g = V.g0 + 2 * (tile - pix * V.spairs) + rank;
                     const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
                     const uint32_t taps = tap_mask(y0, x0) & ltaps;
-                    if (item == first && lane == 0) STRACE(0, layer);
+                    if (item0 && lane == 0) STRACE(0, layer);
                     ++seq;
                     if (layer > 0) {
                         // the scout warp has seen the previous layer's output of this sample group complete at the in-bounds
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    if (item == first && lane == 0) STRACE(1, layer);
+                    if (item0 && lane == 0) STRACE(1, layer);
                     bool first_ks = true;
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!((taps >> tap) & 1u)) continue;
@@ -247,8 +264,10 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const VLayer V = vlayer(p, vl);
                 const int layer = V.layer;
                 const uint32_t ltaps = p.layers[layer].taps;
-                const int first = first_tile(vl);
-                for (int item = first; item < V.ntiles; item += nclusters, ++it) {
+                const int nit = item_count(vl, V.ntiles);
+                for (int ik = 0; ik < nit; ++ik, ++it) {
+                    const int item = item_at(vl, ik);
+                    const bool item0 = ik == 0;
                     const int buf = it & 1;
                     const int tile = item / NSPLIT;
                     const int pix = tile / V.spairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
@@ -262,7 +281,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     for (int ks = 0; ks < ksteps; ++ks) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        if (ks == 0 && item == first && lane == 0) STRACE(2, layer);
+                        if (ks == 0 && item0 && lane == 0) STRACE(2, layer);
                         if (tr4 && ks == 0) g_stack_trace[it * 4 + 2] = gtime_ns();
                         const uint32_t sa = smem_base + A_OFF + stage * A_SLOT, sb = smem_base + B_OFF + stage * B_SLOT;
                         const uint64_t adesc = smem_desc(sa), bdesc = smem_desc(sb);
@@ -276,7 +295,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
                     if (elect_one()) umma_commit_pair(bar_tfull + 8 * buf);
-                    if (item == first && lane == 0) STRACE(3, layer);
+                    if (item0 && lane == 0) STRACE(3, layer);
                     if (tr4) g_stack_trace[it * 4 + 3] = (gtime_ns() - g_stack_trace[it * 4 + 2]) | ((unsigned long long)ksteps << 40);   // issue time | k-steps
                 }
             }
@@ -308,8 +327,10 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
             uint8_t *dst_lo = L->dst_lo ? L->dst_lo + p.elem_off : nullptr;
             const float *res_f32 = L->res_f32 ? L->res_f32 + p.elem_off : nullptr;
             const int act = L->act;
-            const int first = first_tile(vl);
-            for (int item = first; item < V.ntiles; item += nclusters, ++it) {
+            const int nit = item_count(vl, V.ntiles);
+            for (int ik = 0; ik < nit; ++ik, ++it) {
+                const int item = item_at(vl, ik);
+                const bool item0 = ik == 0;
                 const int buf = it & 1;
                 const int tile = item / NSPLIT, nh = item - tile * NSPLIT;
                 const int col0 = nh * NT + half * WCOLS;                     // this warp's WCOLS output channels
@@ -349,7 +370,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 uint32_t acc[2][32];
                 mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
                 tc_fence_after();
-                if (warp == 2 && lane == 0 && item == first) STRACE(4, layer);
+                if (warp == 2 && lane == 0 && item0) STRACE(4, layer);
                 if (res >= 0 && live) {
                     mbar_wait(bar_res, res_phase);
                     res_phase ^= 1;
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     }
                 }
                 __syncwarp();                                                // nobody overwrites the staging tile before the store has read it
-                if (warp == 2 && lane == 0 && item == first) STRACE(5, layer);
+                if (warp == 2 && lane == 0 && item0) STRACE(5, layer);
             }
         }
     } else if (lane == 0) {
@@ -479,8 +500,9 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
             const VLayer V = vlayer(p, vl);
             const int layer = V.layer;
             const uint32_t ltaps = p.layers[layer].taps;
-            const int first = first_tile(vl);
-            for (int item = first; item < V.ntiles; item += nclusters) {
+            const int nit = item_count(vl, V.ntiles);
+            for (int ik = 0; ik < nit; ++ik) {
+                const int item = item_at(vl, ik);
                 const int tile = item / NSPLIT;
                 const int pix = tile / V.spairs, gl = 2 * (tile - pix * V.spairs) + rank, g = V.g0 + gl;
                 const int y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
@@ -691,6 +713,32 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     if (max_clusters < 1) { mzb::set_error("mz_stack_run: no CTA pair of the fused trunk fits on this device"); return -2; }
     int clusters = max_tiles < mzb::kNumSMs / 2 ? max_tiles : mzb::kNumSMs / 2;
     if (clusters > max_clusters) clusters = max_clusters;       // fewer SMs than a full B200 (MIG / MPS limits): still all co-resident
+    // Static balanced schedule for single-slice launches whose layers have only a few items per CTA pair (the rotation of a round-robin
+    // map evens the 4 / 6 / 9-tap item costs out over SEVERAL layers, which needs dependency slack that small batches do not have):
+    // longest-processing-time-first assignment of a layer's items to the pairs, the same in every layer.
+    static int lpt_max = -1;
+    if (lpt_max < 0) { const char *e = getenv("MZB_STACK_LPT_MAX"); lpt_max = e ? atoi(e) : 1792; }
+    if (p.nslices == 1 && nsamples <= lpt_max && max_tiles <= MZ_STACK_MAX_LPT_ITEMS && clusters <= MZ_STACK_MAX_PAIRS) {
+        const int spairs = (p.groups + 1) / 2, nitems = HW * spairs * p.nsplit;
+        int load[MZ_STACK_MAX_PAIRS] = {}, owner[MZ_STACK_MAX_LPT_ITEMS], count[MZ_STACK_MAX_PAIRS] = {};
+        for (int cost = 9; cost >= 1; --cost)                     // items in descending cost (stable in item order)
+            for (int item = 0; item < nitems; ++item) {
+                const int pix = (item / p.nsplit) / spairs, y0 = pix / LAT_W, x0 = pix - y0 * LAT_W;
+                int taps = 0;
+                for (int t = 0; t < 9; ++t) taps += (y0 + t / 3 - 1 >= 0 && y0 + t / 3 - 1 < LAT_H && x0 + t % 3 - 1 >= 0 && x0 + t % 3 - 1 < LAT_W);
+                if (taps != cost) continue;
+                int best = 0;
+                for (int c = 1; c < clusters; ++c) if (load[c] < load[best] || (load[c] == load[best] && count[c] < count[best])) best = c;
+                owner[item] = best; load[best] += cost; count[best] += 1;
+            }
+        int off = 0;
+        for (int c = 0; c < clusters; ++c) {
+            p.lpt_off[c] = (uint16_t)off;
+            for (int item = 0; item < nitems; ++item) if (owner[item] == c) p.lpt_items[off++] = (uint16_t)item;     // ascending item (= pixel) order
+        }
+        p.lpt_off[clusters] = (uint16_t)off;
+        p.use_lpt = 1;
+    }
     cfg.gridDim = dim3(2 * clusters);
     cfg.numAttrs = coop ? 2 : 1;
     if (p.nsplit == 2) {

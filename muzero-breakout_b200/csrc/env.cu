@@ -424,6 +424,26 @@ int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, void 
     uint8_t *io = reinterpret_cast<uint8_t *>(io_dev), *hin = reinterpret_cast<uint8_t *>(host_in);
     const uint8_t *hout = reinterpret_cast<const uint8_t *>(host_out);
     cudaStream_t st = (cudaStream_t)stream;
+    static int zc_max = -1;
+    if (zc_max < 0) { const char *e = getenv("MZB_ENV_ZEROCOPY_MAX"); zc_max = e ? atoi(e) : 2048; }
+    if (B <= zc_max) {
+        // Small batches (config.yaml's 24 environments): no copy engine at all.  Pinned host memory is mapped into the device's address
+        // space (unified addressing), so the step kernel reads the actions / done flags from the pinned output block and writes frames,
+        // rewards, valid-action masks, done flags and the status word straight into it over PCIe: one launch + one synchronisation.
+        uint8_t *ho = reinterpret_cast<uint8_t *>(host_out), *dv = nullptr;
+        MZB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dv), ho, 0));
+        memcpy(ho + off[4], done_host, (size_t)B);
+        memcpy(ho + off[5], action_host, (size_t)B * 8);
+        memset(ho + off[6], 0, 16);
+        int rc = bk_env_step(B, hdr, bricks, reinterpret_cast<const int64_t *>(dv + off[5]), dv + off[4],
+                             want_state ? reinterpret_cast<float *>(dv + off[0]) : nullptr, reinterpret_cast<float *>(dv + off[2]),
+                             reinterpret_cast<float *>(dv + off[3]), want_gray ? reinterpret_cast<float *>(dv + off[1]) : nullptr, rewards4,
+                             reinterpret_cast<int32_t *>(dv + off[6]), stream);
+        if (rc) return rc;
+        MZB_CUDA(cudaStreamSynchronize(st));
+        memcpy(done_host, ho + off[4], (size_t)B);
+        return *reinterpret_cast<const int32_t *>(ho + off[6]) & 0x7fffffff;
+    }
     memcpy(hin, done_host, (size_t)B);                                           // the caller's tensors -> the pinned staging block
     memcpy(hin + (off[5] - off[4]), action_host, (size_t)B * 8);
     memset(hin + (off[6] - off[4]), 0, 16);
