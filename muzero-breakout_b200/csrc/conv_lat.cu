@@ -44,7 +44,7 @@ constexpr int NSLICES = CH / NS;         // 16
 constexpr int KSTEPS = 9 * CH / 16;      // 144 k16 steps per item
 constexpr int WARPS = 8, THREADS = WARPS * 32;
 constexpr int STEPS_PER_WARP = KSTEPS / WARPS;   // 18
-constexpr int KEEP_WAVES = 4;            // items per CTA and layer whose residual stream stays in registers (4 waves = mz_lat_max_samples())
+constexpr int KEEP_WAVES = 4;            // items per CTA and layer whose residual stream stays in registers (covers mz_lat_max_samples() = 3 waves; MZB_LAT_MAX_SAMPLES may raise it to 4)
 constexpr int A_PITCH = CH * 2 + 16;     // 528 B: consecutive rows start 16 bytes apart modulo 128 -> conflict-free ldmatrix without an XOR
 constexpr int A_BYTES = 64 * A_PITCH;    // 33 KB: [64 rows][528 B]
 constexpr int W_UNITS = 9 * (CH / 64);   // 36 (tap, 64-channel chunk) units of [16 rows][128 B]
@@ -568,9 +568,10 @@ size_t mz_lat_layer_bytes(void) { return sizeof(LatLayer); }
 
 int mz_lat_max_layers(void) { return MAX_LAYERS; }
 
-// Measured crossover (profiles/README.md, ms per simulation step, latency mode vs tcgen05 trunk): 27 samples (one wave of 144 items)
-// 0.32 vs 1.20, 81 (three waves) 0.88 vs 1.23, 108 (four) 1.16 vs 1.26, 135 (five) 1.46 vs 1.27 -> up to four waves
-int mz_lat_max_samples(void) { return 4 * RS * (mzb::kNumSMs / NSLICES); }    // 108
+// Measured crossover (profiles/README.md, round 2, ms per simulation step, latency mode vs the tcgen05 trunk with output-channel-split
+// items): 27 samples (one wave of 144 items) 0.29 vs 0.79, 54 (two waves) 0.55 vs 0.79, 81 (three) 0.81 vs 0.80, 108 (four) 1.07 vs 0.83
+// -> up to three waves
+int mz_lat_max_samples(void) { return 3 * RS * (mzb::kNumSMs / NSLICES); }    // 81
 
 int mz_lat_trace(unsigned long long *host_out)   // profiling aid: copies the 8 x 64 trace words
 {

@@ -108,7 +108,7 @@ def test_latency_trunk_host_queries():
     from muzero_breakout_b200.src.networks import MzOp, lat_max_samples
     L = mzb.lib()
     assert L.mz_lat_layer_bytes() == 192 and L.mz_lat_max_layers() == 32
-    assert L.mz_lat_max_samples() == 108 and lat_max_samples() == 108          # four waves of 27 samples
+    assert L.mz_lat_max_samples() == 81 and lat_max_samples() == 81            # three waves of 27 samples
     for n, rtiles in ((1, 1), (24, 8), (25, 9), (108, 36)):
         assert L.mz_lat_scratch_bytes(n) == 2 * rtiles * 60 * 128 * 8 + 4 * (2 + 2 * rtiles)
     ops = (MzOp * 1)()
