@@ -441,6 +441,11 @@ def bench_mcts(args, rank, local, world):
             out["gpu_reference"] = gpu_reference(args, sd, dev, B, step_ms)
         except Exception as e:                # noqa: BLE001
             out["gpu_reference"] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0 and world == 1 and not args.no_aux:
+        try:                                  # one training-loop iteration, drop-in learner vs the reference modules on the same GPU
+            out["train_step"] = bench_train_step(dev)
+        except Exception as e:                # noqa: BLE001
+            out["train_step"] = {"error": f"{type(e).__name__}: {e}"}
     if not args.no_acting:
         out["acting"] = bench_acting(args, m, dev, rank, world)
     if not args.no_aux:
@@ -643,6 +648,99 @@ def bench_train_ends(dev, rank, world, cpu=True):
         t2 = time.perf_counter()
         out["cpu_baseline"] = {"adam_parameters_per_s": ns / (t1 - t0), "loss_ms": (t2 - t1) * 1e3, "cores": 1, "kind": "port",
                                "sample": f"oracle/train_oracle.py (numpy restatement): one Adam update of {ns} parameters, one loss_fn of {B * K} rows"}
+    return out
+
+
+def bench_train_step(dev, minibatch=512, K=5):
+    """One iteration of the reference's training loop body (train_torch.py:385-417: zero_grad, _k_step_rollout :487-528 = representation
+    network + K x (prediction, dynamics), loss_fn :33-66, loss.backward(), optimizer.step()) at config.yaml's minibatch 512 and K = 5:
+    the learner-side drop-in (muzero-breakout_b200/src/agent.py: ResidualBlock trunks forward + backward on the tcgen05 / BatchNorm kernels,
+    mz_loss, mz_adam; stems, head layers, representation network on torch ops) against the unmodified reference modules + its own loss_fn +
+    torch.optim.Adam under torch + cuDNN on the same GPU (TF32 and autocast bf16)."""
+    from muzero_breakout_b200.src.agent import MuZeroAgent
+    from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG
+    from muzero_breakout_b200.train import loss_fn as lib_loss
+    import muzero_breakout_b200 as mzb
+    cfg = dict(DEFAULT_MODEL_CFG, learning_rate=2e-4, device="cuda")
+    g = torch.Generator(device=dev).manual_seed(11)
+    frames = torch.rand((minibatch, 64, 16, 20), device=dev, generator=g)
+    actions = torch.randint(0, 3, (minibatch, K), device=dev, generator=g)
+    obs_r = torch.randint(-1, 2, (minibatch, K), device=dev, generator=g).float()
+    val_t = (torch.rand((minibatch, K), device=dev, generator=g) - 0.5) * 8
+    visits = torch.randint(1, 30, (minibatch, K, 3), device=dev, generator=g).float()
+    supports = torch.linspace(-5, 5, 11, device=dev)
+
+    def rollout(agent):
+        h = agent.create_hidden_state_root(frames)
+        pol, val, rew = [], [], []
+        for k in range(K):
+            p_, v_ = agent.evaluate_state(h)
+            planes = torch.nn.functional.one_hot(actions[:, k], 3).float().view(-1, 3, 1, 1).expand(-1, -1, 4, 5)
+            h, r_ = agent.hidden_state_transition(h, planes)
+            pol.append(p_); val.append(v_); rew.append(r_)
+        return torch.stack(rew, 1), torch.stack(val, 1), torch.stack(pol, 1)
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(reps):
+            fn()
+        b_.record(); torch.cuda.synchronize(dev)
+        return a_.elapsed_time(b_) / reps
+
+    torch.manual_seed(0)
+    agent = MuZeroAgent(cfg)
+    agent.train_mode()
+
+    def lib_step():
+        agent.optimizer.zero_grad()
+        pr, pv, pp = rollout(agent)
+        loss = lib_loss(obs_r, pr, val_t, pv, visits, pp, supports, K)[0]
+        loss.backward()
+        agent.optimizer.step()
+
+    n0 = mzb.launch_count()
+    lib_ms = timed(lib_step)
+    out = {"minibatch": minibatch, "K": K, "library_ms": lib_ms, "library_kernel_launches_per_step": (mzb.launch_count() - n0) // 5,
+           "what": "zero_grad + _k_step_rollout + loss_fn + loss.backward() + optimizer.step() (train_torch.py:385-417); library = drop-in MuZeroAgent "
+                   "(ResidualBlock trunks fwd + bwd on tcgen05 / BatchNorm kernels, bf16 operands; mz_loss; mz_adam; other layers on torch ops)"}
+    del agent
+    torch.cuda.empty_cache()
+    R = _reference()
+    if R is None:
+        out["reference"] = "unavailable: no reference checkout on this box"
+        return out
+    ref, _, rnets, rutils, _ = R
+    import importlib
+    rtrain = importlib.import_module("train_torch")            # the reference's loss_fn (import runs its set_seed(42) only)
+    rcfg = ref.load_cfg()["model"]
+    ragent = rnets.MuZeroAgent(rcfg)
+    ragent.train_mode()
+    st = rutils.ScalarTransforms(rcfg)
+
+    def ref_step(autocast):
+        ragent.optimizer.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            pr, pv, pp = rollout(ragent)
+        loss = rtrain.loss_fn(observed_reward=obs_r, predicted_reward=pr.float(), bootstrapped_reward=val_t, predicted_value=pv.float(), visit_counts=visits,
+                              predicted_policy=pp.float(), target_transformation=st.supports_representation, K=K)[0]
+        loss.backward()
+        ragent.optimizer.step()
+
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    det = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+        out["reference_tf32_ms"] = timed(lambda: ref_step(False))
+        out["reference_autocast_bf16_ms"] = timed(lambda: ref_step(True))
+        out["reference_cudnn_deterministic"] = bool(torch.backends.cudnn.deterministic)     # train_torch.py:22-23 sets it at import
+        out["speedup_vs_best_reference_mode"] = min(out["reference_tf32_ms"], out["reference_autocast_bf16_ms"]) / lib_ms
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det
     return out
 
 

@@ -20,6 +20,8 @@ The rest of the backward pass (weight gradients, training-mode BatchNorm) still 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -307,18 +309,42 @@ class ResidualBlockTrain:
         prog.run()
         return z
 
-    def forward(self, x16: torch.Tensor):
-        """x16: (n, H, W, 256) bf16 channels-last.  Returns (y bf16, y float32)."""
+    def refresh(self, conv1_w, conv1_b, bn1_w, bn1_b, conv2_w, conv2_b, bn2_w, bn2_b, running=None):
+        """Re-pack from the live parameters of a module when any of them changed (version counters: optimizer steps and load_state_dict bump
+        them); `running` = ((mean1, var1), (mean2, var2)) aliases the module's BatchNorm buffers so the kernels update them in place."""
+        params = (conv1_w, conv1_b, bn1_w, bn1_b, conv2_w, conv2_b, bn2_w, bn2_b)
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != getattr(self, "_key", None):
+            dev = self.ones.device
+            f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self.w = [conv1_w.detach(), conv2_w.detach()]
+            self.wt = [self._pack(w, dev) for w in self.w]
+            self.dgrad = [ConvDgrad(w, dev) for w in self.w]
+            self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
+            self._key = key
+        if running is not None:
+            self.running_mean, self.running_var = [running[0][0], running[1][0]], [running[0][1], running[1][1]]
+
+    def forward_fn(self, x16: torch.Tensor):
+        """Functional forward: returns (y bf16, y float32, saved) -- `saved` goes back into backward_fn, so one block object can be called
+        several times per training step (the K unroll steps share their weights, train_torch.py:507-525)."""
         z1 = self._conv(x16, 0)
         h16, _, m1, s1 = bn_train_forward(z1, self.gamma[0], self.beta[0], None, "relu", self.eps, self.momentum, self.running_mean[0], self.running_var[0])
         z2 = self._conv(h16, 1)
         y16, y32, m2, s2 = bn_train_forward(z2, self.gamma[1], self.beta[1], x16, "relu", self.eps, self.momentum, self.running_mean[1], self.running_var[1])
-        self._saved = (x16, z1, h16, z2, m1, s1, m2, s2)
+        return y16, y32, (x16, z1, h16, z2, m1, s1, m2, s2)
+
+    def forward(self, x16: torch.Tensor):
+        """x16: (n, H, W, 256) bf16 channels-last.  Returns (y bf16, y float32)."""
+        y16, y32, self._saved = self.forward_fn(x16)
         return y16, y32
 
     def backward(self, dy: torch.Tensor):
         """dy: float32 gradient of the block output.  Returns (dx float32, {parameter name: gradient})."""
-        x16, z1, h16, z2, m1, s1, m2, s2 = self._saved
+        return self.backward_fn(dy, self._saved)
+
+    def backward_fn(self, dy: torch.Tensor, saved):
+        x16, z1, h16, z2, m1, s1, m2, s2 = saved
         dz2, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu")
         dw2 = conv_wgrad(dz2_16, h16, 3)
         dh = self.dgrad[1](dz2_16)
@@ -378,3 +404,106 @@ class TrunkTrain:
         self._in[0].copy_(x16); self._in[1].copy_(dy)
         self._graph.replay()
         return self._out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# autograd bridge: a run of train-mode ResidualBlocks of an nn.Module (the reference's own ResidualBlock modules, networks.py:19-35, or the
+# drop-in agent's) evaluated by this library's kernels inside loss.backward() (train_torch.py:515)
+_ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "0") == "1"
+
+
+class _TrunkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernels, *params):
+        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)          # channels-last 16-bit, the kernels' layout
+        saved, y32 = [], None
+        for blk in kernels:
+            x16, y32, sv = blk.forward_fn(x16)
+            saved.append(sv)
+        ctx.kernels, ctx.saved_blocks = kernels, saved
+        return y32.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = dy.permute(0, 2, 3, 1).contiguous().float()
+        flat = []
+        for blk, sv in zip(reversed(ctx.kernels), reversed(ctx.saved_blocks)):
+            g, grads = blk.backward_fn(g, sv)
+            zero = torch.zeros(256, device=g.device)           # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient)
+            flat.append((grads["conv1.weight"], zero, grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zero, grads["bn2.weight"], grads["bn2.bias"]))
+        ctx.saved_blocks = None
+        out = [t for blk in reversed(flat) for t in blk]
+        return (g.permute(0, 3, 1, 2).contiguous(), None, *out)
+
+
+def _block_params(m):
+    return (m.conv1.weight, m.conv1.bias, m.bn1.weight, m.bn1.bias, m.conv2.weight, m.conv2.bias, m.bn2.weight, m.bn2.bias)
+
+
+def trunk_supported(blocks, x) -> bool:
+    """Can this run of ResidualBlock modules go through the library kernels?  256 channels, 3x3 convolutions, ReLU, BatchNorm with running
+    statistics at the default eps, a float32 CUDA input, training mode with gradients enabled."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 256 and torch.is_grad_enabled()):
+        return False
+    if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # the 4x5 latent of the dynamics / prediction trunks; other maps: MZB_TRAIN_ANY_HW=1
+        return False
+    for m in blocks:
+        if not (m.training and all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2")) and m.conv1.weight.shape == (256, 256, 3, 3)
+                and m.conv2.weight.shape == (256, 256, 3, 3) and isinstance(getattr(m, "act", None), torch.nn.ReLU)
+                and m.bn1.track_running_stats and m.bn1.eps == 1e-5 and m.bn2.eps == 1e-5 and m.bn1.momentum == m.bn2.momentum and m.bn1.momentum is not None):
+            return False
+    return len(blocks) > 0
+
+
+def trunk_forward(blocks, x: torch.Tensor) -> torch.Tensor:
+    """`for b in blocks: x = b(x)` for train-mode 256-channel ResidualBlock modules, forward AND backward on this library's kernels (tcgen05
+    convolution / data gradient / weight gradient, training-mode BatchNorm kernels): a differentiable torch op whose gradients flow to the
+    modules' own Parameters; the modules' running statistics and num_batches_tracked are updated like nn.BatchNorm2d does."""
+    kernels = []
+    for m in blocks:
+        k = getattr(m, "_mzb_kernels", None)
+        if k is None:
+            k = ResidualBlockTrain(*_block_params(m), device=x.device, eps=m.bn1.eps, momentum=m.bn1.momentum)
+            object.__setattr__(m, "_mzb_kernels", k)          # not a submodule / buffer: invisible to state_dict()
+        k.refresh(*_block_params(m), running=((m.bn1.running_mean, m.bn1.running_var), (m.bn2.running_mean, m.bn2.running_var)))
+        kernels.append(k)
+    with torch.no_grad():
+        for m in blocks:
+            m.bn1.num_batches_tracked += 1
+            m.bn2.num_batches_tracked += 1
+    params = [p for m in blocks for p in _block_params(m)]
+    return _TrunkFn.apply(x, kernels, *params)
+
+
+def accelerate_agent(agent):
+    """Patch a MuZeroAgent-shaped module (the reference's own, networks.py:245-350) in place: the ResidualBlock runs of its dynamics and
+    prediction networks go through trunk_forward whenever trunk_supported says so (training mode on a CUDA device), and the optimizer
+    becomes this library's flat-buffer Adam with torch's hyper-parameters.  Everything else -- stems, head ConvBlocks, Linear heads,
+    `_scale_state`, the representation network -- stays on the module's own torch ops.  Returns the agent."""
+    import types
+
+    def dyn_forward(self, hidden_state):
+        x = self.conv_block(hidden_state)
+        if trunk_supported(self.res_blocks, x):
+            x = trunk_forward(self.res_blocks, x)
+        else:
+            for b in self.res_blocks:
+                x = b(x)
+        return x, self.reward_head(x)
+
+    def pred_forward(self, hidden_state):
+        x = hidden_state
+        if trunk_supported(self.res_blocks, x):
+            x = trunk_forward(self.res_blocks, x)
+        else:
+            for b in self.res_blocks:
+                x = b(x)
+        return self.policy_head(x), self.value_head(x)
+
+    agent.dyn_net.forward = types.MethodType(dyn_forward, agent.dyn_net)
+    agent.pred_net.forward = types.MethodType(pred_forward, agent.pred_net)
+    old = getattr(agent, "optimizer", None)
+    if isinstance(old, torch.optim.Adam) and next(agent.parameters()).is_cuda:
+        g = old.param_groups[0]
+        agent.optimizer = Adam(agent.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
+    return agent

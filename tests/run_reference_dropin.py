@@ -12,6 +12,8 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "dropin"), ROOT]
+if os.environ.get("MZB_DROPIN_AGENT") == "1":          # the learner-side drop-in too: src.networks -> muzero-breakout_b200/src/agent.py
+    sys.path.insert(0, os.path.join(ROOT, "dropin_train"))
 
 import torch  # noqa: E402
 
@@ -62,10 +64,13 @@ t_act = time.perf_counter() - t0
 acting = dict(seconds=t_act, moves=log["steps"], searches=log["searches"], replay_length=int(system.replay_buffer.length),
               trajectories=len(system.observation_trajectories),
               episode_lengths=[int(o.length) for o in system.observation_trajectories][:6])
+import muzero_breakout_b200 as _mzb  # noqa: E402
+n_launch0 = _mzb.launch_count()
 t0 = time.perf_counter()
 system._training_stage()
 t_train = time.perf_counter() - t0
-out = dict(modules=mods, acting=acting, training=dict(seconds=t_train, steps=int(system.training_step)),
+n_launch_train = _mzb.launch_count() - n_launch0
+out = dict(modules=mods, acting=acting, training=dict(seconds=t_train, steps=int(system.training_step), library_launches=int(n_launch_train)),
            search_calls=log["searches"], env_steps=log["steps"], search_batches=sorted(log["batches"]),
            visit_sum_ok=log["visit_sum_ok"], value_finite=log["value_finite"], visits_dtype=log["visits_dtype"], value_device=log["value_device"],
            done_aliased=log["done_aliased"], step_shapes_ok=log["step_shapes_ok"], env_batch_after=int(system.environment.batch),

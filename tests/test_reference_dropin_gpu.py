@@ -12,11 +12,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_unmodified_rlsystem_runs_on_the_dropins(tmp_path):
+@pytest.mark.parametrize("agent_dropin", [False, True], ids=["reference_agent", "dropin_agent"])
+def test_unmodified_rlsystem_runs_on_the_dropins(tmp_path, agent_dropin):
+    """agent_dropin: additionally `src.networks` -> the learner-side drop-in (dropin_train/): the reference's own _training_stage
+    (train_torch.py:369-452: _k_step_rollout, loss_fn, loss.backward(), optimizer.step()) then trains the ResidualBlock trunks on this
+    library's kernels and steps the flat-buffer Adam."""
     from baseline import ref
     if ref.ref_dir() is None:
         pytest.skip("no reference checkout on this box (baseline/_ref is made by __graft_entry__.build() in the build container)")
-    env = dict(os.environ, PYTHONPATH="")
+    env = dict(os.environ, PYTHONPATH="", MZB_DROPIN_AGENT="1" if agent_dropin else "0")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_dropin.py")], capture_output=True, text=True, cwd=tmp_path, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = next(ln for ln in r.stdout.splitlines() if ln.startswith("RESULT "))
@@ -24,7 +28,10 @@ def test_unmodified_rlsystem_runs_on_the_dropins(tmp_path):
     print(json.dumps(out, indent=1))
     m = out["modules"]
     assert m["mcts"] == "muzero_breakout_b200.src.mcts" and m["env"] == "muzero_breakout_b200.environment.parallel_breakout"
-    assert m["replay"] == "muzero_breakout_b200.replay_buffer" and m["agent"] == "src.networks"
+    assert m["replay"] == "muzero_breakout_b200.replay_buffer"
+    assert m["agent"] == ("muzero_breakout_b200.src.agent" if agent_dropin else "src.networks")
+    if agent_dropin:
+        assert out["training"]["library_launches"] >= 2 * 5 * 28 * 10, "the trunk kernels did not run inside _training_stage"
     assert os.path.realpath(ref.ref_dir()) in m["trainer"]                     # train_torch.py is the reference's file
     a = out["acting"]
     assert a["moves"] >= 1 and a["searches"] >= a["moves"] and a["trajectories"] == 24
