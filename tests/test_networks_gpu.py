@@ -158,7 +158,7 @@ def test_bf16_pipeline_tensor_cores_vs_cuda_cores_and_reference(agent, rec):
         assert e <= 1e-2, f"{k}: bf16 pipeline deviates {e:.2e} from the fp32 reference"
 
 
-@pytest.mark.parametrize("n", [5, 130, 1000, 1537, 3000, 9473])      # <= 1536 samples: output-channel-split items (two CTA pairs per pixel tile)
+@pytest.mark.parametrize("n", [5, 130, 1000, 1537, 3000, 4096, 9473])      # <= 1536 samples: output-channel-split items (two CTA pairs per pixel tile)
 def test_fused_trunk_launch_equals_layer_by_layer(agent, n):
     """csrc/conv_stack.cu (whole residual trunk in one persistent launch, layers ordered by per-group device
     counters) must give bit-identical results to one launch per convolution: same tiles, same arithmetic."""
