@@ -82,7 +82,9 @@ int bk_env_step(int B, uint64_t *hdr, uint32_t *bricks, const int64_t *action, u
  *                     [done | action | status] part of the layout; filled by the call); host_out: pinned, `total` bytes, receives
  *                     the whole packed buffer; action_host int64[B] / done_host uint8[B]: the caller's host arrays (done_host is
  *                     read AND written, like the reference's in-place done_mask).  Returns the status bits of this step
- *                     (MZB_ENV_ERR_*, >= 0) or a negative error code. */
+ *                     (MZB_ENV_ERR_*, >= 0) or a negative error code.  Up to MZB_ENV_ZEROCOPY_MAX environments (default 2048) the
+ *                     copy engine is not used at all: pinned host memory is mapped into the device's address space, the kernel reads
+ *                     actions / done flags from host_out's regions and writes every output straight into it (host_in is unused). */
 size_t bk_env_io_layout(int B, int want_state, int want_gray, size_t *off8);
 int bk_env_step_host(int B, uint64_t *hdr, uint32_t *bricks, void *io_dev, void *host_in, void *host_out, const int64_t *action_host,
                      uint8_t *done_host, int want_state, int want_gray, const float *rewards4, void *stream);
