@@ -713,6 +713,7 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     if (max_clusters < 1) { mzb::set_error("mz_stack_run: no CTA pair of the fused trunk fits on this device"); return -2; }
     int clusters = max_tiles < mzb::kNumSMs / 2 ? max_tiles : mzb::kNumSMs / 2;
     if (clusters > max_clusters) clusters = max_clusters;       // fewer SMs than a full B200 (MIG / MPS limits): still all co-resident
+    { static int cap = -1; if (cap < 0) { const char *e = getenv("MZB_STACK_MAX_PAIRS"); cap = e ? atoi(e) : 0; } if (cap > 0 && clusters > cap) clusters = cap; }   // experiments
     // Static balanced schedule for single-slice launches whose layers have only a few items per CTA pair (the rotation of a round-robin
     // map evens the 4 / 6 / 9-tap item costs out over SEVERAL layers, which needs dependency slack that small batches do not have):
     // longest-processing-time-first assignment of a layer's items to the pairs, the same in every layer.
