@@ -154,3 +154,26 @@ def test_repeated_graph_replays_are_deterministic(agent, B):
         assert torch.equal(va, v1) and torch.equal(na, n1), f"replay {rep} of input 1 differs"
         vb, nb = m.search(h2, None, 0, noise=noise, seed=11)
         assert torch.equal(vb, v2) and torch.equal(nb, n2), f"replay {rep} of input 2 differs"
+
+
+def test_full_size_search_properties(agent):
+    """BASELINE.json configs[2]'s size (4096 roots x 50 simulations, the default f16 mode) through size-independent properties:
+    visit counts sum to num_simulations in every tree, finite values, bit-identical repeat calls, and batch independence -- a tree's
+    result depends only on its own latent, noise and tie-break stream, so the first 2560 trees of the 4096-root search equal a 2560-root
+    search on the same inputs (both sizes run the full-width tcgen05 trunk, whose per-sample arithmetic does not depend on the batch)."""
+    B, S = 4096, 50
+    m = make(agent, "f16", output_device="cuda")
+    g = torch.Generator().manual_seed(21)
+    hidden = torch.rand(B, 256, 4, 5, generator=g)
+    noise = dirichlet_noise(B, 9)
+    v1, n1 = m.search(hidden, None, 0, noise=noise, seed=77)
+    assert n1.dtype == torch.int64 and tuple(n1.shape) == (B, 3) and bool((n1.sum(1) == S).all())
+    assert bool(torch.isfinite(v1).all()) and bool((n1 >= 0).all())
+    assert int((n1.max(1).values == S).sum()) < B // 2, "degenerate trees: every simulation went down one action"
+    v2, n2 = m.search(hidden, None, 0, noise=noise, seed=77)          # CUDA-graph replay: bit-identical
+    assert torch.equal(v1, v2) and torch.equal(n1, n2)
+    v3, n3 = m.search(hidden, None, 0, noise=noise, seed=78)          # another tie-break stream: different trees, same invariants
+    assert bool((n3.sum(1) == S).all()) and not torch.equal(n1, n3)
+    sub = 2560
+    vs, ns = m.search(hidden[:sub].contiguous(), None, 0, noise=noise[:sub], seed=77)
+    assert torch.equal(ns, n1[:sub]) and torch.equal(vs, v1[:sub]), "a tree's search must not depend on the other trees of the batch"
