@@ -30,19 +30,38 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> muzero-breakout_b200/libmzb200.so (in-tree)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> muzero-breakout_b200/libmzb200.so (in-tree).  One object per source under
+    csrc/_obj/ (git-ignored), compiled in parallel and re-used while neither the source nor a header changed; `force` recompiles all."""
     if not (force or _stale()):
         return _SO
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("libmzb200.so is missing/stale and nvcc was not found; there is no CPU fallback")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO + ".tmp"] + _sources() + ["-lcuda"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(_CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(_CSRC, "*.cuh")) + [_HDR])
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        r = subprocess.run([nvcc] + cflags + ["-c", src, "-o", obj + ".tmp.o"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        os.replace(obj + ".tmp.o", obj)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        done = list(ex.map(compile_one, _sources()))
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", _SO + ".tmp"] + [o for o, _ in done] + ["-lcuda"], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(_SO + ".tmp", _SO)
     if verbose:
-        print(r.stderr)
+        print("".join(e for _, e in done))
     return _SO
 
 

@@ -73,6 +73,10 @@ struct StackParams {
     int nsplit;                          // items per (pixel, group pair) tile: 1, or 2 output-channel halves (NT = 128)
     int nslices, slice_groups;           // the samples are walked as nslices slices of slice_groups groups (all layers of a slice before the
                                          // next slice, inside the one launch: the live activations of a slice stay in the L2)
+    int sticky_groups;                   // sample groups g < sticky_groups move their activations with an L2 evict_last policy (they stay resident
+                                         // in the L2 from layer to layer), the others with other_policy (0 evict_normal, 1 evict_first)
+    int other_policy;
+    float sticky_frac;                   // fraction of a sticky group's cache lines that get evict_last (createpolicy.fractional)
     long long elem_off;                  // element offset of this launch's first sample in [n][20][256] side tensors (dst_f32, correction planes)
     // static balanced schedule (single-slice launches): the items of a layer cost 4, 6 or 9 tap-units; lpt_items[lpt_off[c] .. lpt_off[c + 1])
     // are the items CTA pair c runs in every layer (longest-processing-time-first assignment, ascending item order within a pair)
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     const int epoch = *reinterpret_cast<const volatile int *>(p.sync);   // advanced by the previous launch's last CTA
+    const uint64_t pol_sticky = l2_policy_evict_last(p.sticky_frac), pol_other = p.other_policy ? l2_policy_evict_first() : l2_policy_evict_normal();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -241,7 +246,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                             if (elect_one()) {
                                 if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * ((do_a ? A_SLOT : 0) + (do_b ? B_BYTES : 0)));
                                 else mbar_arrive_cluster(lead_full + 8 * stage);
-                                if (do_a) tma_load_4d(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M);
+                                if (do_a) tma_load_4d_hint(sa, &p.map_act[src], lead_full + 8 * stage, kc * BLOCK_K, x0 + dx, y0 + dy, g * BLOCK_M,
+                                                           g - V.g0 < p.sticky_groups ? pol_sticky : pol_other);
                                 if (do_b) {
                                     if (NT == CH) tma_load_2d(sb, &L->map_b, lead_full + 8 * stage, 0, (wrow + kc) * N + rank * (N / 2));
                                     else tma_load_2d(sb, &L->map_b64, lead_full + 8 * stage, 0, (wrow + kc) * N + nh * NT + rank * (NT / 2));
@@ -342,6 +348,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                 const bool valid = live && s < p.n;
                 const long long m = (long long)s * HW + pix;                 // global output row
                 const float *ab = (valid && act_bias) ? act_bias + ((size_t)p.act_idx[s] * HW + pix) * N : nullptr;
+                const uint64_t pol = gl < p.sticky_groups ? pol_sticky : pol_other;
                 // correction planes, item-private layout: [group][pixel][split][epilogue warp][2 * NCHUNK][32 lanes] x 16 bytes
                 const size_t lo_off = ((((size_t)g * HW + pix) * NSPLIT + nh) * NUM_EPI_WARPS + ew) * (2 * NCHUNK * 32 * 16) + (size_t)lane * 16;
                 if (layer > 0) {
@@ -360,12 +367,12 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     asm volatile("fence.proxy.async;" ::: "memory");
                     mbar_expect_tx(bar_res, NSUB * 4096);
 #pragma unroll
-                    for (int sub = 0; sub < NSUB; ++sub) tma_load_4d_cta(stg + sub * 4096, &p.map_epi[res], bar_res, col0 + 64 * sub, x0, y0, s0w);
+                    for (int sub = 0; sub < NSUB; ++sub) tma_load_4d_cta_hint(stg + sub * 4096, &p.map_epi[res], bar_res, col0 + 64 * sub, x0, y0, s0w, pol);
                 }
                 uint4 lo_in[2 * NCHUNK];
                 if (res_lo && valid) {
 #pragma unroll
-                    for (int i = 0; i < 2 * NCHUNK; ++i) lo_in[i] = __ldcg(reinterpret_cast<const uint4 *>(res_lo + lo_off + i * 512));
+                    for (int i = 0; i < 2 * NCHUNK; ++i) lo_in[i] = ldcg_hint(res_lo + lo_off + i * 512, pol);
                 }
                 uint32_t acc[2][32];
                 mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
@@ -451,8 +458,8 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                                 hi[e + 1] = split2(v[e * 2 + 2], v[e * 2 + 3], f16, l1);
                                 lw[e >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                             }
-                            __stcg(reinterpret_cast<uint4 *>(dst_lo + lo_off + (2 * c) * 512), make_uint4(lw[0], lw[1], lw[2], lw[3]));
-                            __stcg(reinterpret_cast<uint4 *>(dst_lo + lo_off + (2 * c + 1) * 512), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+                            stcg_hint(dst_lo + lo_off + (2 * c) * 512, make_uint4(lw[0], lw[1], lw[2], lw[3]), pol);
+                            stcg_hint(dst_lo + lo_off + (2 * c + 1) * 512, make_uint4(lw[4], lw[5], lw[6], lw[7]), pol);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 16; ++e) hi[e] = pack2(v[e * 2], v[e * 2 + 1], f16);
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     mbar_arrive_cluster(lead_tempty + 8 * buf);              // accumulator drained: the pair's next-but-one tile may reuse it
                     if (live) {
 #pragma unroll
-                        for (int sub = 0; sub < NSUB; ++sub) tma_store_4d(&p.map_epi[dst], stg + sub * 4096, col0 + 64 * sub, x0, y0, s0w);
+                        for (int sub = 0; sub < NSUB; ++sub) tma_store_4d_hint(&p.map_epi[dst], stg + sub * 4096, col0 + 64 * sub, x0, y0, s0w, pol);
                         tma_store_commit();
                         tma_store_wait();                                    // global writes performed (and the staging tile is free again)
                         asm volatile("fence.proxy.async;" ::: "memory");
@@ -669,6 +676,24 @@ int mz_stack_run(const void *blob_dev, int n_layers, int sample0, int nsamples, 
     p.groups = (nsamples + BLOCK_M - 1) / BLOCK_M;
     p.slice_groups = slice_samples > 0 && slice_samples < nsamples ? slice_samples / BLOCK_M : p.groups;
     p.nslices = (p.groups + p.slice_groups - 1) / p.slice_groups;
+    {   // L2 residency of the activations (see StackParams::sticky_groups).  A slice's live activations (two 16-bit buffers + the correction
+        // plane = 128 x 20 x 256 x 5 bytes per group) stay in the L2 from layer to layer up to ~2048 samples (52 MB); beyond that the L2
+        // thrashes (ncu: 2.7 GB of DRAM traffic per 28-layer launch at 4096 samples = every layer's input read from and output written to
+        // DRAM).  From 3072 samples per slice on, the first MZB_STACK_STICKY_MB (default 45) megabytes' worth of sample groups move with
+        // evict_last and the rest with evict_first (MZB_STACK_OTHER_POLICY, 0 = evict_normal): 2.71 -> 2.14 GB, +0.6 % simulations/s
+        // (profiles/r2_l2_policy.txt; evict_last alone: 2.56 GB -- the hardware treats the hint as a priority, not as a reservation).
+        static int mb = -1, other = 1; static float frac = 1.0f;
+        if (mb < 0) {
+            const char *e = getenv("MZB_STACK_STICKY_MB"); mb = e ? atoi(e) : 45;
+            e = getenv("MZB_STACK_OTHER_POLICY"); other = e ? atoi(e) : 1;
+            e = getenv("MZB_STACK_STICKY_FRAC"); frac = e ? (float)atof(e) : 1.0f;
+        }
+        const double group_mb = BLOCK_M * HW * CH * 5.0 / 1e6 * frac;
+        const bool thrash = p.slice_groups * BLOCK_M >= 3072;
+        p.sticky_groups = thrash && mb > 0 ? (int)(mb / group_mb) : 0;
+        p.other_policy = thrash && mb > 0 ? other : 0;
+        p.sticky_frac = frac;
+    }
     // output-channel-split items (two CTA pairs per pixel tile) while a layer has fewer pixel tiles than ~2 per CTA pair: a pure function
     // of the batch size (the scratch counters of a (trunk, nsamples) always see the same split); MZB_STACK_NSPLIT_MAX overrides the limit
     static int nsplit_max = -1;

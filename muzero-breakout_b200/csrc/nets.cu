@@ -8,8 +8,10 @@
 // utils.py ScalarTransforms.inverted_softmax_expectation :74-81 of the reference.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <cuda_fp8.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -18,6 +20,8 @@ int conv_tc_launch(const mz_op &op, int nsamples, cudaStream_t st);   // conv_tc
 }
 
 namespace {
+
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -363,6 +367,225 @@ int launch_head(const mz_op &o, int n, cudaStream_t st)
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit heads on the warp MMA (round 2).  The CUDA-core head_kernel above re-reads the fp32 weight matrix once per 4 samples
+// (225 KB x 1024 CTAs through L1 at 4096 samples: 37-49 us for 42 MB of activations).  Here a cluster of HC_KS CTAs takes 128 samples:
+// CTA r of the cluster owns the r-th slice of the feature axis, stages that slice of the weights ONCE in shared memory -- split into
+// hi + lo / LO 16-bit halves (two MMAs: the products carry the full fp32 weight, the 16-bit activations are exact) and already in
+// `mma.sync.m16n8k16` B-fragment order -- and each of its 8 warps runs one 16-sample m-tile over the slice with the activations going
+// from global memory straight into A fragments by 16-byte loads: the reduction index of a dot product may be permuted as long as both
+// operands agree, so the thread that owns k columns {2t, 2t+1, 2t+8, 2t+9} of two consecutive MMAs simply loads the 8 consecutive
+// features [8t, 8t+8) of its row.  The slices' partial sums meet through distributed shared memory in a fixed order (deterministic):
+// CTA r adds the HC_KS partials of samples [16r, 16r+16) and finishes them (bias, softmax / support expectation / inverse transform).
+// Up to two heads that share the batch (policy + value) run as the two z-slices of one launch.
+struct HeadDesc {
+    const void *src;
+    const float *w, *bias;
+    float *out, *out_logits;
+    int nout, mode, feat, cin, cstride;
+};
+struct HeadPair {
+    HeadDesc h[2];
+};
+
+template <typename T> __device__ __forceinline__ uint32_t pack_hi_lo(float a, float b, uint32_t &lo);
+template <> __device__ __forceinline__ uint32_t pack_hi_lo<__half>(float a, float b, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_hi_lo<__nv_bfloat16>(float a, float b, uint32_t &lo)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn((a - hf.x) * 256.0f, (b - hf.y) * 256.0f);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <typename T> __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<__half>(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int HC_KS = 8;            // CTAs per cluster = slices of the feature axis
+constexpr int HC_WARPS = 8;         // one 16-sample m-tile per warp
+constexpr int HC_SAMPLES = 16 * HC_WARPS;
+constexpr int HC_UNROLL = 5;        // 32-feature blocks whose activation loads are in flight together (10 x 16 B per thread)
+constexpr int HC_MAX_KB = 20;       // 32-feature blocks per slice: 5120 features / 32 / HC_KS
+constexpr size_t HC_SMEM = (size_t)HC_MAX_KB * 2 * 2 * 32 * 16 + HC_SAMPLES * 16 * 4 + 16 * 16 * 4;
+
+template <typename T>
+__global__ void __cluster_dims__(1, HC_KS, 1) __launch_bounds__(HC_WARPS * 32)
+head_mma_kernel(int n, const __grid_constant__ HeadPair hp)
+{
+    extern __shared__ __align__(16) uint8_t hc_smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const HeadDesc &hd = hp.h[blockIdx.z];
+    const int rank = blockIdx.y;                                  // cluster dims (1, HC_KS, 1): the cluster rank is blockIdx.y
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nkb = hd.feat / (32 * HC_KS);                        // launcher: a multiple of HC_UNROLL, <= HC_MAX_KB
+    const int nt = hd.nout <= 8 ? 1 : 2;                           // n-tiles of 8 outputs
+    uint4 *s_b = reinterpret_cast<uint4 *>(hc_smem);              // [nkb][2 n-tiles][hi, lo][32 lanes]: B fragments of both MMAs of a block
+    float(*s_part)[16] = reinterpret_cast<float(*)[16]>(hc_smem + (size_t)HC_MAX_KB * 2 * 2 * 32 * 16);
+    float(*s_fin)[16] = s_part + HC_SAMPLES;
+
+    // weight slice -> shared memory, split and in fragment order; every global load of the staging and of the first activation blocks is
+    // issued before the first use (one DRAM / L2 latency for the lot)
+    constexpr int ST = HC_MAX_KB * 2 * 32 / (HC_WARPS * 32);       // staging units per thread (5)
+    float4 w0[ST], w1[ST];
+#pragma unroll
+    for (int it = 0; it < ST; ++it) {
+        const int idx = tid + it * HC_WARPS * 32;
+        const int l = idx & 31, j = (idx >> 5) % nt, kb = (idx >> 5) / nt;
+        const int o = j * 8 + (l >> 2), e = (rank * nkb + kb) * 32 + (l & 3) * 8;
+        w0[it] = w1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < nkb * nt * 32 && o < hd.nout) {
+            w0[it] = __ldg(reinterpret_cast<const float4 *>(hd.w + (size_t)o * hd.feat + e));
+            w1[it] = __ldg(reinterpret_cast<const float4 *>(hd.w + (size_t)o * hd.feat + e) + 1);
+        }
+    }
+    const int s0 = blockIdx.x * HC_SAMPLES;
+    const T *src = (const T *)hd.src;
+    const int pixels = hd.feat / hd.cin;
+    const T *row0 = src + (size_t)min(s0 + wid * 16 + g, n - 1) * pixels * hd.cstride;
+    const T *row1 = src + (size_t)min(s0 + wid * 16 + 8 + g, n - 1) * pixels * hd.cstride;
+    const int e_base = rank * nkb * 32 + t * 8;
+    uint4 a[HC_UNROLL][2];
+#pragma unroll
+    for (int q = 0; q < HC_UNROLL; ++q) {
+        const int e = e_base + q * 32;
+        const int off = (e / hd.cin) * hd.cstride + e % hd.cin;
+        a[q][0] = __ldcs(reinterpret_cast<const uint4 *>(row0 + off));
+        a[q][1] = __ldcs(reinterpret_cast<const uint4 *>(row1 + off));
+    }
+#pragma unroll
+    for (int it = 0; it < ST; ++it) {
+        const int idx = tid + it * HC_WARPS * 32;
+        if (idx < nkb * nt * 32) {
+            const int l = idx & 31, j = (idx >> 5) % nt, kb = (idx >> 5) / nt;
+            uint4 hi, lo;
+            hi.x = pack_hi_lo<T>(w0[it].x, w0[it].y, lo.x); hi.y = pack_hi_lo<T>(w0[it].z, w0[it].w, lo.y);
+            hi.z = pack_hi_lo<T>(w1[it].x, w1[it].y, lo.z); hi.w = pack_hi_lo<T>(w1[it].z, w1[it].w, lo.w);
+            s_b[((kb * 2 + j) * 2 + 0) * 32 + l] = hi;
+            s_b[((kb * 2 + j) * 2 + 1) * 32 + l] = lo;
+        }
+    }
+    __syncthreads();
+
+    float acc[2][2][4];                                            // [n-tile][hi, lo][fragment]
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q >> 3][(q >> 2) & 1][q & 3] = 0.0f;
+    for (int kb0 = 0; kb0 < nkb; kb0 += HC_UNROLL) {
+        if (kb0 > 0) {
+#pragma unroll
+            for (int q = 0; q < HC_UNROLL; ++q) {
+                const int e = e_base + (kb0 + q) * 32;
+                const int off = (e / hd.cin) * hd.cstride + e % hd.cin;
+                a[q][0] = __ldcs(reinterpret_cast<const uint4 *>(row0 + off));
+                a[q][1] = __ldcs(reinterpret_cast<const uint4 *>(row1 + off));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < HC_UNROLL; ++q) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j < nt) {
+                    const uint4 bh = s_b[(((kb0 + q) * 2 + j) * 2 + 0) * 32 + lane], bl = s_b[(((kb0 + q) * 2 + j) * 2 + 1) * 32 + lane];
+                    mma16816<T>(acc[j][0], a[q][0].x, a[q][1].x, a[q][0].y, a[q][1].y, bh.x, bh.y);
+                    mma16816<T>(acc[j][0], a[q][0].z, a[q][1].z, a[q][0].w, a[q][1].w, bh.z, bh.w);
+                    mma16816<T>(acc[j][1], a[q][0].x, a[q][1].x, a[q][0].y, a[q][1].y, bl.x, bl.y);
+                    mma16816<T>(acc[j][1], a[q][0].z, a[q][1].z, a[q][0].w, a[q][1].w, bl.z, bl.w);
+                }
+            }
+        }
+    }
+    const float inv_lo = 1.0f / lo_scale_of<T>();
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)                               // c0,c1: row g, cols 2t,2t+1; c2,c3: row g+8
+            s_part[wid * 16 + (q >> 1) * 8 + g][j * 8 + 2 * t + (q & 1)] = acc[j][0][q] + acc[j][1][q] * inv_lo;
+    cluster.sync();
+    {   // CTA `rank` adds the slices' partials of samples [16 rank, 16 rank + 16) in slice order
+        const int sl = tid >> 4, o = tid & 15;
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < HC_KS; ++r) v += cluster.map_shared_rank(&s_part[0][0], r)[(rank * 16 + sl) * 16 + o];
+        s_fin[sl][o] = v;
+    }
+    cluster.sync();                                                // nobody leaves while its partials are still being read
+    const int i = s0 + rank * 16 + tid;
+    if (tid >= 16 || i >= n) return;                              // thread s finishes sample s
+    const int nout = hd.nout;
+    float logit[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        logit[o] = o < nout ? s_fin[tid][o] + hd.bias[o] : -INFINITY;
+        mx = fmaxf(mx, logit[o]);
+        if (hd.out_logits && o < nout) hd.out_logits[(size_t)i * nout + o] = logit[o];
+    }
+    if (hd.mode == 0) return;
+    float den = 0.0f, e[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { e[o] = o < nout ? expf(logit[o] - mx) : 0.0f; den += e[o]; }
+    if (hd.mode == 2) {                                                // softmax probabilities (mcts.py:100,199)
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+            if (o < nout) hd.out[(size_t)i * nout + o] = e[o] / den;
+        return;
+    }
+    // utils.py:66-81, as in head_kernel
+    const float half = 0.5f * (float)(nout - 1);
+    float ex = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+        if (o < nout) ex += (e[o] / den) * ((float)o - half);
+    const float sg = ex > 0.0f ? 1.0f : (ex < 0.0f ? -1.0f : 0.0f);
+    const float tt = fabsf(ex) + 0.999f;
+    hd.out[i] = sg * (tt * tt - 1.0f);
+}
+
+inline bool head_mma_ok(const mz_op &o)
+{
+    const int cstride = o.cout > 0 ? o.cout : o.cin;
+    const int feat = o.H * o.W * o.cin;
+    return o.op == MZ_OP_HEAD && (o.dtype == MZ_BF16 || o.dtype == MZ_F16) && o.cin % 32 == 0 && cstride % 8 == 0 && cstride >= o.cin && o.nout >= 1 &&
+           o.nout <= 16 && feat % (32 * HC_KS * HC_UNROLL) == 0 && feat / (32 * HC_KS) <= HC_MAX_KB && o.src && o.w && o.shift &&
+           (o.head_mode == 0 ? o.out_logits != nullptr : o.out != nullptr) && ((uintptr_t)o.src % 16 == 0) && ((uintptr_t)o.w % 16 == 0);
+}
+
+// one launch for ops[0 .. cnt) (cnt 1 or 2, all head_mma_ok, same dtype)
+int launch_head_mma(const mz_op *ops, int cnt, int n, cudaStream_t st)
+{
+    HeadPair hp;
+    for (int i = 0; i < 2; ++i) {
+        const mz_op &o = ops[i < cnt ? i : 0];
+        hp.h[i] = HeadDesc{o.src, (const float *)o.w, o.shift, o.out, o.out_logits, o.nout, o.head_mode, o.H * o.W * o.cin, o.cin, o.cout > 0 ? o.cout : o.cin};
+    }
+    static bool attr_done[64];
+    if (mzb::first_use_on_device(attr_done)) {
+        MZB_CUDA(cudaFuncSetAttribute(head_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SMEM));
+        MZB_CUDA(cudaFuncSetAttribute(head_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SMEM));
+    }
+    const dim3 grid((n + HC_SAMPLES - 1) / HC_SAMPLES, HC_KS, cnt);
+    if (ops[0].dtype == MZ_F16) head_mma_kernel<__half><<<grid, HC_WARPS * 32, HC_SMEM, st>>>(n, hp);
+    else head_mma_kernel<__nv_bfloat16><<<grid, HC_WARPS * 32, HC_SMEM, st>>>(n, hp);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename T>
 __global__ void nchw_in_kernel(size_t total, int C, int HW, const float *__restrict__ src, T *__restrict__ dst, T *__restrict__ dst2,
                                const int *__restrict__ dst2_slot, long long dst2_stride)
@@ -448,11 +671,18 @@ int run_op(const mz_op &o, int n, cudaStream_t st)
 
 extern "C" int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream)
 {
+    static const bool g_head_simt = getenv("MZB_HEAD_SIMT") && atoi(getenv("MZB_HEAD_SIMT")) != 0;   // A/B switch: the CUDA-core heads
     MZB_CHECK_ARG(ops && n_ops > 0 && nsamples > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     for (int i = 0; i < n_ops; ++i) {
         const mz_op &o = ops[i];
         int rc;
+        if (head_mma_ok(o) && !g_head_simt) {                 // 16-bit heads: warp-MMA kernel, two heads of one batch per launch
+            const int cnt = (i + 1 < n_ops && head_mma_ok(ops[i + 1]) && ops[i + 1].dtype == o.dtype) ? 2 : 1;
+            if (int rc2 = launch_head_mma(ops + i, cnt, nsamples, st)) return rc2;
+            i += cnt - 1;
+            continue;
+        }
         if (o.dtype == MZ_F32) rc = run_op<float>(o, nsamples, st);
         else if (o.dtype == MZ_BF16 || o.dtype == MZ_F16) {
             if (o.op == MZ_OP_CONV && o.use_tc) rc = mzb::conv_tc_launch(o, nsamples, st);

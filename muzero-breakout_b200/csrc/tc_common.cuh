@@ -103,6 +103,57 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sr
         ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// ---- the same copies with an L2 cache-policy operand (createpolicy descriptors: the fused trunk keeps part of its activations
+// resident in the L2 across layers, conv_stack.cu)
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction)
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(fraction));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cta_hint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+        ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ uint4 ldcg_hint(const void *ptr, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stcg_hint(void *ptr, uint4 v, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk stores have READ their shared-memory source (the staging tile may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -62,6 +62,14 @@ def _stackable(o) -> bool:
             and o.cout == 256 and o.H == 4 and o.W == 5 and not o.scale)
 
 
+def _head_mma_ok(o) -> bool:
+    """mirror of csrc/nets.cu head_mma_ok: the heads that run on the warp-MMA kernel (two consecutive ones share a launch)"""
+    feat = o.H * o.W * o.cin
+    cstride = o.cout if o.cout > 0 else o.cin
+    return (o.op == OP_HEAD and o.dtype in (BF16, F16) and o.cin % 32 == 0 and cstride % 8 == 0 and cstride >= o.cin and 1 <= o.nout <= 16
+            and feat % 1280 == 0 and feat // 256 <= 20 and os.environ.get("MZB_HEAD_SIMT", "0") in ("", "0"))
+
+
 def lat_max_samples() -> int:
     """Batches up to this size run their trunks in latency mode (csrc/conv_lat.cu: a single wave of 16 x ceil(n/3) work
     items); larger ones on the tcgen05 trunk (csrc/conv_stack.cu).  MZB_LAT_MAX_SAMPLES overrides (0 = never)."""
@@ -227,9 +235,22 @@ class Program:
 
     @property
     def n_kernels(self) -> int:
+        """kernel launches of one run(): one per plain op record -- except that two consecutive 16-bit heads share a launch (csrc/nets.cu
+        head_mma_kernel, the policy + value pair) -- and one per fused trunk."""
         if self._segs is None:
             self._build()
-        return sum(cnt if kind == "ops" else len(item.chunks) for kind, item, cnt in self._segs)
+        total = 0
+        for kind, item, cnt in self._segs:
+            if kind != "ops":
+                total += len(item.chunks)
+                continue
+            i = 0
+            while i < cnt:
+                if _head_mma_ok(item[i]) and i + 1 < cnt and _head_mma_ok(item[i + 1]) and item[i + 1].dtype == item[i].dtype:
+                    i += 1
+                total += 1
+                i += 1
+        return total
 
 
 DEFAULT_MODEL_CFG = {  # config.yaml:27-50

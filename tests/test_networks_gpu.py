@@ -261,3 +261,42 @@ def test_residual_stream_correction_plane():
             errs[with_lo] = rel(out32.permute(0, 3, 1, 2).cpu(), want)
         print(f"n={n} {H}x{W} c={c} use_tc={use_tc}: residual with correction plane {errs[True]:.2e}, without {errs[False]:.2e}")
         assert errs[True] <= 1.5e-4 and errs[False] > 3 * errs[True], errs
+
+
+@pytest.mark.parametrize("n", [1, 15, 33, 300, 2500, 9500])
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_mma_heads_vs_fp64(n, dt):
+    """The 16-bit heads on the warp MMA (csrc/nets.cu head_mma_kernel: Flatten + Linear + softmax / support expectation / inverse transform,
+    networks.py:147-149,207-209,221-223 + utils.py:74-81): a dense 256-channel head (reward), and the policy (3 outputs) + value (11) pair
+    reading the two 128-channel halves of one buffer in ONE launch, against an fp64 evaluation of the same 16-bit activations and fp32
+    weights -- the kernel's only rounding is its fp32 accumulation (weights enter as hi + lo halves), so the bound is 2e-6 of the logits' range (bf16: 3e-5);
+    batch sizes cover single and ragged CTAs and both samples-per-CTA variants."""
+    from muzero_breakout_b200.src.networks import BF16, F16, OP_HEAD, Program
+    g = torch.Generator().manual_seed(n)
+    tdt, code = (torch.float16, F16) if dt == "f16" else (torch.bfloat16, BF16)
+    x = (torch.rand(n, 20, 256, generator=g) * 2).to(tdt).cuda()
+    ws = {k: ((torch.rand(o, f, generator=g) * 2 - 1) / f ** 0.5 * 8).cuda() for k, (o, f) in {"r": (11, 5120), "p": (3, 2560), "v": (11, 2560)}.items()}
+    bs = {k: (torch.rand(w.shape[0], generator=g) - 0.5).cuda() for k, w in ws.items()}
+    out = {k: torch.full((n,) if k != "p" else (n, 3), float("nan"), device="cuda") for k in ws}
+    lg = {k: torch.full((n, ws[k].shape[0]), float("nan"), device="cuda") for k in ws}
+    prog = Program(n)
+    prog.add(op=OP_HEAD, dtype=code, H=4, W=5, cin=256, nout=11, head_mode=1, src=x, w=ws["r"], shift=bs["r"], out=out["r"], out_logits=lg["r"])
+    prog.add(op=OP_HEAD, dtype=code, H=4, W=5, cin=128, cout=256, nout=3, head_mode=2, src=x, w=ws["p"], shift=bs["p"], out=out["p"], out_logits=lg["p"])
+    prog.add(op=OP_HEAD, dtype=code, H=4, W=5, cin=128, cout=256, nout=11, head_mode=1, src=x.view(-1)[128:], w=ws["v"], shift=bs["v"], out=out["v"],
+             out_logits=lg["v"])
+    prog.run()
+    torch.cuda.synchronize()
+    xd = x.double()
+    feats = {"r": xd.reshape(n, 5120), "p": xd[:, :, :128].reshape(n, 2560), "v": xd[:, :, 128:].reshape(n, 2560)}
+    sup = torch.arange(-5, 6, dtype=torch.float64, device="cuda")
+    for k in ws:
+        ref = feats[k] @ ws[k].double().T + bs[k].double()
+        tol = 2e-6 if dt == "f16" else 3e-5                    # bf16 weights enter as 8 + 8 significant bits
+        assert rel(lg[k], ref) <= tol, f"{k} logits {rel(lg[k], ref):.2e}"
+        p = torch.softmax(ref, 1)
+        if k == "p":
+            assert rel(out[k], p) <= 5e-6 + tol
+        else:
+            e = (p * sup).sum(1)
+            y = torch.sign(e) * ((e.abs() + 0.999) ** 2 - 1)
+            assert float((out[k].double() - y).abs().max()) <= (2e-5 + 10 * tol) * max(1.0, float(y.abs().max()))
