@@ -395,6 +395,12 @@ int mz_loss(int rows, int K, int n_supports, int n_actions, const float *support
             float *losses, float *d_reward, float *d_value, float *d_policy, void *scratch, void *stream);
 int mz_adam(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, double lr, double beta1, double beta2,
             double eps, double weight_decay, int step, void *stream);
+/* The same update with the step count on the device, for a training step replayed as a CUDA graph: `state` is MZ_ADAM_STATE_BYTES of
+ * device memory, 16-byte aligned, whose first int32 holds the number of updates done so far (zero it once, or store torch's state["step"]);
+ * the call increments it and derives this update's bias corrections from it on the device (two launches, no host value of the step). */
+#define MZ_ADAM_STATE_BYTES 64
+int mz_adam_dev(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, double lr, double beta1, double beta2,
+                double eps, double weight_decay, void *state, void *stream);
 
 /* Weight gradient of a stride-1 "same" 3x3 / 1x1 convolution with 256 input and 256 output channels (the residual trunks,
  * networks.py:24-25; autograd of nn.Conv2d inside loss.backward(), train_torch.py:515) on the tensor cores (csrc/wgrad.cu):
@@ -406,6 +412,10 @@ int mz_wgrad_padded_samples(int n);
 size_t mz_wgrad_partial_bytes(int ksize, int n);
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream);
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
+/* accumulate != 0: dw += the gradient (one rounding per call, in call order): the K unroll steps of a training step share their weights
+ * (train_torch.py:507-525) and add straight into the parameter's .grad instead of through K separate add kernels */
+int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, int accumulate,
+                        void *stream);
 
 /* Training-mode nn.BatchNorm2d of a ConvBlock / ResidualBlock (networks.py:12,16-17,26-35 under train_mode(), train_torch.py:372)
  * on channels-last rows: z float32[M][C] = the convolution output incl. its bias, M = samples * H * W.

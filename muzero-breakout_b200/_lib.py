@@ -126,8 +126,10 @@ def _declare(L: C.CDLL) -> None:
     sig.update({
         "mz_loss": [i32, i32, i32, i32] + [vp] * 13,
         "mz_adam": [C.c_longlong, vp, vp, vp, vp] + [C.c_double] * 5 + [i32, vp],
+        "mz_adam_dev": [C.c_longlong, vp, vp, vp, vp] + [C.c_double] * 5 + [vp, vp],
         "mz_wgrad_transpose": [i32, i32, i32, vp, vp, vp],
         "mz_conv_wgrad": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "mz_conv_wgrad_accum": [i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     })
     sig.update({
         "mz_bn_train_fwd": [i32, i32, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double] + [vp] * 8,

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         if (act == MZ_ACT_RELU) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                        } else {
+                        } else if (act != MZ_ACT_NONE) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = activate(v[j], act);
                         }

@@ -224,6 +224,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long m = valid ? ((long long)s * p.H + y) * p.W + x : -1;   // global output row, -1 = nothing to write
             const float *ab = (valid && p.act_bias) ? p.act_bias + ((size_t)p.act_idx[s] * p.H * p.W + (y * p.W + x)) * N : nullptr;
             const bool has_res = p.res != nullptr;
+            // fp32 output without a 16-bit residual (every convolution of a training step: BatchNorm reads the fp32 sums): each 32-column
+            // chunk goes through the staging tile and leaves as whole 128-byte row segments.  (Row-per-lane float4 stores touch 32 rows
+            // 20 KB apart per instruction: 44 us per 512-sample layer against 10 us of MMAs.)  The 16-bit copy is optional then.
+            const bool f32_staged = p.dst_f32 != nullptr && !has_res;
             // correction planes: [CTA tile][epilogue warp][2 * nchunks][32 lanes] x 16 bytes (same as conv_stack.cu in pixel mode)
             const size_t lo_tile = p.mode == 1 ? (size_t)(t.s0 / BLOCK_M) * (p.H * p.W) + (size_t)(t.y0 * p.W + t.x0) : (size_t)2 * tile + rank;
             const size_t lo_off = (lo_tile * NUM_EPI_WARPS + (warp - 2)) * (2 * nchunks * 512) + (size_t)lane * 16;
@@ -315,8 +319,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 v[q * 4] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
                             }
                         }
+                        if (kRelu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = kRelu ? fmaxf(v[j], 0.0f) : activate(v[j], p.act);
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        } else if (p.act != MZ_ACT_NONE) {               // one uniform branch per chunk: the per-element switch of activate() costs
+#pragma unroll                                                          // ~8 dependent branches per element (6 us per 32-column chunk: every
+                            for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);   // convolution of a training step has act = none)
+                        }
                         uint32_t hi[16];
                         if (p.dst_lo) {
                             uint32_t lw[8];
@@ -333,14 +342,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int e = 0; e < 16; ++e) hi[e] = pack2(v[e * 2], v[e * 2 + 1], p.f16);
                         }
+                        if (f32_staged) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
-                        if (p.dst_f32) {
-                            float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4 *>(stg + lane * 128 + 16 * (q ^ (lane & 7))) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                            if (p.dst) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<uint4 *>(stg + 4096 + lane * 64 + 16 * (q ^ (lane & 3))) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<uint4 *>(srow + 16 * ((c * 4 + q) ^ (lane & (units - 1)))) = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+                            if (p.dst_f32) {
+                                float4 *fp = reinterpret_cast<float4 *>(p.dst_f32 + m * N + c0);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) fp[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                            }
                         }
+                    }
+                    if (f32_staged) {
+                        const int c0 = col0 + c * 32;
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {                    // 8 lanes cover one row's 128-byte fp32 segment, 4 rows per instruction
+                            const int rr = k * 4 + (lane >> 3), u = lane & 7;
+                            const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                            if (mr >= 0)
+                                *(reinterpret_cast<float4 *>(p.dst_f32 + mr * N + c0) + u) = *reinterpret_cast<const float4 *>(stg + rr * 128 + 16 * (u ^ (rr & 7)));
+                        }
+                        if (p.dst) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {                // 4 lanes cover one row's 64-byte 16-bit segment, 8 rows per instruction
+                                const int rr = k * 8 + (lane >> 2), u = lane & 3;
+                                const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                                if (mr >= 0)
+                                    *(reinterpret_cast<uint4 *>(p.dst + mr * N + c0) + u) = *reinterpret_cast<const uint4 *>(stg + 4096 + rr * 64 + 16 * (u ^ (rr & 3)));
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -352,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < units; ++k) {
                 const int rr = k * rows_per_it + my_rsub;
-                const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                const long long mr = f32_staged ? -1 : __shfl_sync(0xffffffffu, m, rr);
                 if (mr >= 0) {
                     const uint4 v4 = *reinterpret_cast<const uint4 *>(stg + rr * row_bytes + 16 * (my_u ^ (rr & (units - 1))));
                     *(reinterpret_cast<uint4 *>(p.dst + mr * N + col0) + my_u) = v4;
@@ -421,7 +462,7 @@ namespace mzb {
 
 int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
 {
-    MZB_CHECK_ARG(o.src && o.dst && o.w && o.shift, "conv_tc: null pointer");
+    MZB_CHECK_ARG(o.src && o.w && o.shift && (o.dst || (o.dst_f32 && !o.res && !o.dst_lo)), "conv_tc: null pointer (dst may be NULL only for an fp32-only output without residual)");
     MZB_CHECK_ARG((o.ksize == 1 || o.ksize == 3) && o.cin % BLOCK_K == 0 && (o.cout == 128 || o.cout == 256), "conv_tc: unsupported shape");
     MZB_CHECK_ARG(!o.act_bias || o.act_idx, "conv_tc: act_bias needs act_idx");
     EncodeTiledFn enc = encode_fn();

@@ -182,6 +182,48 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n4, long long n, fl
     for (long long i = n4 * 4 + tid; i < n; i += stride) adam_one(param[i], grad[i], exp_avg[i], exp_avg_sq[i], c);
 }
 
+// mz_adam_dev: the same update with the step count kept on the DEVICE, so that a CUDA-graph replay of a whole training step advances it.
+// state: int32 step count (updates done so far) at byte 0, this update's constants at byte 16.
+struct adam_hyper {
+    double lr, beta1, beta2, eps, wd;
+};
+__global__ void adam_prep_kernel(void *state, const adam_hyper h)
+{
+    int *step = reinterpret_cast<int *>(state);
+    adam_consts *c = reinterpret_cast<adam_consts *>(reinterpret_cast<char *>(state) + 16);
+    const int t = *step + 1;
+    *step = t;
+    const double bc1 = 1.0 - pow(h.beta1, (double)t), bc2 = 1.0 - pow(h.beta2, (double)t);
+    c->wd = (float)h.wd;
+    c->one_minus_b1 = (float)(1.0 - h.beta1);
+    c->b2 = (float)h.beta2;
+    c->one_minus_b2 = (float)(1.0 - h.beta2);
+    c->bc2_sqrt = (float)sqrt(bc2);
+    c->eps = (float)h.eps;
+    c->neg_step_size = (float)(-(h.lr / bc1));
+}
+__global__ void __launch_bounds__(256) adam_dev_kernel(long long n4, long long n, float *__restrict__ param, const float *__restrict__ grad,
+                                                       float *__restrict__ exp_avg, float *__restrict__ exp_avg_sq, const void *state)
+{
+    const adam_consts c = *reinterpret_cast<const adam_consts *>(reinterpret_cast<const char *>(state) + 16);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = tid; i < n4; i += stride) {
+        float4 p = reinterpret_cast<float4 *>(param)[i];
+        const float4 g = __ldcs(reinterpret_cast<const float4 *>(grad) + i);
+        float4 m = reinterpret_cast<float4 *>(exp_avg)[i];
+        float4 v = reinterpret_cast<float4 *>(exp_avg_sq)[i];
+        adam_one(p.x, g.x, m.x, v.x, c);
+        adam_one(p.y, g.y, m.y, v.y, c);
+        adam_one(p.z, g.z, m.z, v.z, c);
+        adam_one(p.w, g.w, m.w, v.w, c);
+        reinterpret_cast<float4 *>(param)[i] = p;
+        reinterpret_cast<float4 *>(exp_avg)[i] = m;
+        reinterpret_cast<float4 *>(exp_avg_sq)[i] = v;
+    }
+    for (long long i = n4 * 4 + tid; i < n; i += stride) adam_one(param[i], grad[i], exp_avg[i], exp_avg_sq[i], c);
+}
+
 }  // namespace mzb
 
 extern "C" {
@@ -244,6 +286,24 @@ int mz_adam(long long n, float *param, const float *grad, float *exp_avg, float 
     const long long cap = (long long)kNumSMs * 8;       // 8 CTAs of 256 threads per SM, grid-stride
     const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n4, n, param, grad, exp_avg, exp_avg_sq, c);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int mz_adam_dev(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, double lr, double beta1, double beta2,
+                double eps, double weight_decay, void *state, void *stream)
+{
+    using namespace mzb;
+    MZB_CHECK_ARG(n > 0 && param && grad && exp_avg && exp_avg_sq && state, "bad argument");
+    MZB_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)state) & 15) == 0, "buffers must be 16-byte aligned");
+    adam_hyper h{lr, beta1, beta2, eps, weight_decay};
+    adam_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, h);
+    MZB_LAUNCH_CHECK();
+    const long long n4 = n / 4;
+    long long want = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;
+    const int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n4, n, param, grad, exp_avg, exp_avg_sq, state);
     MZB_LAUNCH_CHECK();
     return 0;
 }

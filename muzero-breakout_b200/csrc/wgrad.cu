@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int
 
 // dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order.  One thread per (tap, co, ci):
 // its <= 8 loads are independent and coalesced over ci; grid (256 * 256 / 256, taps)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, const float *__restrict__ partial, float *__restrict__ dw)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, const float *__restrict__ partial, float *__restrict__ dw, int accumulate)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;            // co * 256 + ci
     const int tap = blockIdx.y;
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits,
     float acc = 0.0f;
 #pragma unroll
     for (int s = 0; s < WG_MAX_SPLITS; ++s) acc += v[s];     // index order; the padding terms are exact zeros
-    dw[(size_t)i * taps + tap] = acc;
+    float *out = dw + (size_t)i * taps + tap;
+    *out = accumulate ? *out + acc : acc;                    // accumulate: the K unroll steps of a training step add into the parameter's .grad
 }
 
 int wg_splits(int ns) { const int chunks = ns / BLOCK_K; return chunks < WG_MAX_SPLITS ? chunks : WG_MAX_SPLITS; }
@@ -250,6 +251,11 @@ int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *st
 }
 
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream)
+{
+    return mz_conv_wgrad_accum(n, H, W, ksize, dtype, dy_t, x_t, partial, dw, 0, stream);
+}
+
+int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, int accumulate, void *stream)
 {
     MZB_CHECK_ARG(n > 0 && H > 0 && W > 0 && (ksize == 1 || ksize == 3) && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
     MZB_CHECK_ARG(dy_t && x_t && partial && dw, "null pointer");
@@ -293,7 +299,7 @@ int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, c
     cfg.numAttrs = 1;
     MZB_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel, maps[0], maps[1], p));
     MZB_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<dim3(WG_C * WG_C / 256, p.taps), 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw);
+    wgrad_reduce_kernel<<<dim3(WG_C * WG_C / 256, p.taps), 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw, accumulate);
     MZB_LAUNCH_CHECK();
     return 0;
 }

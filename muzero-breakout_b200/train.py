@@ -116,12 +116,18 @@ class Adam:
                 p.data = seg
                 p.grad = gseg
         self._offsets = offs
+        self._skip_steps = 0
+        self._dev_state = torch.zeros(16, dtype=torch.int32, device=dev)      # MZ_ADAM_STATE_BYTES: step count + this update's constants
+        self._dev_step = 0
 
     def zero_grad(self, set_to_none: bool = False):
         """Zeros the flat gradient (the views stay attached: `set_to_none` is accepted and ignored)."""
         self.flat_grad.zero_()
 
     def step(self):
+        if self._skip_steps > 0:                 # a graphed training step (GraphedTrainStep) has already applied this update
+            self._skip_steps -= 1
+            return
         self.step_count += 1
         dev = self.flat_param.device
         with torch.cuda.device(dev):
@@ -131,6 +137,21 @@ class Adam:
         # the kernel writes through raw pointers: bump the parameters' version counters like an in-place torch op would, so that
         # anything keyed on them (MCTSSearchVec's re-pack check, autograd's saved-tensor checks) sees the update
         torch.autograd.graph.increment_version(self.params)
+
+    def step_dev(self):
+        """The same update with the step count read from (and advanced in) device memory -- mz_adam_dev -- so that it can sit inside a CUDA
+        graph.  The caller keeps `step_count` in step with the replays (GraphedTrainStep does)."""
+        dev = self.flat_param.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().mz_adam_dev(self.flat_param.numel(), _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                              self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, _p(self._dev_state),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+
+    def sync_dev_step(self):
+        """device step counter := step_count (after eager steps or load_state_dict)"""
+        if self._dev_step != self.step_count:
+            self._dev_state[0] = self.step_count
+            self._dev_step = self.step_count
 
     def state_dict(self):
         """torch.optim.Adam's own layout ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [...]}), so the checkpoint the
@@ -205,18 +226,18 @@ class ConvDgrad:
         n, H, W, c = dy.shape
         if c != self.cout or dy.dtype != torch.bfloat16 or not dy.is_cuda or not dy.is_contiguous():
             raise ValueError("ConvDgrad: dy must be a contiguous CUDA bf16 tensor (n, H, W, cout)")
-        dx16 = torch.empty((n, H, W, self.cin), dtype=torch.bfloat16, device=dy.device)
         dx = torch.empty((n, H, W, self.cin), dtype=torch.float32, device=dy.device)
-        prog = Program(n)
+        prog = Program(n)                                # fp32-only output (dst = NULL): staged, coalesced stores (csrc/conv_tc.cu)
         prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=self.cout, cout=self.cin, ksize=self.k, act=ACT["none"], use_tc=1, w_layout=1,
-                 src=dy, dst=dx16, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift)
+                 src=dy, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift)
         prog.run()
         return dx
 
 
-def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int) -> torch.Tensor:
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: torch.Tensor | None = None) -> torch.Tensor:
     """dL/dweight of `y = conv2d(x, weight, padding=ksize//2)` for the 256 -> 256 trunk convolutions, (256, 256, k, k) float32, on the
-    tensor cores (mz_conv_wgrad, csrc/wgrad.cu).  Channels-last 16-bit tensors: dy (n, H, W, 256), x (n, H, W, 256)."""
+    tensor cores (mz_conv_wgrad, csrc/wgrad.cu).  Channels-last 16-bit tensors: dy (n, H, W, 256), x (n, H, W, 256).
+    accumulate_into: add the gradient to this tensor (a parameter's .grad) instead of returning a new one."""
     _lib.require_cuda()
     n, H, W, c = x.shape
     if dy.shape != x.shape or c != 256 or x.dtype != dy.dtype or x.dtype not in (torch.bfloat16, torch.float16) or not (x.is_cuda and dy.is_cuda):
@@ -227,11 +248,15 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int) -> torch.Tensor:
     dy_t = torch.empty((256, H * W, ns), dtype=x.dtype, device=dev)
     x_t = torch.empty_like(dy_t)
     partial = torch.empty(L.mz_wgrad_partial_bytes(ksize, n) // 4, dtype=torch.float32, device=dev)
-    dw = torch.empty((256, 256, ksize, ksize), dtype=torch.float32, device=dev)
+    acc = accumulate_into is not None
+    if acc and not (accumulate_into.shape == (256, 256, ksize, ksize) and accumulate_into.dtype == torch.float32 and accumulate_into.is_contiguous()
+                    and accumulate_into.device == dev):
+        raise ValueError("conv_wgrad: accumulate_into must be a contiguous float32 (256, 256, k, k) tensor on the operands' device")
+    dw = accumulate_into if acc else torch.empty((256, 256, ksize, ksize), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(dy.contiguous()), _p(dy_t), st))
         _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(x.contiguous()), _p(x_t), st))
-        _lib.check(L.mz_conv_wgrad(n, H, W, ksize, 2 if x.dtype == torch.float16 else 1, _p(dy_t), _p(x_t), _p(partial), _p(dw), st))
+        _lib.check(L.mz_conv_wgrad_accum(n, H, W, ksize, 2 if x.dtype == torch.float16 else 1, _p(dy_t), _p(x_t), _p(partial), _p(dw), int(acc), st))
     return dw
 
 
@@ -301,10 +326,9 @@ class ResidualBlockTrain:
     def _conv(self, x16, i):
         from .src.networks import ACT, BF16, OP_CONV, Program
         n, H, W, _ = x16.shape
-        z16 = torch.empty_like(x16)
         z = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
         prog = Program(n)
-        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=256, cout=256, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst=z16, dst_f32=z,
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=256, cout=256, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst_f32=z,
                  w=self.wt[i], scale=self.ones, shift=self.b[i])
         prog.run()
         return z
@@ -343,13 +367,17 @@ class ResidualBlockTrain:
         """dy: float32 gradient of the block output.  Returns (dx float32, {parameter name: gradient})."""
         return self.backward_fn(dy, self._saved)
 
-    def backward_fn(self, dy: torch.Tensor, saved):
+    def backward_fn(self, dy: torch.Tensor, saved, grad_into=(None, None)):
+        """grad_into: (conv1.weight.grad, conv2.weight.grad) to accumulate the weight gradients into (the entries of the returned dict are
+        then None), or None entries for fresh tensors."""
         x16, z1, h16, z2, m1, s1, m2, s2 = saved
         dz2, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu")
-        dw2 = conv_wgrad(dz2_16, h16, 3)
+        dw2 = conv_wgrad(dz2_16, h16, 3, grad_into[1])
+        dw2 = None if grad_into[1] is not None else dw2
         dh = self.dgrad[1](dz2_16)
         dz1, dz1_16, dg1, db1, _ = bn_train_backward(z1, dh, self.gamma[0], self.beta[0], m1, s1, None, "relu")
-        dw1 = conv_wgrad(dz1_16, x16, 3)
+        dw1 = conv_wgrad(dz1_16, x16, 3, grad_into[0])
+        dw1 = None if grad_into[0] is not None else dw1
         dx = self.dgrad[0](dz1_16)
         dx += dres                                      # the skip connection's gradient
         return dx, {"conv1.weight": dw1, "bn1.weight": dg1, "bn1.bias": db1, "conv2.weight": dw2, "bn2.weight": dg2, "bn2.bias": db2}
@@ -415,25 +443,32 @@ _ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "0") == "1"
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernels, *params):
-        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)          # channels-last 16-bit, the kernels' layout
+        # channels-last 16-bit, the kernels' layout (a channels_last input -- what the drop-in agent's layers produce -- is permuted for free)
+        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         saved, y32 = [], None
         for blk in kernels:
             x16, y32, sv = blk.forward_fn(x16)
             saved.append(sv)
-        ctx.kernels, ctx.saved_blocks = kernels, saved
-        return y32.permute(0, 3, 1, 2).contiguous()
+        ctx.kernels, ctx.saved_blocks, ctx.params = kernels, saved, params
+        return y32.permute(0, 3, 1, 2)                     # NCHW shape, channels_last strides: no copy
 
     @staticmethod
     def backward(ctx, dy):
         g = dy.permute(0, 2, 3, 1).contiguous().float()
         flat = []
-        for blk, sv in zip(reversed(ctx.kernels), reversed(ctx.saved_blocks)):
-            g, grads = blk.backward_fn(g, sv)
-            zero = torch.zeros(256, device=g.device)           # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient)
-            flat.append((grads["conv1.weight"], zero, grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zero, grads["bn2.weight"], grads["bn2.bias"]))
+        nb = len(ctx.kernels)
+        for i, (blk, sv) in enumerate(zip(reversed(ctx.kernels), reversed(ctx.saved_blocks))):
+            ps = ctx.params[8 * (nb - 1 - i):8 * (nb - i)]           # conv1.w, conv1.b, bn1.w, bn1.b, conv2.w, conv2.b, bn2.w, bn2.b
+            # a parameter that already has a contiguous .grad (always, under this module's flat-buffer Adam) takes its weight gradient by
+            # in-kernel accumulation; autograd then gets None for it (one add kernel less per convolution and unroll step)
+            into = tuple(p.grad if (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32) else None for p in (ps[0], ps[4]))
+            g, grads = blk.backward_fn(g, sv, into)
+            # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient): None where a .grad exists, zeros otherwise
+            zb = [None if p.grad is not None else torch.zeros(256, device=g.device) for p in (ps[1], ps[5])]
+            flat.append((grads["conv1.weight"], zb[0], grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zb[1], grads["bn2.weight"], grads["bn2.bias"]))
         ctx.saved_blocks = None
         out = [t for blk in reversed(flat) for t in blk]
-        return (g.permute(0, 3, 1, 2).contiguous(), None, *out)
+        return (g.permute(0, 3, 1, 2), None, *out)
 
 
 def _block_params(m):
@@ -507,3 +542,135 @@ def accelerate_agent(agent):
         g = old.param_groups[0]
         agent.optimizer = Adam(agent.parameters(), lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])
     return agent
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# one iteration of the training loop as ONE CUDA graph
+def k_step_rollout(agent, input_states, input_actions, k_step_actions, K, latent_resolution=(4, 5), n_actions=3):
+    """What RLSystem._k_step_rollout does (train_torch.py:487-528) with any MuZeroAgent-shaped module: representation network on
+    cat(states, action planes), then K x (prediction, dynamics on the one-hot action planes of :295-311).  Returns the stacked
+    (reward, value, policy) logits, (batch, K, .)."""
+    h = agent.create_hidden_state_root(torch.cat((input_states, input_actions), dim=1))
+    pol, val, rew = [], [], []
+    for k in range(K):
+        p_, v_ = agent.evaluate_state(h)
+        planes = torch.nn.functional.one_hot(k_step_actions[:, k].long(), num_classes=n_actions).float().view(-1, n_actions, 1, 1)
+        h, r_ = agent.hidden_state_transition(h, planes.expand(-1, -1, latent_resolution[0], latent_resolution[1]))
+        pol.append(p_); val.append(v_); rew.append(r_)
+    return torch.stack(rew, dim=1), torch.stack(val, dim=1), torch.stack(pol, dim=1)
+
+
+def _trunk_kernels(agent):
+    return [m._mzb_kernels for m in agent.modules() if getattr(m, "_mzb_kernels", None) is not None]
+
+
+class GraphedTrainStep:
+    """The body of the reference's training loop (train_torch.py:385-417: zero_grad, _k_step_rollout, loss_fn, loss.backward(),
+    optimizer.step()) captured once per minibatch shape as ONE CUDA graph and replayed: ~3 400 library launches + ~1 500 torch kernels
+    of an eager step become one graph launch (the eager step is launch-bound: DESIGN.md section 9).  `agent` is the learner-side drop-in
+    (src/agent.py) or a reference MuZeroAgent after accelerate_agent(); its optimizer must be this module's Adam (the step count lives on
+    the device, mz_adam_dev).  Same arithmetic as the eager step: the captured kernels are the ones the eager path launches.
+
+        step = GraphedTrainStep(agent, scalar_transforms.supports_representation, K)
+        loss, reward_loss, value_loss, policy_loss = step(states, action_planes, k_actions, k_rewards, k_values, k_visit_counts)
+
+    Capture needs one warm-up pass (kernel attributes, cuDNN plans, allocator); it runs on a snapshot: parameters, BatchNorm buffers and
+    optimizer state are restored before the capture, so the first call counts as exactly one update."""
+
+    def __init__(self, agent, target_transformation, K, latent_resolution=(4, 5), n_actions=3, rollout=None):
+        _lib.require_cuda()
+        if not isinstance(getattr(agent, "optimizer", None), Adam):
+            raise TypeError("GraphedTrainStep needs the flat-buffer Adam (the drop-in agent, or accelerate_agent(reference_agent))")
+        self.agent, self.opt, self.K = agent, agent.optimizer, int(K)
+        self.supports = _supports_of(target_transformation)
+        self.res, self.n_actions = tuple(latent_resolution), int(n_actions)
+        self.rollout = rollout or (lambda *inp: k_step_rollout(self.agent, *inp, self.K, self.res, self.n_actions))
+        self._graphs = {}
+        self.replays = 0
+
+    def _body(self, st):
+        self.opt.flat_grad.zero_()
+        pr, pv, pp = self.rollout(st[0], st[1], st[2])
+        out = loss_fn(st[3], pr, st[4], pv, st[5], pp, self.supports, self.K)
+        out[0].backward()
+        self.opt.step_dev()
+        return torch.stack([o.detach() for o in out])
+
+    def _capture(self, inputs):
+        dev = self.opt.flat_param.device
+        st = [torch.empty_like(t, device=dev) for t in inputs]
+        for d, t in zip(st, inputs):
+            d.copy_(t)
+        # warm-up on a snapshot of everything a step mutates
+        sd = {k: v.clone() for k, v in self.agent.state_dict().items()}
+        m, v, steps = self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(), self.opt.step_count
+        self.opt.sync_dev_step()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._body(st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.agent.load_state_dict(sd)
+        self.opt.exp_avg.copy_(m); self.opt.exp_avg_sq.copy_(v)
+        self.opt.step_count = steps
+        self.opt._dev_step = -1
+        self.opt.sync_dev_step()
+        for k in _trunk_kernels(self.agent):           # the weight re-packs must be part of the graph: they run before every replayed step
+            k._key = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._body(st)
+        return g, st, out
+
+    def __call__(self, input_states, input_actions, k_step_actions, k_step_rewards, k_step_values, k_step_policies):
+        inputs = (input_states, input_actions, k_step_actions, k_step_rewards, k_step_values, k_step_policies)
+        key = tuple((tuple(t.shape), t.dtype) for t in inputs)
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(inputs)
+        g, st, out = self._graphs[key]
+        for d, t in zip(st, inputs):
+            d.copy_(t, non_blocking=True)
+        self.opt.sync_dev_step()
+        g.replay()
+        self.opt.step_count += 1
+        self.opt._dev_step += 1
+        self.replays += 1
+        torch.autograd.graph.increment_version(self.opt.params)        # what the in-place update would have done (MCTSSearchVec's re-pack check)
+        res = out.clone()
+        return res[0], res[1], res[2], res[3]
+
+
+def accelerate_training_stage(system, trainer_module=None):
+    """Make the reference's UNMODIFIED `RLSystem._training_stage` (train_torch.py:369-452) run each loop iteration as one GraphedTrainStep
+    replay.  The loop body is eager Python that calls, in order, optimizer.zero_grad(), self._k_step_rollout(...), the module-global
+    loss_fn(...), loss.item(), loss.backward(), optimizer.step(); this patches three of those plug points on the live objects:
+      * `system._k_step_rollout` only records its inputs and returns placeholders;
+      * the trainer module's `loss_fn` -- when it is handed those placeholders -- replays the graph (rollout, loss, backward, Adam) with the
+        recorded inputs and the targets it receives, and returns the four losses (`loss.backward()` on the result is then a no-op);
+      * the following `optimizer.step()` is skipped once (the graph has applied the update).
+    `system.mu_zero` must be the drop-in agent or an accelerate_agent()-ed reference agent.  Returns the GraphedTrainStep."""
+    import sys
+    mod = trainer_module or sys.modules[type(system).__module__]
+    agent = system.mu_zero
+    step = GraphedTrainStep(agent, system.scalar_transforms.supports_representation, system.K, tuple(system.latent_resolution), system.n_actions)
+    marker = tuple(torch.empty(0) for _ in range(3))
+    pending = {}
+    eager_loss = mod.loss_fn
+
+    def deferred_rollout(input_states, input_actions, k_step_actions):
+        pending["inputs"] = (input_states, input_actions, k_step_actions)
+        return marker
+
+    def graphed_loss_fn(observed_reward, predicted_reward, bootstrapped_reward, predicted_value, visit_counts, predicted_policy, target_transformation, K):
+        if predicted_reward is not marker[0]:
+            return eager_loss(observed_reward=observed_reward, predicted_reward=predicted_reward, bootstrapped_reward=bootstrapped_reward,
+                              predicted_value=predicted_value, visit_counts=visit_counts, predicted_policy=predicted_policy,
+                              target_transformation=target_transformation, K=K)
+        states, planes, acts = pending.pop("inputs")
+        loss, rl, vl, pl = step(states, planes, acts, observed_reward, bootstrapped_reward, visit_counts)
+        agent.optimizer._skip_steps = 1
+        return loss.clone().requires_grad_(True), rl, vl, pl          # a leaf: the caller's loss.backward() touches nothing else
+
+    system._k_step_rollout = deferred_rollout
+    mod.loss_fn = graphed_loss_fn
+    return step

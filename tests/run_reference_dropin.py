@@ -58,6 +58,12 @@ def step(state, action, done_mask):
 
 
 mcts.search, env.step = search, step
+graph_step = None
+if os.environ.get("MZB_GRAPH_TRAIN") == "1":      # the unmodified _training_stage, each loop iteration ONE CUDA-graph replay
+    from muzero_breakout_b200 import train as _train
+    if type(system.mu_zero).__module__ == "src.networks":
+        _train.accelerate_agent(system.mu_zero)
+    graph_step = _train.accelerate_training_stage(system)
 t0 = time.perf_counter()
 system._acting_stage()
 t_act = time.perf_counter() - t0
@@ -70,7 +76,9 @@ t0 = time.perf_counter()
 system._training_stage()
 t_train = time.perf_counter() - t0
 n_launch_train = _mzb.launch_count() - n_launch0
-out = dict(modules=mods, acting=acting, training=dict(seconds=t_train, steps=int(system.training_step), library_launches=int(n_launch_train)),
+out = dict(modules=mods, acting=acting, training=dict(seconds=t_train, steps=int(system.training_step), library_launches=int(n_launch_train),
+                                                      graph_replays=None if graph_step is None else int(graph_step.replays),
+                                                      optimizer_steps=int(getattr(system.mu_zero.optimizer, "step_count", -1))),
            search_calls=log["searches"], env_steps=log["steps"], search_batches=sorted(log["batches"]),
            visit_sum_ok=log["visit_sum_ok"], value_finite=log["value_finite"], visits_dtype=log["visits_dtype"], value_device=log["value_device"],
            done_aliased=log["done_aliased"], step_shapes_ok=log["step_shapes_ok"], env_batch_after=int(system.environment.batch),

@@ -43,3 +43,19 @@ def test_unmodified_rlsystem_runs_on_the_dropins(tmp_path, agent_dropin):
     assert out["training"]["steps"] >= 1
     assert out["search_batches"] == [2, 24]                                     # acting at n_parallel, the test rollout at batch 2 (:448-452)
     assert out["env_batch_after"] == 24 and out["mcts_net_is_target"]
+
+
+def test_unmodified_training_stage_as_graph_replays(tmp_path):
+    """train.accelerate_training_stage: the reference's own, unmodified `_training_stage` loop (train_torch.py:369-452) with every iteration
+    ONE CUDA-graph replay (rollout + loss + backward + Adam; the reference's `_k_step_rollout`, `loss_fn` and `optimizer.step()` plug points
+    patched on the live objects) -- graph replays == training steps == optimizer updates, then the 2-env test rollout on the updated net."""
+    from baseline import ref
+    if ref.ref_dir() is None:
+        pytest.skip("no reference checkout on this box")
+    env = dict(os.environ, PYTHONPATH="", MZB_DROPIN_AGENT="1", MZB_GRAPH_TRAIN="1", MZB_REF_BATCHES="3")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_dropin.py")], capture_output=True, text=True, cwd=tmp_path, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    out = json.loads(next(ln for ln in r.stdout.splitlines() if ln.startswith("RESULT "))[len("RESULT "):])
+    t = out["training"]
+    assert t["steps"] == 3 and t["graph_replays"] == 3 and t["optimizer_steps"] == 3, t
+    assert out["search_batches"] == [2, 24] and out["mcts_net_is_target"] and out["value_finite"]

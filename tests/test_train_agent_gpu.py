@@ -177,3 +177,56 @@ def test_accelerate_agent_patches_a_reference_shaped_module():
     assert float((va.detach() - vb.detach()).abs().max() / vb.detach().abs().max()) <= 5e-2
     (pa.sum() + va.sum()).backward()
     assert agent.pred_net.res_blocks[0].conv1.weight.grad is not None
+
+
+def _minibatch(n, K, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    states = torch.rand((n, 32, 16, 20), device="cuda", generator=g)
+    planes = torch.randint(0, 3, (n, 32, 1, 1), device="cuda", generator=g).float().expand(-1, -1, 16, 20) / 3
+    acts = torch.randint(0, 3, (n, K), device="cuda", generator=g)
+    rew = torch.randint(-1, 2, (n, K), device="cuda", generator=g).float()
+    val = (torch.rand((n, K), device="cuda", generator=g) - 0.5) * 8
+    vis = torch.randint(1, 30, (n, K, 3), device="cuda", generator=g).float()
+    return states, planes.contiguous(), acts, rew, val, vis
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """train.GraphedTrainStep (the loop body of train_torch.py:385-417 as one CUDA-graph replay, optimizer step count on the device)
+    against the same iterations run eagerly on a second agent with the same initial weights: the captured kernels are the ones the eager
+    path launches, so the first step's losses agree to 1e-5 and the following ones (each depends on the previous updates) to 2e-2, the BatchNorm
+    running statistics and step counters match, and the first call counts as exactly ONE update although capture needs a warm-up pass."""
+    from muzero_breakout_b200 import train
+    from muzero_breakout_b200.src.agent import MuZeroAgent
+    cfg = dict(DEFAULT_MODEL_CFG, learning_rate=2e-4, device="cuda")
+    K, n = 3, 48
+    sup = torch.linspace(-5, 5, 11, device="cuda")
+    torch.manual_seed(5); a = MuZeroAgent(cfg); a.train_mode()
+    torch.manual_seed(5); b = MuZeroAgent(cfg); b.train_mode()
+    w0 = b.dyn_net.res_blocks[3].conv1.weight.detach().clone()
+    step = train.GraphedTrainStep(b, sup, K)
+    la, lb = [], []
+    for it in range(3):
+        mb = _minibatch(n, K, 100 + it)
+        a.optimizer.zero_grad()
+        pr, pv, pp = train.k_step_rollout(a, mb[0], mb[1], mb[2], K)
+        out = train.loss_fn(mb[3], pr, mb[4], pv, mb[5], pp, sup, K)
+        out[0].backward()
+        a.optimizer.step()
+        la.append([float(o) for o in out])
+        lb.append([float(o) for o in step(*mb)])
+    assert step.replays == 3 and b.optimizer.step_count == 3 == a.optimizer.step_count
+    assert int(b.optimizer._dev_state[0]) == 3, "device step counter"
+    # step 1 sees identical weights; from step 2 on the two runs differ by what Adam makes of last-bit gradient differences in the torch / cuDNN
+    # layers (algorithm choice under capture, atomics): the first update is -lr * sign(g) for EVERY parameter, noise-level gradients included
+    for it, (x, y) in enumerate(zip(la, lb)):
+        for u, v in zip(x, y):
+            assert abs(u - v) <= (1e-5 if it == 0 else 2e-2) * max(1.0, abs(u)), (la, lb)
+    bn_a, bn_b = a.pred_net.res_blocks[5].bn2, b.pred_net.res_blocks[5].bn2
+    assert int(bn_b.num_batches_tracked) == int(bn_a.num_batches_tracked) == 3 * K
+    assert _rel(bn_b.running_mean, bn_a.running_mean) <= 2e-2 and _rel(bn_b.running_var, bn_a.running_var) <= 2e-2
+    wa, wb = a.dyn_net.res_blocks[3].conv1.weight, b.dyn_net.res_blocks[3].conv1.weight
+    assert float((wb - w0).abs().max()) > 1e-5, "the graph did not update the parameters"
+    cos = _cos(wa - w0, wb - w0)
+    print(f"losses eager {la} graph {lb}; cosine of the accumulated trunk-weight updates {cos:.4f}")
+    assert cos >= 0.9, f"accumulated updates of a trunk convolution after 3 steps: cosine {cos:.4f}"
+    assert wb._version > 0
