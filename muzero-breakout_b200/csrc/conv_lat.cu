@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_lat_kernel(const LatParams p)
             if (r < nrows) {
                 float x0 = (v[h * 2] + ab[h].x) + sf.x + rs[h].x;
                 float x1 = (v[h * 2 + 1] + ab[h].y) + sf.y + rs[h].y;
-                x0 = activate(x0, L->act);
-                x1 = activate(x1, L->act);
+                if (L->act == MZ_ACT_RELU) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                else if (L->act != MZ_ACT_NONE) { x0 = activate(x0, L->act); x1 = activate(x1, L->act); }
                 const size_t o = ((size_t)s0 * HW + r) * cout + co;
                 uint32_t packed;
                 if (reg_stream && (L->k1 & 16)) {

@@ -94,6 +94,15 @@ __device__ __forceinline__ unsigned long long gtime_ns()
 }
 #define STRACE(slot, layer) do { if (p.trace == 1 && blockIdx.x == 0 && (layer) < 64) g_stack_trace[(slot) * 64 + (layer)] = gtime_ns(); } while (0)
 
+// generic proxy <-> async proxy ordering of GLOBAL memory (acquired counters -> TMA loads of what they guard; TMA stores -> the release
+// that publishes them).  mode (experiments, StackParams::debug bits 8 / 16): 0 = .global form, 8 = the all-spaces form, 16 = none (timing only)
+__device__ __forceinline__ void proxy_fence_global(int mode)
+{
+    if (mode & 16) return;
+    if (mode & 8) asm volatile("fence.proxy.async;" ::: "memory");
+    else asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t tap_mask(int y, int x)
 {
     uint32_t m = 0u;
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                             if (v >= seq) break;
                             if (++spins > (1u << 28)) __trap();
                         }
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        proxy_fence_global(p.debug);
                     }
                     if (item0 && lane == 0) STRACE(1, layer);
                     bool first_ks = true;
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                     }
                 }
                 if (res >= 0 && live && elect_one()) {
-                    asm volatile("fence.proxy.async;" ::: "memory");
+                    proxy_fence_global(p.debug);
                     mbar_expect_tx(bar_res, NSUB * 4096);
 #pragma unroll
                     for (int sub = 0; sub < NSUB; ++sub) tma_load_4d_cta_hint(stg + sub * 4096, &p.map_epi[res], bar_res, col0 + 64 * sub, x0, y0, s0w, pol);
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(STACK_THREADS, 1) conv_stack_kernel(const __gr
                         for (int sub = 0; sub < NSUB; ++sub) tma_store_4d_hint(&p.map_epi[dst], stg + sub * 4096, col0 + 64 * sub, x0, y0, s0w, pol);
                         tma_store_commit();
                         tma_store_wait();                                    // global writes performed (and the staging tile is free again)
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        proxy_fence_global(p.debug);
                         // publish: this warp's part of (layer, group g, pixel pix) is in global memory -- the TMA stores above and, through
                         // the __syncwarp, every lane's correction-plane / fp32 stores (release is cumulative)
                         asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.done + ((size_t)layer * p.groups + g) * HW + pix) : "memory");
