@@ -546,17 +546,31 @@ def accelerate_agent(agent):
 
 # ------------------------------------------------------------------------------------------------------------------------------------
 # one iteration of the training loop as ONE CUDA graph
-def k_step_rollout(agent, input_states, input_actions, k_step_actions, K, latent_resolution=(4, 5), n_actions=3):
+def k_step_rollout(agent, input_states, input_actions, k_step_actions, K, latent_resolution=(4, 5), n_actions=3, side_stream=None):
     """What RLSystem._k_step_rollout does (train_torch.py:487-528) with any MuZeroAgent-shaped module: representation network on
     cat(states, action planes), then K x (prediction, dynamics on the one-hot action planes of :295-311).  Returns the stacked
-    (reward, value, policy) logits, (batch, K, .)."""
+    (reward, value, policy) logits, (batch, K, .).
+    side_stream: evaluate the prediction network of step k on this stream while the dynamics network of step k runs on the current one
+    (both only read h_k; autograd replays the split in the backward pass): at a 512-sample minibatch a trunk convolution fills 80 of the
+    148 SMs, so the two networks overlap instead of queueing."""
     h = agent.create_hidden_state_root(torch.cat((input_states, input_actions), dim=1))
+    cur = torch.cuda.current_stream(h.device) if h.is_cuda else None
     pol, val, rew = [], [], []
     for k in range(K):
-        p_, v_ = agent.evaluate_state(h)
         planes = torch.nn.functional.one_hot(k_step_actions[:, k].long(), num_classes=n_actions).float().view(-1, n_actions, 1, 1)
+        if side_stream is not None:
+            side_stream.wait_stream(cur)
+            with torch.cuda.stream(side_stream):
+                p_, v_ = agent.evaluate_state(h)
+            h.record_stream(side_stream)
+        else:
+            p_, v_ = agent.evaluate_state(h)
         h, r_ = agent.hidden_state_transition(h, planes.expand(-1, -1, latent_resolution[0], latent_resolution[1]))
         pol.append(p_); val.append(v_); rew.append(r_)
+    if side_stream is not None:
+        cur.wait_stream(side_stream)
+        for t in pol + val:
+            t.record_stream(cur)
     return torch.stack(rew, dim=1), torch.stack(val, dim=1), torch.stack(pol, dim=1)
 
 
@@ -577,14 +591,16 @@ class GraphedTrainStep:
     Capture needs one warm-up pass (kernel attributes, cuDNN plans, allocator); it runs on a snapshot: parameters, BatchNorm buffers and
     optimizer state are restored before the capture, so the first call counts as exactly one update."""
 
-    def __init__(self, agent, target_transformation, K, latent_resolution=(4, 5), n_actions=3, rollout=None):
+    def __init__(self, agent, target_transformation, K, latent_resolution=(4, 5), n_actions=3, rollout=None, two_streams=True):
         _lib.require_cuda()
         if not isinstance(getattr(agent, "optimizer", None), Adam):
             raise TypeError("GraphedTrainStep needs the flat-buffer Adam (the drop-in agent, or accelerate_agent(reference_agent))")
         self.agent, self.opt, self.K = agent, agent.optimizer, int(K)
         self.supports = _supports_of(target_transformation)
         self.res, self.n_actions = tuple(latent_resolution), int(n_actions)
-        self.rollout = rollout or (lambda *inp: k_step_rollout(self.agent, *inp, self.K, self.res, self.n_actions))
+        # MZB_TRAIN_STREAMS=1: everything on one stream
+        self.side = torch.cuda.Stream(device=agent.optimizer.flat_param.device) if (two_streams and os.environ.get("MZB_TRAIN_STREAMS", "2") != "1") else None
+        self.rollout = rollout or (lambda *inp: k_step_rollout(self.agent, *inp, self.K, self.res, self.n_actions, side_stream=self.side))
         self._graphs = {}
         self.replays = 0
 
