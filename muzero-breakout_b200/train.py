@@ -367,17 +367,31 @@ class ResidualBlockTrain:
         """dy: float32 gradient of the block output.  Returns (dx float32, {parameter name: gradient})."""
         return self.backward_fn(dy, self._saved)
 
-    def backward_fn(self, dy: torch.Tensor, saved, grad_into=(None, None)):
+    def backward_fn(self, dy: torch.Tensor, saved, grad_into=(None, None), side=None):
         """grad_into: (conv1.weight.grad, conv2.weight.grad) to accumulate the weight gradients into (the entries of the returned dict are
-        then None), or None entries for fresh tensors."""
+        then None), or None entries for fresh tensors.  side: a CUDA stream for the weight-gradient chain (transposes, mz_conv_wgrad, split
+        reduction) when both gradients accumulate in place -- it only shares its inputs with the data-gradient chain, and at a 512-sample
+        minibatch neither fills the chip; the caller joins the stream."""
         x16, z1, h16, z2, m1, s1, m2, s2 = saved
+        if side is not None and (grad_into[0] is None or grad_into[1] is None):
+            side = None
+        cur = torch.cuda.current_stream(dy.device) if side is not None else None
+
+        def wgrad(dz16, act16, into):
+            if side is None:
+                dw = conv_wgrad(dz16, act16, 3, into)
+                return None if into is not None else dw
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                conv_wgrad(dz16, act16, 3, into)
+            dz16.record_stream(side); act16.record_stream(side)
+            return None
+
         dz2, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu")
-        dw2 = conv_wgrad(dz2_16, h16, 3, grad_into[1])
-        dw2 = None if grad_into[1] is not None else dw2
+        dw2 = wgrad(dz2_16, h16, grad_into[1])
         dh = self.dgrad[1](dz2_16)
         dz1, dz1_16, dg1, db1, _ = bn_train_backward(z1, dh, self.gamma[0], self.beta[0], m1, s1, None, "relu")
-        dw1 = conv_wgrad(dz1_16, x16, 3, grad_into[0])
-        dw1 = None if grad_into[0] is not None else dw1
+        dw1 = wgrad(dz1_16, x16, grad_into[0])
         dx = self.dgrad[0](dz1_16)
         dx += dres                                      # the skip connection's gradient
         return dx, {"conv1.weight": dw1, "bn1.weight": dg1, "bn1.bias": db1, "conv2.weight": dw2, "bn2.weight": dg2, "bn2.bias": db2}
@@ -440,6 +454,19 @@ class TrunkTrain:
 _ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "0") == "1"
 
 
+# GraphedTrainStep switches this on while it warms up / captures: inside a CUDA graph a stream fork costs nothing, eagerly the event
+# record / wait pairs would eat the gain
+_WGRAD_SIDE = {"on": False, "streams": {}}
+
+
+def _wgrad_side_stream(cur):
+    key = (cur.device, cur.cuda_stream)
+    st = _WGRAD_SIDE["streams"].get(key)
+    if st is None:
+        st = _WGRAD_SIDE["streams"][key] = torch.cuda.Stream(device=cur.device)
+    return st
+
+
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernels, *params):
@@ -457,16 +484,20 @@ class _TrunkFn(torch.autograd.Function):
         g = dy.permute(0, 2, 3, 1).contiguous().float()
         flat = []
         nb = len(ctx.kernels)
+        cur = torch.cuda.current_stream(g.device)
+        side = _wgrad_side_stream(cur) if _WGRAD_SIDE["on"] else None
         for i, (blk, sv) in enumerate(zip(reversed(ctx.kernels), reversed(ctx.saved_blocks))):
             ps = ctx.params[8 * (nb - 1 - i):8 * (nb - i)]           # conv1.w, conv1.b, bn1.w, bn1.b, conv2.w, conv2.b, bn2.w, bn2.b
             # a parameter that already has a contiguous .grad (always, under this module's flat-buffer Adam) takes its weight gradient by
             # in-kernel accumulation; autograd then gets None for it (one add kernel less per convolution and unroll step)
             into = tuple(p.grad if (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32) else None for p in (ps[0], ps[4]))
-            g, grads = blk.backward_fn(g, sv, into)
+            g, grads = blk.backward_fn(g, sv, into, side)
             # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient): None where a .grad exists, zeros otherwise
             zb = [None if p.grad is not None else torch.zeros(256, device=g.device) for p in (ps[1], ps[5])]
             flat.append((grads["conv1.weight"], zb[0], grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zb[1], grads["bn2.weight"], grads["bn2.bias"]))
         ctx.saved_blocks = None
+        if side is not None:
+            cur.wait_stream(side)                            # the accumulated weight gradients are complete when this node is
         out = [t for blk in reversed(flat) for t in blk]
         return (g.permute(0, 3, 1, 2), None, *out)
 
@@ -605,6 +636,13 @@ class GraphedTrainStep:
         self.replays = 0
 
     def _body(self, st):
+        _WGRAD_SIDE["on"] = self.side is not None
+        try:
+            return self._body_inner(st)
+        finally:
+            _WGRAD_SIDE["on"] = False
+
+    def _body_inner(self, st):
         self.opt.flat_grad.zero_()
         pr, pv, pp = self.rollout(st[0], st[1], st[2])
         out = loss_fn(st[3], pr, st[4], pv, st[5], pp, self.supports, self.K)
