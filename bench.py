@@ -41,7 +41,7 @@ ENV_BYTES_PER_STEP = 3898       # 3840 frame + 4 reward 
 ENV_TRAFFIC_PER_ENV = (1.92e6 + 196.2e6) / 65536     # r1_env_step_final_full.txt, 65 536 envs per launch (the L2 keeps part of the frames)
 # DRAM bytes per (sample, trunk layer) of conv_stack_kernel: profiles/r1_conv_stack_scout_full.txt, the 28-layer prediction trunk at
 # 4096 samples per launch read 801.7 MB and wrote 1078.1 MB
-TRUNK_TRAFFIC_PER_SAMPLE_LAYER = (801.693952e6 + 1078.071e6) / (28 * 4096)
+TRUNK_TRAFFIC_PER_SAMPLE_LAYER = (1039.678e6 + 1073.946e6) / (29 * 4096)   # profiles/r2_conv_stack_final_full.txt: prediction trunk, 29 layer records
 FLOP_TRUNK_LAYER_VALID = 130 * 256 * 256 * 2           # one 3x3 256->256 conv on the 4x5 latent, in-bounds taps only, per sample
 
 
@@ -434,7 +434,7 @@ def bench_mcts(args, rank, local, world):
         out["collectives"] = collectives
     out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                        "frac": achieved / peaks["bf16_sustained"], "traffic": TRUNK_TRAFFIC_PER_SAMPLE_LAYER * n_trunk * B / trunk_launches,
-                       "traffic_source": "profiles/r1_conv_stack_scout_full.txt (ncu --set full, 28-layer trunk launch at 4096 samples, scaled by layers x samples per launch)",
+                       "traffic_source": "profiles/r2_conv_stack_final_full.txt (ncu --set full, the 29-record prediction-trunk launch at 4096 samples: 1.04 GB read + 1.07 GB written, scaled by layers x samples per launch)",
                        "peak_source": peaks["src"] + " (sustained cuBLAS bf16, same power cap)",
                        "kernel": f"{kernel_name}: {n_trunk} conv layers of one simulation step in {trunk_launches} launches", "flop_convention": "valid taps only (BASELINE.md section 3)",
                        "flop_per_launch": trunk_flop * B / trunk_launches, "kernel_ms": trunk_ms / trunk_launches,
