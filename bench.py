@@ -298,6 +298,7 @@ def bench_mcts(args, rank, local, world):
         from muzero_breakout_b200 import parallel
         coll = {"bc_ms": [], "ag_ms": [], "bytes_bc": 0}
         rec = torch.zeros((B, parallel.RECORD_FLOATS), device=dev)
+        gather = parallel.AsyncTrajectoryGather(B, parallel.RECORD_FLOATS, device=dev, depth=2)
 
     def one_search(i, timed):
         if coll is not None and i % 15 == 0:
@@ -309,22 +310,28 @@ def bench_mcts(args, rank, local, world):
         if coll is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
-            rec[:, 322:325] = visits; rec[:, 325] = value                 # this move's record (the frame / action / reward columns come from the env step)
-            gathered = parallel.all_gather_trajectory(rec, equal_shards=True)
+            slot = gather.slot()                                          # waits only for the collective of two moves ago
+            slot[:, 322:325] = visits; slot[:, 325] = value               # this move's record (the frame / action / reward columns come from the env step)
+            gather.submit()                                               # asynchronous: the next search does not wait for the other ranks
             ev[1].record()
-            assert gathered.shape[0] == world * B
             if timed:
                 coll["ag_ms"].append(ev)
         return value, visits
 
     for i in range(W):
         one_search(i, False)
+    if coll is not None:
+        gather.drain()
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(K):
             value, visits = one_search(i, True)
+        if coll is not None:
+            gathered = gather.drain()                                     # every record of the timed searches has arrived before the clock stops
+            assert len(gathered) >= min(K, 2) and all(g_.shape[0] == world * B for g_ in gathered)
+            torch.cuda.current_stream(dev).synchronize()
         e1.record()
         barrier_sync(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world)
@@ -406,7 +413,8 @@ def bench_mcts(args, rank, local, world):
                        "trajectory_allgather_ms_in_loop": ag_ms, "trajectory_allgather_ms_alone": ag_alone,
                        "trajectory_allgather_GBps_per_rank_in": rec_bytes * (world - 1) / ag_alone / 1e6,
                        "share_of_step": (bc_ms * len(coll["bc_ms"]) + ag_ms * len(coll["ag_ms"])) / ms,
-                       "note": "in_loop = per call inside the timed searches, waiting for the slowest rank's search included; alone = back to back after a barrier"}
+                       "trajectory_allgather_mode": "asynchronous, two staging slots (parallel.AsyncTrajectoryGather): the next search starts without waiting for the other ranks; all records drained before the clock stops",
+                       "note": "in_loop = time on the acting stream per call inside the timed searches (broadcast: waits for the slowest rank; all-gather: the slot hand-over only); alone = blocking, back to back after a barrier"}
 
     peaks = measured_peaks()
     sims = world * B * S * K
@@ -418,7 +426,7 @@ def bench_mcts(args, rank, local, world):
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "tolerance_met": tol_met,
         "config": {"workload": f"mcts: MCTSSearchVec.search, {B} roots x {S} simulations per GPU, random-init MuZero networks (config.yaml sizes), {args.precision}",
                    "trees_per_gpu": B, "num_simulations": S, "step": "one search() call = root prediction + S x (dynamics + prediction + backup/select)"
-                   + (" + the trajectory all-gather; target-weight broadcast every 15th search" if world > 1 else ""),
+                   + (" + the asynchronous trajectory all-gather; target-weight broadcast every 15th search" if world > 1 else ""),
                    "l2": f"latent store {B * (S + 2) * 10240 * (4 if args.precision == 'f32' else 2) // 2 / 1e9:.2f} GB per GPU, far larger than the 126 MB L2",
                    "cuda_graph": bool(m.use_graph),
                    "arithmetic": {"f16": "fp16 tensor-core operands, fp32 accumulation and epilogues, residual stream as fp16 + e4m3 correction", "bf16": "bf16 operands, fp32 accumulation",

@@ -8,6 +8,7 @@ only where the reference has an exchange step:
   broadcast_weights      target-network refresh: the reference copies the learner's state_dict into the
                          target network every 15 iterations (train_torch.py:137-138, 361-367); here the
                          learner rank broadcasts the PACKED weights (84 MB bf16) in one flat bucket per dtype.
+  AsyncTrajectoryGather  the same exchange per move, asynchronous and double-buffered (the acting loop never waits for it)
   all_gather_trajectory  per-step trajectory records (gray frame, action, reward, visit counts, value --
                          what train_torch.py:204-208 appends to ObservationTrajectory) gathered from every
                          rank into the replay-buffer owner's tensor, ordered by global env index.
@@ -102,6 +103,55 @@ def all_gather_trajectory(local: torch.Tensor, group=None, equal_shards: bool = 
     out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+class AsyncTrajectoryGather:
+    """The per-move trajectory exchange WITHOUT stalling the acting loop.  A blocking all-gather after every search makes the ranks run in
+    lock step: every move costs the slowest rank's search plus the collective (measured at 8 GPUs: 4.7 % of a step).  Nothing on the acting
+    path reads the gathered records -- only the replay-buffer append at the end of an episode does -- so the collective can run on the
+    process group's own stream while the next search is already under way: `submit(local)` copies the record into one of `depth` staging
+    slots (waiting only for the collective that used the slot `depth` moves ago) and launches `all_gather_into_tensor(async_op=True)`;
+    `drain()` waits for everything in flight and returns the gathered tensors in submission order.  Ranks may drift apart by up to `depth`
+    moves; equal shard sizes on all ranks (the acting loop's case)."""
+
+    def __init__(self, rows: int, cols: int = RECORD_FLOATS, device=None, dtype=torch.float32, depth: int = 2, group=None):
+        self.group, self.depth = group, int(depth)
+        world = dist.get_world_size(group)
+        self.local = [torch.zeros((rows, cols), dtype=dtype, device=device) for _ in range(self.depth)]
+        self.out = [torch.empty((world * rows, cols), dtype=dtype, device=device) for _ in range(self.depth)]
+        self.work = [None] * self.depth
+        self.ready = []                 # gathered tensors whose slot was recycled (cloned), in submission order
+        self.pending = []               # slot indices in flight, in submission order
+        self.n = 0
+
+    def _retire(self, slot, clone):
+        self.work[slot].wait()
+        self.work[slot] = None
+        self.pending.remove(slot)
+        self.ready.append(self.out[slot].clone() if clone else self.out[slot])
+
+    def slot(self) -> torch.Tensor:
+        """the staging tensor of the next submit(), free to be filled in place (e.g. by slice assignment from the search's outputs)"""
+        k = self.n % self.depth
+        if self.work[k] is not None:
+            self._retire(k, clone=True)
+        return self.local[k]
+
+    def submit(self, local: torch.Tensor | None = None):
+        """local: this rank's (rows, cols) record, or None when slot() was filled in place"""
+        k = self.n % self.depth
+        buf = self.slot()
+        if local is not None:
+            buf.copy_(local)
+        self.work[k] = dist.all_gather_into_tensor(self.out[k], buf, group=self.group, async_op=True)
+        self.pending.append(k)
+        self.n += 1
+
+    def drain(self):
+        for k in list(self.pending):
+            self._retire(k, clone=False)
+        out, self.ready = self.ready, []
+        return out
 
 
 EPISODE_FIELDS = ("action", "reward", "value", "visits", "frames", "recorded")

@@ -55,6 +55,19 @@ def _worker(rank, world, port, q):
             full = torch.arange(total)
             assert torch.equal(a2, full % 3) and torch.equal(r2, full.float() * 0.5) and torch.equal(n2[:, 0], full)
             assert torch.equal(g2[:, 0, 0, 0], (full % 2).float()) and torch.allclose(v2, full.float() / 7)
+        # asynchronous per-move exchange: 5 moves through 2 staging slots, results in submission order, equal to the blocking form
+        ag = parallel.AsyncTrajectoryGather(4, 6, depth=2)
+        want_moves = []
+        for mv in range(5):
+            loc = torch.arange(24, dtype=torch.float32).view(4, 6) + 100 * rank + 1000 * mv
+            if mv % 2:
+                ag.slot().copy_(loc); ag.submit()             # filled in place
+            else:
+                ag.submit(loc)
+            want_moves.append(torch.cat([torch.arange(24, dtype=torch.float32).view(4, 6) + 100 * r + 1000 * mv for r in range(world)]))
+        got = ag.drain()
+        assert len(got) == 5 and all(torch.equal(g_, w_) for g_, w_ in zip(got, want_moves))
+        assert ag.drain() == []
         # whole-episode exchange: ranks played different numbers of moves with different shard sizes
         lo, hi = parallel.shard_range(7, rank, world)
         B, T = hi - lo, 5 + 3 * rank
