@@ -9,8 +9,10 @@ What runs where in a training step (`loss.backward()` included):
   * the ResidualBlock runs of the dynamics and prediction networks (2 x 14 blocks, K = 5 unroll steps: 280 of the ~330 convolutions of a
     step) -- forward, data gradient, weight gradient on tcgen05 and the training-mode BatchNorm kernels, through train.trunk_forward;
   * the optimizer -- train.Adam (one mz_adam launch over flat buffers);
-  * the representation network, the dynamics ConvBlock with its action planes, the three head ConvBlocks + Linear heads and
-    `_scale_state` -- torch ops (cuDNN / cuBLAS) on the same device.  Not built as library kernels yet.
+  * opt-in (MZB_TRAIN_ANY_HW=1): the representation network's 256-channel ResidualBlocks (3 at 16x20, 3 at 8x10) on the same kernels;
+  * the representation network (by default), its stem convolutions, 128-channel blocks and pools, the dynamics ConvBlock with its action planes, the three
+    head ConvBlocks + Linear heads and `_scale_state` -- torch ops (cuDNN / cuBLAS, channels_last) on the same device.  Not built as library
+    kernels yet.
 In eval mode / under no_grad the module runs plain torch ops; acting does not call it at all (MCTSSearchVec packs its state_dict).
 There is no CPU path for the accelerated parts: on a CPU tensor the module is an ordinary torch module.
 """
@@ -84,8 +86,16 @@ class RepresentationNetwork(nn.Module):
             # channels_last activations from here on: cuDNN then runs its NHWC kernels without the NCHW <-> NHWC conversion pair around every
             # convolution (5.8 ms of a 512-sample training step), and the library trunks take / return their channels-last layout without a copy
             state = state.contiguous(memory_format=torch.channels_last)
-        for m in self.blocks:
+        run = []                                       # consecutive ResidualBlocks go through the library as one call (no layout / precision
+        for m in self.blocks:                          # round trip between them); 128-channel blocks and the other layers run on torch ops
+            if isinstance(m, ResidualBlock):
+                run.append(m)
+                continue
+            if run:
+                state, run = _run_blocks(run, state), []
             state = m(state)
+        if run:
+            state = _run_blocks(run, state)
         return state
 
 

@@ -451,6 +451,10 @@ class TrunkTrain:
 # ------------------------------------------------------------------------------------------------------------------------------------
 # autograd bridge: a run of train-mode ResidualBlocks of an nn.Module (the reference's own ResidualBlock modules, networks.py:19-35, or the
 # drop-in agent's) evaluated by this library's kernels inside loss.backward() (train_torch.py:515)
+# 1: also the representation network's 256-channel blocks at 16x20 / 8x10 (the kernels take any image size: same errors as at 4x5,
+# profiles/prof_train_any_hw.py).  Off by default: a training iteration drops from 46 to 43 ms, but bf16 operands at the ROOT of the
+# rollout cost fidelity everywhere downstream (forward outputs 0.07-0.09 -> 0.18-0.21 of range from the fp32 modules, worst trunk
+# weight-gradient cosine 0.84 -> 0.65; torch's own autocast bf16: 0.38-0.56 and 0.35) -- tests/test_train_agent_gpu.py prints both
 _ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "0") == "1"
 
 
@@ -511,7 +515,7 @@ def trunk_supported(blocks, x) -> bool:
     statistics at the default eps, a float32 CUDA input, training mode with gradients enabled."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 256 and torch.is_grad_enabled()):
         return False
-    if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # the 4x5 latent of the dynamics / prediction trunks; other maps: MZB_TRAIN_ANY_HW=1
+    if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # other maps than the 4x5 latent: the representation network's 16x20 / 8x10 blocks (opt-in)
         return False
     for m in blocks:
         if not (m.training and all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2")) and m.conv1.weight.shape == (256, 256, 3, 3)
