@@ -411,6 +411,9 @@ int mz_adam_dev(long long n, float *param, const float *grad, float *exp_avg, fl
 int mz_wgrad_padded_samples(int n);
 size_t mz_wgrad_partial_bytes(int ksize, int n);
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream);
+/* f16_to_bf16 != 0: src is float16, dst bfloat16 -- the activations of an fp16 forward pass as the bf16 operand next to bf16 gradients
+ * (one tcgen05 kind::f16 MMA cannot mix A / B element types) */
+int mz_wgrad_transpose_cvt(int n, int P, int C, const void *src, void *dst, int f16_to_bf16, void *stream);
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
 /* accumulate != 0: dw += the gradient (one rounding per call, in call order): the K unroll steps of a training step share their weights
  * (train_torch.py:507-525) and add straight into the parameter's .grad instead of through K separate add kernels */
@@ -434,6 +437,11 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
 int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int act,
                     const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres, void *scratch,
                     void *stream);
+/* the same with separate element types for res (dtype: what the forward pass produced) and dz16 (dz_dtype: the operand of the convolution
+ * gradients): an fp16 forward pass with bf16 gradients */
+int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
+                          int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres,
+                          void *scratch, void *stream);
 
 #ifdef __cplusplus
 }

@@ -170,8 +170,8 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, const float *__restrict__ dy, const float *__restrict__ mean,
                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res,
-                    int f16, int act, const float *__restrict__ dgamma, const float *__restrict__ dbeta, float *__restrict__ dz, uint16_t *__restrict__ dz16,
-                    float *__restrict__ dres)
+                    int f16, int dz_f16, int act, const float *__restrict__ dgamma, const float *__restrict__ dbeta, float *__restrict__ dz,
+                    uint16_t *__restrict__ dz16, float *__restrict__ dres)
 {
     const size_t i = (size_t)blockIdx.x * BN_THREADS + threadIdx.x;
     if (i >= total4) return;
@@ -188,7 +188,7 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
         o[k] = gamma[c + k] * invstd[c + k] * (g[k] - dbeta[c + k] * inv_m - xh * dgamma[c + k] * inv_m);
     }
     if (dz) reinterpret_cast<float4 *>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
-    if (dz16) store4_16(dz16 + i * 4, f16 != 0, o);
+    if (dz16) store4_16(dz16 + i * 4, dz_f16 != 0, o);
     if (dres) reinterpret_cast<float4 *>(dres)[i] = make_float4(g[0], g[1], g[2], g[3]);
 }
 
@@ -227,6 +227,14 @@ int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *
                     const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres, void *scratch,
                     void *stream)
 {
+    return mz_bn_train_bwd_mixed(M, C, z, dy, gamma, beta, res, dtype, dtype, act, save_mean, save_invstd, dgamma, dbeta, dz, dz16, dres, scratch, stream);
+}
+
+int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
+                          int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres,
+                          void *scratch, void *stream)
+{
+    MZB_CHECK_ARG(dz_dtype == MZ_BF16 || dz_dtype == MZ_F16, "dz16 is 16-bit: dz_dtype must be MZ_BF16 or MZ_F16");
     MZB_CHECK_ARG(bn_shape_ok(M, C), "M must be positive and C one of 4 * {1, 2, 4, ..., 256}");
     MZB_CHECK_ARG(z && dy && gamma && beta && save_mean && save_invstd && dgamma && dbeta && scratch && (dz || dz16), "null pointer");
     MZB_CHECK_ARG(dtype == MZ_BF16 || dtype == MZ_F16, "dz16 / res are 16-bit: dtype must be MZ_BF16 or MZ_F16");
@@ -241,7 +249,7 @@ int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
     bn_bwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
-                                                                                                 (const uint16_t *)res, dtype == MZ_F16, act, dgamma, dbeta, dz,
+                                                                                                 (const uint16_t *)res, dtype == MZ_F16, dz_dtype == MZ_F16, act, dgamma, dbeta, dz,
                                                                                                  (uint16_t *)dz16, dres);
     MZB_LAUNCH_CHECK();
     return 0;

@@ -237,6 +237,11 @@ __device__ __forceinline__ uint32_t instr_desc(int N, bool f16 = false)
     const uint32_t fmt = f16 ? 0u : 1u;
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
 }
+// the same with separate operand formats (A = dy bf16, B = x fp16 in the weight gradient of an fp16-forward training step)
+__device__ __forceinline__ uint32_t instr_desc_ab(int N, bool a_f16, bool b_f16)
+{
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+}
 // two packed 16-bit activations <-> floats; `f16` is uniform per launch
 __device__ __forceinline__ float2 unpack2(uint32_t u, bool f16)
 {

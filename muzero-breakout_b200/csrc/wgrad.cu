@@ -22,7 +22,7 @@ constexpr int WG_MAX_SPLITS = 8;
 constexpr size_t WG_SMEM = (size_t)STAGES * STAGE_BYTES + 256;
 
 struct WgradParams {
-    int ns, H, W, taps, chunks, splits, ntiles, f16;
+    int ns, H, W, taps, chunks, splits, ntiles, a_f16, b_f16;     // element types of dy (A operand) and x (B operand)
     float *partial;                             // [taps][splits][256][256]
 };
 
@@ -101,7 +101,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc(WG_C, p.f16 != 0);
+            const uint32_t idesc = instr_desc_ab(WG_C, p.a_f16 != 0, p.b_f16 != 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -180,7 +180,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
 
 // [n][P][C] (channels-last, 16-bit) -> [C][P][ns], samples n..ns-1 zero.  One CTA = 64 samples x 64 channels of one pixel: 32-byte
 // loads along the channels, 32-byte stores along the samples, through a padded shared-memory tile.  grid (ns/64, C/64, P), 256 threads
-__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst)
+// cvt: 1 = the source is fp16 and the destination bf16 (the activations of an fp16 forward pass as the weight gradient's bf16 operand: one MMA
+// cannot mix A / B element types in kind::f16 -- the hardware answers "illegal instruction")
+__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt)
 {
     __shared__ uint16_t tile[64][64 + 2];                    // row pitch 132 bytes = 33 words: column reads hit 32 different banks
     const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, pix = blockIdx.z;
@@ -195,7 +197,15 @@ __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int
         const uint32_t *w = reinterpret_cast<const uint32_t *>(v);
         uint32_t *t32 = reinterpret_cast<uint32_t *>(&tile[r][q]);   // (r * 66 + q) * 2 bytes: 4-byte aligned (q even)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t32[i] = w[i];
+        for (int i = 0; i < 8; ++i) {
+            uint32_t u = w[i];
+            if (cvt) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&u));
+                const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+                u = *reinterpret_cast<const uint32_t *>(&b);
+            }
+            t32[i] = u;
+        }
     }
     __syncthreads();
     {
@@ -241,11 +251,16 @@ size_t mz_wgrad_partial_bytes(int ksize, int n)
 
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream)
 {
+    return mz_wgrad_transpose_cvt(n, P, C, src, dst, 0, stream);
+}
+
+int mz_wgrad_transpose_cvt(int n, int P, int C, const void *src, void *dst, int f16_to_bf16, void *stream)
+{
     MZB_CHECK_ARG(n > 0 && P > 0 && C > 0 && C % 64 == 0 && src && dst, "bad argument");
     MZB_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "buffers must be 16-byte aligned");
     const int ns = mz_wgrad_padded_samples(n);
     MZB_CHECK_ARG(P <= 65535 && C / 64 <= 65535, "image or channel count too large");
-    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst);
+    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst, f16_to_bf16 != 0);
     MZB_LAUNCH_CHECK();
     return 0;
 }
@@ -268,7 +283,8 @@ int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *d
     p.chunks = p.ns / BLOCK_K;
     p.splits = wg_splits(p.ns);
     p.ntiles = p.taps * p.splits;
-    p.f16 = dtype == MZ_F16;
+    p.a_f16 = dtype == MZ_F16;
+    p.b_f16 = dtype == MZ_F16;
     p.partial = partial;
     const long long K = (long long)H * W * p.ns;
     MZB_CHECK_ARG(K < (1ll << 31), "samples x pixels too large for one launch");
@@ -279,7 +295,7 @@ int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *d
         cuuint64_t strides[1] = {(cuuint64_t)K * 2};
         cuuint32_t box[2] = {BLOCK_K, 128};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&maps[i], p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptrs[i]), dims, strides, box, estr,
+        CUresult r = enc(&maps[i], (i == 0 ? p.a_f16 : p.b_f16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptrs[i]), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mzb::set_error("mz_conv_wgrad: cuTensorMapEncodeTiled failed: %d", (int)r); return -2; }
     }

@@ -7,10 +7,11 @@ initial weights), same methods (`create_hidden_state_root`, `hidden_state_transi
 
 What runs where in a training step (`loss.backward()` included):
   * the ResidualBlock runs of the dynamics and prediction networks (2 x 14 blocks, K = 5 unroll steps: 280 of the ~330 convolutions of a
-    step) -- forward, data gradient, weight gradient on tcgen05 and the training-mode BatchNorm kernels, through train.trunk_forward;
+    step) -- forward (fp16 operands), data gradient and weight gradient (bf16 gradients) on tcgen05 and the training-mode BatchNorm kernels, through
+    train.trunk_forward;
   * the optimizer -- train.Adam (one mz_adam launch over flat buffers);
-  * opt-in (MZB_TRAIN_ANY_HW=1): the representation network's 256-channel ResidualBlocks (3 at 16x20, 3 at 8x10) on the same kernels;
-  * the representation network (by default), its stem convolutions, 128-channel blocks and pools, the dynamics ConvBlock with its action planes, the three
+  * the representation network's 256-channel ResidualBlocks (3 at 16x20, 3 at 8x10) on the same kernels (MZB_TRAIN_ANY_HW=0: torch ops);
+  * the representation network's stem convolutions, 128-channel blocks and pools, the dynamics ConvBlock with its action planes, the three
     head ConvBlocks + Linear heads and `_scale_state` -- torch ops (cuDNN / cuBLAS, channels_last) on the same device.  Not built as library
     kernels yet.
 In eval mode / under no_grad the module runs plain torch ops; acting does not call it at all (MCTSSearchVec packs its state_dict).

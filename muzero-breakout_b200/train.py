@@ -31,6 +31,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+# 16-bit element type of the FORWARD operands of the training kernels (activations and weights of the convolutions).  fp16: 11 significant
+# bits like TF32, which the reference's own training uses on a GPU (8 for bf16) -- the activations of these networks are O(1), far from
+# fp16's range.  The gradients that feed the convolution gradients (dz) stay bf16: they need the exponent range.  MZB_TRAIN_FWD=bf16 reverts.
+FWD_DTYPE = torch.bfloat16 if os.environ.get("MZB_TRAIN_FWD", "f16") == "bf16" else torch.float16
+
+
 def _supports_of(target_transformation) -> torch.Tensor:
     if isinstance(target_transformation, torch.Tensor):
         return target_transformation
@@ -240,13 +246,15 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: t
     accumulate_into: add the gradient to this tensor (a parameter's .grad) instead of returning a new one."""
     _lib.require_cuda()
     n, H, W, c = x.shape
-    if dy.shape != x.shape or c != 256 or x.dtype != dy.dtype or x.dtype not in (torch.bfloat16, torch.float16) or not (x.is_cuda and dy.is_cuda):
-        raise ValueError("conv_wgrad: dy and x must be CUDA bf16 / fp16 tensors of the same shape (n, H, W, 256)")
+    # (dy bf16, x fp16) = a training step with fp16 forward operands: x is converted to bf16 inside its transpose
+    combos = {(torch.bfloat16, torch.bfloat16): 1, (torch.float16, torch.float16): 2, (torch.bfloat16, torch.float16): 1}
+    if dy.shape != x.shape or c != 256 or (dy.dtype, x.dtype) not in combos or not (x.is_cuda and dy.is_cuda):
+        raise ValueError("conv_wgrad: dy and x must be CUDA tensors of the same shape (n, H, W, 256), both bf16, both fp16, or dy bf16 with x fp16")
     L, dev = _lib.lib(), x.device
     ns = L.mz_wgrad_padded_samples(n)
     st = torch.cuda.current_stream(dev).cuda_stream
-    dy_t = torch.empty((256, H * W, ns), dtype=x.dtype, device=dev)
-    x_t = torch.empty_like(dy_t)
+    dy_t = torch.empty((256, H * W, ns), dtype=dy.dtype, device=dev)
+    x_t = torch.empty((256, H * W, ns), dtype=dy.dtype, device=dev)
     partial = torch.empty(L.mz_wgrad_partial_bytes(ksize, n) // 4, dtype=torch.float32, device=dev)
     acc = accumulate_into is not None
     if acc and not (accumulate_into.shape == (256, 256, ksize, ksize) and accumulate_into.dtype == torch.float32 and accumulate_into.is_contiguous()
@@ -255,8 +263,8 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: t
     dw = accumulate_into if acc else torch.empty((256, 256, ksize, ksize), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(dy.contiguous()), _p(dy_t), st))
-        _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(x.contiguous()), _p(x_t), st))
-        _lib.check(L.mz_conv_wgrad_accum(n, H, W, ksize, 2 if x.dtype == torch.float16 else 1, _p(dy_t), _p(x_t), _p(partial), _p(dw), int(acc), st))
+        _lib.check(L.mz_wgrad_transpose_cvt(n, H * W, 256, _p(x.contiguous()), _p(x_t), int(x.dtype != dy.dtype), st))
+        _lib.check(L.mz_conv_wgrad_accum(n, H, W, ksize, combos[(dy.dtype, x.dtype)], _p(dy_t), _p(x_t), _p(partial), _p(dw), int(acc), st))
     return dw
 
 
@@ -284,7 +292,8 @@ def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.
 
 
 def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16):
-    """Backward of bn_train_forward.  dy: float32 gradient of the block output.  Returns (dz float32, dz 16-bit, dgamma, dbeta, dres float32)."""
+    """Backward of bn_train_forward.  dy: float32 gradient of the block output.  Returns (dz float32, dz 16-bit, dgamma, dbeta, dres float32).
+    res keeps the element type the forward pass gave it (fp16 or bf16); out_dtype is that of the 16-bit dz."""
     _lib.require_cuda()
     L, dev, C_ = _lib.lib(), z.device, z.shape[-1]
     M = z.numel() // C_
@@ -293,8 +302,9 @@ def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", ou
     dgamma, dbeta = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
     scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.mz_bn_train_bwd(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta),
-                                     _p(dz), _p(dz16), _p(dres), _p(scratch), torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(L.mz_bn_train_bwd_mixed(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(res.dtype if res is not None else out_dtype), _dt(out_dtype),
+                                           _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta), _p(dz), _p(dz16), _p(dres), _p(scratch),
+                                           torch.cuda.current_stream(dev).cuda_stream))
     return dz, dz16, dgamma, dbeta, dres
 
 
@@ -308,8 +318,9 @@ class ResidualBlockTrain:
     def __init__(self, conv1_w, conv1_b, bn1_w, bn1_b, conv2_w, conv2_b, bn2_w, bn2_b, device="cuda", eps=1e-5, momentum=0.1):
         _lib.require_cuda()
         f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.fwd_dtype = FWD_DTYPE
         self.w = [conv1_w.detach(), conv2_w.detach()]
-        self.wt = [self._pack(w, device) for w in self.w]                  # forward: tile-contiguous [tap][cin/64][cout][64] bf16
+        self.wt = {self.fwd_dtype: [self._pack(w, device, self.fwd_dtype) for w in self.w]}     # forward: tile-contiguous [tap][cin/64][cout][64], 16-bit
         self.dgrad = [ConvDgrad(w, device) for w in self.w]
         self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
         self.running_mean = [torch.zeros(256, device=device) for _ in range(2)]
@@ -319,17 +330,24 @@ class ResidualBlockTrain:
         self._saved = None
 
     @staticmethod
-    def _pack(w, device):
+    def _pack(w, device, dtype=torch.bfloat16):
         cout, cin, k, _ = w.shape
-        return w.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k, cin // 64, 64).permute(1, 2, 0, 3).contiguous().to(device=device, dtype=torch.bfloat16)
+        return w.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k, cin // 64, 64).permute(1, 2, 0, 3).contiguous().to(device=device, dtype=dtype)
+
+    def _weights(self, dtype):
+        """the forward pack in the element type of the activations it meets (packed on first use per refresh)"""
+        if dtype not in self.wt:
+            self.wt[dtype] = [self._pack(w, self.ones.device, dtype) for w in self.w]
+        return self.wt[dtype]
 
     def _conv(self, x16, i):
-        from .src.networks import ACT, BF16, OP_CONV, Program
+        from .src.networks import ACT, BF16, F16, OP_CONV, Program
         n, H, W, _ = x16.shape
+        BF16 = F16 if x16.dtype == torch.float16 else BF16
         z = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
         prog = Program(n)
         prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=256, cout=256, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst_f32=z,
-                 w=self.wt[i], scale=self.ones, shift=self.b[i])
+                 w=self._weights(x16.dtype)[i], scale=self.ones, shift=self.b[i])
         prog.run()
         return z
 
@@ -342,7 +360,7 @@ class ResidualBlockTrain:
             dev = self.ones.device
             f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
             self.w = [conv1_w.detach(), conv2_w.detach()]
-            self.wt = [self._pack(w, dev) for w in self.w]
+            self.wt = {self.fwd_dtype: [self._pack(w, dev, self.fwd_dtype) for w in self.w]}
             self.dgrad = [ConvDgrad(w, dev) for w in self.w]
             self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
             self._key = key
@@ -353,9 +371,11 @@ class ResidualBlockTrain:
         """Functional forward: returns (y bf16, y float32, saved) -- `saved` goes back into backward_fn, so one block object can be called
         several times per training step (the K unroll steps share their weights, train_torch.py:507-525)."""
         z1 = self._conv(x16, 0)
-        h16, _, m1, s1 = bn_train_forward(z1, self.gamma[0], self.beta[0], None, "relu", self.eps, self.momentum, self.running_mean[0], self.running_var[0])
+        h16, _, m1, s1 = bn_train_forward(z1, self.gamma[0], self.beta[0], None, "relu", self.eps, self.momentum, self.running_mean[0], self.running_var[0],
+                                          out_dtype=x16.dtype)
         z2 = self._conv(h16, 1)
-        y16, y32, m2, s2 = bn_train_forward(z2, self.gamma[1], self.beta[1], x16, "relu", self.eps, self.momentum, self.running_mean[1], self.running_var[1])
+        y16, y32, m2, s2 = bn_train_forward(z2, self.gamma[1], self.beta[1], x16, "relu", self.eps, self.momentum, self.running_mean[1], self.running_var[1],
+                                            out_dtype=x16.dtype)
         return y16, y32, (x16, z1, h16, z2, m1, s1, m2, s2)
 
     def forward(self, x16: torch.Tensor):
@@ -451,11 +471,12 @@ class TrunkTrain:
 # ------------------------------------------------------------------------------------------------------------------------------------
 # autograd bridge: a run of train-mode ResidualBlocks of an nn.Module (the reference's own ResidualBlock modules, networks.py:19-35, or the
 # drop-in agent's) evaluated by this library's kernels inside loss.backward() (train_torch.py:515)
-# 1: also the representation network's 256-channel blocks at 16x20 / 8x10 (the kernels take any image size: same errors as at 4x5,
-# profiles/prof_train_any_hw.py).  Off by default: a training iteration drops from 46 to 43 ms, but bf16 operands at the ROOT of the
-# rollout cost fidelity everywhere downstream (forward outputs 0.07-0.09 -> 0.18-0.21 of range from the fp32 modules, worst trunk
-# weight-gradient cosine 0.84 -> 0.65; torch's own autocast bf16: 0.38-0.56 and 0.35) -- tests/test_train_agent_gpu.py prints both
-_ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "0") == "1"
+# The representation network's 256-channel blocks at 16x20 / 8x10 run on the same kernels (any image size: same errors as at 4x5,
+# profiles/prof_train_any_hw.py); MZB_TRAIN_ANY_HW=0 keeps them on torch ops.  Fidelity against the fp32 modules on the whole K-step rollout
+# (tests/test_train_agent_gpu.py prints it): forward outputs 0.022-0.026 of range and worst trunk weight-gradient cosine 0.93 with them,
+# 0.010-0.013 and 0.98 without -- torch's TF32 convolutions, what the reference trains with on a GPU: 0.05-0.06 and 0.87; autocast bf16:
+# 0.38-0.56 and 0.35.  (With bf16 forward operands, the build before FWD_DTYPE: 0.18-0.21 / 0.65 and 0.07-0.09 / 0.84.)
+_ANY_HW = os.environ.get("MZB_TRAIN_ANY_HW", "1") == "1"
 
 
 # GraphedTrainStep switches this on while it warms up / captures: inside a CUDA graph a stream fork costs nothing, eagerly the event
@@ -475,7 +496,7 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernels, *params):
         # channels-last 16-bit, the kernels' layout (a channels_last input -- what the drop-in agent's layers produce -- is permuted for free)
-        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(FWD_DTYPE)
         saved, y32 = [], None
         for blk in kernels:
             x16, y32, sv = blk.forward_fn(x16)
@@ -515,7 +536,7 @@ def trunk_supported(blocks, x) -> bool:
     statistics at the default eps, a float32 CUDA input, training mode with gradients enabled."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 256 and torch.is_grad_enabled()):
         return False
-    if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # other maps than the 4x5 latent: the representation network's 16x20 / 8x10 blocks (opt-in)
+    if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # other maps than the 4x5 latent: the representation network's 16x20 / 8x10 blocks
         return False
     for m in blocks:
         if not (m.training and all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2")) and m.conv1.weight.shape == (256, 256, 3, 3)

@@ -50,7 +50,7 @@ def test_trunk_forward_matches_torch_autograd():
     ya = train.trunk_forward(blocks, xa)
     # reference 1: the same modules on torch ops with the kernels' rounding points emulated (bf16 convolution operands, straight-through
     # gradient) -- isolates the kernels' arithmetic from the ReLU-mask flips any reduced-precision forward causes
-    r16 = lambda t: t + (t.bfloat16().float() - t).detach()
+    r16 = lambda t: t + (t.to(train.FWD_DTYPE).float() - t).detach()       # the forward operands' element type (fp16 by default)
     yb = xb
     for m in ref:
         xin = r16(yb)
@@ -145,13 +145,26 @@ def test_dropin_agent_training_step_vs_oracle_agent():
     print(f"forward outputs vs the fp32 modules (max error / range): library {err}, torch autocast bf16 {err_ac}")
     for name in err:
         assert err[name] <= max(1e-1, 1.5 * err_ac[name]), f"{name}: {err[name]:.3f} (autocast {err_ac[name]:.3f})"
-    worst, worst_ac = 1.0, 1.0
-    for (name, pa), po, pc in zip(agent.named_parameters(), oracle.parameters(), ac.parameters()):
+    # second yardstick: TF32 convolutions, what the reference's own training runs on a GPU (torch's cuDNN default)
+    tf = copy.deepcopy(oracle)
+    for p_ in tf.parameters():
+        p_.grad = None
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        outs_t = _rollout(tf, frames, actions, K)
+        sum((o * wi).sum() for o, wi in zip(outs_t, w)).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    err_tf = {name: float((c.detach() - o.detach()).abs().max() / o.detach().abs().max()) for c, o, name in zip(outs_t, outs_o, ("reward", "value", "policy"))}
+    print(f"forward outputs, torch TF32: {err_tf}")
+    worst, worst_ac, worst_tf = 1.0, 1.0, 1.0
+    for (name, pa), po, pc, pt in zip(agent.named_parameters(), oracle.parameters(), ac.parameters(), tf.parameters()):
         if "res_blocks" in name and name.endswith("weight") and "conv" in name:   # the tensors the library kernels produce
-            c, c_ac = _cos(pa.grad, po.grad), _cos(pc.grad, po.grad)
-            worst, worst_ac = min(worst, c), min(worst_ac, c_ac)
+            c, c_ac, c_tf = _cos(pa.grad, po.grad), _cos(pc.grad, po.grad), _cos(pt.grad, po.grad)
+            worst, worst_ac, worst_tf = min(worst, c), min(worst_ac, c_ac), min(worst_tf, c_tf)
             assert c >= min(0.95, c_ac - 0.1), f"{name}: cosine vs fp32 autograd {c:.4f}, autocast bf16 reaches {c_ac:.4f}"
-    print(f"worst cosine similarity of a trunk convolution's weight gradient vs fp32 autograd: library {worst:.4f}, torch autocast bf16 {worst_ac:.4f}")
+    print(f"worst cosine similarity of a trunk convolution's weight gradient vs fp32 autograd: library {worst:.4f}, torch autocast bf16 {worst_ac:.4f}, "
+          f"torch TF32 {worst_tf:.4f}")
     v0 = [p._version for p in agent.parameters()]
     agent.optimizer.step()
     assert all(p._version > v for p, v in zip(agent.parameters(), v0))

@@ -187,17 +187,20 @@ def test_conv_dgrad_on_tensor_cores_vs_autograd(case):
     assert err <= 2e-4, f"dgrad rel err {err:.2e}"
 
 
+@pytest.mark.parametrize("dts", [(torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float16), (torch.float16, torch.float16)], ids=["bf16", "dy_bf16_x_f16", "f16"])
 @pytest.mark.parametrize("case", [(512, 4, 5, 3), (77, 4, 5, 3), (1, 4, 5, 3), (300, 4, 5, 1), (40, 8, 10, 3), (2560, 4, 5, 3)], ids=lambda c: "n%d_%dx%d_k%d" % c)
-def test_conv_wgrad_on_tensor_cores_vs_autograd(case):
+def test_conv_wgrad_on_tensor_cores_vs_autograd(case, dts):
     """The weight gradient of the trunks' 256 -> 256 convolutions (tcgen05, K = samples x pixels, csrc/wgrad.cu) against torch autograd in
-    fp32 on the same bf16-rounded operands; deterministic (fixed-order split reduction)."""
+    fp32 on the same 16-bit-rounded operands; deterministic (fixed-order split reduction).  dy bf16 with x fp16 is the form of a training step:
+    fp16 activations from the forward pass (rounded to bf16 inside their transpose: the reference sees that rounding too), bf16 gradients."""
     from muzero_breakout_b200.train import conv_wgrad
     n, H, W, k = case
     g = torch.Generator().manual_seed(n + H + k)
-    x = torch.randn(n, 256, H, W, generator=g).bfloat16()
-    dy = torch.randn(n, 256, H, W, generator=g).bfloat16()
+    x = torch.randn(n, 256, H, W, generator=g).to(dts[1])
+    dy = torch.randn(n, 256, H, W, generator=g).to(dts[0])
     w = torch.zeros(256, 256, k, k, requires_grad=True)
-    torch.nn.functional.conv2d(x.float(), w, padding=k // 2).backward(dy.float())
+    x_seen = x.to(dts[0]) if dts[0] != dts[1] else x
+    torch.nn.functional.conv2d(x_seen.float(), w, padding=k // 2).backward(dy.float())
     cl = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()
     got = conv_wgrad(cl(dy), cl(x), k)
     assert torch.isfinite(got).all()
@@ -251,6 +254,16 @@ def test_bn_train_forward_backward_vs_torch(case):
     if use_res:
         tol(back(dres), res.grad, 1e-5, "dres", keep)
     assert keep.mean() > 0.999
+    if use_res:
+        # the form of a training step with fp16 forward operands: an fp16 residual, fp16 y, bf16 dz (mz_bn_train_bwd_mixed)
+        r16 = res16.float().half()
+        if torch.equal(r16.float(), res16.float()):        # bf16 values that fp16 holds exactly: same reference
+            y16h, y32h, mean_h, invstd_h = bn_train_forward(cl(z), gam, bet, res=cl(r16), act=act, running_mean=rm0.cuda(), running_var=rv0.cuda(),
+                                                            out_dtype=torch.float16)
+            dz_h, dz16_h, dg_h, db_h, dres_h = bn_train_backward(cl(z), cl(dy), gam, bet, mean_h, invstd_h, res=cl(r16), act=act)
+            assert y16h.dtype == torch.float16 and dz16_h.dtype == torch.bfloat16
+            assert torch.equal(y32h, y32) and torch.equal(dz_h, dz) and torch.equal(dz16_h, dz16) and torch.equal(dg_h, dgamma) and torch.equal(dres_h, dres)
+            tol(back(y16h), want.detach(), 1e-3, "y (fp16)")
 
 
 @pytest.mark.parametrize("n", [512, 77])
