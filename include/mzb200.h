@@ -420,6 +420,15 @@ int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, c
 int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, int accumulate,
                         void *stream);
 
+/* The same for the other convolutions of the three networks (representation stems :47,65 and 128-channel blocks, head ConvBlocks
+ * :139,201,213, the 256 hidden-state input channels of the dynamics ConvBlock :117): cout in {128, 256}, cin in {64, 128, 256}.
+ * dy_t is [cout][H*W][ns], x_t [cin][H*W][ns]; dw float32[cout][dw_cin][ksize][ksize] with dw_cin >= cin: the gradient of the FIRST cin
+ * input channels (the dynamics ConvBlock has 256 + 3 action-plane channels: mz_planes_conv_wgrad fills the rest);
+ * partial: mz_wgrad_partial_bytes_any() bytes. */
+size_t mz_wgrad_partial_bytes_any(int ksize, int n, int cout, int cin);
+int mz_conv_wgrad_any(int n, int H, int W, int ksize, int dtype, int cout, int cin, int dw_cin, const void *dy_t, const void *x_t, float *partial,
+                      float *dw, int accumulate, void *stream);
+
 /* Training-mode nn.BatchNorm2d of a ConvBlock / ResidualBlock (networks.py:12,16-17,26-35 under train_mode(), train_torch.py:372)
  * on channels-last rows: z float32[M][C] = the convolution output incl. its bias, M = samples * H * W.
  *   forward:  batch mean / biased variance per channel -> save_mean, save_invstd = 1/sqrt(var + eps) (float32[C]);
@@ -442,6 +451,46 @@ int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *
 int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
                           int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres,
                           void *scratch, void *stream);
+
+/* out[c] (+)= sum over the M rows of x float32[M][C]: the bias gradient of a convolution that no BatchNorm follows (the representation
+ * network's stem convolutions, networks.py:47,65).  scratch: mz_bn_scratch_bytes(M, C) bytes.  Deterministic. */
+int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The small layers of a training step around the convolutions (csrc/train_layers.cu), forward and backward, on channels-last
+ * float32 tensors [n][H][W][C].  All deterministic (fixed-order reductions).
+ *
+ * mz_cvt16             n float32 values (n % 4 == 0) -> 16-bit (dtype MZ_BF16 / MZ_F16): the operand of the next convolution
+ * mz_pool2_train_fwd   nn.AvgPool2d(2, 2) (networks.py:43,82,92): x [n][H][W][C] -> y float32 and / or y16 [n][H/2][W/2][C]
+ * mz_pool2_train_bwd   dx [n][H][W][C] = dy [n][H/2][W/2][C] / 4
+ * mz_linear_fwd        nn.Flatten + nn.Linear of a head (:147-149,207-209,221-223): out[n][O] = x[n][HW*C] . w[O][C*HW]^T + bias.  x is
+ *                      channels-last (index pixel * C + channel), w keeps nn.Flatten's (channel, pixel) column order -- the kernels
+ *                      permute the index, no packed copy of the weights exists.  O <= 16.
+ * mz_linear_bwd        g = d loss / d out [n][O]: dx[n][HW*C] (may be NULL), dw[O][C*HW] and db[O] (dw NULL: neither) -- written, or added
+ *                      to when accumulate != 0 (the K unroll steps share the heads).  scratch: mz_linear_scratch_bytes() bytes.
+ * mz_scale_train_fwd   MuZeroAgent._scale_state (:314-328) per sample over E = H*W*C elements: y = (x - min) / (max - min + 1e-8) as
+ *                      float32 and / or 16-bit; stats float32[n][4] = {min, max, argmin, argmax (int bits)} for the backward pass
+ * mz_scale_train_bwd   dx = g / r, plus the gradients that flow through min and max to their (first) arg positions, as torch's
+ *                      autograd does for tensor.min(dim) / max(dim)
+ * mz_planes_conv_fwd   z[n][H*W][cout] += the 3x3 "same" convolution of the A <= 4 action planes (input channels c0 .. c0+A-1 of
+ *                      w float32[cout][cin_total][3][3]; the dynamics ConvBlock's torch.cat, :295 / :117-122).  planes float32 with
+ *                      ELEMENT strides (sn, sa, sy, sx): the reference passes an expanded (n, A, 1, 1) view.  H*W <= 64.
+ * mz_planes_conv_wgrad dw[co][c0+a][tap] (+)= sum_{n,p} dz[n][p][co] * planes[n][a][p + tap]; scratch: mz_planes_wgrad_scratch_bytes()
+ */
+int mz_cvt16(long long n, const float *src, void *dst, int dtype, void *stream);
+int mz_pool2_train_fwd(int n, int H, int W, int C, const float *x, float *y, void *y16, int dtype, void *stream);
+int mz_pool2_train_bwd(int n, int H, int W, int C, const float *dy, float *dx, void *stream);
+int mz_linear_fwd(int n, int HW, int C, int O, const float *x, const float *w, const float *bias, float *out, void *stream);
+size_t mz_linear_scratch_bytes(int n, int HW, int C, int O);
+int mz_linear_bwd(int n, int HW, int C, int O, const float *x, const float *w, const float *g, float *dx, float *dw, float *db, int accumulate,
+                  void *scratch, void *stream);
+int mz_scale_train_fwd(int n, int E, const float *x, float *y, void *y16, int dtype, float *stats, void *stream);
+int mz_scale_train_bwd(int n, int E, const float *x, const float *g, const float *stats, float *dx, void *stream);
+int mz_planes_conv_fwd(int n, int H, int W, int A, int cout, int cin_total, int c0, const float *planes, long long sn, long long sa, long long sy,
+                       long long sx, const float *w, float *z, void *stream);
+size_t mz_planes_wgrad_scratch_bytes(int n, int cout);
+int mz_planes_conv_wgrad(int n, int H, int W, int A, int cout, int cin_total, int c0, const float *planes, long long sn, long long sa, long long sy,
+                         long long sx, const float *dz, float *dw, int accumulate, void *scratch, void *stream);
 
 #ifdef __cplusplus
 }

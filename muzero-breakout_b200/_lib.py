@@ -137,6 +137,23 @@ def _declare(L: C.CDLL) -> None:
         "mz_bn_train_bwd": [i32, i32, vp, vp, vp, vp, vp, i32, i32] + [vp] * 9,
         "mz_bn_train_bwd_mixed": [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32] + [vp] * 9,
     })
+    ll = C.c_longlong
+    sig.update({
+        "mz_conv_wgrad_any": [i32] * 8 + [vp, vp, vp, vp, i32, vp],
+        "mz_colsum": [i32, i32, vp, vp, i32, vp, vp],
+        "mz_cvt16": [ll, vp, vp, i32, vp],
+        "mz_pool2_train_fwd": [i32, i32, i32, i32, vp, vp, vp, i32, vp],
+        "mz_pool2_train_bwd": [i32, i32, i32, i32, vp, vp, vp],
+        "mz_linear_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "mz_linear_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp],
+        "mz_scale_train_fwd": [i32, i32, vp, vp, vp, i32, vp, vp],
+        "mz_scale_train_bwd": [i32, i32, vp, vp, vp, vp, vp],
+        "mz_planes_conv_fwd": [i32] * 7 + [vp, ll, ll, ll, ll, vp, vp, vp],
+        "mz_planes_conv_wgrad": [i32] * 7 + [vp, ll, ll, ll, ll, vp, vp, i32, vp, vp],
+    })
+    L.mz_wgrad_partial_bytes_any.argtypes, L.mz_wgrad_partial_bytes_any.restype = [i32, i32, i32, i32], C.c_size_t
+    L.mz_linear_scratch_bytes.argtypes, L.mz_linear_scratch_bytes.restype = [i32, i32, i32, i32], C.c_size_t
+    L.mz_planes_wgrad_scratch_bytes.argtypes, L.mz_planes_wgrad_scratch_bytes.restype = [i32, i32], C.c_size_t
     L.mz_bn_scratch_bytes.argtypes, L.mz_bn_scratch_bytes.restype = [i32, i32], C.c_size_t
     L.mz_wgrad_padded_samples.argtypes, L.mz_wgrad_padded_samples.restype = [i32], i32
     L.mz_wgrad_partial_bytes.argtypes, L.mz_wgrad_partial_bytes.restype = [i32, i32], C.c_size_t

@@ -147,6 +147,18 @@ bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, f
     dgamma[c] = (float)q;
 }
 
+// column sums (the bias gradient of a convolution that no BatchNorm follows): out[c] (+)= sum of the per-CTA partial sums, one warp per channel
+__global__ void __launch_bounds__(BN_THREADS)
+colsum_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ out, int accumulate)
+{
+    const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double s, q;
+    bn_warp_sums(C, nblocks, partial, c, lane, s, q);
+    if (lane != 0) return;
+    out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
 // y = act(gamma * (z - mean) * invstd + beta (+ res))
 __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ invstd,
@@ -219,6 +231,20 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     const size_t total4 = (size_t)M * C / 4;
     bn_fwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
                                                                                                  dtype == MZ_F16, act, (uint16_t *)y, y_f32);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *scratch, void *stream)
+{
+    MZB_CHECK_ARG(bn_shape_ok(M, C), "M must be positive and C one of 4 * {1, 2, 4, ..., 256}");
+    MZB_CHECK_ARG(x && out && scratch, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
+    const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
+    bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch);
+    MZB_LAUNCH_CHECK();
+    colsum_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, out, accumulate);
     MZB_LAUNCH_CHECK();
     return 0;
 }

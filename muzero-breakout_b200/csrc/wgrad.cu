@@ -1,4 +1,5 @@
-// Weight gradient of the 3x3 / 1x1 256 -> 256 convolutions (autograd of nn.Conv2d, src/networks.py:11,24-25, inside
+// Weight gradient of the 3x3 / 1x1 convolutions (256 -> 256 trunks; 64 / 128 / 256 -> 128 / 256 stems, head ConvBlocks and the
+// representation network's 128-channel blocks: autograd of nn.Conv2d, src/networks.py:11,24-25,47,65,117,139,201,213, inside
 // loss.backward() train_torch.py:515) on the B200 tensor cores:  dW[co][ci][ky][kx] = sum over (sample n, pixel (y,x)) of
 // dY[n][y][x][co] * X[n][y+ky-1][x+kx-1][ci].
 //
@@ -13,6 +14,11 @@
 // its 256 x 256 fp32 partial in TMEM and writes it to `partial[tap][split]`; wgrad_reduce_kernel sums the splits in a fixed order
 // (deterministic) into PyTorch's weight layout (cout, cin, k, k).
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (pair leader), warps 2-9 epilogue.
+//
+// Other channel counts (mz_conv_wgrad_any): the GEMM is P[tap][r][c] = sum_pix A[r][pix] * B[c][pix + tap offset] with Ca <= 256 rows of A
+// (the pair's M = 256; with Ca = 128 the second CTA's rows are never loaded nor read) and N = Cb in {64, 128, 256} columns.  cout = 256:
+// A = dY, B = X.  cout = 128, cin = 256: operands SWAPPED (A = X, B = dY, so that M stays 256): P[tap] is then the transposed gradient of
+// the mirrored tap, which the reduction kernel undoes.  cout = 128, cin <= 128: A = dY with half of the pair's rows idle.
 #include "tc_common.cuh"
 
 namespace {
@@ -22,8 +28,9 @@ constexpr int WG_MAX_SPLITS = 8;
 constexpr size_t WG_SMEM = (size_t)STAGES * STAGE_BYTES + 256;
 
 struct WgradParams {
-    int ns, H, W, taps, chunks, splits, ntiles, a_f16, b_f16;     // element types of dy (A operand) and x (B operand)
-    float *partial;                             // [taps][splits][256][256]
+    int ns, H, W, taps, chunks, splits, ntiles, a_f16, b_f16;     // element types of the A and B operands
+    int Ca, Cb;                                 // rows of A that exist (128 or 256), columns N of the product (64, 128, 256)
+    float *partial;                             // [taps][splits][256][Cb]
 };
 
 // k-steps of tile (tap, split): pixels whose shifted partner is inside the image x the split's 64-sample chunks
@@ -78,6 +85,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
         // ===================== TMA producer (one lane per CTA) =====================
         if (lane == 0) {
             const uint32_t lead_full = map_to_cta(bar_full, 0);
+            const uint32_t tx_bytes = (uint32_t)((p.Ca > 128 ? 2 : 1) * A_STAGE_BYTES + p.Cb * BLOCK_K * 2);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
@@ -89,10 +97,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
                     for (int c = t.c0; c < t.c1; ++c) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * STAGE_BYTES);      // bytes of both CTAs
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, tx_bytes);              // bytes of both CTAs
                         else mbar_arrive_cluster(lead_full + 8 * stage);
-                        tma_load_2d(sa, &map_dy, lead_full + 8 * stage, pix * p.ns + c * BLOCK_K, rank * 128);    // my 128 co rows
-                        tma_load_2d(sb, &map_x, lead_full + 8 * stage, pix2 * p.ns + c * BLOCK_K, rank * 128);    // my half of the ci rows
+                        if (rank * 128 < p.Ca) tma_load_2d(sa, &map_dy, lead_full + 8 * stage, pix * p.ns + c * BLOCK_K, rank * 128);    // my 128 rows of A
+                        tma_load_2d(sb, &map_x, lead_full + 8 * stage, pix2 * p.ns + c * BLOCK_K, rank * (p.Cb >> 1));                   // my half of the B rows
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -101,7 +109,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = instr_desc_ab(WG_C, p.a_f16 != 0, p.b_f16 != 0);
+            const uint32_t idesc = instr_desc_ab(p.Cb, p.a_f16 != 0, p.b_f16 != 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -146,22 +154,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
                 npix += (y + t.dy >= 0 && y + t.dy < p.H && x + t.dx >= 0 && x + t.dx < p.W) ? 1 : 0;
             }
             const bool empty = npix * (t.c1 - t.c0) == 0;                // no k-step: nothing was accumulated, the partial is zero
-            float *dst = p.partial + ((size_t)tile * WG_C + co) * WG_C + half * 128;
+            const int hcols = p.Cb >> 1, nch = p.Cb >> 6;                // columns / 32-column chunks of this warp's half
+            float *dst = p.partial + ((size_t)tile * WG_C + co) * p.Cb + half * hcols;
             uint32_t acc[2][32];
             mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * WG_C + half * 128);
-            tmem_ld32_async(taddr, acc[0]);
+            if (rank * 128 < p.Ca) {                                     // CTA-uniform: with Ca = 128 the second CTA's accumulator rows are idle
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * WG_C + half * hcols);
+                tmem_ld32_async(taddr, acc[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_wait(acc[c & 1]);
-                if (c + 1 < 4) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
-                float4 *fp = reinterpret_cast<float4 *>(dst + c * 32);
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {
+                        tmem_wait(acc[c & 1]);
+                        if (c + 1 < nch) tmem_ld32_async(taddr + (uint32_t)((c + 1) * 32), acc[(c + 1) & 1]);
+                        float4 *fp = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    fp[q] = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                  : make_float4(__uint_as_float(acc[c & 1][q * 4]), __uint_as_float(acc[c & 1][q * 4 + 1]),
-                                                __uint_as_float(acc[c & 1][q * 4 + 2]), __uint_as_float(acc[c & 1][q * 4 + 3]));
+                        for (int q = 0; q < 8; ++q)
+                            fp[q] = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                          : make_float4(__uint_as_float(acc[c & 1][q * 4]), __uint_as_float(acc[c & 1][q * 4 + 1]),
+                                                        __uint_as_float(acc[c & 1][q * 4 + 2]), __uint_as_float(acc[c & 1][q * 4 + 3]));
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -218,24 +231,31 @@ __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int
     }
 }
 
-// dw[co][ci][tap] = sum over splits of partial[tap][split][co][ci], splits added in index order.  One thread per (tap, co, ci):
-// its <= 8 loads are independent and coalesced over ci; grid (256 * 256 / 256, taps)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, const float *__restrict__ partial, float *__restrict__ dw, int accumulate)
+// dw[co][ci][tap] = sum over splits of partial[tap'][split][row][col], splits added in index order.  Not swapped: row = co, col = ci,
+// tap' = tap.  Swapped operands: row = ci, col = co, tap' = taps - 1 - tap (the mirrored offset).  One thread per (tap, row, col):
+// its <= 8 loads are independent and coalesced over col; grid (rows * Cb / 256, taps)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int taps, int splits, int rows, int Cb, int swap, int dw_cin, const float *__restrict__ partial,
+                                                           float *__restrict__ dw, int accumulate)
 {
-    const int i = blockIdx.x * 256 + threadIdx.x;            // co * 256 + ci
-    const int tap = blockIdx.y;
-    const float *src = partial + (size_t)tap * splits * WG_C * WG_C + i;
+    const int i = blockIdx.x * 256 + threadIdx.x;            // row * Cb + col
+    if (i >= rows * Cb) return;
+    const int row = i / Cb, col = i - row * Cb;
+    const int tp = blockIdx.y;                               // tap' of the partial
+    const size_t tile_stride = (size_t)WG_C * Cb;
+    const float *src = partial + (size_t)tp * splits * tile_stride + (size_t)row * Cb + col;
     float v[WG_MAX_SPLITS];
 #pragma unroll
-    for (int s = 0; s < WG_MAX_SPLITS; ++s) v[s] = s < splits ? __ldcs(src + (size_t)s * WG_C * WG_C) : 0.0f;
+    for (int s = 0; s < WG_MAX_SPLITS; ++s) v[s] = s < splits ? __ldcs(src + (size_t)s * tile_stride) : 0.0f;
     float acc = 0.0f;
 #pragma unroll
     for (int s = 0; s < WG_MAX_SPLITS; ++s) acc += v[s];     // index order; the padding terms are exact zeros
-    float *out = dw + (size_t)i * taps + tap;
+    // PyTorch's (cout, dw_cin, k, k); the gradient covers its first cin input channels (not swapped cin = Cb, swapped cin = rows)
+    float *out = swap ? dw + ((size_t)col * dw_cin + row) * taps + (taps - 1 - tp) : dw + ((size_t)row * dw_cin + col) * taps + tp;
     *out = accumulate ? *out + acc : acc;                    // accumulate: the K unroll steps of a training step add into the parameter's .grad
 }
 
 int wg_splits(int ns) { const int chunks = ns / BLOCK_K; return chunks < WG_MAX_SPLITS ? chunks : WG_MAX_SPLITS; }
+bool wg_shape_ok(int cout, int cin) { return (cout == 128 || cout == 256) && (cin == 64 || cin == 128 || cin == 256); }
 
 }  // namespace
 
@@ -243,10 +263,13 @@ extern "C" {
 
 int mz_wgrad_padded_samples(int n) { return n <= 0 ? 0 : (n + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
 
-size_t mz_wgrad_partial_bytes(int ksize, int n)
+size_t mz_wgrad_partial_bytes(int ksize, int n) { return mz_wgrad_partial_bytes_any(ksize, n, WG_C, WG_C); }
+
+size_t mz_wgrad_partial_bytes_any(int ksize, int n, int cout, int cin)
 {
-    if ((ksize != 1 && ksize != 3) || n <= 0) return 0;
-    return (size_t)ksize * ksize * wg_splits(mz_wgrad_padded_samples(n)) * WG_C * WG_C * sizeof(float);
+    if ((ksize != 1 && ksize != 3) || n <= 0 || !wg_shape_ok(cout, cin)) return 0;
+    const int Cb = (cout == 128 && cin == 256) ? cout : cin;
+    return (size_t)ksize * ksize * wg_splits(mz_wgrad_padded_samples(n)) * WG_C * Cb * sizeof(float);
 }
 
 int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *stream)
@@ -272,11 +295,20 @@ int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, c
 
 int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, int accumulate, void *stream)
 {
+    return mz_conv_wgrad_any(n, H, W, ksize, dtype, WG_C, WG_C, WG_C, dy_t, x_t, partial, dw, accumulate, stream);
+}
+
+int mz_conv_wgrad_any(int n, int H, int W, int ksize, int dtype, int cout, int cin, int dw_cin, const void *dy_t, const void *x_t, float *partial,
+                      float *dw, int accumulate, void *stream)
+{
+    MZB_CHECK_ARG(dw_cin >= cin, "dw_cin (input channels of the dw tensor) must be >= cin");
     MZB_CHECK_ARG(n > 0 && H > 0 && W > 0 && (ksize == 1 || ksize == 3) && (dtype == MZ_BF16 || dtype == MZ_F16), "bad argument");
+    MZB_CHECK_ARG(wg_shape_ok(cout, cin), "cout must be 128 or 256, cin 64, 128 or 256");
     MZB_CHECK_ARG(dy_t && x_t && partial && dw, "null pointer");
     MZB_CHECK_ARG((((uintptr_t)dy_t | (uintptr_t)x_t | (uintptr_t)partial) & 15) == 0, "buffers must be 16-byte aligned");
     EncodeTiledFn enc = encode_fn();
     if (!enc) { mzb::set_error("mz_conv_wgrad: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+    const bool swap = cout == 128 && cin == 256;              // keep M = 256: A = x (rows ci), B = dy (columns co)
     WgradParams p{};
     p.ns = mz_wgrad_padded_samples(n);
     p.H = H; p.W = W; p.taps = ksize * ksize;
@@ -285,15 +317,18 @@ int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *d
     p.ntiles = p.taps * p.splits;
     p.a_f16 = dtype == MZ_F16;
     p.b_f16 = dtype == MZ_F16;
+    p.Ca = swap ? cin : cout;
+    p.Cb = swap ? cout : cin;
     p.partial = partial;
     const long long K = (long long)H * W * p.ns;
     MZB_CHECK_ARG(K < (1ll << 31), "samples x pixels too large for one launch");
     CUtensorMap maps[2];
-    const void *ptrs[2] = {dy_t, x_t};
+    const void *ptrs[2] = {swap ? x_t : dy_t, swap ? dy_t : x_t};
+    const int chans[2] = {p.Ca, p.Cb};
     for (int i = 0; i < 2; ++i) {
-        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)WG_C};
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)chans[i]};
         cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-        cuuint32_t box[2] = {BLOCK_K, 128};
+        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(i == 0 ? 128 : p.Cb / 2)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&maps[i], (i == 0 ? p.a_f16 : p.b_f16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptrs[i]), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -315,7 +350,7 @@ int mz_conv_wgrad_accum(int n, int H, int W, int ksize, int dtype, const void *d
     cfg.numAttrs = 1;
     MZB_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel, maps[0], maps[1], p));
     MZB_LAUNCH_CHECK();
-    wgrad_reduce_kernel<<<dim3(WG_C * WG_C / 256, p.taps), 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, partial, dw, accumulate);
+    wgrad_reduce_kernel<<<dim3((p.Ca * p.Cb + 255) / 256, p.taps), 256, 0, (cudaStream_t)stream>>>(p.taps, p.splits, p.Ca, p.Cb, swap ? 1 : 0, dw_cin, partial, dw, accumulate);
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -12,8 +12,10 @@ What runs where in a training step (`loss.backward()` included):
   * the optimizer -- train.Adam (one mz_adam launch over flat buffers);
   * the representation network's 256-channel ResidualBlocks (3 at 16x20, 3 at 8x10) on the same kernels (MZB_TRAIN_ANY_HW=0: torch ops);
   * the representation network's stem convolutions, 128-channel blocks and pools, the dynamics ConvBlock with its action planes, the three
-    head ConvBlocks + Linear heads and `_scale_state` -- torch ops (cuDNN / cuBLAS, channels_last) on the same device.  Not built as library
-    kernels yet.
+    head ConvBlocks + Linear heads and `_scale_state` -- library kernels as well (train_layers.py: tcgen05 convolution / data / weight
+    gradients, csrc/train_layers.cu for the pools, Linear heads, `_scale_state` and the action-plane channels; MZB_TRAIN_LAYERS=0: torch
+    ops).  What is left to torch inside a step is glue: torch.cat / stack / one_hot of the rollout, autograd's gradient accumulation adds,
+    the 16-bit weight re-packs.
 In eval mode / under no_grad the module runs plain torch ops; acting does not call it at all (MCTSSearchVec packs its state_dict).
 There is no CPU path for the accelerated parts: on a CPU tensor the module is an ordinary torch module.
 """
@@ -23,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import train as _train
+from .. import train_layers as _layers
 
 _ACTS = {"relu": nn.ReLU, "leaky_relu": nn.LeakyReLU, "silu": nn.SiLU, "gelu": nn.GELU}      # utils.py:99-108
 
@@ -35,6 +38,8 @@ class ConvBlock(nn.Module):
         self.act = _ACTS[activation]()
 
     def forward(self, x):
+        if _layers.convblock_supported(self, x):
+            return _layers.convblock_forward(self, x)
         return self.act(self.bn(self.conv(x)))
 
 
@@ -52,6 +57,11 @@ class ResidualBlock(nn.Module):
             return _train.trunk_forward([self], x)
         y = self.act(self.bn1(self.conv1(x)))
         return self.act(self.bn2(self.conv2(y)) + x)
+
+
+def _is_resblock(m) -> bool:
+    """this module's ResidualBlock or the reference's (networks.py:19-35): accelerate_agent() binds these forwards to reference modules"""
+    return all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2"))
 
 
 def _run_blocks(blocks, x):
@@ -83,18 +93,23 @@ class RepresentationNetwork(nn.Module):
         self.blocks.append(self.avg_pool)
 
     def forward(self, state):
-        if state.is_cuda:
-            # channels_last activations from here on: cuDNN then runs its NHWC kernels without the NCHW <-> NHWC conversion pair around every
+        if state.is_cuda and not _layers.conv_supported(self.blocks[0], state):
+            # (torch-op path) channels_last activations from here on: cuDNN then runs its NHWC kernels without the NCHW <-> NHWC conversion pair around every
             # convolution (5.8 ms of a 512-sample training step), and the library trunks take / return their channels-last layout without a copy
             state = state.contiguous(memory_format=torch.channels_last)
         run = []                                       # consecutive ResidualBlocks go through the library as one call (no layout / precision
-        for m in self.blocks:                          # round trip between them); 128-channel blocks and the other layers run on torch ops
-            if isinstance(m, ResidualBlock):
+        for m in self.blocks:                          # round trip between them); the stems and pools through their own bridges
+            if _is_resblock(m):
                 run.append(m)
                 continue
             if run:
                 state, run = _run_blocks(run, state), []
-            state = m(state)
+            if isinstance(m, nn.Conv2d) and _layers.conv_supported(m, state):
+                state = _layers.conv_forward(m, state)
+            elif _layers.pool_supported(m, state):
+                state = _layers.pool_forward(state)
+            else:
+                state = m(state)
         if run:
             state = _run_blocks(run, state)
         return state
@@ -111,9 +126,20 @@ class DynamicsNetwork(nn.Module):
         self.reward_head = nn.Sequential(ConvBlock(act, in_ch, in_ch, 1, kernel_size=1, padding=0), nn.Flatten(1, -1),
                                          nn.Linear(in_ch * latent_resolution[0] * latent_resolution[1], cfg["num_supports"]))
 
-    def forward(self, hidden_state):
-        x = _run_blocks(self.res_blocks, self.conv_block(hidden_state))
-        return x, self.reward_head(x)
+    def forward(self, hidden_state, action_planes=None):
+        """hidden_state: the reference's torch.cat([latent, action planes], 1) (networks.py:295) -- or the latent alone with the planes as a
+        second argument (MuZeroAgent.hidden_state_transition below: no concatenated copy)"""
+        if action_planes is None and hidden_state.shape[1] == self.conv_block.conv.weight.shape[1]:
+            n_lat = self.conv_block.bn.num_features
+            h, planes = hidden_state[:, :n_lat], hidden_state[:, n_lat:]
+        else:
+            h, planes = hidden_state, action_planes
+        if planes is not None and _layers.convblock_supported(self.conv_block, h, planes):
+            x = _layers.convblock_forward(self.conv_block, h, planes)
+        else:
+            x = self.conv_block(hidden_state if action_planes is None else torch.cat([hidden_state, action_planes], dim=1))
+        x = _run_blocks(self.res_blocks, x)
+        return x, _layers.head_forward(self.reward_head, x)
 
 
 class PredictionNetwork(nn.Module):
@@ -130,7 +156,7 @@ class PredictionNetwork(nn.Module):
 
     def forward(self, hidden_state):
         x = _run_blocks(self.res_blocks, hidden_state)
-        return self.policy_head(x), self.value_head(x)
+        return _layers.head_forward(self.policy_head, x), _layers.head_forward(self.value_head, x)
 
 
 class MuZeroAgent(nn.Module):
@@ -153,16 +179,21 @@ class MuZeroAgent(nn.Module):
         return self._scale_state(self.rep_net(state.to(self.device)))
 
     def hidden_state_transition(self, prev_hidden_state: torch.Tensor, action: torch.Tensor):
-        x = torch.cat([prev_hidden_state, action], dim=1)
-        if x.is_cuda:
-            x = x.contiguous(memory_format=torch.channels_last)           # see RepresentationNetwork.forward
-        hidden_state, reward = self.dyn_net(x)
+        if _layers.convblock_supported(self.dyn_net.conv_block, prev_hidden_state, action):
+            hidden_state, reward = self.dyn_net(prev_hidden_state, action)        # no concatenated copy: the planes go to their own kernel
+        else:
+            x = torch.cat([prev_hidden_state, action], dim=1)
+            if x.is_cuda:
+                x = x.contiguous(memory_format=torch.channels_last)       # see RepresentationNetwork.forward
+            hidden_state, reward = self.dyn_net(x)
         return self._scale_state(hidden_state), reward
 
     def evaluate_state(self, hidden_state: torch.Tensor):
         return self.pred_net(hidden_state)
 
     def _scale_state(self, hidden_state: torch.Tensor):
+        if _layers.scale_supported(hidden_state):
+            return _layers.scale_state(hidden_state)
         flat = hidden_state.reshape(hidden_state.shape[0], -1)
         s_min = flat.min(dim=1, keepdim=True)[0].view(-1, 1, 1, 1)
         s_max = flat.max(dim=1, keepdim=True)[0].view(-1, 1, 1, 1)

@@ -241,30 +241,37 @@ class ConvDgrad:
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: torch.Tensor | None = None) -> torch.Tensor:
-    """dL/dweight of `y = conv2d(x, weight, padding=ksize//2)` for the 256 -> 256 trunk convolutions, (256, 256, k, k) float32, on the
-    tensor cores (mz_conv_wgrad, csrc/wgrad.cu).  Channels-last 16-bit tensors: dy (n, H, W, 256), x (n, H, W, 256).
-    accumulate_into: add the gradient to this tensor (a parameter's .grad) instead of returning a new one."""
+    """dL/dweight of `y = conv2d(x, weight, padding=ksize//2)`, (cout, cin, k, k) float32, on the tensor cores (mz_conv_wgrad_any,
+    csrc/wgrad.cu): cout in {128, 256}, cin in {64, 128, 256} -- the trunks' 256 -> 256 convolutions, the representation network's stems and
+    128-channel blocks, the head ConvBlocks.  Channels-last 16-bit tensors: dy (n, H, W, cout), x (n, H, W, cin).
+    accumulate_into: add the gradient to this tensor (a parameter's .grad) instead of returning a new one; it may have MORE input channels
+    than x (cout, cin + extra, k, k): the gradient goes to the first cin (the dynamics ConvBlock's 256 hidden-state channels of 259)."""
     _lib.require_cuda()
-    n, H, W, c = x.shape
+    n, H, W, cin = x.shape
+    cout = dy.shape[-1]
     # (dy bf16, x fp16) = a training step with fp16 forward operands: x is converted to bf16 inside its transpose
     combos = {(torch.bfloat16, torch.bfloat16): 1, (torch.float16, torch.float16): 2, (torch.bfloat16, torch.float16): 1}
-    if dy.shape != x.shape or c != 256 or (dy.dtype, x.dtype) not in combos or not (x.is_cuda and dy.is_cuda):
-        raise ValueError("conv_wgrad: dy and x must be CUDA tensors of the same shape (n, H, W, 256), both bf16, both fp16, or dy bf16 with x fp16")
+    if (dy.shape[:3] != x.shape[:3] or cout not in (128, 256) or cin not in (64, 128, 256) or (dy.dtype, x.dtype) not in combos
+            or not (x.is_cuda and dy.is_cuda)):
+        raise ValueError("conv_wgrad: dy (n, H, W, cout in {128, 256}) and x (n, H, W, cin in {64, 128, 256}) must be CUDA tensors, both bf16, "
+                         "both fp16, or dy bf16 with x fp16")
     L, dev = _lib.lib(), x.device
     ns = L.mz_wgrad_padded_samples(n)
     st = torch.cuda.current_stream(dev).cuda_stream
-    dy_t = torch.empty((256, H * W, ns), dtype=dy.dtype, device=dev)
-    x_t = torch.empty((256, H * W, ns), dtype=dy.dtype, device=dev)
-    partial = torch.empty(L.mz_wgrad_partial_bytes(ksize, n) // 4, dtype=torch.float32, device=dev)
+    dy_t = torch.empty((cout, H * W, ns), dtype=dy.dtype, device=dev)
+    x_t = torch.empty((cin, H * W, ns), dtype=dy.dtype, device=dev)
+    partial = torch.empty(L.mz_wgrad_partial_bytes_any(ksize, n, cout, cin) // 4, dtype=torch.float32, device=dev)
     acc = accumulate_into is not None
-    if acc and not (accumulate_into.shape == (256, 256, ksize, ksize) and accumulate_into.dtype == torch.float32 and accumulate_into.is_contiguous()
-                    and accumulate_into.device == dev):
-        raise ValueError("conv_wgrad: accumulate_into must be a contiguous float32 (256, 256, k, k) tensor on the operands' device")
-    dw = accumulate_into if acc else torch.empty((256, 256, ksize, ksize), dtype=torch.float32, device=dev)
+    if acc and not (accumulate_into.dim() == 4 and accumulate_into.shape[0] == cout and accumulate_into.shape[1] >= cin
+                    and tuple(accumulate_into.shape[2:]) == (ksize, ksize) and accumulate_into.dtype == torch.float32
+                    and accumulate_into.is_contiguous() and accumulate_into.device == dev):
+        raise ValueError("conv_wgrad: accumulate_into must be a contiguous float32 (cout, >= cin, k, k) tensor on the operands' device")
+    dw = accumulate_into if acc else torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.mz_wgrad_transpose(n, H * W, 256, _p(dy.contiguous()), _p(dy_t), st))
-        _lib.check(L.mz_wgrad_transpose_cvt(n, H * W, 256, _p(x.contiguous()), _p(x_t), int(x.dtype != dy.dtype), st))
-        _lib.check(L.mz_conv_wgrad_accum(n, H, W, ksize, combos[(dy.dtype, x.dtype)], _p(dy_t), _p(x_t), _p(partial), _p(dw), int(acc), st))
+        _lib.check(L.mz_wgrad_transpose(n, H * W, cout, _p(dy.contiguous()), _p(dy_t), st))
+        _lib.check(L.mz_wgrad_transpose_cvt(n, H * W, cin, _p(x.contiguous()), _p(x_t), int(x.dtype != dy.dtype), st))
+        _lib.check(L.mz_conv_wgrad_any(n, H, W, ksize, combos[(dy.dtype, x.dtype)], cout, cin, dw.shape[1], _p(dy_t), _p(x_t), _p(partial), _p(dw),
+                                       int(acc), st))
     return dw
 
 
@@ -275,14 +282,38 @@ def _dt(t):
     return 2 if t == torch.float16 else 1
 
 
-def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.1, running_mean=None, running_var=None, out_dtype=torch.bfloat16):
+def rows16(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """An NCHW-shaped float32 CUDA activation -> the kernels' contiguous channels-last 16-bit rows (n, H, W, C), on library kernels:
+    mz_cvt16 when the tensor already has channels_last strides (what every bridge of this module returns), MZ_OP_NCHW_IN for a contiguous
+    NCHW tensor (the representation network's input)."""
+    _lib.require_cuda()
+    from .src.networks import BF16, F16, OP_NCHW_IN, Program
+    dtype = dtype or FWD_DTYPE
+    x = x.detach()
+    n, C_, H, W = x.shape
+    out = torch.empty((n, H, W, C_), dtype=dtype, device=x.device)
+    cl = x.permute(0, 2, 3, 1)
+    if cl.is_contiguous() and x.dtype == torch.float32 and x.numel() % 4 == 0:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mz_cvt16(x.numel(), _p(cl), _p(out), _dt(dtype), torch.cuda.current_stream(x.device).cuda_stream))
+        return out
+    x = x.float().contiguous()
+    with torch.cuda.device(x.device):
+        prog = Program(n)
+        prog.add(op=OP_NCHW_IN, dtype=F16 if dtype == torch.float16 else BF16, H=H, W=W, cin=C_, src=x, dst=out)
+        prog.run()
+    return out
+
+
+def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.1, running_mean=None, running_var=None, out_dtype=torch.bfloat16,
+                     want16=True):
     """Training-mode BatchNorm2d (+ residual) + activation of a ConvBlock / ResidualBlock (networks.py:16-17,31-35) on channels-last rows.
     z: float32 (..., C) convolution output incl. bias.  Returns (y 16-bit, y float32, save_mean, save_invstd); running stats updated in place."""
     _lib.require_cuda()
     L, dev, C_ = _lib.lib(), z.device, z.shape[-1]
     M = z.numel() // C_
     z = z.contiguous()
-    y, y32 = torch.empty(z.shape, dtype=out_dtype, device=dev), torch.empty_like(z)
+    y, y32 = (torch.empty(z.shape, dtype=out_dtype, device=dev) if want16 else None), torch.empty_like(z)
     mean, invstd = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
     scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
@@ -291,14 +322,16 @@ def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.
     return y, y32, mean, invstd
 
 
-def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16):
+def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16, want32=True, want_res=True):
     """Backward of bn_train_forward.  dy: float32 gradient of the block output.  Returns (dz float32, dz 16-bit, dgamma, dbeta, dres float32).
     res keeps the element type the forward pass gave it (fp16 or bf16); out_dtype is that of the 16-bit dz."""
     _lib.require_cuda()
     L, dev, C_ = _lib.lib(), z.device, z.shape[-1]
     M = z.numel() // C_
     z, dy = z.contiguous(), dy.contiguous()
-    dz, dz16, dres = torch.empty_like(z), torch.empty(z.shape, dtype=out_dtype, device=dev), torch.empty_like(z)
+    dz = torch.empty_like(z) if want32 else None
+    dz16 = torch.empty(z.shape, dtype=out_dtype, device=dev)
+    dres = torch.empty_like(z) if want_res else None
     dgamma, dbeta = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
     scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
@@ -309,7 +342,7 @@ def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", ou
 
 
 class ResidualBlockTrain:
-    """One training step through a ResidualBlock (networks.py:19-35: relu(bn2(conv2(relu(bn1(conv1 x)))) + x), 256 channels, train mode) made of
+    """One training step through a ResidualBlock (networks.py:19-35: relu(bn2(conv2(relu(bn1(conv1 x)))) + x), 128 or 256 channels, train mode) made of
     this library's kernels only: tcgen05 convolutions (forward: conv_tc.cu; data gradient: the same kernel on the transposed, flipped weights;
     weight gradient: wgrad.cu) and the training-mode BatchNorm kernels (bn.cu).  Channels-last bf16 activations, fp32 statistics and gradients.
     The convolution biases get no gradient here: a BatchNorm follows each convolution and subtracts the batch mean, so d loss / d bias is zero
@@ -319,13 +352,14 @@ class ResidualBlockTrain:
         _lib.require_cuda()
         f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
         self.fwd_dtype = FWD_DTYPE
+        self.C = C_ = int(conv1_w.shape[0])
         self.w = [conv1_w.detach(), conv2_w.detach()]
         self.wt = {self.fwd_dtype: [self._pack(w, device, self.fwd_dtype) for w in self.w]}     # forward: tile-contiguous [tap][cin/64][cout][64], 16-bit
         self.dgrad = [ConvDgrad(w, device) for w in self.w]
         self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
-        self.running_mean = [torch.zeros(256, device=device) for _ in range(2)]
-        self.running_var = [torch.ones(256, device=device) for _ in range(2)]
-        self.ones = torch.ones(256, device=device)
+        self.running_mean = [torch.zeros(C_, device=device) for _ in range(2)]
+        self.running_var = [torch.ones(C_, device=device) for _ in range(2)]
+        self.ones = torch.ones(C_, device=device)
         self.eps, self.momentum = eps, momentum
         self._saved = None
 
@@ -346,7 +380,7 @@ class ResidualBlockTrain:
         BF16 = F16 if x16.dtype == torch.float16 else BF16
         z = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
         prog = Program(n)
-        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=256, cout=256, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst_f32=z,
+        prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=self.C, cout=self.C, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst_f32=z,
                  w=self._weights(x16.dtype)[i], scale=self.ones, shift=self.b[i])
         prog.run()
         return z
@@ -496,7 +530,7 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernels, *params):
         # channels-last 16-bit, the kernels' layout (a channels_last input -- what the drop-in agent's layers produce -- is permuted for free)
-        x16 = x.detach().permute(0, 2, 3, 1).contiguous().to(FWD_DTYPE)
+        x16 = rows16(x)
         saved, y32 = [], None
         for blk in kernels:
             x16, y32, sv = blk.forward_fn(x16)
@@ -518,7 +552,7 @@ class _TrunkFn(torch.autograd.Function):
             into = tuple(p.grad if (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32) else None for p in (ps[0], ps[4]))
             g, grads = blk.backward_fn(g, sv, into, side)
             # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient): None where a .grad exists, zeros otherwise
-            zb = [None if p.grad is not None else torch.zeros(256, device=g.device) for p in (ps[1], ps[5])]
+            zb = [None if p.grad is not None else torch.zeros(p.shape[0], device=g.device) for p in (ps[1], ps[5])]
             flat.append((grads["conv1.weight"], zb[0], grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zb[1], grads["bn2.weight"], grads["bn2.bias"]))
         ctx.saved_blocks = None
         if side is not None:
@@ -532,15 +566,16 @@ def _block_params(m):
 
 
 def trunk_supported(blocks, x) -> bool:
-    """Can this run of ResidualBlock modules go through the library kernels?  256 channels, 3x3 convolutions, ReLU, BatchNorm with running
-    statistics at the default eps, a float32 CUDA input, training mode with gradients enabled."""
-    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 256 and torch.is_grad_enabled()):
+    """Can this run of ResidualBlock modules go through the library kernels?  128 or 256 channels, 3x3 convolutions, ReLU, BatchNorm with
+    running statistics at the default eps, a float32 CUDA input, training mode with gradients enabled."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] in (128, 256) and torch.is_grad_enabled()):
         return False
+    C_ = x.shape[1]
     if x.shape[2] * x.shape[3] != 20 and not _ANY_HW:        # other maps than the 4x5 latent: the representation network's 16x20 / 8x10 blocks
         return False
     for m in blocks:
-        if not (m.training and all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2")) and m.conv1.weight.shape == (256, 256, 3, 3)
-                and m.conv2.weight.shape == (256, 256, 3, 3) and isinstance(getattr(m, "act", None), torch.nn.ReLU)
+        if not (m.training and all(hasattr(m, a) for a in ("conv1", "bn1", "conv2", "bn2")) and m.conv1.weight.shape == (C_, C_, 3, 3)
+                and m.conv2.weight.shape == (C_, C_, 3, 3) and isinstance(getattr(m, "act", None), torch.nn.ReLU)
                 and m.bn1.track_running_stats and m.bn1.eps == 1e-5 and m.bn2.eps == 1e-5 and m.bn1.momentum == m.bn2.momentum and m.bn1.momentum is not None):
             return False
     return len(blocks) > 0
@@ -567,32 +602,20 @@ def trunk_forward(blocks, x: torch.Tensor) -> torch.Tensor:
 
 
 def accelerate_agent(agent):
-    """Patch a MuZeroAgent-shaped module (the reference's own, networks.py:245-350) in place: the ResidualBlock runs of its dynamics and
-    prediction networks go through trunk_forward whenever trunk_supported says so (training mode on a CUDA device), and the optimizer
-    becomes this library's flat-buffer Adam with torch's hyper-parameters.  Everything else -- stems, head ConvBlocks, Linear heads,
-    `_scale_state`, the representation network -- stays on the module's own torch ops.  Returns the agent."""
+    """Patch a MuZeroAgent-shaped module (the reference's own, networks.py:245-350) in place: in training mode on a CUDA device its three
+    networks run forward AND backward on this library's kernels -- the ResidualBlock runs through trunk_forward, the stems, pools,
+    ConvBlocks (incl. the dynamics ConvBlock's action planes), Linear heads and `_scale_state` through train_layers.py -- by binding the
+    drop-in agent's forwards (src/agent.py; they only use the reference's attribute names) to the reference's modules; whatever a bridge
+    does not take (eval mode, no_grad, other shapes) stays on the module's own torch ops.  The optimizer becomes this library's flat-buffer
+    Adam with torch's hyper-parameters.  Returns the agent."""
     import types
+    from .src import agent as A
 
-    def dyn_forward(self, hidden_state):
-        x = self.conv_block(hidden_state)
-        if trunk_supported(self.res_blocks, x):
-            x = trunk_forward(self.res_blocks, x)
-        else:
-            for b in self.res_blocks:
-                x = b(x)
-        return x, self.reward_head(x)
-
-    def pred_forward(self, hidden_state):
-        x = hidden_state
-        if trunk_supported(self.res_blocks, x):
-            x = trunk_forward(self.res_blocks, x)
-        else:
-            for b in self.res_blocks:
-                x = b(x)
-        return self.policy_head(x), self.value_head(x)
-
-    agent.dyn_net.forward = types.MethodType(dyn_forward, agent.dyn_net)
-    agent.pred_net.forward = types.MethodType(pred_forward, agent.pred_net)
+    agent.rep_net.forward = types.MethodType(A.RepresentationNetwork.forward, agent.rep_net)
+    agent.dyn_net.forward = types.MethodType(A.DynamicsNetwork.forward, agent.dyn_net)
+    agent.pred_net.forward = types.MethodType(A.PredictionNetwork.forward, agent.pred_net)
+    agent.hidden_state_transition = types.MethodType(A.MuZeroAgent.hidden_state_transition, agent)
+    agent._scale_state = types.MethodType(A.MuZeroAgent._scale_state, agent)
     old = getattr(agent, "optimizer", None)
     if isinstance(old, torch.optim.Adam) and next(agent.parameters()).is_cuda:
         g = old.param_groups[0]

@@ -1,0 +1,360 @@
+"""The layers of a training step AROUND the ResidualBlock trunks, forward and backward on this library's kernels:
+
+    reference (src/networks.py)                                    here (autograd bridges; kernels through the C ABI)
+    ConvBlock :7-17  conv -> BatchNorm2d(train) -> act             convblock_forward: tcgen05 convolution (csrc/conv_tc.cu), training-mode
+        the three head ConvBlocks :139,201,213 and the             BatchNorm (csrc/bn.cu); backward: BatchNorm backward, weight gradient
+        dynamics ConvBlock :117 with its action planes             mz_conv_wgrad_any (csrc/wgrad.cu), data gradient = the convolution kernel on
+                                                                   the transposed, flipped filter; the 3 action-plane input channels (torch.cat,
+                                                                   :295) by mz_planes_conv_fwd / _wgrad (csrc/train_layers.cu)
+    nn.Conv2d stems of the representation network :47,65           conv_forward: the same kernels without a BatchNorm; bias gradient mz_colsum
+    nn.AvgPool2d(2, 2) :43,82,92                                   pool_forward: mz_pool2_train_fwd / _bwd
+    nn.Flatten + nn.Linear of the heads :147-149,207-209,221-223   flatten_linear: mz_linear_fwd / mz_linear_bwd (channels-last activations against
+                                                                   the weight's (channel, pixel) column order, no packed copy)
+    MuZeroAgent._scale_state :314-328                              scale_state: mz_scale_train_fwd / _bwd (gradient through min and max included)
+
+Every bridge takes and returns NCHW-shaped float32 tensors with channels_last strides (the kernels' row layout, no copies between
+bridges), and hands gradients to the modules' own Parameters -- accumulated in place when the parameter already has a contiguous .grad
+(always under train.Adam's flat buffers).  MZB_TRAIN_LAYERS=0 keeps these layers on torch ops.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import train as T
+
+ENABLED = os.environ.get("MZB_TRAIN_LAYERS", "1") == "1"
+GRAD_DTYPE = torch.bfloat16          # the 16-bit operand of the convolution gradients (exponent range), as in train.py
+
+_p = T._p
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped tensor -> contiguous float32 channels-last rows (n, H, W, C); free when it already has channels_last strides"""
+    t = x.detach().permute(0, 2, 3, 1)
+    return t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+
+
+def _grad_slot(p: torch.Tensor):
+    """(tensor to accumulate the gradient into, what backward() returns for it): the parameter's own contiguous float32 .grad -> autograd gets
+    None; otherwise a fresh zero tensor that autograd receives"""
+    g = p.grad
+    if g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.device == p.device:
+        return g, None
+    z = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+    return z, z
+
+
+def _act_name(m):
+    if isinstance(m, nn.ReLU):
+        return "relu"
+    if isinstance(m, nn.LeakyReLU) and m.negative_slope == 0.01:
+        return "leaky_relu"
+    if isinstance(m, nn.Identity):
+        return "none"
+    return None
+
+
+def cvt16(t: torch.Tensor, dtype) -> torch.Tensor:
+    """contiguous float32 -> 16-bit, same shape (mz_cvt16)"""
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().mz_cvt16(t.numel(), _p(t), _p(out), T._dt(dtype), _stream(t.device)))
+    return out
+
+
+class ConvKernels:
+    """One stride-1 "same" nn.Conv2d (k = 1 or 3; cout in {128, 256}; the first `cin` in {64, 128, 256} input channels) on the tensor cores:
+    forward, data gradient and weight gradient.  Packs are rebuilt when the parameters' version counters move (optimizer steps,
+    load_state_dict) -- inside a captured training step the re-pack is part of the graph."""
+
+    def __init__(self, conv: nn.Conv2d, cin: int | None = None, need_dgrad: bool = True):
+        self.cout, self.cin_total, self.k = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
+        self.cin = cin or self.cin_total
+        self.need_dgrad = need_dgrad
+        self._key = None
+
+    def refresh(self, conv: nn.Conv2d):
+        w, b = conv.weight, conv.bias
+        key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+        if key != self._key:
+            dev = w.device
+            wt = w.detach()[:, :self.cin]
+            self.wf = T.ResidualBlockTrain._pack(wt, dev, T.FWD_DTYPE)
+            self.dg = T.ConvDgrad(wt, dev) if self.need_dgrad else None
+            self.bias = (torch.zeros(self.cout, device=dev) if b is None else b.detach().float().contiguous())
+            self.ones = torch.ones(self.cout, device=dev)
+            self._key = key
+        return self
+
+    def fwd(self, x16: torch.Tensor) -> torch.Tensor:
+        """x16 (n, H, W, cin) 16-bit rows -> z float32 (n, H, W, cout) = conv + bias"""
+        from .src.networks import ACT, BF16, F16, OP_CONV, Program
+        n, H, W, _ = x16.shape
+        z = torch.empty((n, H, W, self.cout), dtype=torch.float32, device=x16.device)
+        with torch.cuda.device(x16.device):
+            prog = Program(n)
+            prog.add(op=OP_CONV, dtype=F16 if x16.dtype == torch.float16 else BF16, H=H, W=W, cin=self.cin, cout=self.cout, ksize=self.k, act=ACT["none"],
+                     use_tc=1, w_layout=1, src=x16, dst_f32=z, w=self.wf, scale=self.ones, shift=self.bias)
+            prog.run()
+        return z
+
+
+def _kernels(conv: nn.Conv2d, cin=None, need_dgrad=True) -> ConvKernels:
+    k = getattr(conv, "_mzb_kernels", None)
+    if k is None:
+        k = ConvKernels(conv, cin, need_dgrad)
+        object.__setattr__(conv, "_mzb_kernels", k)          # not a submodule / buffer: invisible to state_dict()
+    return k.refresh(conv)
+
+
+def _conv_ok(conv, x, cin_extra=0) -> bool:
+    if not (isinstance(conv, nn.Conv2d) and conv.kernel_size in ((1, 1), (3, 3)) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.padding == (conv.kernel_size[0] // 2,) * 2 and conv.padding_mode == "zeros"):
+        return False
+    cout, cin = conv.weight.shape[:2]
+    return cout in (128, 256) and cin - cin_extra in (64, 128, 256) and x.shape[1] == cin - cin_extra and x.shape[3] <= 256
+
+
+def _live(x) -> bool:
+    return ENABLED and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and torch.is_grad_enabled()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# ConvBlock: conv -> BatchNorm2d (training mode) -> activation, optionally with extra constant-plane input channels
+class _ConvBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, planes, kern, bn, act, w, b, gamma, beta):
+        L, dev = _lib.lib(), x.device
+        x16 = T.rows16(x)
+        z = kern.fwd(x16)
+        n, H, W, cout = z.shape
+        if planes is not None:
+            sn, sa, sy, sx = planes.stride()
+            with torch.cuda.device(dev):
+                _lib.check(L.mz_planes_conv_fwd(n, H, W, planes.shape[1], cout, kern.cin_total, kern.cin, _p(planes), sn, sa, sy, sx, _p(w.detach()), _p(z),
+                                                _stream(dev)))
+        _, y32, mean, invstd = T.bn_train_forward(z, gamma.detach(), beta.detach(), None, act, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                                                  out_dtype=x16.dtype, want16=False)
+        ctx.kern, ctx.act, ctx.planes = kern, act, planes
+        ctx.params = (w, b, gamma, beta)
+        ctx.saved = (x16, z, mean, invstd, gamma.detach(), beta.detach())
+        return y32.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x16, z, mean, invstd, gamma, beta = ctx.saved
+        w, b, _, _ = ctx.params
+        kern, planes = ctx.kern, ctx.planes
+        dev = z.device
+        n, H, W, cout = z.shape
+        g = _cl(dy)
+        dz, dz16, dgamma, dbeta, _ = T.bn_train_backward(z, g, gamma, beta, mean, invstd, None, ctx.act, out_dtype=GRAD_DTYPE,
+                                                         want32=planes is not None, want_res=False)
+        into, ret_w = _grad_slot(w)
+        T.conv_wgrad(dz16, x16, kern.k, into)
+        if planes is not None:
+            sn, sa, sy, sx = planes.stride()
+            scratch = torch.empty(L.mz_planes_wgrad_scratch_bytes(n, cout) // 4, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.mz_planes_conv_wgrad(n, H, W, planes.shape[1], cout, kern.cin_total, kern.cin, _p(planes), sn, sa, sy, sx, _p(dz), _p(into), 1,
+                                                  _p(scratch), _stream(dev)))
+        dx = kern.dg(dz16).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        # the conv bias: a BatchNorm follows and subtracts the batch mean (exactly zero gradient)
+        zb = None if (b is None or b.grad is not None) else torch.zeros_like(b)
+        ctx.saved = None
+        return dx, None, None, None, None, ret_w, zb, dgamma, dbeta
+
+
+def convblock_supported(m, x, planes=None) -> bool:
+    """a reference-shaped ConvBlock (networks.py:7-17) in training mode on a float32 CUDA activation"""
+    if not (_live(x) and m.training and all(hasattr(m, a) for a in ("conv", "bn", "act"))):
+        return False
+    extra = 0 if planes is None else planes.shape[1]
+    if planes is not None and (planes.requires_grad or planes.dtype != torch.float32 or extra > 4 or x.shape[2] * x.shape[3] > 64
+                               or m.conv.kernel_size != (3, 3) or planes.shape[0] != x.shape[0] or tuple(planes.shape[2:]) != tuple(x.shape[2:])):
+        return False
+    bn = m.bn
+    return (_conv_ok(m.conv, x, extra) and isinstance(bn, nn.BatchNorm2d) and bn.track_running_stats and bn.momentum is not None and bn.affine
+            and _act_name(m.act) is not None)
+
+
+def convblock_forward(m, x, planes=None):
+    """`m(torch.cat([x, planes], 1))` (planes None: `m(x)`) for a train-mode ConvBlock, forward and backward on library kernels"""
+    extra = 0 if planes is None else planes.shape[1]
+    kern = _kernels(m.conv, m.conv.weight.shape[1] - extra, True)
+    with torch.no_grad():
+        m.bn.num_batches_tracked += 1
+    return _ConvBlockFn.apply(x, planes, kern, m.bn, _act_name(m.act), m.conv.weight, m.conv.bias, m.bn.weight, m.bn.bias)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# plain nn.Conv2d (the representation network's stems): no BatchNorm follows, so the bias has a gradient
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kern, w, b):
+        x16 = T.rows16(x)
+        z = kern.fwd(x16)
+        ctx.kern, ctx.params, ctx.saved = kern, (w, b), x16
+        return z.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        kern, (w, b), x16 = ctx.kern, ctx.params, ctx.saved
+        g = _cl(dy)
+        dev = g.device
+        n, H, W, cout = g.shape
+        g16 = cvt16(g, GRAD_DTYPE)
+        into, ret_w = _grad_slot(w)
+        T.conv_wgrad(g16, x16, kern.k, into)
+        ret_b = None
+        if b is not None:
+            into_b, ret_b = _grad_slot(b)
+            M = n * H * W
+            scratch = torch.empty(L.mz_bn_scratch_bytes(M, cout) // 8, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.mz_colsum(M, cout, _p(g), _p(into_b), 1, _p(scratch), _stream(dev)))
+        dx = kern.dg(g16).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        ctx.saved = None
+        return dx, None, ret_w, ret_b
+
+
+def conv_supported(conv, x) -> bool:
+    # an input that needs a gradient: the data gradient is a convolution with cin and cout swapped, and the kernel's N is 128 or 256
+    return _live(x) and _conv_ok(conv, x) and conv.weight.requires_grad and (not x.requires_grad or conv.weight.shape[1] in (128, 256))
+
+
+def conv_forward(conv, x):
+    """`conv(x)` for a stride-1 "same" nn.Conv2d, forward and backward on library kernels"""
+    kern = _kernels(conv, None, x.requires_grad)
+    if x.requires_grad and kern.dg is None:              # first seen with an input that needed no gradient
+        kern.need_dgrad, kern._key = True, None
+        kern.refresh(conv)
+    return _ConvFn.apply(x, kern, conv.weight, conv.bias)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+class _PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xc = _cl(x)
+        n, H, W, C_ = xc.shape
+        y = torch.empty((n, H // 2, W // 2, C_), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mz_pool2_train_fwd(n, H, W, C_, _p(xc), _p(y), None, 0, _stream(x.device)))
+        ctx.shape = (n, H, W, C_)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = _cl(dy)
+        n, H, W, C_ = ctx.shape
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().mz_pool2_train_bwd(n, H, W, C_, _p(g), _p(dx), _stream(g.device)))
+        return dx.permute(0, 3, 1, 2)
+
+
+def pool_supported(m, x) -> bool:
+    return (_live(x) and isinstance(m, nn.AvgPool2d) and m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2)) and m.padding in (0, (0, 0))
+            and not m.ceil_mode and x.shape[1] % 4 == 0 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0)
+
+
+def pool_forward(x):
+    return _PoolFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+class _FlattenLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xc = _cl(x)
+        n, H, W, C_ = xc.shape
+        O = w.shape[0]
+        out = torch.empty((n, O), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mz_linear_fwd(n, H * W, C_, O, _p(xc), _p(w.detach()), _p(b.detach()), _p(out), _stream(x.device)))
+        ctx.saved, ctx.params = xc, (w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        xc, (w, b) = ctx.saved, ctx.params
+        n, H, W, C_ = xc.shape
+        O, dev = w.shape[0], xc.device
+        g = g.contiguous().float()
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        into_w, ret_w = _grad_slot(w)
+        into_b, ret_b = _grad_slot(b)
+        scratch = torch.empty(L.mz_linear_scratch_bytes(n, H * W, C_, O) // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.mz_linear_bwd(n, H * W, C_, O, _p(xc), _p(w.detach()), _p(g), _p(dx), _p(into_w), _p(into_b), 1, _p(scratch), _stream(dev)))
+        ctx.saved = None
+        return (None if dx is None else dx.permute(0, 3, 1, 2)), ret_w, ret_b
+
+
+def flatten_linear_supported(lin, x) -> bool:
+    return (_live(x) and isinstance(lin, nn.Linear) and lin.bias is not None and lin.out_features <= 16
+            and lin.in_features == x.shape[1] * x.shape[2] * x.shape[3] and lin.weight.is_contiguous())
+
+
+def flatten_linear(lin, x):
+    """`lin(torch.flatten(x, 1))` for an NCHW-shaped activation, forward and backward on library kernels"""
+    return _FlattenLinearFn.apply(x, lin.weight, lin.bias)
+
+
+def head_forward(seq, x):
+    """A head `nn.Sequential(ConvBlock, nn.Flatten, nn.Linear)` (networks.py:138-149,200-223): both parts on library kernels when they qualify,
+    the module's own torch ops otherwise."""
+    mods = list(seq)
+    if (len(mods) == 3 and isinstance(mods[1], nn.Flatten) and mods[1].start_dim == 1 and mods[1].end_dim == -1 and convblock_supported(mods[0], x)):
+        y = convblock_forward(mods[0], x)
+        if flatten_linear_supported(mods[2], y):
+            return flatten_linear(mods[2], y)
+        return mods[2](mods[1](y))
+    return seq(x)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+class _ScaleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xc = _cl(x)
+        n = xc.shape[0]
+        E = xc.numel() // n
+        y = torch.empty_like(xc)
+        stats = torch.empty((n, 4), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mz_scale_train_fwd(n, E, _p(xc), _p(y), None, 0, _p(stats), _stream(x.device)))
+        ctx.saved = (xc, stats)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, stats = ctx.saved
+        g = _cl(dy)
+        n = xc.shape[0]
+        dx = torch.empty_like(xc)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().mz_scale_train_bwd(n, xc.numel() // n, _p(xc), _p(g), _p(stats), _p(dx), _stream(g.device)))
+        ctx.saved = None
+        return dx.permute(0, 3, 1, 2)
+
+
+def scale_supported(x) -> bool:
+    return _live(x) and (x.numel() // max(1, x.shape[0])) % 4 == 0 and x.shape[0] > 0
+
+
+def scale_state(x):
+    """MuZeroAgent._scale_state (networks.py:314-328), forward and backward on library kernels"""
+    return _ScaleFn.apply(x)

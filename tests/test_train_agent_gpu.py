@@ -165,6 +165,19 @@ def test_dropin_agent_training_step_vs_oracle_agent():
             assert c >= min(0.95, c_ac - 0.1), f"{name}: cosine vs fp32 autograd {c:.4f}, autocast bf16 reaches {c_ac:.4f}"
     print(f"worst cosine similarity of a trunk convolution's weight gradient vs fp32 autograd: library {worst:.4f}, torch autocast bf16 {worst_ac:.4f}, "
           f"torch TF32 {worst_tf:.4f}")
+    # every other weight (stems, ConvBlocks, Linear heads, 128-channel blocks, BatchNorm affine parameters): library kernels as well
+    # (train_layers.py), same yardstick
+    worst_o, worst_o_ac, worst_name = 1.0, 1.0, ""
+    for (name, pa), po, pc in zip(agent.named_parameters(), oracle.parameters(), ac.parameters()):
+        trunk_conv = "res_blocks" in name and name.endswith("weight") and "conv" in name
+        if trunk_conv or pa.grad is None or float(po.grad.abs().max()) < 1e-12 or (name.endswith("bias") and "conv" in name and "rep_net.blocks.0." not in name
+                                                                                     and "rep_net.blocks.3." not in name):
+            continue                                        # conv biases under a BatchNorm: exactly zero here, rounding noise in torch
+        c, c_ac = _cos(pa.grad, po.grad), _cos(pc.grad, po.grad)
+        if c < worst_o:
+            worst_o, worst_o_ac, worst_name = c, c_ac, name
+        assert c >= min(0.9, c_ac - 0.1), f"{name}: cosine vs fp32 autograd {c:.4f}, autocast bf16 reaches {c_ac:.4f}"
+    print(f"worst cosine of any other parameter's gradient vs fp32 autograd: library {worst_o:.4f} ({worst_name}; torch autocast bf16 there {worst_o_ac:.4f})")
     v0 = [p._version for p in agent.parameters()]
     agent.optimizer.step()
     assert all(p._version > v for p, v in zip(agent.parameters(), v0))
