@@ -414,6 +414,10 @@ int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *st
 /* f16_to_bf16 != 0: src is float16, dst bfloat16 -- the activations of an fp16 forward pass as the bf16 operand next to bf16 gradients
  * (one tcgen05 kind::f16 MMA cannot mix A / B element types) */
 int mz_wgrad_transpose_cvt(int n, int P, int C, const void *src, void *dst, int f16_to_bf16, void *stream);
+/* the same into the sample columns [s_offset, s_offset + mz_wgrad_padded_samples(n)) of a destination with ns_total sample columns per
+ * (channel, pixel) row (both multiples of 64): several activations that share a weight -- the K unroll steps of a training step --
+ * concatenated along the GEMM's reduction axis, so that ONE mz_conv_wgrad_any(n = ns_total) call gives the sum of their weight gradients */
+int mz_wgrad_transpose_into(int n, int P, int C, const void *src, void *dst, int ns_total, int s_offset, int f16_to_bf16, void *stream);
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
 /* accumulate != 0: dw += the gradient (one rounding per call, in call order): the K unroll steps of a training step share their weights
  * (train_torch.py:507-525) and add straight into the parameter's .grad instead of through K separate add kernels */
@@ -451,6 +455,11 @@ int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *
 int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
                           int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres,
                           void *scratch, void *stream);
+/* the same, and dgamma_acc[c] += dgamma[c], dbeta_acc[c] += dbeta[c] when those pointers are not NULL: the parameters' own .grad tensors
+ * (the K unroll steps of a training step share their layers, train_torch.py:507-525) without an add kernel per parameter and call */
+int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
+                        int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dgamma_acc, float *dbeta_acc,
+                        float *dz, void *dz16, float *dres, void *scratch, void *stream);
 
 /* out[c] (+)= sum over the M rows of x float32[M][C]: the bias gradient of a convolution that no BatchNorm follows (the representation
  * network's stem convolutions, networks.py:47,65).  scratch: mz_bn_scratch_bytes(M, C) bytes.  Deterministic. */

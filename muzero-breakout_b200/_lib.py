@@ -129,6 +129,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_adam_dev": [C.c_longlong, vp, vp, vp, vp] + [C.c_double] * 5 + [vp, vp],
         "mz_wgrad_transpose": [i32, i32, i32, vp, vp, vp],
         "mz_wgrad_transpose_cvt": [i32, i32, i32, vp, vp, i32, vp],
+        "mz_wgrad_transpose_into": [i32, i32, i32, vp, vp, i32, i32, i32, vp],
         "mz_conv_wgrad": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "mz_conv_wgrad_accum": [i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     })
@@ -136,6 +137,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_bn_train_fwd": [i32, i32, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double] + [vp] * 8,
         "mz_bn_train_bwd": [i32, i32, vp, vp, vp, vp, vp, i32, i32] + [vp] * 9,
         "mz_bn_train_bwd_mixed": [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32] + [vp] * 9,
+        "mz_bn_train_bwd_acc": [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32] + [vp] * 11,
     })
     ll = C.c_longlong
     sig.update({

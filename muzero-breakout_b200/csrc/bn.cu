@@ -136,7 +136,8 @@ bn_fwd_finalize_kernel(int M, int C, int nblocks, const double *__restrict__ par
 
 // backward finalize (one warp per channel): d beta = sum g, d gamma = sum g * xhat
 __global__ void __launch_bounds__(BN_THREADS)
-bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ dgamma, float *__restrict__ dbeta)
+bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                       float *__restrict__ dgamma_acc, float *__restrict__ dbeta_acc)
 {
     const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -145,6 +146,9 @@ bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, f
     if (lane != 0) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)q;
+    // the parameters' own .grad (the K unroll steps share the layer: one rounding per call, in call order, like autograd's accumulation)
+    if (dbeta_acc) dbeta_acc[c] += (float)s;
+    if (dgamma_acc) dgamma_acc[c] += (float)q;
 }
 
 // column sums (the bias gradient of a convolution that no BatchNorm follows): out[c] (+)= sum of the per-CTA partial sums, one warp per channel
@@ -260,6 +264,14 @@ int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const f
                           int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres,
                           void *scratch, void *stream)
 {
+    return mz_bn_train_bwd_acc(M, C, z, dy, gamma, beta, res, dtype, dz_dtype, act, save_mean, save_invstd, dgamma, dbeta, nullptr, nullptr, dz, dz16, dres,
+                               scratch, stream);
+}
+
+int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,
+                        int act, const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dgamma_acc, float *dbeta_acc,
+                        float *dz, void *dz16, float *dres, void *scratch, void *stream)
+{
     MZB_CHECK_ARG(dz_dtype == MZ_BF16 || dz_dtype == MZ_F16, "dz16 is 16-bit: dz_dtype must be MZ_BF16 or MZ_F16");
     MZB_CHECK_ARG(bn_shape_ok(M, C), "M must be positive and C one of 4 * {1, 2, 4, ..., 256}");
     MZB_CHECK_ARG(z && dy && gamma && beta && save_mean && save_invstd && dgamma && dbeta && scratch && (dz || dz16), "null pointer");
@@ -271,7 +283,7 @@ int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const f
     bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
                                                    (double *)scratch);
     MZB_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc);
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
     bn_bwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,

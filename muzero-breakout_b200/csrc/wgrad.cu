@@ -195,7 +195,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
 // loads along the channels, 32-byte stores along the samples, through a padded shared-memory tile.  grid (ns/64, C/64, P), 256 threads
 // cvt: 1 = the source is fp16 and the destination bf16 (the activations of an fp16 forward pass as the weight gradient's bf16 operand: one MMA
 // cannot mix A / B element types in kind::f16 -- the hardware answers "illegal instruction")
-__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt)
+// ns = row length of dst (all samples of the K-concatenated operand), s_off = first sample column of this call
+__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int s_off, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt)
 {
     __shared__ uint16_t tile[64][64 + 2];                    // row pitch 132 bytes = 33 words: column reads hit 32 different banks
     const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, pix = blockIdx.z;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = (uint32_t)tile[q + 2 * i][r] | ((uint32_t)tile[q + 2 * i + 1][r] << 16);   // channel c0 + r, samples n0 + q ..
-        uint4 *g = reinterpret_cast<uint4 *>(dst + ((size_t)(c0 + r) * P + pix) * ns + n0 + q);
+        uint4 *g = reinterpret_cast<uint4 *>(dst + ((size_t)(c0 + r) * P + pix) * ns + s_off + n0 + q);
         g[0] = make_uint4(w[0], w[1], w[2], w[3]);
         g[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
@@ -279,11 +280,18 @@ int mz_wgrad_transpose(int n, int P, int C, const void *src, void *dst, void *st
 
 int mz_wgrad_transpose_cvt(int n, int P, int C, const void *src, void *dst, int f16_to_bf16, void *stream)
 {
+    return mz_wgrad_transpose_into(n, P, C, src, dst, mz_wgrad_padded_samples(n), 0, f16_to_bf16, stream);
+}
+
+int mz_wgrad_transpose_into(int n, int P, int C, const void *src, void *dst, int ns_total, int s_offset, int f16_to_bf16, void *stream)
+{
     MZB_CHECK_ARG(n > 0 && P > 0 && C > 0 && C % 64 == 0 && src && dst, "bad argument");
     MZB_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "buffers must be 16-byte aligned");
     const int ns = mz_wgrad_padded_samples(n);
+    MZB_CHECK_ARG(s_offset >= 0 && s_offset % BLOCK_K == 0 && ns_total % BLOCK_K == 0 && s_offset + ns <= ns_total, "sample window outside the destination rows");
     MZB_CHECK_ARG(P <= 65535 && C / 64 <= 65535, "image or channel count too large");
-    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns, P, C, (const uint16_t *)src, (uint16_t *)dst, f16_to_bf16 != 0);
+    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns_total, s_offset, P, C, (const uint16_t *)src, (uint16_t *)dst,
+                                                                                       f16_to_bf16 != 0);
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -227,15 +227,21 @@ class ConvDgrad:
         """(cout, cin, k, k) forward filter -> (cin, cout, k, k) filter whose "same" convolution with dy is dx: channels swapped, taps flipped."""
         return weight.detach().to(torch.float32).transpose(0, 1).flip(2, 3)
 
-    def __call__(self, dy: torch.Tensor) -> torch.Tensor:
+    def __call__(self, dy: torch.Tensor, add: torch.Tensor | None = None) -> torch.Tensor:
+        """add: float32 (n, H, W, cin) added in the kernel's epilogue (the skip connection's gradient of a ResidualBlock)"""
         from .src.networks import ACT, BF16, OP_CONV, Program
         n, H, W, c = dy.shape
         if c != self.cout or dy.dtype != torch.bfloat16 or not dy.is_cuda or not dy.is_contiguous():
             raise ValueError("ConvDgrad: dy must be a contiguous CUDA bf16 tensor (n, H, W, cout)")
         dx = torch.empty((n, H, W, self.cin), dtype=torch.float32, device=dy.device)
         prog = Program(n)                                # fp32-only output (dst = NULL): staged, coalesced stores (csrc/conv_tc.cu)
+        extra = {}
+        if add is not None:
+            if add.shape != dx.shape or add.dtype != torch.float32 or not add.is_contiguous():
+                raise ValueError("ConvDgrad: add must be a contiguous float32 tensor of the output's shape")
+            extra["res_f32"] = add
         prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=self.cout, cout=self.cin, ksize=self.k, act=ACT["none"], use_tc=1, w_layout=1,
-                 src=dy, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift)
+                 src=dy, dst_f32=dx, w=self.w, scale=self.scale, shift=self.shift, **extra)
         prog.run()
         return dx
 
@@ -273,6 +279,66 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: t
         _lib.check(L.mz_conv_wgrad_any(n, H, W, ksize, combos[(dy.dtype, x.dtype)], cout, cin, dw.shape[1], _p(dy_t), _p(x_t), _p(partial), _p(dw),
                                        int(acc), st))
     return dw
+
+
+# Deferred weight gradients.  The K unroll steps of a training step share every convolution (train_torch.py:507-525), so a weight's gradient is
+# the sum of K small GEMMs (512 samples: 72 tiles of 100 k-steps, 23 us each at 340 TFLOP/s + a split reduction each).  Inside a graphed
+# training step (GraphedTrainStep switches this on) the (dz, x) operand pairs are only queued during loss.backward(); flush_wgrads() then
+# concatenates the pairs of a weight along the GEMM's reduction axis and runs ONE GEMM per weight (2560 samples: ~900 TFLOP/s, one split
+# reduction, the K partial sums added in the fp32 accumulator instead of through K roundings of .grad).  Eager steps keep the immediate form:
+# their .grad must be complete when backward() returns.
+_DEFER = {"on": False, "q": {}}
+
+
+def wgrad_or_defer(dy16, x16, ksize, into):
+    """conv_wgrad(dy16, x16, ksize, into) now, or -- in a graphed step, with an in-place destination -- queued for flush_wgrads()"""
+    if _DEFER["on"] and into is not None:
+        ent = _DEFER["q"].get(id(into))
+        if ent is None:
+            ent = _DEFER["q"][id(into)] = (into, ksize, [])
+        ent[2].append((dy16, x16))
+        return None
+    return conv_wgrad(dy16, x16, ksize, into)
+
+
+def flush_wgrads(side=None):
+    """Run the queued weight gradients: per weight, the operand pairs transposed into one K-concatenated pair ([C][H*W][sum of padded sample
+    counts], mz_wgrad_transpose_into) and one mz_conv_wgrad_any that adds to the weight's .grad.  side: a second stream; the weights alternate
+    between it and the current stream (the transposes of one weight run next to the GEMM of the other)."""
+    q, _DEFER["q"] = _DEFER["q"], {}
+    if not q:
+        return
+    L = _lib.lib()
+    combos = {(torch.bfloat16, torch.bfloat16): 1, (torch.float16, torch.float16): 2, (torch.bfloat16, torch.float16): 1}
+    dev = next(iter(q.values()))[0].device
+    cur = torch.cuda.current_stream(dev)
+    if side is not None:
+        side.wait_stream(cur)
+    for i, (into, ksize, items) in enumerate(q.values()):
+        stream = side if (side is not None and i % 2 == 1) else cur
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            st = stream.cuda_stream
+            dy0, x0 = items[0]
+            _, H, W, cin = x0.shape
+            cout = dy0.shape[-1]
+            ns = [L.mz_wgrad_padded_samples(dy.shape[0]) for dy, _ in items]
+            tot = sum(ns)
+            dy_t = torch.empty((cout, H * W, tot), dtype=dy0.dtype, device=dev)
+            x_t = torch.empty((cin, H * W, tot), dtype=dy0.dtype, device=dev)
+            off = 0
+            for (dy, x), n_i in zip(items, ns):
+                if dy.shape[1:3] != (H, W) or x.shape[-1] != cin or dy.shape[-1] != cout or dy.dtype != dy0.dtype or x.dtype != x0.dtype:
+                    raise ValueError("flush_wgrads: the operand pairs queued for one weight differ in shape or element type")
+                _lib.check(L.mz_wgrad_transpose_into(dy.shape[0], H * W, cout, _p(dy), _p(dy_t), tot, off, 0, st))
+                _lib.check(L.mz_wgrad_transpose_into(x.shape[0], H * W, cin, _p(x), _p(x_t), tot, off, int(x.dtype != dy.dtype), st))
+                if stream is not cur:
+                    dy.record_stream(stream); x.record_stream(stream)
+                off += n_i
+            partial = torch.empty(L.mz_wgrad_partial_bytes_any(ksize, tot, cout, cin) // 4, dtype=torch.float32, device=dev)
+            _lib.check(L.mz_conv_wgrad_any(tot, H, W, ksize, combos[(dy0.dtype, x0.dtype)], cout, cin, into.shape[1], _p(dy_t), _p(x_t), _p(partial),
+                                           _p(into), 1, st))
+    if side is not None:
+        cur.wait_stream(side)
 
 
 _ACT = {"none": 0, "relu": 1, "leaky_relu": 2}
@@ -322,7 +388,7 @@ def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.
     return y, y32, mean, invstd
 
 
-def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16, want32=True, want_res=True):
+def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", out_dtype=torch.bfloat16, want32=True, want_res=True, acc=(None, None)):
     """Backward of bn_train_forward.  dy: float32 gradient of the block output.  Returns (dz float32, dz 16-bit, dgamma, dbeta, dres float32).
     res keeps the element type the forward pass gave it (fp16 or bf16); out_dtype is that of the 16-bit dz."""
     _lib.require_cuda()
@@ -335,9 +401,10 @@ def bn_train_backward(z, dy, gamma, beta, mean, invstd, res=None, act="relu", ou
     dgamma, dbeta = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
     scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.mz_bn_train_bwd_mixed(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(res.dtype if res is not None else out_dtype), _dt(out_dtype),
-                                           _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta), _p(dz), _p(dz16), _p(dres), _p(scratch),
-                                           torch.cuda.current_stream(dev).cuda_stream))
+        # acc = (gamma.grad, beta.grad): the kernel also adds the two gradients to them (contiguous float32 [C])
+        _lib.check(L.mz_bn_train_bwd_acc(M, C_, _p(z), _p(dy), _p(gamma), _p(beta), _p(res), _dt(res.dtype if res is not None else out_dtype), _dt(out_dtype),
+                                         _ACT[act], _p(mean), _p(invstd), _p(dgamma), _p(dbeta), _p(acc[0]), _p(acc[1]), _p(dz), _p(dz16), _p(dres), _p(scratch),
+                                         torch.cuda.current_stream(dev).cuda_stream))
     return dz, dz16, dgamma, dbeta, dres
 
 
@@ -421,7 +488,7 @@ class ResidualBlockTrain:
         """dy: float32 gradient of the block output.  Returns (dx float32, {parameter name: gradient})."""
         return self.backward_fn(dy, self._saved)
 
-    def backward_fn(self, dy: torch.Tensor, saved, grad_into=(None, None), side=None):
+    def backward_fn(self, dy: torch.Tensor, saved, grad_into=(None, None), side=None, bn_into=((None, None), (None, None))):
         """grad_into: (conv1.weight.grad, conv2.weight.grad) to accumulate the weight gradients into (the entries of the returned dict are
         then None), or None entries for fresh tensors.  side: a CUDA stream for the weight-gradient chain (transposes, mz_conv_wgrad, split
         reduction) when both gradients accumulate in place -- it only shares its inputs with the data-gradient chain, and at a 512-sample
@@ -432,6 +499,8 @@ class ResidualBlockTrain:
         cur = torch.cuda.current_stream(dy.device) if side is not None else None
 
         def wgrad(dz16, act16, into):
+            if _DEFER["on"] and into is not None:
+                return wgrad_or_defer(dz16, act16, 3, into)
             if side is None:
                 dw = conv_wgrad(dz16, act16, 3, into)
                 return None if into is not None else dw
@@ -441,14 +510,16 @@ class ResidualBlockTrain:
             dz16.record_stream(side); act16.record_stream(side)
             return None
 
-        dz2, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu")
+        # bn_into: ((bn1.weight.grad, bn1.bias.grad), (bn2...)) -- gradients the kernels add to in place (their dict entries are then None)
+        _, dz2_16, dg2, db2, dres = bn_train_backward(z2, dy, self.gamma[1], self.beta[1], m2, s2, x16, "relu", want32=False, acc=bn_into[1])
         dw2 = wgrad(dz2_16, h16, grad_into[1])
         dh = self.dgrad[1](dz2_16)
-        dz1, dz1_16, dg1, db1, _ = bn_train_backward(z1, dh, self.gamma[0], self.beta[0], m1, s1, None, "relu")
+        _, dz1_16, dg1, db1, _ = bn_train_backward(z1, dh, self.gamma[0], self.beta[0], m1, s1, None, "relu", want32=False, want_res=False, acc=bn_into[0])
         dw1 = wgrad(dz1_16, x16, grad_into[0])
-        dx = self.dgrad[0](dz1_16)
-        dx += dres                                      # the skip connection's gradient
-        return dx, {"conv1.weight": dw1, "bn1.weight": dg1, "bn1.bias": db1, "conv2.weight": dw2, "bn2.weight": dg2, "bn2.bias": db2}
+        dx = self.dgrad[0](dz1_16, add=dres)            # + the skip connection's gradient, in the convolution's epilogue
+        (g1a, b1a), (g2a, b2a) = bn_into
+        return dx, {"conv1.weight": dw1, "bn1.weight": None if g1a is not None else dg1, "bn1.bias": None if b1a is not None else db1,
+                    "conv2.weight": dw2, "bn2.weight": None if g2a is not None else dg2, "bn2.bias": None if b2a is not None else db2}
 
 
 class TrunkTrain:
@@ -544,13 +615,16 @@ class _TrunkFn(torch.autograd.Function):
         flat = []
         nb = len(ctx.kernels)
         cur = torch.cuda.current_stream(g.device)
-        side = _wgrad_side_stream(cur) if _WGRAD_SIDE["on"] else None
+        # (deferred weight gradients: nothing runs on the side stream here, and a stream that never joined the capture must not be waited for)
+        side = _wgrad_side_stream(cur) if (_WGRAD_SIDE["on"] and not _DEFER["on"]) else None
         for i, (blk, sv) in enumerate(zip(reversed(ctx.kernels), reversed(ctx.saved_blocks))):
             ps = ctx.params[8 * (nb - 1 - i):8 * (nb - i)]           # conv1.w, conv1.b, bn1.w, bn1.b, conv2.w, conv2.b, bn2.w, bn2.b
             # a parameter that already has a contiguous .grad (always, under this module's flat-buffer Adam) takes its weight gradient by
             # in-kernel accumulation; autograd then gets None for it (one add kernel less per convolution and unroll step)
-            into = tuple(p.grad if (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32) else None for p in (ps[0], ps[4]))
-            g, grads = blk.backward_fn(g, sv, into, side)
+            slot = lambda p: p.grad if (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32) else None
+            into = (slot(ps[0]), slot(ps[4]))
+            bn_into = ((slot(ps[2]), slot(ps[3])), (slot(ps[6]), slot(ps[7])))
+            g, grads = blk.backward_fn(g, sv, into, side, bn_into)
             # conv biases: a BatchNorm follows and subtracts the batch mean (exactly zero gradient): None where a .grad exists, zeros otherwise
             zb = [None if p.grad is not None else torch.zeros(p.shape[0], device=g.device) for p in (ps[1], ps[5])]
             flat.append((grads["conv1.weight"], zb[0], grads["bn1.weight"], grads["bn1.bias"], grads["conv2.weight"], zb[1], grads["bn2.weight"], grads["bn2.bias"]))
@@ -685,16 +759,19 @@ class GraphedTrainStep:
 
     def _body(self, st):
         _WGRAD_SIDE["on"] = self.side is not None
+        _DEFER["on"], _DEFER["q"] = os.environ.get("MZB_TRAIN_DEFER_WGRAD", "1") == "1", {}
         try:
             return self._body_inner(st)
         finally:
             _WGRAD_SIDE["on"] = False
+            _DEFER["on"], _DEFER["q"] = False, {}
 
     def _body_inner(self, st):
         self.opt.flat_grad.zero_()
         pr, pv, pp = self.rollout(st[0], st[1], st[2])
         out = loss_fn(st[3], pr, st[4], pv, st[5], pp, self.supports, self.K)
         out[0].backward()
+        flush_wgrads(self.side)                          # one weight-gradient GEMM per convolution over all its K uses
         self.opt.step_dev()
         return torch.stack([o.detach() for o in out])
 

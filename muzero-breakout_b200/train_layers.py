@@ -157,10 +157,14 @@ class _ConvBlockFn(torch.autograd.Function):
         dev = z.device
         n, H, W, cout = z.shape
         g = _cl(dy)
-        dz, dz16, dgamma, dbeta, _ = T.bn_train_backward(z, g, gamma, beta, mean, invstd, None, ctx.act, out_dtype=GRAD_DTYPE,
-                                                         want32=planes is not None, want_res=False)
+        _, _, gamma_p, beta_p = ctx.params
+        acc_g, ret_g = _grad_slot(gamma_p)
+        acc_b, ret_b = _grad_slot(beta_p)
+        dz, dz16, _, _, _ = T.bn_train_backward(z, g, gamma, beta, mean, invstd, None, ctx.act, out_dtype=GRAD_DTYPE,
+                                                want32=planes is not None, want_res=False, acc=(acc_g, acc_b))
         into, ret_w = _grad_slot(w)
-        T.conv_wgrad(dz16, x16, kern.k, into)
+        # the parameter's own .grad: may be queued for the step's batched weight-gradient pass; a fresh tensor for autograd: now
+        T.wgrad_or_defer(dz16, x16, kern.k, into) if ret_w is None else T.conv_wgrad(dz16, x16, kern.k, into)
         if planes is not None:
             sn, sa, sy, sx = planes.stride()
             scratch = torch.empty(L.mz_planes_wgrad_scratch_bytes(n, cout) // 4, dtype=torch.float32, device=dev)
@@ -171,7 +175,7 @@ class _ConvBlockFn(torch.autograd.Function):
         # the conv bias: a BatchNorm follows and subtracts the batch mean (exactly zero gradient)
         zb = None if (b is None or b.grad is not None) else torch.zeros_like(b)
         ctx.saved = None
-        return dx, None, None, None, None, ret_w, zb, dgamma, dbeta
+        return dx, None, None, None, None, ret_w, zb, ret_g, ret_b
 
 
 def convblock_supported(m, x, planes=None) -> bool:
@@ -215,7 +219,7 @@ class _ConvFn(torch.autograd.Function):
         n, H, W, cout = g.shape
         g16 = cvt16(g, GRAD_DTYPE)
         into, ret_w = _grad_slot(w)
-        T.conv_wgrad(g16, x16, kern.k, into)
+        T.wgrad_or_defer(g16, x16, kern.k, into) if ret_w is None else T.conv_wgrad(g16, x16, kern.k, into)
         ret_b = None
         if b is not None:
             into_b, ret_b = _grad_slot(b)
