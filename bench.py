@@ -666,8 +666,8 @@ def bench_train_ends(dev, rank, world, cpu=True):
 def bench_train_step(dev, minibatch=512, K=5):
     """One iteration of the reference's training loop body (train_torch.py:385-417: zero_grad, _k_step_rollout :487-528 = representation
     network + K x (prediction, dynamics), loss_fn :33-66, loss.backward(), optimizer.step()) at config.yaml's minibatch 512 and K = 5:
-    the learner-side drop-in (muzero-breakout_b200/src/agent.py: ResidualBlock trunks forward + backward on the tcgen05 / BatchNorm kernels,
-    mz_loss, mz_adam; stems, head layers, representation network on torch ops) against the unmodified reference modules + its own loss_fn +
+    the learner-side drop-in (muzero-breakout_b200/src/agent.py: every layer of the three networks forward + backward on this library's kernels --
+    tcgen05 convolution / data / weight gradients, BatchNorm, pools, Linear heads, _scale_state -- plus mz_loss and mz_adam) against the unmodified reference modules + its own loss_fn +
     torch.optim.Adam under torch + cuDNN on the same GPU (TF32 and autocast bf16)."""
     from muzero_breakout_b200.src.agent import MuZeroAgent
     from muzero_breakout_b200.src.networks import DEFAULT_MODEL_CFG
@@ -725,7 +725,8 @@ def bench_train_step(dev, minibatch=512, K=5):
     out = {"minibatch": minibatch, "K": K, "library_ms": graph_ms, "library_eager_ms": lib_ms, "library_kernel_launches_per_step": launches_per_step,
            "library_mode": "one CUDA-graph replay per loop iteration (train.GraphedTrainStep / accelerate_training_stage); library_eager_ms = the same kernels launched eagerly",
            "what": "zero_grad + _k_step_rollout + loss_fn + loss.backward() + optimizer.step() (train_torch.py:385-417); library = drop-in MuZeroAgent "
-                   "(ResidualBlock trunks fwd + bwd on tcgen05 / BatchNorm kernels, bf16 operands; mz_loss; mz_adam; other layers on torch ops)"}
+                   "(all layers of the three networks fwd + bwd on library kernels: tcgen05 conv / dgrad / wgrad with fp16 forward and bf16 gradient operands, "
+                   "BatchNorm, pools, Linear heads, _scale_state; weight gradients batched over the K unroll steps; mz_loss; mz_adam)"}
     del agent
     torch.cuda.empty_cache()
     R = _reference()

@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(int E, const float *__re
 // w float32 [cout][cin_total][3][3], the planes are input channels c0 .. c0 + A - 1.  A <= 4, H * W <= 64.
 constexpr int PL_MAX_A = 4;
 constexpr int PL_MAX_HW = 64;
-constexpr int PL_S = 4;              // samples per CTA (forward)
-constexpr int PL_CHUNK = 16;         // samples per CTA (weight gradient)
+constexpr int PL_S = 2;              // samples per CTA (forward): 1280 CTAs at the 2560 samples of a training step's unroll
+constexpr int PL_CHUNK = 4;          // samples per CTA (weight gradient): 640 CTAs; 16 samples = 160 CTAs took 175 us per call
 
 struct PlaneArgs {
     int n, H, W, A, cout, cin_total, c0;
@@ -382,7 +382,17 @@ __global__ void __launch_bounds__(256) planes_dw_reduce_kernel(const PlaneArgs a
     if (i >= a.cout * a.A * 9) return;
     const int co = i / (a.A * 9), k = i - co * (a.A * 9);
     float v = 0.0f;
-    for (int c = 0; c < chunks; ++c) v += partial[((size_t)c * a.cout + co) * (PL_MAX_A * 9) + k];
+    const float *src = partial + (size_t)co * (PL_MAX_A * 9) + k;
+    const size_t stride = (size_t)a.cout * (PL_MAX_A * 9);
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {                      // eight loads in flight, added in index order
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldcs(src + (size_t)(c + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; c < chunks; ++c) v += __ldcs(src + (size_t)c * stride);
     float *dst = dw + ((size_t)co * a.cin_total + a.c0) * 9 + k;
     *dst = accumulate ? *dst + v : v;
 }

@@ -16,7 +16,10 @@ backed by csrc/train.cu through the C ABI (mz_loss / mz_adam, include/mzb200.h).
         networks.py:11,24-25, inside loss.backward())              convolution of dY with the transposed, tap-flipped weights, so it runs on the
                                                                    acting path's tcgen05 kernel (csrc/conv_tc.cu) with re-packed weights
 
-The rest of the backward pass (weight gradients, training-mode BatchNorm) still runs in PyTorch.  There is no CPU fallback.
+    weight gradients, training-mode BatchNorm, the autograd bridge    conv_wgrad / flush_wgrads (csrc/wgrad.cu), bn_train_forward / _backward
+        of the ResidualBlock runs, the graphed loop iteration          (csrc/bn.cu), trunk_forward, GraphedTrainStep / accelerate_training_stage
+
+The layers around the ResidualBlock runs (stems, pools, ConvBlocks, Linear heads, _scale_state) are in train_layers.py.  There is no CPU fallback.
 """
 from __future__ import annotations
 
