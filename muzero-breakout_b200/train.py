@@ -290,56 +290,126 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, ksize: int, accumulate_into: t
 # concatenates the pairs of a weight along the GEMM's reduction axis and runs ONE GEMM per weight (2560 samples: ~900 TFLOP/s, one split
 # reduction, the K partial sums added in the fp32 accumulator instead of through K roundings of .grad).  Eager steps keep the immediate form:
 # their .grad must be complete when backward() returns.
-_DEFER = {"on": False, "q": {}}
+_DEFER = {"on": False, "q": {}, "expect": {}, "sides": []}
+_COMBOS = {(torch.bfloat16, torch.bfloat16): 1, (torch.float16, torch.float16): 2, (torch.bfloat16, torch.float16): 1}
+
+
+class _Pending:
+    """the queued uses of one weight: `count` x (dy, x) pairs of `n` samples.  When the previous step has shown how many uses to expect, the
+    K-concatenated operands exist from the first use on and every pair is transposed into its sample columns right away (on the weight-gradient
+    side stream, next to the data-gradient chain); flush_wgrads() is then left with the GEMM."""
+
+    def __init__(self, into, ksize, dy, x, expect):
+        self.into, self.ksize = into, ksize
+        self.shape = (dy.shape[0], dy.shape[1], dy.shape[2], dy.shape[3], x.shape[3], dy.dtype, x.dtype)
+        self.items, self.keep, self.filled, self.bufs, self.count, self.done = [], [], 0, None, 0, False
+        if expect is not None and expect[1] == self.shape and expect[0] > 0:
+            n, H, W, cout, cin = self.shape[:5]
+            self.ns = _lib.lib().mz_wgrad_padded_samples(n)
+            self.count = expect[0]
+            self.bufs = (torch.empty((cout, H * W, self.count * self.ns), dtype=dy.dtype, device=dy.device),
+                         torch.empty((cin, H * W, self.count * self.ns), dtype=dy.dtype, device=dy.device))
+
+
+def _transpose_pair(L, dy, x, dy_t, x_t, tot, off, st):
+    n, H, W, cout = dy.shape
+    _lib.check(L.mz_wgrad_transpose_into(n, H * W, cout, _p(dy), _p(dy_t), tot, off, 0, st))
+    _lib.check(L.mz_wgrad_transpose_into(n, H * W, x.shape[3], _p(x), _p(x_t), tot, off, int(x.dtype != dy.dtype), st))
+
+
+def _pending_gemm(L, ent, dy_t, x_t, tot, stream, cur):
+    n, H, W, cout, cin, dt_dy, dt_x = ent.shape
+    dev = ent.into.device
+    partial = torch.empty(L.mz_wgrad_partial_bytes_any(ent.ksize, tot, cout, cin) // 4, dtype=torch.float32, device=dev)
+    _lib.check(L.mz_conv_wgrad_any(tot, H, W, ent.ksize, _COMBOS[(dt_dy, dt_x)], cout, cin, ent.into.shape[1], _p(dy_t), _p(x_t), _p(partial),
+                                   _p(ent.into), 1, stream.cuda_stream))
+    if stream is not cur:
+        for t in (dy_t, x_t, partial):
+            t.record_stream(stream)
+    ent.keep.append(partial)
 
 
 def wgrad_or_defer(dy16, x16, ksize, into):
     """conv_wgrad(dy16, x16, ksize, into) now, or -- in a graphed step, with an in-place destination -- queued for flush_wgrads()"""
-    if _DEFER["on"] and into is not None:
-        ent = _DEFER["q"].get(id(into))
-        if ent is None:
-            ent = _DEFER["q"][id(into)] = (into, ksize, [])
-        ent[2].append((dy16, x16))
-        return None
-    return conv_wgrad(dy16, x16, ksize, into)
+    if not (_DEFER["on"] and into is not None):
+        return conv_wgrad(dy16, x16, ksize, into)
+    dy16, x16 = dy16.contiguous(), x16.contiguous()
+    key = into.data_ptr()                                 # one entry per parameter (its .grad is a fixed view of the flat gradient buffer)
+    ent = _DEFER["q"].get(key)
+    if ent is None:
+        ent = _DEFER["q"][key] = _Pending(into, ksize, dy16, x16, _DEFER["expect"].get(key))
+    shape = (dy16.shape[0], dy16.shape[1], dy16.shape[2], dy16.shape[3], x16.shape[3], dy16.dtype, x16.dtype)
+    if ent.bufs is not None and ent.filled < ent.count and shape == ent.shape:
+        dev = dy16.device
+        cur = torch.cuda.current_stream(dev)
+        side = _wgrad_side_stream(cur) if _WGRAD_SIDE["on"] else None
+        stream = side if side is not None else cur
+        if side is not None:
+            side.wait_stream(cur)
+            if side not in _DEFER["sides"]:
+                _DEFER["sides"].append(side)
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            _transpose_pair(_lib.lib(), dy16, x16, ent.bufs[0], ent.bufs[1], ent.count * ent.ns, ent.filled * ent.ns, stream.cuda_stream)
+            if ent.filled + 1 == ent.count and _DEFER.get("eager_gemm", False):
+                # the last expected use: the GEMM follows its transposes on the same stream, next to what is left of the backward pass
+                _pending_gemm(_lib.lib(), ent, ent.bufs[0], ent.bufs[1], ent.count * ent.ns, stream, cur)
+                ent.done = True
+        if side is not None:
+            dy16.record_stream(side); x16.record_stream(side)
+            for b in ent.bufs:
+                b.record_stream(side)
+        ent.keep.append((dy16, x16))                      # alive until the flush: their memory is not handed out again under the side stream's reads
+        ent.filled += 1
+    else:
+        ent.items.append((dy16, x16))
+    return None
 
 
 def flush_wgrads(side=None):
-    """Run the queued weight gradients: per weight, the operand pairs transposed into one K-concatenated pair ([C][H*W][sum of padded sample
-    counts], mz_wgrad_transpose_into) and one mz_conv_wgrad_any that adds to the weight's .grad.  side: a second stream; the weights alternate
-    between it and the current stream (the transposes of one weight run next to the GEMM of the other)."""
+    """Run the queued weight gradients: per weight ONE mz_conv_wgrad_any over the K-concatenated operand pair ([C][H*W][sum of padded sample
+    counts]) that adds to the weight's .grad.  Pairs that were not transposed on arrival (first step: the number of uses was unknown) are
+    transposed here.  side: a second stream; the weights alternate between it and the current stream."""
     q, _DEFER["q"] = _DEFER["q"], {}
+    sides, _DEFER["sides"] = _DEFER["sides"], []
     if not q:
         return
     L = _lib.lib()
-    combos = {(torch.bfloat16, torch.bfloat16): 1, (torch.float16, torch.float16): 2, (torch.bfloat16, torch.float16): 1}
-    dev = next(iter(q.values()))[0].device
+    dev = next(iter(q.values())).into.device
     cur = torch.cuda.current_stream(dev)
+    for s_ in sides:                                      # the transposes issued during the backward pass
+        cur.wait_stream(s_)
     if side is not None:
         side.wait_stream(cur)
-    for i, (into, ksize, items) in enumerate(q.values()):
+    for i, ent in enumerate(q.values()):
         stream = side if (side is not None and i % 2 == 1) else cur
+        n, H, W, cout, cin, dt_dy, dt_x = ent.shape
         with torch.cuda.device(dev), torch.cuda.stream(stream):
             st = stream.cuda_stream
-            dy0, x0 = items[0]
-            _, H, W, cin = x0.shape
-            cout = dy0.shape[-1]
-            ns = [L.mz_wgrad_padded_samples(dy.shape[0]) for dy, _ in items]
-            tot = sum(ns)
-            dy_t = torch.empty((cout, H * W, tot), dtype=dy0.dtype, device=dev)
-            x_t = torch.empty((cin, H * W, tot), dtype=dy0.dtype, device=dev)
-            off = 0
-            for (dy, x), n_i in zip(items, ns):
-                if dy.shape[1:3] != (H, W) or x.shape[-1] != cin or dy.shape[-1] != cout or dy.dtype != dy0.dtype or x.dtype != x0.dtype:
-                    raise ValueError("flush_wgrads: the operand pairs queued for one weight differ in shape or element type")
-                _lib.check(L.mz_wgrad_transpose_into(dy.shape[0], H * W, cout, _p(dy), _p(dy_t), tot, off, 0, st))
-                _lib.check(L.mz_wgrad_transpose_into(x.shape[0], H * W, cin, _p(x), _p(x_t), tot, off, int(x.dtype != dy.dtype), st))
-                if stream is not cur:
-                    dy.record_stream(stream); x.record_stream(stream)
-                off += n_i
-            partial = torch.empty(L.mz_wgrad_partial_bytes_any(ksize, tot, cout, cin) // 4, dtype=torch.float32, device=dev)
-            _lib.check(L.mz_conv_wgrad_any(tot, H, W, ksize, combos[(dy0.dtype, x0.dtype)], cout, cin, into.shape[1], _p(dy_t), _p(x_t), _p(partial),
-                                           _p(into), 1, st))
+
+            def gemm(dy_t, x_t, tot):
+                _pending_gemm(L, ent, dy_t, x_t, tot, stream, cur)
+
+            if ent.bufs is not None and not ent.done:
+                tot = ent.count * ent.ns
+                if ent.filled < ent.count:                # fewer uses than the step before: the unused sample columns must be zero
+                    for b in ent.bufs:
+                        b[:, :, ent.filled * ent.ns:].zero_()
+                gemm(ent.bufs[0], ent.bufs[1], tot)
+            if ent.items:
+                ns = [L.mz_wgrad_padded_samples(dy.shape[0]) for dy, _ in ent.items]
+                tot = sum(ns)
+                dy_t = torch.empty((cout, H * W, tot), dtype=dt_dy, device=dev)
+                x_t = torch.empty((cin, H * W, tot), dtype=dt_dy, device=dev)
+                off = 0
+                for (dy, x), n_i in zip(ent.items, ns):
+                    if dy.shape[1:] != (H, W, cout) or x.shape[3] != cin or dy.dtype != dt_dy or x.dtype != dt_x:
+                        raise ValueError("flush_wgrads: the operand pairs queued for one weight differ in shape or element type")
+                    _transpose_pair(L, dy, x, dy_t, x_t, tot, off, st)
+                    if stream is not cur:
+                        dy.record_stream(stream); x.record_stream(stream)
+                    off += n_i
+                gemm(dy_t, x_t, tot)
+        _DEFER["expect"][ent.into.data_ptr()] = (ent.filled + len(ent.items), ent.shape)
     if side is not None:
         cur.wait_stream(side)
 
@@ -762,12 +832,13 @@ class GraphedTrainStep:
 
     def _body(self, st):
         _WGRAD_SIDE["on"] = self.side is not None
-        _DEFER["on"], _DEFER["q"] = os.environ.get("MZB_TRAIN_DEFER_WGRAD", "1") == "1", {}
+        _DEFER["on"], _DEFER["q"], _DEFER["sides"] = os.environ.get("MZB_TRAIN_DEFER_WGRAD", "1") == "1", {}, []
+        _DEFER["eager_gemm"] = os.environ.get("MZB_TRAIN_WGRAD_AT_LAST_USE", "0") == "1"      # measured: 36.3 vs 35.7 ms with the GEMMs at the end
         try:
             return self._body_inner(st)
         finally:
             _WGRAD_SIDE["on"] = False
-            _DEFER["on"], _DEFER["q"] = False, {}
+            _DEFER["on"], _DEFER["q"], _DEFER["sides"] = False, {}, []
 
     def _body_inner(self, st):
         self.opt.flat_grad.zero_()
