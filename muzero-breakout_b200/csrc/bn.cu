@@ -62,6 +62,8 @@ bn_reduce_kernel(int M, int C, int mode, const float *__restrict__ z, const floa
                  const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res,
                  int f16, int act, double *__restrict__ partial)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     extern __shared__ double s_red[];                       // [row lanes][2][C]
     const int tpr = C / 4, lanes = BN_THREADS / tpr;
     const int cq = (threadIdx.x % tpr) * 4, rl = threadIdx.x / tpr;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_finalize_kernel(int M, int C, int nblocks, const double *__restrict__ partial, double eps, double momentum, float *__restrict__ running_mean,
                        float *__restrict__ running_var, float *__restrict__ save_mean, float *__restrict__ save_invstd)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;                                   // warp-uniform
     double s, q;
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ dgamma, float *__restrict__ dbeta,
                        float *__restrict__ dgamma_acc, float *__restrict__ dbeta_acc)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s, q;
@@ -155,6 +161,8 @@ bn_bwd_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, f
 __global__ void __launch_bounds__(BN_THREADS)
 colsum_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, float *__restrict__ out, int accumulate)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     const int c = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s, q;
@@ -169,6 +177,8 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
                     const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res, int f16, int act,
                     uint16_t *__restrict__ y, float *__restrict__ y_f32)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     const size_t i = (size_t)blockIdx.x * BN_THREADS + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)((i * 4) % C);
@@ -189,6 +199,8 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
                     int f16, int dz_f16, int act, const float *__restrict__ dgamma, const float *__restrict__ dbeta, float *__restrict__ dz,
                     uint16_t *__restrict__ dz16, float *__restrict__ dres)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     const size_t i = (size_t)blockIdx.x * BN_THREADS + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)((i * 4) % C);
@@ -228,13 +240,13 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 0, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch);
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 0, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
     MZB_LAUNCH_CHECK();
-    bn_fwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd);
+    MZB_CUDA(mzb::launch_chain_small(bn_fwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    bn_fwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
-                                                                                                 dtype == MZ_F16, act, (uint16_t *)y, y_f32);
+    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
+                                                                                                 dtype == MZ_F16, act, (uint16_t *)y, y_f32));
     MZB_LAUNCH_CHECK();
     return 0;
 }
@@ -246,9 +258,9 @@ int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *sc
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch);
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
     MZB_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, out, accumulate);
+    MZB_CUDA(mzb::launch_chain_small(colsum_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, out, accumulate));
     MZB_LAUNCH_CHECK();
     return 0;
 }
@@ -280,15 +292,15 @@ int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const flo
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    bn_reduce_kernel<<<nb, BN_THREADS, smem, st>>>(M, C, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
-                                                   (double *)scratch);
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
+                                                   (double *)scratch));
     MZB_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc);
+    MZB_CUDA(mzb::launch_chain_small(bn_bwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    bn_bwd_apply_kernel<<<(unsigned)((total4 + BN_THREADS - 1) / BN_THREADS), BN_THREADS, 0, st>>>(total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
+    MZB_CUDA(mzb::launch_chain(bn_bwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
                                                                                                  (const uint16_t *)res, dtype == MZ_F16, dz_dtype == MZ_F16, act, dgamma, dbeta, dz,
-                                                                                                 (uint16_t *)dz16, dres);
+                                                                                                 (uint16_t *)dz16, dres));
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -113,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();                  // the driver honours __align__(1024) on the dynamic segment; fail loudly if not
 
-    for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale ? p.scale[i] : 1.0f; s_shift[i] = p.shift[i]; }
+    mzb::pdl_trigger();                               // (training-step chains, common.cuh) the successor may become resident
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -130,6 +130,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     cluster_sync_all();                               // the peer's barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    // everything above touched only shared / tensor memory: it may overlap the tail of the previous kernel in the stream.  From here on
+    // global memory is read (per-channel constants, operands) and written
+    mzb::pdl_wait();
+    for (int i = threadIdx.x; i < N; i += NUM_THREADS) { s_scale[i] = p.scale ? p.scale[i] : 1.0f; s_shift[i] = p.shift[i]; }
+    __syncthreads();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -528,6 +533,14 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    cudaLaunchAttribute attr2[2];
+    if (!o.dst && mzb::pdl_enabled()) {               // fp32-only output = a convolution of a training step: part of a kernel chain (common.cuh)
+        attr2[0] = attr[0];
+        attr2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr2[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr2;
+        cfg.numAttrs = 2;
+    }
     const bool relu = o.act == MZ_ACT_RELU;
     if (o.cout == 256) {
         if (relu) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, map_a, map_b, p));

@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -19,6 +21,12 @@ void set_error(const char *fmt, ...)
 }
 
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int pdl_level()
+{
+    static const int lvl = [] { const char *e = getenv("MZB_PDL"); return e ? atoi(e) : 0; }();
+    return lvl;
+}
 
 }  // namespace mzb
 

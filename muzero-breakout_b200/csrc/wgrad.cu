@@ -198,6 +198,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
 // ns = row length of dst (all samples of the K-concatenated operand), s_off = first sample column of this call
 __global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int s_off, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt)
 {
+    mzb::pdl_trigger();
+    mzb::pdl_wait();
     __shared__ uint16_t tile[64][64 + 2];                    // row pitch 132 bytes = 33 words: column reads hit 32 different banks
     const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, pix = blockIdx.z;
     const int r = threadIdx.x >> 2, q = (threadIdx.x & 3) * 16;
@@ -290,8 +292,8 @@ int mz_wgrad_transpose_into(int n, int P, int C, const void *src, void *dst, int
     const int ns = mz_wgrad_padded_samples(n);
     MZB_CHECK_ARG(s_offset >= 0 && s_offset % BLOCK_K == 0 && ns_total % BLOCK_K == 0 && s_offset + ns <= ns_total, "sample window outside the destination rows");
     MZB_CHECK_ARG(P <= 65535 && C / 64 <= 65535, "image or channel count too large");
-    wgrad_transpose_kernel<<<dim3(ns / 64, C / 64, P), 256, 0, (cudaStream_t)stream>>>(n, ns_total, s_offset, P, C, (const uint16_t *)src, (uint16_t *)dst,
-                                                                                       f16_to_bf16 != 0);
+    MZB_CUDA(mzb::launch_chain(wgrad_transpose_kernel, dim3(ns / 64, C / 64, P), dim3(256), 0, (cudaStream_t)stream, n, ns_total, s_offset, P, C,
+                               (const uint16_t *)src, (uint16_t *)dst, f16_to_bf16 != 0));
     MZB_LAUNCH_CHECK();
     return 0;
 }
