@@ -487,6 +487,11 @@ int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *sc
  * mz_planes_conv_wgrad dw[co][c0+a][tap] (+)= sum_{n,p} dz[n][p][co] * planes[n][a][p + tap]; scratch: mz_planes_wgrad_scratch_bytes()
  */
 int mz_cvt16(long long n, const float *src, void *dst, int dtype, void *stream);
+/* The two 16-bit packs of a convolution weight w float32[cout][cin_total][ksize][ksize] (its first cin input channels; cout, cin multiples
+ * of 64) in ONE launch: fwd (may be NULL) = the tile-contiguous forward operand [tap][cin/64][cout][64] (mz_op.w_layout 1) in fwd_dtype;
+ * dgrad (may be NULL) = the same layout of the transposed, tap-flipped filter [tap][cout/64][cin][64] in bf16, whose "same" convolution with
+ * dy is the data gradient.  Run before every training iteration's first use of the weight (the optimizer has changed it). */
+int mz_pack_conv(int cout, int cin_total, int cin, int ksize, const float *w, void *fwd, int fwd_dtype, void *dgrad, void *stream);
 int mz_pool2_train_fwd(int n, int H, int W, int C, const float *x, float *y, void *y16, int dtype, void *stream);
 int mz_pool2_train_bwd(int n, int H, int W, int C, const float *dy, float *dx, void *stream);
 int mz_linear_fwd(int n, int HW, int C, int O, const float *x, const float *w, const float *bias, float *out, void *stream);

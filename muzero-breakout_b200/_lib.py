@@ -144,6 +144,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_conv_wgrad_any": [i32] * 8 + [vp, vp, vp, vp, i32, vp],
         "mz_colsum": [i32, i32, vp, vp, i32, vp, vp],
         "mz_cvt16": [ll, vp, vp, i32, vp],
+        "mz_pack_conv": [i32, i32, i32, i32, vp, vp, i32, vp, vp],
         "mz_pool2_train_fwd": [i32, i32, i32, i32, vp, vp, vp, i32, vp],
         "mz_pool2_train_bwd": [i32, i32, i32, i32, vp, vp, vp],
         "mz_linear_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp],

@@ -397,6 +397,35 @@ __global__ void __launch_bounds__(256) planes_dw_reduce_kernel(const PlaneArgs a
     *dst = accumulate ? *dst + v : v;
 }
 
+// ---------------------------------------------------------------- weight packs of a convolution for the tensor-core kernels
+// w float32 [cout][cin_total][taps] (PyTorch's (cout, cin, k, k)), the first cin input channels are packed:
+//   fwd   [tap][cin/64][cout][64]   element (t, cb, co, c) = w[co][cb*64 + c][t]                 (forward operand, 16-bit type of the activations)
+//   dgrad [tap][cout/64][cin][64]   element (t, ob, ci, o) = w[ob*64 + o][ci][taps - 1 - t]      (transposed, tap-flipped filter: bf16)
+// one thread per packed element, both packs in one launch (a torch permute / flip / contiguous / convert chain is 5-7 tiny kernels per
+// convolution, ~550 per training iteration, in front of each layer's first use)
+__global__ void __launch_bounds__(256) pack_conv_kernel(int cout, int cin_total, int cin, int taps, const float *__restrict__ w, uint16_t *__restrict__ fwd,
+                                                        int fwd_f16, uint16_t *__restrict__ dgrad)
+{
+    const int total = taps * cin * cout;
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < total) {
+        if (!fwd) return;
+        const int c = i & 63;
+        int r = i >> 6;
+        const int co = r % cout; r /= cout;
+        const int cb = r % (cin >> 6), t = r / (cin >> 6);
+        fwd[i] = tl_to16(__ldg(w + ((size_t)co * cin_total + cb * 64 + c) * taps + t), fwd_f16 != 0);
+        return;
+    }
+    i -= total;
+    if (i >= total || !dgrad) return;
+    const int o = i & 63;
+    int r = i >> 6;
+    const int ci = r % cin; r /= cin;
+    const int ob = r % (cout >> 6), t = r / (cout >> 6);
+    dgrad[i] = tl_to16(__ldg(w + ((size_t)(ob * 64 + o) * cin_total + ci) * taps + (taps - 1 - t)), false);
+}
+
 bool pl_args_ok(const PlaneArgs &a)
 {
     return a.n > 0 && a.H > 0 && a.W > 0 && a.H * a.W <= PL_MAX_HW && a.A >= 1 && a.A <= PL_MAX_A && a.cout >= 32 && a.cout <= 1024 && a.cout % 32 == 0 &&
@@ -414,6 +443,18 @@ int mz_cvt16(long long n, const float *src, void *dst, int dtype, void *stream)
     MZB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "src must be 16-byte, dst 8-byte aligned");
     const size_t n4 = (size_t)n / 4;
     cvt16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n4, (const float4 *)src, (uint16_t *)dst, dtype == MZ_F16);
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int mz_pack_conv(int cout, int cin_total, int cin, int ksize, const float *w, void *fwd, int fwd_dtype, void *dgrad, void *stream)
+{
+    MZB_CHECK_ARG(cout > 0 && cout % 64 == 0 && cin > 0 && cin % 64 == 0 && cin <= cin_total && (ksize == 1 || ksize == 3), "cout and cin must be multiples of 64");
+    MZB_CHECK_ARG(w && (fwd || dgrad), "null pointer");
+    MZB_CHECK_ARG(!fwd || fwd_dtype == MZ_BF16 || fwd_dtype == MZ_F16, "fwd_dtype must be MZ_BF16 or MZ_F16");
+    const int total = ksize * ksize * cin * cout;
+    pack_conv_kernel<<<(2 * total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cout, cin_total, cin, ksize * ksize, w, (uint16_t *)fwd, fwd_dtype == MZ_F16,
+                                                                              (uint16_t *)dgrad);
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -208,22 +208,46 @@ class Adam:
         self.step_count = steps.pop() if steps else 0
 
 
+def pack_conv(weight: torch.Tensor, cin: int | None = None, fwd_dtype=None, fwd_out: torch.Tensor | None = None, dgrad_out: torch.Tensor | None = None):
+    """The 16-bit operand packs of a convolution weight (cout, cin_total, k, k) -- its first `cin` input channels -- in ONE launch
+    (mz_pack_conv): the forward pack [tap][cin/64][cout][64] in fwd_dtype (written to fwd_out, or allocated when fwd_dtype is given) and / or
+    the data-gradient pack [tap][cout/64][cin][64] in bf16 (dgrad_out).  Returns (fwd pack or None, dgrad pack or None)."""
+    _lib.require_cuda()
+    cout, cin_total, k, _ = weight.shape
+    cin = cin or cin_total
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    if fwd_out is None and fwd_dtype is not None:
+        fwd_out = torch.empty((k * k, cin // 64, cout, 64), dtype=fwd_dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib().mz_pack_conv(cout, cin_total, cin, k, _p(w), _p(fwd_out), _dt(fwd_out.dtype) if fwd_out is not None else 0, _p(dgrad_out),
+                                           torch.cuda.current_stream(w.device).cuda_stream))
+    return fwd_out, dgrad_out
+
+
 class ConvDgrad:
     """dL/dx of `y = conv2d(x, weight, padding=k//2)` (stride 1; the only convolution form in networks.py) on the tensor cores:
     dx = conv2d(dy, weight.transpose(0, 1).flip(2, 3), padding=k//2), evaluated by the acting path's tcgen05 implicit-GEMM kernel with
     bf16 operands and fp32 accumulation.  Channels-last tensors: dy (n, H, W, cout) bf16 in, dx (n, H, W, cin) fp32 out."""
 
-    def __init__(self, weight: torch.Tensor, device="cuda"):
+    def __init__(self, weight: torch.Tensor, device="cuda", cin: int | None = None):
+        """cin: use only the first cin input channels of the weight (the dynamics ConvBlock's 256 hidden-state channels of 259)"""
         _lib.require_cuda()
-        cout, cin, k, _ = weight.shape
+        cout, cin_total, k, _ = weight.shape
+        cin = cin or cin_total
         if k not in (1, 3) or cout % 64 or cin not in (128, 256):
             raise ValueError("ConvDgrad: built for the 1x1 / 3x3 convolutions of networks.py with cout % 64 == 0 and cin in (128, 256) (one UMMA N)")
-        wt = self.dgrad_filter(weight)
-        wp = wt.permute(0, 2, 3, 1).reshape(cin, k * k, cout // 64, 64).permute(1, 2, 0, 3)    # tile-contiguous [tap][cout/64][cin][64], as networks.py _conv
-        self.w = wp.contiguous().to(device=device, dtype=torch.bfloat16)
         self.cin, self.cout, self.k = cin, cout, k
+        # tile-contiguous [tap][cout/64][cin][64] of the transposed, tap-flipped filter, as networks.py _conv packs a forward weight
+        self.w = torch.empty((k * k, cout // 64, cin, 64), dtype=torch.bfloat16, device=device)
+        self.repack(weight)
         self.scale = torch.ones(cin, dtype=torch.float32, device=device)
         self.shift = torch.zeros(cin, dtype=torch.float32, device=device)
+
+    def repack(self, weight: torch.Tensor):
+        """re-pack in place from the (updated) weight: one mz_pack_conv launch"""
+        pack_conv(weight.to(self.w.device), self.cin, None, None, self.w)
 
     @staticmethod
     def dgrad_filter(weight: torch.Tensor) -> torch.Tensor:
@@ -495,7 +519,7 @@ class ResidualBlockTrain:
         self.C = C_ = int(conv1_w.shape[0])
         self.w = [conv1_w.detach(), conv2_w.detach()]
         self.wt = {self.fwd_dtype: [self._pack(w, device, self.fwd_dtype) for w in self.w]}     # forward: tile-contiguous [tap][cin/64][cout][64], 16-bit
-        self.dgrad = [ConvDgrad(w, device) for w in self.w]
+        self.dgrad = [ConvDgrad(w.to(device), device) for w in self.w]
         self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
         self.running_mean = [torch.zeros(C_, device=device) for _ in range(2)]
         self.running_var = [torch.ones(C_, device=device) for _ in range(2)]
@@ -534,8 +558,14 @@ class ResidualBlockTrain:
             dev = self.ones.device
             f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
             self.w = [conv1_w.detach(), conv2_w.detach()]
-            self.wt = {self.fwd_dtype: [self._pack(w, dev, self.fwd_dtype) for w in self.w]}
-            self.dgrad = [ConvDgrad(w, dev) for w in self.w]
+            if all(w.is_cuda and w.device == dev for w in self.w):
+                # both packs of a convolution in one launch, into the buffers of the step before (no allocation, no torch kernels)
+                self.wt = {self.fwd_dtype: self.wt[self.fwd_dtype]}
+                for i, w in enumerate(self.w):
+                    pack_conv(w, None, None, self.wt[self.fwd_dtype][i], self.dgrad[i].w)
+            else:
+                self.wt = {self.fwd_dtype: [self._pack(w, dev, self.fwd_dtype) for w in self.w]}
+                self.dgrad = [ConvDgrad(w.to(dev), dev) for w in self.w]
             self.b, self.gamma, self.beta = [f(conv1_b), f(conv2_b)], [f(bn1_w), f(bn2_w)], [f(bn1_b), f(bn2_b)]
             self._key = key
         if running is not None:
@@ -740,10 +770,8 @@ def trunk_forward(blocks, x: torch.Tensor) -> torch.Tensor:
             object.__setattr__(m, "_mzb_kernels", k)          # not a submodule / buffer: invisible to state_dict()
         k.refresh(*_block_params(m), running=((m.bn1.running_mean, m.bn1.running_var), (m.bn2.running_mean, m.bn2.running_var)))
         kernels.append(k)
-    with torch.no_grad():
-        for m in blocks:
-            m.bn1.num_batches_tracked += 1
-            m.bn2.num_batches_tracked += 1
+    with torch.no_grad():                                  # one multi-tensor kernel instead of two tiny ones per block
+        torch._foreach_add_([b.num_batches_tracked for m in blocks for b in (m.bn1, m.bn2)], 1)
     params = [p for m in blocks for p in _block_params(m)]
     return _TrunkFn.apply(x, kernels, *params)
 

@@ -79,18 +79,21 @@ class ConvKernels:
         self.cout, self.cin_total, self.k = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
         self.cin = cin or self.cin_total
         self.need_dgrad = need_dgrad
-        self._key = None
+        self._key, self.dg = None, None
 
     def refresh(self, conv: nn.Conv2d):
         w, b = conv.weight, conv.bias
         key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
         if key != self._key:
             dev = w.device
-            wt = w.detach()[:, :self.cin]
-            self.wf = T.ResidualBlockTrain._pack(wt, dev, T.FWD_DTYPE)
-            self.dg = T.ConvDgrad(wt, dev) if self.need_dgrad else None
-            self.bias = (torch.zeros(self.cout, device=dev) if b is None else b.detach().float().contiguous())
-            self.ones = torch.ones(self.cout, device=dev)
+            if self._key is None or (self.need_dgrad and self.dg is None):
+                self.wf = torch.empty((self.k * self.k, self.cin // 64, self.cout, 64), dtype=T.FWD_DTYPE, device=dev)
+                self.dg = T.ConvDgrad(w, dev, self.cin) if self.need_dgrad else None
+                self.ones = torch.ones(self.cout, device=dev)
+                self.zeros = torch.zeros(self.cout, device=dev)
+            # both packs in one launch, into the same buffers every step
+            T.pack_conv(w, self.cin, None, self.wf, self.dg.w if self.dg is not None else None)
+            self.bias = self.zeros if b is None else b.detach().float().contiguous()
             self._key = key
         return self
 
