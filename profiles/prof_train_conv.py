@@ -32,6 +32,10 @@ if int(os.environ.get("MZB_TC_DEBUG", "0")) & 8:
     t = buf.reshape(8, 64).astype(np.int64)
     t0 = t[0, 0]
     names = ["mma:wait_tempty", "mma:start_issue", "mma:issued", "epi:start", "epi:res_loaded", "epi:tfull", "epi:drained", "epi:stored"]
+    fine = buf[32:48].astype(np.int64).reshape(4, 4)
+    if fine[0, 0]:
+        for c in range(4):
+            print(f"  epilogue warp 2, tile 0, chunk {c}: start {(fine[c, 0] - t0) / 1e3:6.2f}  tmem_wait done {(fine[c, 1] - t0) / 1e3:6.2f}  staged {(fine[c, 2] - t0) / 1e3:6.2f}  stored {(fine[c, 3] - t0) / 1e3:6.2f}")
     for it in range(3):
         if t[0, it] == 0: break
         print("tile", it, " ".join(f"{n}={(t[k, it] - t0) / 1e3:7.2f}" for k, n in enumerate(names)))
