@@ -220,9 +220,15 @@ typedef struct mz_op {
     void *dst_lo;            /* conv, 16-bit: correction plane of dst or NULL (not kept) */
     const float *res_f32;    /* conv, 16-bit: the residual as float32 [n][H][W][cout] INSTEAD of res / res_lo (a stream that enters
                                 the network as float32, e.g. the latent argument of MuZeroAgent.evaluate_state), or NULL */
+    double *bn_partial;      /* conv, training form only (dst == NULL, dst_f32 set, act none, no residual but res_f32): the kernel also
+                                writes the per-channel sums and sums of squares of its float32 output over every 32-row group of its tiles,
+                                [mz_conv_stats_blocks()][2][cout] doubles -- the partial sums of the training-mode BatchNorm that follows
+                                (mz_bn_train_fwd_pre), so that no separate reduction pass reads the output again.  NULL: not computed */
 } mz_op;
 
 int mz_run(const mz_op *ops, int n_ops, int nsamples, void *stream);
+/* number of partial-sum blocks a tensor-core convolution over nsamples images of H x W writes to mz_op.bn_partial */
+int mz_conv_stats_blocks(int nsamples, int H, int W, int ksize);
 /* bytes of a correction plane (res_lo / dst_lo) of an [nsamples][H][W][cout] convolution output */
 size_t mz_conv_lo_bytes(int nsamples, int H, int W, int cout, int ksize);
 
@@ -450,6 +456,11 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
 int mz_bn_train_bwd(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int act,
                     const float *save_mean, const float *save_invstd, float *dgamma, float *dbeta, float *dz, void *dz16, float *dres, void *scratch,
                     void *stream);
+/* mz_bn_train_fwd with the statistics' partial sums already computed by the producing convolution (mz_op.bn_partial: nblocks =
+ * mz_conv_stats_blocks() blocks of [2][C] doubles): finalize + apply only */
+int mz_bn_train_fwd_pre(int M, int C, int nblocks, const double *partial, const float *z, const float *gamma, const float *beta, const void *res,
+                        int dtype, int act, double eps, double momentum, float *running_mean, float *running_var, float *save_mean,
+                        float *save_invstd, void *y, float *y_f32, void *stream);
 /* the same with separate element types for res (dtype: what the forward pass produced) and dz16 (dz_dtype: the operand of the convolution
  * gradients): an fp16 forward pass with bf16 gradients */
 int mz_bn_train_bwd_mixed(int M, int C, const float *z, const float *dy, const float *gamma, const float *beta, const void *res, int dtype, int dz_dtype,

@@ -137,6 +137,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_bn_train_fwd": [i32, i32, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double] + [vp] * 8,
         "mz_bn_train_bwd": [i32, i32, vp, vp, vp, vp, vp, i32, i32] + [vp] * 9,
         "mz_bn_train_bwd_mixed": [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32] + [vp] * 9,
+        "mz_bn_train_fwd_pre": [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, C.c_double, C.c_double] + [vp] * 7,
         "mz_bn_train_bwd_acc": [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32] + [vp] * 11,
     })
     ll = C.c_longlong
@@ -158,6 +159,7 @@ def _declare(L: C.CDLL) -> None:
     L.mz_linear_scratch_bytes.argtypes, L.mz_linear_scratch_bytes.restype = [i32, i32, i32, i32], C.c_size_t
     L.mz_planes_wgrad_scratch_bytes.argtypes, L.mz_planes_wgrad_scratch_bytes.restype = [i32, i32], C.c_size_t
     L.mz_bn_scratch_bytes.argtypes, L.mz_bn_scratch_bytes.restype = [i32, i32], C.c_size_t
+    L.mz_conv_stats_blocks.argtypes, L.mz_conv_stats_blocks.restype = [i32, i32, i32, i32], i32
     L.mz_wgrad_padded_samples.argtypes, L.mz_wgrad_padded_samples.restype = [i32], i32
     L.mz_wgrad_partial_bytes.argtypes, L.mz_wgrad_partial_bytes.restype = [i32, i32], C.c_size_t
     for name, args in sig.items():

@@ -251,6 +251,25 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     return 0;
 }
 
+int mz_bn_train_fwd_pre(int M, int C, int nblocks, const double *partial, const float *z, const float *gamma, const float *beta, const void *res,
+                        int dtype, int act, double eps, double momentum, float *running_mean, float *running_var, float *save_mean,
+                        float *save_invstd, void *y, float *y_f32, void *stream)
+{
+    MZB_CHECK_ARG(bn_shape_ok(M, C) && nblocks > 0, "M must be positive and C one of 4 * {1, 2, 4, ..., 256}");
+    MZB_CHECK_ARG(partial && z && gamma && beta && save_mean && save_invstd && (y || y_f32), "null pointer");
+    MZB_CHECK_ARG(dtype == MZ_BF16 || dtype == MZ_F16, "y / res are 16-bit: dtype must be MZ_BF16 or MZ_F16");
+    MZB_CHECK_ARG(act == MZ_ACT_NONE || act == MZ_ACT_RELU || act == MZ_ACT_LEAKY_RELU, "activation not built for training (none / relu / leaky_relu)");
+    cudaStream_t st = (cudaStream_t)stream;
+    MZB_CUDA(mzb::launch_chain_small(bn_fwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, M, C, nblocks, partial, eps, momentum,
+                                     running_mean, running_var, save_mean, save_invstd));
+    MZB_LAUNCH_CHECK();
+    const size_t total4 = (size_t)M * C / 4;
+    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd,
+                               gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act, (uint16_t *)y, y_f32));
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
 int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *scratch, void *stream)
 {
     MZB_CHECK_ARG(bn_shape_ok(M, C), "M must be positive and C one of 4 * {1, 2, 4, ..., 256}");

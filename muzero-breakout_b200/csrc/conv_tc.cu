@@ -53,6 +53,8 @@ struct ConvParams {
     const uint8_t *res_lo;   // e4m3 correction planes of the residual / the output (tc_common.cuh: split2 / lo2), tile-private layout
     uint8_t *dst_lo;
     const float *res_f32;    // fp32 residual instead of res / res_lo
+    double *bn_partial;      // training form: per 32-row group of a tile, the column sums and sums of squares of the float32 output
+                             // [(tile * 2 + CTA rank) * 4 + lane quarter][2][cout] -- the partial sums of the BatchNorm that follows
 };
 
 // profiling trace (debug & 8): per-tile timestamps of cluster 0's leader CTA, read back with mz_conv_trace()
@@ -382,6 +384,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int c0 = col0 + c * 32;
                         TRACE_CHUNK(c, 2);
                         __syncwarp();
+                        if (kTrain && p.bn_partial) {
+                            // lane = column c0 + lane: sum and sum of squares over the warp's 32 staged rows (rows outside the tensor skipped;
+                            // a row's 32 floats are one conflict-free shared-memory request), two float32 runs of 16 rows added in fp64
+                            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+                            double ds = 0.0, dq = 0.0;
+#pragma unroll
+                            for (int hrow = 0; hrow < 2; ++hrow) {
+                                float sa = 0.0f, sq = 0.0f;
+#pragma unroll
+                                for (int r2 = 0; r2 < 16; ++r2) {
+                                    const int rr = hrow * 16 + r2;
+                                    const float xv = *reinterpret_cast<const float *>(stg + rr * 128 + 16 * ((lane >> 2) ^ (rr & 7)) + (lane & 3) * 4);
+                                    if ((vm >> rr) & 1u) { sa += xv; sq = fmaf(xv, xv, sq); }
+                                }
+                                ds += (double)sa; dq += (double)sq;
+                            }
+                            double *bp = p.bn_partial + ((((size_t)tile * 2 + rank) * 4 + quarter) * 2) * N + c0 + lane;
+                            bp[0] = ds;
+                            bp[N] = dq;
+                        }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {                    // 8 lanes cover one row's 128-byte fp32 segment, 4 rows per instruction
                             const int rr = k * 4 + (lane >> 3), u = lane & 7;
@@ -476,6 +498,12 @@ extern "C" size_t mz_conv_lo_bytes(int nsamples, int H, int W, int cout, int ksi
     return (size_t)t3.ntiles * 2 * BLOCK_M * cout;
 }
 
+extern "C" int mz_conv_stats_blocks(int nsamples, int H, int W, int ksize)
+{
+    if (nsamples <= 0 || H <= 0 || W <= 0 || W > 256 || (ksize != 1 && ksize != 3)) return 0;
+    return choose_tiling(nsamples, H, W, ksize).ntiles * 8;
+}
+
 namespace mzb {
 
 int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
@@ -497,6 +525,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     MZB_CHECK_ARG(!o.res_lo || o.res, "conv_tc: res_lo without res");
     MZB_CHECK_ARG(!o.res_f32 || !o.res, "conv_tc: res_f32 replaces res / res_lo");
     p.res_f32 = o.res_f32;
+    p.bn_partial = o.bn_partial;
     p.w_tiled = o.w_layout == 1;
     p.f16 = o.dtype == MZ_F16;
     const CUtensorMapDataType tm_type = p.f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -560,6 +589,7 @@ int conv_tc_launch(const mz_op &o, int n, cudaStream_t st)
     // the training form (see the template comment): float32 output only, no activation, no 16-bit residual / action bias / correction planes
     const bool train_form = !o.dst && o.dst_f32 && !o.res && !o.res_lo && !o.dst_lo && !o.act_bias && o.act == MZ_ACT_NONE &&
                             !(getenv("MZB_TC_GENERAL_EPILOGUE") && atoi(getenv("MZB_TC_GENERAL_EPILOGUE")));
+    MZB_CHECK_ARG(!o.bn_partial || train_form, "conv_tc: bn_partial needs the training form (float32 output only, no activation / residual)");
     if (train_form) {
         if (o.cout == 256) MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, false, true>, map_a, map_b, p));
         else MZB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false, true>, map_a, map_b, p));

@@ -49,7 +49,7 @@ class MzOp(C.Structure):
                 ("src", C.c_void_p), ("dst", C.c_void_p), ("res", C.c_void_p), ("dst_f32", C.c_void_p), ("w", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("act_bias", C.c_void_p), ("act_idx", C.c_void_p),
                 ("dst2", C.c_void_p), ("dst2_slot", C.c_void_p), ("dst2_stride", C.c_int64),
-                ("out", C.c_void_p), ("out_logits", C.c_void_p), ("res_lo", C.c_void_p), ("dst_lo", C.c_void_p), ("res_f32", C.c_void_p)]
+                ("out", C.c_void_p), ("out_logits", C.c_void_p), ("res_lo", C.c_void_p), ("dst_lo", C.c_void_p), ("res_f32", C.c_void_p), ("bn_partial", C.c_void_p)]
 
 
 def _p(t):

@@ -468,8 +468,18 @@ def rows16(x: torch.Tensor, dtype=None) -> torch.Tensor:
     return out
 
 
+# BatchNorm statistics from the producing convolution's epilogue (mz_op.bn_partial) instead of a reduction pass over its output; MZB_TRAIN_CONV_STATS=0: off
+CONV_STATS = os.environ.get("MZB_TRAIN_CONV_STATS", "1") == "1"
+
+
+def conv_stats_buffer(n, H, W, ksize, cout, device):
+    """the partial-sum blocks a training-form convolution writes for the BatchNorm that follows: float64 [blocks][2][cout]"""
+    nb = _lib.lib().mz_conv_stats_blocks(n, H, W, ksize)
+    return torch.empty((nb, 2, cout), dtype=torch.float64, device=device)
+
+
 def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.1, running_mean=None, running_var=None, out_dtype=torch.bfloat16,
-                     want16=True):
+                     want16=True, stats=None):
     """Training-mode BatchNorm2d (+ residual) + activation of a ConvBlock / ResidualBlock (networks.py:16-17,31-35) on channels-last rows.
     z: float32 (..., C) convolution output incl. bias.  Returns (y 16-bit, y float32, save_mean, save_invstd); running stats updated in place."""
     _lib.require_cuda()
@@ -478,6 +488,11 @@ def bn_train_forward(z, gamma, beta, res=None, act="relu", eps=1e-5, momentum=0.
     z = z.contiguous()
     y, y32 = (torch.empty(z.shape, dtype=out_dtype, device=dev) if want16 else None), torch.empty_like(z)
     mean, invstd = torch.empty(C_, device=dev), torch.empty(C_, device=dev)
+    if stats is not None:                                  # the producing convolution has already written the partial sums (conv_stats)
+        with torch.cuda.device(dev):
+            _lib.check(L.mz_bn_train_fwd_pre(M, C_, stats.shape[0], _p(stats), _p(z), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], eps, momentum,
+                                             _p(running_mean), _p(running_var), _p(mean), _p(invstd), _p(y), _p(y32), torch.cuda.current_stream(dev).cuda_stream))
+        return y, y32, mean, invstd
     scratch = torch.empty(L.mz_bn_scratch_bytes(M, C_) // 8, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.mz_bn_train_fwd(M, C_, _p(z), _p(gamma), _p(beta), _p(res), _dt(out_dtype), _ACT[act], eps, momentum, _p(running_mean), _p(running_var),
@@ -538,16 +553,18 @@ class ResidualBlockTrain:
             self.wt[dtype] = [self._pack(w, self.ones.device, dtype) for w in self.w]
         return self.wt[dtype]
 
-    def _conv(self, x16, i):
+    def _conv(self, x16, i, with_stats=False):
+        """z = conv_i(x16) + bias as float32; with_stats: (z, the BatchNorm partial sums its epilogue wrote, or None)"""
         from .src.networks import ACT, BF16, F16, OP_CONV, Program
         n, H, W, _ = x16.shape
         BF16 = F16 if x16.dtype == torch.float16 else BF16
         z = torch.empty(x16.shape, dtype=torch.float32, device=x16.device)
+        stats = conv_stats_buffer(n, H, W, 3, self.C, x16.device) if (with_stats and CONV_STATS) else None
         prog = Program(n)
         prog.add(op=OP_CONV, dtype=BF16, H=H, W=W, cin=self.C, cout=self.C, ksize=3, act=ACT["none"], use_tc=1, w_layout=1, src=x16, dst_f32=z,
-                 w=self._weights(x16.dtype)[i], scale=self.ones, shift=self.b[i])
+                 w=self._weights(x16.dtype)[i], scale=self.ones, shift=self.b[i], **({"bn_partial": stats} if stats is not None else {}))
         prog.run()
-        return z
+        return (z, stats) if with_stats else z
 
     def refresh(self, conv1_w, conv1_b, bn1_w, bn1_b, conv2_w, conv2_b, bn2_w, bn2_b, running=None):
         """Re-pack from the live parameters of a module when any of them changed (version counters: optimizer steps and load_state_dict bump
@@ -574,12 +591,12 @@ class ResidualBlockTrain:
     def forward_fn(self, x16: torch.Tensor):
         """Functional forward: returns (y bf16, y float32, saved) -- `saved` goes back into backward_fn, so one block object can be called
         several times per training step (the K unroll steps share their weights, train_torch.py:507-525)."""
-        z1 = self._conv(x16, 0)
+        z1, st1 = self._conv(x16, 0, True)
         h16, _, m1, s1 = bn_train_forward(z1, self.gamma[0], self.beta[0], None, "relu", self.eps, self.momentum, self.running_mean[0], self.running_var[0],
-                                          out_dtype=x16.dtype)
-        z2 = self._conv(h16, 1)
+                                          out_dtype=x16.dtype, stats=st1)
+        z2, st2 = self._conv(h16, 1, True)
         y16, y32, m2, s2 = bn_train_forward(z2, self.gamma[1], self.beta[1], x16, "relu", self.eps, self.momentum, self.running_mean[1], self.running_var[1],
-                                            out_dtype=x16.dtype)
+                                            out_dtype=x16.dtype, stats=st2)
         return y16, y32, (x16, z1, h16, z2, m1, s1, m2, s2)
 
     def forward(self, x16: torch.Tensor):

@@ -97,17 +97,19 @@ class ConvKernels:
             self._key = key
         return self
 
-    def fwd(self, x16: torch.Tensor) -> torch.Tensor:
-        """x16 (n, H, W, cin) 16-bit rows -> z float32 (n, H, W, cout) = conv + bias"""
+    def fwd(self, x16: torch.Tensor, with_stats: bool = False):
+        """x16 (n, H, W, cin) 16-bit rows -> z float32 (n, H, W, cout) = conv + bias; with_stats: (z, the partial sums of the BatchNorm that
+        follows, written by the convolution's epilogue -- or None when switched off)"""
         from .src.networks import ACT, BF16, F16, OP_CONV, Program
         n, H, W, _ = x16.shape
         z = torch.empty((n, H, W, self.cout), dtype=torch.float32, device=x16.device)
+        stats = T.conv_stats_buffer(n, H, W, self.k, self.cout, x16.device) if (with_stats and T.CONV_STATS) else None
         with torch.cuda.device(x16.device):
             prog = Program(n)
             prog.add(op=OP_CONV, dtype=F16 if x16.dtype == torch.float16 else BF16, H=H, W=W, cin=self.cin, cout=self.cout, ksize=self.k, act=ACT["none"],
-                     use_tc=1, w_layout=1, src=x16, dst_f32=z, w=self.wf, scale=self.ones, shift=self.bias)
+                     use_tc=1, w_layout=1, src=x16, dst_f32=z, w=self.wf, scale=self.ones, shift=self.bias, **({"bn_partial": stats} if stats is not None else {}))
             prog.run()
-        return z
+        return (z, stats) if with_stats else z
 
 
 def _kernels(conv: nn.Conv2d, cin=None, need_dgrad=True) -> ConvKernels:
@@ -137,7 +139,8 @@ class _ConvBlockFn(torch.autograd.Function):
     def forward(ctx, x, planes, kern, bn, act, w, b, gamma, beta):
         L, dev = _lib.lib(), x.device
         x16 = T.rows16(x)
-        z = kern.fwd(x16)
+        # (with action planes their kernel adds to z after the convolution: the statistics then need their own pass)
+        z, stats = kern.fwd(x16, True) if planes is None else (kern.fwd(x16), None)
         n, H, W, cout = z.shape
         if planes is not None:
             sn, sa, sy, sx = planes.stride()
@@ -145,7 +148,7 @@ class _ConvBlockFn(torch.autograd.Function):
                 _lib.check(L.mz_planes_conv_fwd(n, H, W, planes.shape[1], cout, kern.cin_total, kern.cin, _p(planes), sn, sa, sy, sx, _p(w.detach()), _p(z),
                                                 _stream(dev)))
         _, y32, mean, invstd = T.bn_train_forward(z, gamma.detach(), beta.detach(), None, act, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
-                                                  out_dtype=x16.dtype, want16=False)
+                                                  out_dtype=x16.dtype, want16=False, stats=stats)
         ctx.kern, ctx.act, ctx.planes = kern, act, planes
         ctx.params = (w, b, gamma, beta)
         ctx.saved = (x16, z, mean, invstd, gamma.detach(), beta.detach())

@@ -175,3 +175,29 @@ def test_planes_conv_kernels_vs_torch():
                                       scratch.data_ptr(), st))
     refw = torch.nn.grad.conv2d_weight(planes, (cout, A, 3, 3), dz.permute(0, 3, 1, 2), padding=1)
     assert _rel(dw[:, 256:], refw) <= 1e-5 and float(dw[:, :256].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,k,n,H,W", [(256, 256, 3, 70, 4, 5), (256, 128, 1, 300, 4, 5), (128, 128, 3, 9, 16, 20), (64, 128, 3, 5, 16, 20), (256, 256, 3, 33, 8, 10)])
+def test_conv_epilogue_batchnorm_statistics(cin, cout, k, n, H, W):
+    """mz_op.bn_partial: the training-form convolution writes the per-channel sums / sums of squares of its float32 output per 32-row group
+    (ragged sample counts: rows outside the tensor must not count); BatchNorm from those partial sums = BatchNorm with its own reduction pass."""
+    from muzero_breakout_b200 import train, train_layers as TL
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + n)
+    torch.manual_seed(n)
+    conv = nn.Conv2d(cin, cout, k, 1, k // 2).cuda()
+    kern = TL.ConvKernels(conv, None, False).refresh(conv)
+    x16 = torch.randn(n, H, W, cin, device="cuda", generator=g).to(train.FWD_DTYPE)
+    z, stats = kern.fwd(x16, True)
+    assert stats is not None and stats.shape[1:] == (2, cout)
+    zz = z.double().reshape(-1, cout)
+    assert _rel(stats[:, 0].sum(0), zz.sum(0)) <= 1e-6 and _rel(stats[:, 1].sum(0), (zz * zz).sum(0)) <= 1e-6
+    assert torch.equal(z, kern.fwd(x16))                           # the output itself does not depend on the side computation
+    gam, bet = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    rm = [torch.zeros(cout, device="cuda") for _ in range(2)]
+    rv = [torch.ones(cout, device="cuda") for _ in range(2)]
+    a = train.bn_train_forward(z, gam, bet, None, "relu", running_mean=rm[0], running_var=rv[0], stats=stats)
+    b = train.bn_train_forward(z, gam, bet, None, "relu", running_mean=rm[1], running_var=rv[1])
+    for i, (u, v) in enumerate(zip(a, b)):                         # (y 16-bit, y float32, mean, invstd)
+        tol = 2.0 ** -7 if i == 0 else 2e-6                        # the 16-bit copy: one rounding step where a value sits on a boundary
+        assert float((u.float() - v.float()).abs().max()) <= tol * max(1.0, float(v.float().abs().max())), i
+    assert torch.allclose(rm[0], rm[1], atol=1e-6) and torch.allclose(rv[0], rv[1], rtol=1e-5)
