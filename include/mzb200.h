@@ -375,8 +375,9 @@ int rb_gather_input(const rb_ring *ring, int n, const int64_t *idx, int n_action
 
 
 /* ------------------------------------------------------------------------------------------------
- * Training step, first slice: the loss and the optimizer update.  The
- * backward passes of the three networks are not part of this library yet.
+ * Training step: the loss and the optimizer update here; the forward and backward passes of the
+ * three networks further down (weight gradients, training-mode BatchNorm, the small layers: pools, Linear heads, _scale_state,
+ * action planes); the data gradient of a convolution is mz_run's MZ_OP_CONV on the transposed, tap-flipped filter (mz_pack_conv).
  *
  * mz_loss replaces loss_fn (train_torch.py:33-66) + ScalarTransforms.supports_representation
  * (utils.py:30-64) + what loss.backward() (train_torch.py:515) produces for the three logit tensors.
