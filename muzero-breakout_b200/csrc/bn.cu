@@ -4,6 +4,8 @@
 //   forward   read z (4 B) twice + write y (2 B [+ 4 B])            backward   read dy, z (+ y) twice + write dz (4 B [+ 2 B])
 // Reductions over the M rows go through per-CTA fp64 partial sums that one warp per channel adds in a fixed order: deterministic, and the
 // sum / sum-of-squares variance does not lose digits to cancellation.
+#include <stdlib.h>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -171,7 +173,9 @@ colsum_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, f
     out[c] = accumulate ? out[c] + (float)s : (float)s;
 }
 
-// y = act(gamma * (z - mean) * invstd + beta (+ res))
+// y = act(gamma * (z - mean) * invstd + beta (+ res)).  A thread takes BN_U float4 groups a grid stride apart (the stride is a multiple of
+// C / 4 groups: the same 4 channels, whose constants are loaded once); all its loads are issued before the first use.
+constexpr int BN_U = 4;
 __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ invstd,
                     const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res, int f16, int act,
@@ -179,20 +183,40 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
 {
     mzb::pdl_trigger();
     mzb::pdl_wait();
-    const size_t i = (size_t)blockIdx.x * BN_THREADS + threadIdx.x;
-    if (i >= total4) return;
-    const int c = (int)((i * 4) % C);
-    const float4 z4 = __ldcs(reinterpret_cast<const float4 *>(z) + i);
-    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-    float rr[4] = {0.f, 0.f, 0.f, 0.f}, v[4];
-    if (res) load4_16(res + i * 4, f16 != 0, rr);
+    const size_t i0 = (size_t)blockIdx.x * BN_THREADS + threadIdx.x, stride = (size_t)gridDim.x * BN_THREADS;
+    if (i0 >= total4) return;
+    const int c = (int)((i0 * 4) % C);
+    float ga[4], mu[4], is[4], be[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = act_fwd(fmaf(gamma[c + k], (zz[k] - mean[c + k]) * invstd[c + k], beta[c + k]) + rr[k], act);
-    if (y) store4_16(y + i * 4, f16 != 0, v);
-    if (y_f32) reinterpret_cast<float4 *>(y_f32)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    for (int k = 0; k < 4; ++k) { ga[k] = gamma[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; be[k] = beta[c + k]; }
+    float4 z4[BN_U];
+    uint2 r2[BN_U];
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i < total4) {
+            z4[u] = __ldcs(reinterpret_cast<const float4 *>(z) + i);
+            if (res) r2[u] = *reinterpret_cast<const uint2 *>(res + i * 4);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i >= total4) break;
+        const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
+        float rr[4] = {0.f, 0.f, 0.f, 0.f}, v[4];
+        if (res) {
+            rr[0] = from16((uint16_t)(r2[u].x & 0xffff), f16 != 0); rr[1] = from16((uint16_t)(r2[u].x >> 16), f16 != 0);
+            rr[2] = from16((uint16_t)(r2[u].y & 0xffff), f16 != 0); rr[3] = from16((uint16_t)(r2[u].y >> 16), f16 != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = act_fwd(fmaf(ga[k], (zz[k] - mu[k]) * is[k], be[k]) + rr[k], act);
+        if (y) store4_16(y + i * 4, f16 != 0, v);
+        if (y_f32) reinterpret_cast<float4 *>(y_f32)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
 }
 
-// dz = gamma * invstd * (g - dbeta / M - xhat * dgamma / M), g = dy * act'(pre); dres = g
+// dz = gamma * invstd * (g - dbeta / M - xhat * dgamma / M), g = dy * act'(pre); dres = g.  Same thread mapping as the forward kernel.
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, const float *__restrict__ dy, const float *__restrict__ mean,
                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res,
@@ -201,23 +225,54 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
 {
     mzb::pdl_trigger();
     mzb::pdl_wait();
-    const size_t i = (size_t)blockIdx.x * BN_THREADS + threadIdx.x;
-    if (i >= total4) return;
-    const int c = (int)((i * 4) % C);
-    const float4 z4 = __ldcs(reinterpret_cast<const float4 *>(z) + i), d4 = __ldcs(reinterpret_cast<const float4 *>(dy) + i);
-    const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    float rr[4] = {0.f, 0.f, 0.f, 0.f}, g[4], o[4];
-    if (res) load4_16(res + i * 4, f16 != 0, rr);
+    const size_t i0 = (size_t)blockIdx.x * BN_THREADS + threadIdx.x, stride = (size_t)gridDim.x * BN_THREADS;
+    if (i0 >= total4) return;
+    const int c = (int)((i0 * 4) % C);
     const float inv_m = 1.0f / (float)M;
+    float ga[4], mu[4], is[4], be[4], dgm[4], dbm[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float xh = (zz[k] - mean[c + k]) * invstd[c + k];
-        g[k] = dd[k] * act_grad(fmaf(gamma[c + k], xh, beta[c + k]) + rr[k], act);
-        o[k] = gamma[c + k] * invstd[c + k] * (g[k] - dbeta[c + k] * inv_m - xh * dgamma[c + k] * inv_m);
+        ga[k] = gamma[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; be[k] = beta[c + k];
+        dgm[k] = dgamma[c + k] * inv_m; dbm[k] = dbeta[c + k] * inv_m;
     }
-    if (dz) reinterpret_cast<float4 *>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
-    if (dz16) store4_16(dz16 + i * 4, dz_f16 != 0, o);
-    if (dres) reinterpret_cast<float4 *>(dres)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    float4 z4[BN_U], d4[BN_U];
+    uint2 r2[BN_U];
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i < total4) {
+            z4[u] = __ldcs(reinterpret_cast<const float4 *>(z) + i);
+            d4[u] = __ldcs(reinterpret_cast<const float4 *>(dy) + i);
+            if (res) r2[u] = *reinterpret_cast<const uint2 *>(res + i * 4);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i >= total4) break;
+        const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w}, dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+        float rr[4] = {0.f, 0.f, 0.f, 0.f}, g[4], o[4];
+        if (res) {
+            rr[0] = from16((uint16_t)(r2[u].x & 0xffff), f16 != 0); rr[1] = from16((uint16_t)(r2[u].x >> 16), f16 != 0);
+            rr[2] = from16((uint16_t)(r2[u].y & 0xffff), f16 != 0); rr[3] = from16((uint16_t)(r2[u].y >> 16), f16 != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (zz[k] - mu[k]) * is[k];
+            g[k] = dd[k] * act_grad(fmaf(ga[k], xh, be[k]) + rr[k], act);
+            o[k] = ga[k] * is[k] * (g[k] - dbm[k] - xh * dgm[k]);
+        }
+        if (dz) reinterpret_cast<float4 *>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dz16) store4_16(dz16 + i * 4, dz_f16 != 0, o);
+        if (dres) reinterpret_cast<float4 *>(dres)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+}
+
+// float4 groups per thread of the apply kernels as launched: BN_U, or 1 with MZB_BN_U=1 (profiling: one group per thread, the form before)
+int bn_u()
+{
+    static const int v = [] { const char *e = getenv("MZB_BN_U"); return (e && atoi(e) == 1) ? 1 : BN_U; }();
+    return v;
 }
 
 bool bn_shape_ok(int M, int C) { return M > 0 && C >= 4 && C % 4 == 0 && C / 4 <= BN_THREADS && BN_THREADS % (C / 4) == 0; }
@@ -245,7 +300,7 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     MZB_CUDA(mzb::launch_chain_small(bn_fwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
+    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
                                                                                                  dtype == MZ_F16, act, (uint16_t *)y, y_f32));
     MZB_LAUNCH_CHECK();
     return 0;
@@ -264,7 +319,7 @@ int mz_bn_train_fwd_pre(int M, int C, int nblocks, const double *partial, const 
                                      running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd,
+    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd,
                                gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act, (uint16_t *)y, y_f32));
     MZB_LAUNCH_CHECK();
     return 0;
@@ -317,7 +372,7 @@ int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const flo
     MZB_CUDA(mzb::launch_chain_small(bn_bwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_bwd_apply_kernel, dim3((unsigned)((total4 + BN_THREADS - 1) / BN_THREADS)), dim3(BN_THREADS), 0, st, total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
+    MZB_CUDA(mzb::launch_chain(bn_bwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
                                                                                                  (const uint16_t *)res, dtype == MZ_F16, dz_dtype == MZ_F16, act, dgamma, dbeta, dz,
                                                                                                  (uint16_t *)dz16, dres));
     MZB_LAUNCH_CHECK();
