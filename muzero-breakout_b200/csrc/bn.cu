@@ -76,23 +76,43 @@ bn_reduce_kernel(int M, int C, int mode, const float *__restrict__ z, const floa
 #pragma unroll
         for (int i = 0; i < 4; ++i) { mu[i] = mean[cq + i]; is[i] = invstd[cq + i]; ga[i] = gamma[cq + i]; be[i] = beta[cq + i]; }
     }
-    for (int r = r0 + rl; r < r1; r += lanes) {
-        const float4 z4 = *reinterpret_cast<const float4 *>(z + (size_t)r * C + cq);
-        const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-        if (mode == 0) {
+    // four rows per trip: every load of the trip is issued before its first use (the order of the additions stays row by row)
+    constexpr int RU = 4;
+    for (int r = r0 + rl; r < r1; r += RU * lanes) {
+        float4 z4[RU], d4[RU];
+        uint2 r2[RU];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] += zz[i]; b[i] = fmaf(zz[i], zz[i], b[i]); }
-        } else {
-            const float4 d4 = *reinterpret_cast<const float4 *>(dy + (size_t)r * C + cq);
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            float rr[4] = {0.f, 0.f, 0.f, 0.f};
-            if (res) load4_16(res + (size_t)r * C + cq, f16 != 0, rr);
+        for (int u = 0; u < RU; ++u) {
+            const int ru = r + u * lanes;
+            if (ru < r1) {
+                z4[u] = *reinterpret_cast<const float4 *>(z + (size_t)ru * C + cq);
+                if (mode == 1) {
+                    d4[u] = *reinterpret_cast<const float4 *>(dy + (size_t)ru * C + cq);
+                    if (res) r2[u] = *reinterpret_cast<const uint2 *>(res + (size_t)ru * C + cq);
+                }
+            }
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float xh = (zz[i] - mu[i]) * is[i];
-                const float g = dd[i] * act_grad(fmaf(ga[i], xh, be[i]) + rr[i], act);
-                a[i] += g;
-                b[i] = fmaf(g, xh, b[i]);
+        for (int u = 0; u < RU; ++u) {
+            if (r + u * lanes >= r1) break;
+            const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
+            if (mode == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] += zz[i]; b[i] = fmaf(zz[i], zz[i], b[i]); }
+            } else {
+                const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+                float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                if (res) {
+                    rr[0] = from16((uint16_t)(r2[u].x & 0xffff), f16 != 0); rr[1] = from16((uint16_t)(r2[u].x >> 16), f16 != 0);
+                    rr[2] = from16((uint16_t)(r2[u].y & 0xffff), f16 != 0); rr[3] = from16((uint16_t)(r2[u].y >> 16), f16 != 0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (zz[i] - mu[i]) * is[i];
+                    const float g = dd[i] * act_grad(fmaf(ga[i], xh, be[i]) + rr[i], act);
+                    a[i] += g;
+                    b[i] = fmaf(g, xh, b[i]);
+                }
             }
         }
     }
@@ -176,6 +196,7 @@ colsum_finalize_kernel(int C, int nblocks, const double *__restrict__ partial, f
 // y = act(gamma * (z - mean) * invstd + beta (+ res)).  A thread takes BN_U float4 groups a grid stride apart (the stride is a multiple of
 // C / 4 groups: the same 4 channels, whose constants are loaded once); all its loads are issued before the first use.
 constexpr int BN_U = 4;
+template <int U>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const float *__restrict__ mean, const float *__restrict__ invstd,
                     const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res, int f16, int act,
@@ -189,10 +210,10 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
     float ga[4], mu[4], is[4], be[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { ga[k] = gamma[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; be[k] = beta[c + k]; }
-    float4 z4[BN_U];
-    uint2 r2[BN_U];
+    float4 z4[U];
+    uint2 r2[U];
 #pragma unroll
-    for (int u = 0; u < BN_U; ++u) {
+    for (int u = 0; u < U; ++u) {
         const size_t i = i0 + u * stride;
         if (i < total4) {
             z4[u] = __ldcs(reinterpret_cast<const float4 *>(z) + i);
@@ -200,7 +221,7 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
         }
     }
 #pragma unroll
-    for (int u = 0; u < BN_U; ++u) {
+    for (int u = 0; u < U; ++u) {
         const size_t i = i0 + u * stride;
         if (i >= total4) break;
         const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
@@ -217,6 +238,7 @@ bn_fwd_apply_kernel(size_t total4, int C, const float *__restrict__ z, const flo
 }
 
 // dz = gamma * invstd * (g - dbeta / M - xhat * dgamma / M), g = dy * act'(pre); dres = g.  Same thread mapping as the forward kernel.
+template <int U>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, const float *__restrict__ dy, const float *__restrict__ mean,
                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res,
@@ -235,10 +257,10 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
         ga[k] = gamma[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; be[k] = beta[c + k];
         dgm[k] = dgamma[c + k] * inv_m; dbm[k] = dbeta[c + k] * inv_m;
     }
-    float4 z4[BN_U], d4[BN_U];
-    uint2 r2[BN_U];
+    float4 z4[U], d4[U];
+    uint2 r2[U];
 #pragma unroll
-    for (int u = 0; u < BN_U; ++u) {
+    for (int u = 0; u < U; ++u) {
         const size_t i = i0 + u * stride;
         if (i < total4) {
             z4[u] = __ldcs(reinterpret_cast<const float4 *>(z) + i);
@@ -247,7 +269,7 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
         }
     }
 #pragma unroll
-    for (int u = 0; u < BN_U; ++u) {
+    for (int u = 0; u < U; ++u) {
         const size_t i = i0 + u * stride;
         if (i >= total4) break;
         const float zz[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w}, dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
@@ -271,9 +293,16 @@ bn_bwd_apply_kernel(size_t total4, int M, int C, const float *__restrict__ z, co
 // float4 groups per thread of the apply kernels as launched: BN_U, or 1 with MZB_BN_U=1 (profiling: one group per thread, the form before)
 int bn_u()
 {
-    static const int v = [] { const char *e = getenv("MZB_BN_U"); return (e && atoi(e) == 1) ? 1 : BN_U; }();
+    static const int v = [] { const char *e = getenv("MZB_BN_U"); const int u = e ? atoi(e) : BN_U; return (u == 1 || u == 2 || u == 8) ? u : BN_U; }();
     return v;
 }
+#define BN_DISPATCH_U(call_with_U)          \
+    switch (bn_u()) {                       \
+        case 1: { constexpr int U_ = 1; call_with_U; break; } \
+        case 2: { constexpr int U_ = 2; call_with_U; break; } \
+        case 8: { constexpr int U_ = 8; call_with_U; break; } \
+        default: { constexpr int U_ = 4; call_with_U; break; } \
+    }
 
 bool bn_shape_ok(int M, int C) { return M > 0 && C >= 4 && C % 4 == 0 && C / 4 <= BN_THREADS && BN_THREADS % (C / 4) == 0; }
 int bn_blocks(int M) { return (M + BN_ROWS - 1) / BN_ROWS; }
@@ -300,8 +329,8 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     MZB_CUDA(mzb::launch_chain_small(bn_fwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
-                                                                                                 dtype == MZ_F16, act, (uint16_t *)y, y_f32));
+    BN_DISPATCH_U(MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel<U_>, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd, gamma, beta, (const uint16_t *)res,
+                                                                                                 dtype == MZ_F16, act, (uint16_t *)y, y_f32)));
     MZB_LAUNCH_CHECK();
     return 0;
 }
@@ -319,8 +348,8 @@ int mz_bn_train_fwd_pre(int M, int C, int nblocks, const double *partial, const 
                                      running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd,
-                               gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act, (uint16_t *)y, y_f32));
+    BN_DISPATCH_U(MZB_CUDA(mzb::launch_chain(bn_fwd_apply_kernel<U_>, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, C, z, save_mean, save_invstd,
+                               gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act, (uint16_t *)y, y_f32)));
     MZB_LAUNCH_CHECK();
     return 0;
 }
@@ -372,9 +401,9 @@ int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const flo
     MZB_CUDA(mzb::launch_chain_small(bn_bwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc));
     MZB_LAUNCH_CHECK();
     const size_t total4 = (size_t)M * C / 4;
-    MZB_CUDA(mzb::launch_chain(bn_bwd_apply_kernel, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
+    BN_DISPATCH_U(MZB_CUDA(mzb::launch_chain(bn_bwd_apply_kernel<U_>, dim3((unsigned)((total4 + (size_t)BN_THREADS * bn_u() - 1) / ((size_t)BN_THREADS * bn_u()))), dim3(BN_THREADS), 0, st, total4, M, C, z, dy, save_mean, save_invstd, gamma, beta,
                                                                                                  (const uint16_t *)res, dtype == MZ_F16, dz_dtype == MZ_F16, act, dgamma, dbeta, dz,
-                                                                                                 (uint16_t *)dz16, dres));
+                                                                                                 (uint16_t *)dz16, dres)));
     MZB_LAUNCH_CHECK();
     return 0;
 }
