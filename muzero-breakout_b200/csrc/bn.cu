@@ -14,7 +14,7 @@
 namespace {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_ROWS = 32;          // rows per CTA of the reduction kernels (320 CTAs at a 512-sample minibatch of 4x5 latents)
+const int BN_ROWS = [] { const char *e = getenv("MZB_BN_ROWS"); const int v = e ? atoi(e) : 128; return v >= 16 && v <= 1024 ? v : 128; }();   // rows per CTA of the reduction kernels (128: 80 CTAs at a 512-sample minibatch of 4x5 latents; MZB_BN_ROWS = 32 / 64 / 128: 31.0 / 30.2 / 30.0 ms per graphed training iteration, four rows' loads in flight per thread)
 
 __device__ __forceinline__ float from16(uint16_t u, bool f16)
 {
@@ -60,7 +60,7 @@ __device__ __forceinline__ float act_grad(float pre, int act)      // d act / d 
 // g = dy * act'(pre), xhat = (z - mean) * invstd, pre = gamma * xhat + beta (+ res).
 // Thread = 4 consecutive channels x every (256 / (C/4))-th row of the slab; partial[blockIdx][2][C] in fp64.
 __global__ void __launch_bounds__(BN_THREADS)
-bn_reduce_kernel(int M, int C, int mode, const float *__restrict__ z, const float *__restrict__ dy, const float *__restrict__ mean,
+bn_reduce_kernel(int M, int C, int rows_per, int mode, const float *__restrict__ z, const float *__restrict__ dy, const float *__restrict__ mean,
                  const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, const uint16_t *__restrict__ res,
                  int f16, int act, double *__restrict__ partial)
 {
@@ -69,7 +69,7 @@ bn_reduce_kernel(int M, int C, int mode, const float *__restrict__ z, const floa
     extern __shared__ double s_red[];                       // [row lanes][2][C]
     const int tpr = C / 4, lanes = BN_THREADS / tpr;
     const int cq = (threadIdx.x % tpr) * 4, rl = threadIdx.x / tpr;
-    const int r0 = blockIdx.x * BN_ROWS, r1 = min(M, r0 + BN_ROWS);
+    const int r0 = blockIdx.x * rows_per, r1 = min(M, r0 + rows_per);
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     float mu[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {1.f, 1.f, 1.f, 1.f}, ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
     if (mode == 1) {
@@ -324,7 +324,7 @@ int mz_bn_train_fwd(int M, int C, const float *z, const float *gamma, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 0, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, BN_ROWS, 0, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
     MZB_LAUNCH_CHECK();
     MZB_CUDA(mzb::launch_chain_small(bn_fwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, M, C, nb, (const double *)scratch, eps, momentum, running_mean, running_var, save_mean, save_invstd));
     MZB_LAUNCH_CHECK();
@@ -361,7 +361,7 @@ int mz_colsum(int M, int C, const float *x, float *out, int accumulate, void *sc
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, BN_ROWS, 0, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, (double *)scratch));
     MZB_LAUNCH_CHECK();
     MZB_CUDA(mzb::launch_chain_small(colsum_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, out, accumulate));
     MZB_LAUNCH_CHECK();
@@ -395,7 +395,7 @@ int mz_bn_train_bwd_acc(int M, int C, const float *z, const float *dy, const flo
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = bn_blocks(M), lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
+    MZB_CUDA(mzb::launch_chain(bn_reduce_kernel, dim3(nb), dim3(BN_THREADS), smem, st, M, C, BN_ROWS, 1, z, dy, save_mean, save_invstd, gamma, beta, (const uint16_t *)res, dtype == MZ_F16, act,
                                                    (double *)scratch));
     MZB_LAUNCH_CHECK();
     MZB_CUDA(mzb::launch_chain_small(bn_bwd_finalize_kernel, dim3((C * 32 + BN_THREADS - 1) / BN_THREADS), dim3(BN_THREADS), 0, st, C, nb, (const double *)scratch, dgamma, dbeta, dgamma_acc, dbeta_acc));

@@ -161,7 +161,7 @@ def test_training_ends_mirror_reference_signature():
     assert L.mz_conv_wgrad(512, 4, 5, 3, 0, 64, 64, 64, 64, None) != 0          # fp32 operands are not built
     assert L.mz_conv_wgrad(512, 4, 5, 3, 1, None, 64, 64, 64, None) != 0 and b"null" in L.mzb_last_error()
     assert L.mz_wgrad_transpose(512, 20, 100, 64, 64, None) != 0                 # channels not a multiple of 64
-    assert L.mz_bn_scratch_bytes(10240, 256) == 320 * 2 * 256 * 8 and L.mz_bn_scratch_bytes(10240, 6) == 0
+    assert L.mz_bn_scratch_bytes(10240, 256) == 80 * 2 * 256 * 8 and L.mz_bn_scratch_bytes(10240, 6) == 0      # 128 rows per partial-sum block
     assert L.mz_bn_train_fwd(0, 256, *([None] * 4), 1, 1, 1e-5, 0.1, *([None] * 8)) != 0 and b"M must be positive" in L.mzb_last_error()
     assert L.mz_bn_train_fwd(64, 256, 64, 64, 64, None, 1, 3, 1e-5, 0.1, None, None, 64, 64, 64, None, 64, None) != 0 and b"activation" in L.mzb_last_error()
     assert L.mz_bn_train_bwd(64, 256, 64, 64, 64, 64, None, 0, 1, *([64] * 4), 64, None, None, 64, None) != 0 and b"16-bit" in L.mzb_last_error()
