@@ -425,6 +425,9 @@ int mz_wgrad_transpose_cvt(int n, int P, int C, const void *src, void *dst, int 
  * (channel, pixel) row (both multiples of 64): several activations that share a weight -- the K unroll steps of a training step --
  * concatenated along the GEMM's reduction axis, so that ONE mz_conv_wgrad_any(n = ns_total) call gives the sum of their weight gradients */
 int mz_wgrad_transpose_into(int n, int P, int C, const void *src, void *dst, int ns_total, int s_offset, int f16_to_bf16, void *stream);
+/* both operands of one weight gradient (a: dy with Ca channels, b: x with Cb channels; cvt_*: float16 -> bfloat16) in ONE launch */
+int mz_wgrad_transpose_pair(int n, int P, int Ca, const void *src_a, void *dst_a, int cvt_a, int Cb, const void *src_b, void *dst_b, int cvt_b, int ns_total,
+                            int s_offset, void *stream);
 int mz_conv_wgrad(int n, int H, int W, int ksize, int dtype, const void *dy_t, const void *x_t, float *partial, float *dw, void *stream);
 /* accumulate != 0: dw += the gradient (one rounding per call, in call order): the K unroll steps of a training step share their weights
  * (train_torch.py:507-525) and add straight into the parameter's .grad instead of through K separate add kernels */

@@ -130,6 +130,7 @@ def _declare(L: C.CDLL) -> None:
         "mz_wgrad_transpose": [i32, i32, i32, vp, vp, vp],
         "mz_wgrad_transpose_cvt": [i32, i32, i32, vp, vp, i32, vp],
         "mz_wgrad_transpose_into": [i32, i32, i32, vp, vp, i32, i32, i32, vp],
+        "mz_wgrad_transpose_pair": [i32, i32, i32, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp],
         "mz_conv_wgrad": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "mz_conv_wgrad_accum": [i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp],
     })

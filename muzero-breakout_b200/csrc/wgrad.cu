@@ -196,12 +196,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__
 // cvt: 1 = the source is fp16 and the destination bf16 (the activations of an fp16 forward pass as the weight gradient's bf16 operand: one MMA
 // cannot mix A / B element types in kind::f16 -- the hardware answers "illegal instruction")
 // ns = row length of dst (all samples of the K-concatenated operand), s_off = first sample column of this call
-__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int s_off, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt)
+// A launch may carry a second tensor (src2 / dst2 with C2 channels: the other operand of the same weight gradient): blockIdx.y >= C / 64
+// belongs to it -- one launch per (dy, x) pair instead of two.
+__global__ void __launch_bounds__(256) wgrad_transpose_kernel(int n, int ns, int s_off, int P, int C, const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int cvt,
+                                                              int C2, const uint16_t *__restrict__ src2, uint16_t *__restrict__ dst2, int cvt2)
 {
     mzb::pdl_trigger();
     mzb::pdl_wait();
     __shared__ uint16_t tile[64][64 + 2];                    // row pitch 132 bytes = 33 words: column reads hit 32 different banks
-    const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, pix = blockIdx.z;
+    int by = blockIdx.y;
+    if (by >= C / 64) { by -= C / 64; C = C2; src = src2; dst = dst2; cvt = cvt2; }
+    const int n0 = blockIdx.x * 64, c0 = by * 64, pix = blockIdx.z;
     const int r = threadIdx.x >> 2, q = (threadIdx.x & 3) * 16;
     {
         const int s = n0 + r;
@@ -293,7 +298,21 @@ int mz_wgrad_transpose_into(int n, int P, int C, const void *src, void *dst, int
     MZB_CHECK_ARG(s_offset >= 0 && s_offset % BLOCK_K == 0 && ns_total % BLOCK_K == 0 && s_offset + ns <= ns_total, "sample window outside the destination rows");
     MZB_CHECK_ARG(P <= 65535 && C / 64 <= 65535, "image or channel count too large");
     MZB_CUDA(mzb::launch_chain(wgrad_transpose_kernel, dim3(ns / 64, C / 64, P), dim3(256), 0, (cudaStream_t)stream, n, ns_total, s_offset, P, C,
-                               (const uint16_t *)src, (uint16_t *)dst, f16_to_bf16 != 0));
+                               (const uint16_t *)src, (uint16_t *)dst, f16_to_bf16 != 0, 0, (const uint16_t *)nullptr, (uint16_t *)nullptr, 0));
+    MZB_LAUNCH_CHECK();
+    return 0;
+}
+
+int mz_wgrad_transpose_pair(int n, int P, int Ca, const void *src_a, void *dst_a, int cvt_a, int Cb, const void *src_b, void *dst_b, int cvt_b, int ns_total,
+                            int s_offset, void *stream)
+{
+    MZB_CHECK_ARG(n > 0 && P > 0 && Ca > 0 && Ca % 64 == 0 && Cb > 0 && Cb % 64 == 0 && src_a && dst_a && src_b && dst_b, "bad argument");
+    MZB_CHECK_ARG((((uintptr_t)src_a | (uintptr_t)dst_a | (uintptr_t)src_b | (uintptr_t)dst_b) & 15) == 0, "buffers must be 16-byte aligned");
+    const int ns = mz_wgrad_padded_samples(n);
+    MZB_CHECK_ARG(s_offset >= 0 && s_offset % BLOCK_K == 0 && ns_total % BLOCK_K == 0 && s_offset + ns <= ns_total, "sample window outside the destination rows");
+    MZB_CHECK_ARG(P <= 65535 && (Ca + Cb) / 64 <= 65535, "image or channel count too large");
+    MZB_CUDA(mzb::launch_chain(wgrad_transpose_kernel, dim3(ns / 64, (Ca + Cb) / 64, P), dim3(256), 0, (cudaStream_t)stream, n, ns_total, s_offset, P, Ca,
+                               (const uint16_t *)src_a, (uint16_t *)dst_a, cvt_a != 0, Cb, (const uint16_t *)src_b, (uint16_t *)dst_b, cvt_b != 0));
     MZB_LAUNCH_CHECK();
     return 0;
 }

@@ -337,6 +337,9 @@ class _Pending:
 
 def _transpose_pair(L, dy, x, dy_t, x_t, tot, off, st):
     n, H, W, cout = dy.shape
+    if os.environ.get("MZB_TRAIN_TRANSPOSE_PAIR", "0") == "1":       # both operands in one launch (measured neutral: 30.3 vs 30.2 ms; off)
+        _lib.check(L.mz_wgrad_transpose_pair(n, H * W, cout, _p(dy), _p(dy_t), 0, x.shape[3], _p(x), _p(x_t), int(x.dtype != dy.dtype), tot, off, st))
+        return
     _lib.check(L.mz_wgrad_transpose_into(n, H * W, cout, _p(dy), _p(dy_t), tot, off, 0, st))
     _lib.check(L.mz_wgrad_transpose_into(n, H * W, x.shape[3], _p(x), _p(x_t), tot, off, int(x.dtype != dy.dtype), st))
 
