@@ -201,3 +201,20 @@ def test_conv_epilogue_batchnorm_statistics(cin, cout, k, n, H, W):
         tol = 2.0 ** -7 if i == 0 else 2e-6                        # the 16-bit copy: one rounding step where a value sits on a boundary
         assert float((u.float() - v.float()).abs().max()) <= tol * max(1.0, float(v.float().abs().max())), i
     assert torch.allclose(rm[0], rm[1], atol=1e-6) and torch.allclose(rv[0], rv[1], rtol=1e-5)
+
+
+@pytest.mark.parametrize("cout,cin_total,cin,k", [(256, 256, 256, 3), (128, 256, 256, 1), (256, 259, 256, 3), (128, 64, 64, 3)])
+def test_pack_conv_equals_the_torch_formulas(cout, cin_total, cin, k):
+    """mz_pack_conv (one launch) against the permute / flip / convert chains it replaces: the forward operand [tap][cin/64][cout][64] and the
+    data-gradient operand [tap][cout/64][cin][64] of the transposed, tap-flipped filter -- bit for bit."""
+    from muzero_breakout_b200 import train
+    torch.manual_seed(cout + cin_total + k)
+    w = torch.randn(cout, cin_total, k, k, device="cuda")
+    fwd = torch.empty((k * k, cin // 64, cout, 64), dtype=train.FWD_DTYPE, device="cuda")
+    dg = torch.empty((k * k, cout // 64, cin, 64), dtype=torch.bfloat16, device="cuda")
+    train.pack_conv(w, cin, None, fwd, dg)
+    ws = w[:, :cin]
+    want_fwd = train.ResidualBlockTrain._pack(ws, "cuda", train.FWD_DTYPE)
+    wt = train.ConvDgrad.dgrad_filter(ws)                                  # (cin, cout, k, k)
+    want_dg = wt.permute(0, 2, 3, 1).reshape(cin, k * k, cout // 64, 64).permute(1, 2, 0, 3).contiguous().to(torch.bfloat16)
+    assert torch.equal(fwd, want_fwd) and torch.equal(dg, want_dg)
