@@ -1,5 +1,6 @@
-"""Loss and optimizer ends of the reference's training step on the device (first slice),
-backed by csrc/train.cu through the C ABI (mz_loss / mz_adam, include/mzb200.h).
+"""The reference's training step on the device: loss and optimizer (csrc/train.cu: mz_loss / mz_adam), the
+convolutions' data and weight gradients, training-mode BatchNorm, the ResidualBlock autograd bridge and the graphed loop iteration -- all
+through the C ABI (include/mzb200.h).
 
     reference                                                      here
     loss_fn(observed_reward, predicted_reward, ...,                same call, same return tuple; ONE launch computes the three
